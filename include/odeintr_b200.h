@@ -1,0 +1,165 @@
+/* include/odeintr_b200.h — C-ABI of the B200-native odeintr integration engine.
+ *
+ * This is the drop-in boundary for the reference's hot path: everything the reference does inside
+ * the translation unit it generates from inst/templates/compile_sys_template.cpp (and the
+ * _openmp / _implicit variants) and hands to Rcpp::sourceCpp (R/odeintr.R:340) happens behind these
+ * entry points instead.  The host generator (R or Python) emits a CUDA translation unit holding the
+ * user's snippet as a __device__ functor; odeintr_compile() NVRTC-compiles it for sm_100a together
+ * with the hand-written stepper kernels and loads it.  The remaining functions are what the
+ * reference's generated Rcpp exports call into Boost odeint for, generalised from one trajectory to
+ * an ensemble of m independent instances (initial-condition batches / parameter sweeps).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every host buffer, the library owns every
+ *    device buffer until odeintr_destroy().
+ *  - every function returns 0 on success and a non-zero ODEINTR_E_* code on failure;
+ *    odeintr_last_error() returns the message for the calling thread (what the R glue passes to
+ *    Rcpp::stop()).
+ *  - ensemble arrays are structure-of-arrays with the instance index fastest:
+ *        state  x[v * m + i]          v < sys_dim, i < m
+ *        params p[k * m + i]          k < n_pars
+ *        output out[(s * sys_dim + v) * m + i]   s < rows
+ *    With m == 1 these degenerate to the reference's single-trajectory vectors and the output to the
+ *    data-frame columns X1..XN of name_get_output() (compile_sys_template.cpp:58-73).
+ *  - there is no CPU fallback: every compute entry point fails with ODEINTR_E_CUDA when no
+ *    sm_100-class device is usable.
+ */
+#ifndef ODEINTR_B200_H
+#define ODEINTR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct odeintr_system_s* odeintr_system_t;
+
+enum {
+  ODEINTR_OK = 0,
+  ODEINTR_E_INVALID = 1,   /* bad argument ("Invalid initial state", "Invalid parameter vector", ...) */
+  ODEINTR_E_COMPILE = 2,   /* NVRTC rejected the generated translation unit (see odeintr_compile_log) */
+  ODEINTR_E_CUDA = 3,      /* CUDA runtime / driver error, or no usable device */
+  ODEINTR_E_STEP = 4,      /* at least one instance hit Boost's 500-failed-steps overflow */
+  ODEINTR_E_STATE = 5      /* call sequence error (e.g. continue_at with an empty record) */
+};
+
+/* compile flags */
+#define ODEINTR_FLAG_FMAD 1u            /* allow FMA contraction (fast mode; NOT bit-compatible with the reference) */
+#define ODEINTR_FLAG_KEEP_ZERO_TERMS 2u /* also add Boost's zero tableau entries (x + 0*dt*k) */
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Replaces Rcpp::sourceCpp(code = code, env = env) at R/odeintr.R:340,457,602.
+ * cuda_src  : translation unit emitted by the generator (templates/compile_*_template.cu)
+ * sys_dim   : N  (__SYS_SIZE__, compile_sys_template.cpp:17)
+ * n_pars    : number of run-time parameters (0 when pars are const / absent)
+ * atol,rtol : error tolerances baked into the stepper constructor by R/utils.R:22-32 and
+ *             compile_implicit_template.cpp:30-33
+ */
+int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_pars, double atol, double rtol,
+                    unsigned flags, odeintr_system_t* out);
+
+/* Compile only (no device needed): NVRTC -> sm_100a cubin.  *cubin_size receives the size; when
+ * cubin is non-null and cubin_cap is large enough the image is copied out.  Used by the CPU-side
+ * build check and tests. */
+int odeintr_compile_cubin(const char* cuda_src, unsigned flags, void* cubin, size_t cubin_cap, size_t* cubin_size);
+
+int odeintr_destroy(odeintr_system_t h);
+const char* odeintr_last_error(void);
+const char* odeintr_compile_log(odeintr_system_t h);
+/* Select the CUDA device (ordinal) that later odeintr_compile() calls on this thread bind to;
+ * one process per GPU calls this once with its local rank. */
+int odeintr_set_device(int device);
+/* Use an existing CUDA stream (cudaStream_t / CUstream) for all work of this system; 0 = own stream. */
+int odeintr_set_stream(odeintr_system_t h, void* cuda_stream);
+int odeintr_synchronize(odeintr_system_t h);
+
+/* ---- state and parameters ------------------------------------------------------------------- */
+
+/* name_set_state(new_state), compile_sys_template.cpp:75-83.  x holds sys_dim x n_inst doubles (SoA).
+ * n_inst instances are resident afterwards.  Fails with "Invalid initial state" when n_values is not
+ * sys_dim * n_inst. */
+int odeintr_set_state(odeintr_system_t h, const double* x, size_t n_values, size_t n_inst);
+/* name_get_state(), compile_sys_template.cpp:86-90.  Copies sys_dim x n_inst doubles. */
+int odeintr_get_state(odeintr_system_t h, double* x, size_t n_values);
+/* name_set_params(...), pars_setter_template.cpp:1-5 / pars_vec_setter_template.cpp:1-7.
+ * p holds n_pars x n_inst doubles; n_inst == 1 broadcasts one parameter set to every instance.
+ * Fails with "Invalid parameter vector" on a size mismatch. */
+int odeintr_set_params(odeintr_system_t h, const double* p, size_t n_values, size_t n_inst);
+/* name_get_params(), pars_getter_template.cpp:1-7. */
+int odeintr_get_params(odeintr_system_t h, double* p, size_t n_values);
+size_t odeintr_n_instances(odeintr_system_t h);
+size_t odeintr_n_param_sets(odeintr_system_t h);
+
+/* Synthetic ensembles generated on the device: x[v][i] = lo[v] + (hi[v]-lo[v]) * u, u from
+ * Philox4x32-10 with key = seed and counter = (first_instance + i, v / 2); instance i of a shard gets
+ * the same numbers whatever the sharding. */
+int odeintr_fill_state_uniform(odeintr_system_t h, size_t n_inst, unsigned long long seed,
+                               unsigned long long first_instance, const double* lo, const double* hi);
+/* p[k][i] = lo[k] + (hi[k]-lo[k]) * (first_instance + i) / (total_instances - 1)  (parameter sweep) */
+int odeintr_fill_params_linspace(odeintr_system_t h, size_t n_inst, unsigned long long first_instance,
+                                 unsigned long long total_instances, const double* lo, const double* hi);
+
+/* ---- integration (the hot path) ------------------------------------------------------------- */
+
+/* odeint::integrate_const(stepper, sys, state, t0, t1, dt, obs) — compile_sys_template.cpp:154
+ * (record != 0) and :121,:134 (record == 0, the advance-to-first-time call of name_at).
+ * obs_stride > 1 is the ensemble extension "observe every obs_stride-th step" for plain steppers
+ * (1 = the reference's behaviour). */
+int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt, long long obs_stride, int record);
+/* odeint::integrate_times(stepper, sys, state, times.begin(), times.end(), dt, obs) — :123,:136 */
+int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_times, double dt);
+/* odeint::integrate_adaptive(stepper, sys, state, t0, t1, dt[, obs]) — :107 (record) and :168 */
+int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double dt, int record);
+
+/* ---- observer record ------------------------------------------------------------------------ */
+
+/* name_reset_observer(), compile_sys_template.cpp:92-97 */
+int odeintr_reset_observer(odeintr_system_t h);
+/* rows currently recorded (length of rec_t) */
+size_t odeintr_output_rows(odeintr_system_t h);
+/* rec_t: the Time column (instance independent for const/times integration) */
+int odeintr_get_output_times(odeintr_system_t h, double* t, size_t n_values);
+/* name_get_output() for instances [inst_begin, inst_begin + inst_count): x receives, per instance,
+ * sys_dim columns of `rows` doubles:  x[((j * sys_dim) + v) * rows + s]. */
+int odeintr_get_output(odeintr_system_t h, double* x, size_t n_values, size_t inst_begin, size_t inst_count);
+/* the whole record in device layout out[(s * sys_dim + v) * m + i] (rows * sys_dim * m doubles) */
+int odeintr_get_output_soa(odeintr_system_t h, double* out, size_t n_values);
+/* per-instance row counts / times for ragged records (integrate_adaptive with adaptive steppers) */
+int odeintr_get_output_rows_per_instance(odeintr_system_t h, int* rows, size_t n_values);
+int odeintr_get_output_times_per_instance(odeintr_system_t h, double* t, size_t n_values, size_t inst);
+
+/* accepted / rejected step counts and ODEINTR_STATUS_* per instance (adaptive steppers) */
+int odeintr_get_stats(odeintr_system_t h, long long* accepted, long long* rejected, int* status, size_t n_inst);
+/* number of fixed steps the last plain-stepper call executed per instance */
+long long odeintr_last_steps(odeintr_system_t h);
+
+/* ---- device-resident access and measurement -------------------------------------------------- */
+
+double* odeintr_state_device_ptr(odeintr_system_t h);   /* sys_dim x m */
+double* odeintr_output_device_ptr(odeintr_system_t h);  /* rows x sys_dim x m */
+double* odeintr_params_device_ptr(odeintr_system_t h);
+/* device time (CUDA events on the system's stream) and kernel launches of the last integrate call */
+double odeintr_last_kernel_ms(odeintr_system_t h);
+long long odeintr_last_launches(odeintr_system_t h);
+long long odeintr_total_launches(void);
+int odeintr_kernel_attributes(odeintr_system_t h, const char* kernel, int* regs, int* local_bytes,
+                              int* shared_bytes, int* max_threads);
+
+/* pinned host memory for end-to-end transfers */
+void* odeintr_host_alloc(size_t bytes);
+int odeintr_host_free(void* p);
+
+/* FP64-pipe issue-rate probe (roofline denominator for the compute-bound ensembles): returns DP
+ * instructions per second summed over the device; kind 0 = DFMA, 1 = DADD/DMUL mix (no FMA). */
+int odeintr_fp64_probe(int kind, int device, double* dp_instr_per_s, double* ms);
+/* device-to-device copy bandwidth probe in bytes (read + write) per second */
+int odeintr_hbm_probe(int device, size_t bytes, double* bytes_per_s);
+int odeintr_device_info(int device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                        size_t* total_mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODEINTR_B200_H */

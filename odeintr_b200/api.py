@@ -1,0 +1,61 @@
+"""compile_sys / compile_sys_openmp / compile_implicit -- the reference's user-facing generator calls
+(``/root/reference/R/odeintr.R:293-357,418-470,559-612``) with the same arguments and defaults.
+
+Like the reference, each call returns the generated code (a ``str``; the reference returns it
+invisibly) and, when ``compile=True``, installs the generated functions ``NAME``, ``NAME_at``, ... into
+``env`` (a dict, the analogue of the R environment that gets ``attach()``-ed under ``name``).  The
+returned string also carries ``.system`` (the CompiledSystem) and ``.env``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+from . import codegen
+from .codegen import OdeintrError
+
+#: name -> env, the analogue of R's search path entries created by attach(env, name = name)
+attached: Dict[str, Dict[str, object]] = {}
+
+
+class GeneratedCode(str):
+    """The code string returned by compile_*; ``.system`` / ``.env`` are set when it was compiled."""
+    system = None
+    env = None
+
+
+def _install(gen: codegen.Generated, compile: bool, env: Optional[dict], flags: int) -> GeneratedCode:
+    code = GeneratedCode(gen.code)
+    if compile:
+        from .system import CompiledSystem
+
+        system = CompiledSystem(gen, flags=flags)
+        if env is None:
+            env = {}
+        env.update(system.exports())
+        attached[gen.name] = env  # re-attaching a name replaces the previous entry (R/odeintr.R:350-352)
+        code.system = system
+        code.env = env
+    return code
+
+
+def compile_sys(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, atol=1e-6, rtol=1e-6, globals="",
+                headers="", footers="", compile=True, observer=None, env=None, flags=0):
+    """R/odeintr.R:293-357.  ``observer`` (an R closure in the reference) is out of scope."""
+    if observer is not None:
+        raise OdeintrError("custom observer functions are not provided by odeintr_b200")
+    gen = codegen.generate_sys(name, sys, pars, const, method, sys_dim, atol, rtol, globals, headers, footers)
+    return _install(gen, compile, env, flags)
+
+
+def compile_sys_openmp(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, atol=1e-6, rtol=1e-6,
+                       globals="", headers="", footers="", compile=True, env=None, flags=0):
+    """R/odeintr.R:418-470: the large-system variant (Boost openmp_range_algebra in the reference)."""
+    gen = codegen.generate_sys_openmp(name, sys, pars, const, method, sys_dim, atol, rtol, globals, headers, footers)
+    return _install(gen, compile, env, flags)
+
+
+def compile_implicit(name, sys, pars=None, const=False, sys_dim=-1, jacobian=None, atol=1e-6, rtol=1e-6, globals="",
+                     headers="", footers="", compile=True, env=None, flags=0):
+    """R/odeintr.R:559-612: rosenbrock4 with controller and dense output, symbolic Jacobian by default."""
+    gen = codegen.generate_implicit(name, sys, pars, const, sys_dim, jacobian, atol, rtol, globals, headers, footers)
+    return _install(gen, compile, env, flags)

@@ -1,0 +1,787 @@
+// odeintr_b200/csrc/abi.cu — implementation of the C-ABI declared in include/odeintr_b200.h.
+//
+// Host side of the hot path: NVRTC-compiles the generated translation unit (user __device__ functor +
+// hand-written stepper kernels from csrc/kernels/, embedded in this library as strings), owns the
+// device-resident ensemble (state, parameters, observer record) and turns the reference's
+// integrate_const / integrate_times / integrate_adaptive calls
+// (/root/reference inst/templates/compile_sys_template.cpp:107,121,123,134,136,154,168) into kernel
+// launches.  Step schedules that do not depend on the state (fixed-step steppers) are computed here
+// with Boost's own loop conditions so the device executes exactly the reference's step sequence.
+//
+// There is deliberately no CPU path: without a device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/odeintr_b200.h"
+#include "builtin_kernels.h"
+#include "kernels/abi_args.h"
+#include "embedded_headers.inc"  // generated: k_header_names[], k_header_srcs[], k_num_headers
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_total_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(ODEINTR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+// ---- util/detail/less_with_sign.hpp (Boost), SURVEY.md Appendix A --------------------------------
+const double kEps = std::numeric_limits<double>::epsilon();
+inline bool less_with_sign(double t1, double t2, double dt) { return dt > 0 ? (t2 - t1 > kEps) : (t1 - t2 > kEps); }
+inline bool less_eq_with_sign(double t1, double t2, double dt) {
+  return dt > 0 ? (t1 - t2 <= kEps) : (t2 - t1 <= kEps);
+}
+inline double min_abs(double a, double b) { return a > 0 ? std::min(a, b) : std::max(a, b); }
+
+// number of steps integrate_const's plain loop takes: first `step` for which
+// less_eq_with_sign(fl(t0 + step*dt) + dt, t1, dt) is false (the condition is monotone in step).
+long long const_step_count(double t0, double t1, double dt) {
+  auto cond = [&](long long s) { return less_eq_with_sign((t0 + static_cast<double>(s) * dt) + dt, t1, dt); };
+  const double est = std::floor((t1 - t0) / dt);
+  if (!(est >= 0)) return 0;
+  long long s = est > 4 ? static_cast<long long>(est) - 4 : 0;
+  while (s > 0 && !cond(s - 1)) --s;
+  while (cond(s)) ++s;
+  return s;
+}
+
+template <class T>
+struct dev_buf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+std::vector<std::string> nvrtc_options(unsigned flags) {
+  std::vector<std::string> o;
+  o.push_back("--gpu-architecture=sm_100a");
+  o.push_back("--std=c++17");
+  o.push_back("-default-device");
+  o.push_back("-lineinfo");
+  o.push_back((flags & ODEINTR_FLAG_FMAD) ? "--fmad=true" : "--fmad=false");
+  if (flags & ODEINTR_FLAG_KEEP_ZERO_TERMS) o.push_back("-DODEINTR_KEEP_ZERO_TERMS=1");
+  return o;
+}
+
+int nvrtc_to_cubin(const char* src, unsigned flags, std::vector<char>& cubin, std::string& log) {
+  nvrtcProgram prog;
+  nvrtcResult r = nvrtcCreateProgram(&prog, src, "odeintr_system.cu", k_num_headers, k_header_srcs, k_header_names);
+  if (r != NVRTC_SUCCESS) return fail(ODEINTR_E_COMPILE, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
+  std::vector<std::string> opts = nvrtc_options(flags);
+  std::vector<const char*> copts;
+  for (auto& s : opts) copts.push_back(s.c_str());
+  r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+  size_t log_size = 0;
+  nvrtcGetProgramLogSize(prog, &log_size);
+  log.assign(log_size, '\0');
+  if (log_size) nvrtcGetProgramLog(prog, &log[0]);
+  if (r != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    return fail(ODEINTR_E_COMPILE, std::string("NVRTC compilation failed: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t sz = 0;
+  r = nvrtcGetCUBINSize(prog, &sz);
+  if (r != NVRTC_SUCCESS || sz == 0) {
+    nvrtcDestroyProgram(&prog);
+    return fail(ODEINTR_E_COMPILE, "nvrtcGetCUBINSize failed");
+  }
+  cubin.resize(sz);
+  nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return ODEINTR_OK;
+}
+
+}  // namespace
+
+struct odeintr_system_s {
+  std::string name, log;
+  int N = 0, P = 0, device = 0;
+  double atol = 1e-6, rtol = 1e-6;
+  unsigned flags = 0;
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr;
+  int block_plain = 128, block_adaptive = 128;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+
+  dev_buf<double> x, pars, out, stage, t_rec;
+  dev_buf<long long> seg_nfull, accepted, rejected;
+  dev_buf<double> seg_hrem, seg_t, times_dev;
+  dev_buf<unsigned char> seg_obs;
+  dev_buf<int> status, rows_inst;
+  dev_buf<unsigned long long> work_counter;
+  size_t m = 0;          // resident instances
+  size_t par_sets = 0;   // 0 (none set), 1 (broadcast) or m
+  std::vector<double> rec_t;  // Time column of the record
+  size_t rows = 0;
+  size_t out_m = 0;      // instance count the record was written with
+  bool ragged = false;   // per-instance row counts (adaptive record)
+  int max_rows = 0;
+  long long last_steps = 0, last_launches = 0;
+};
+
+namespace {
+
+int activate(odeintr_system_t h) {
+  if (!h) return fail(ODEINTR_E_INVALID, "null system handle");
+  CU_TRY(cudaSetDevice(h->device));
+  return ODEINTR_OK;
+}
+
+int begin_timing(odeintr_system_t h) {
+  h->last_launches = 0;
+  CU_TRY(cudaEventRecord(h->ev0, h->stream));
+  return ODEINTR_OK;
+}
+int end_timing(odeintr_system_t h) {
+  CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return ODEINTR_OK;
+}
+
+int launch(odeintr_system_t h, cudaKernel_t k, unsigned grid, unsigned block, void* args_struct) {
+  void* params[1] = {args_struct};
+  CU_TRY(cudaLaunchKernel((const void*)k, dim3(grid), dim3(block), params, 0, h->stream));
+  h->last_launches += 1;
+  g_total_launches += 1;
+  return ODEINTR_OK;
+}
+
+int upload(odeintr_system_t h, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return ODEINTR_OK;
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return ODEINTR_OK;
+}
+
+// device pointer + strides for the parameter block of the current ensemble
+int param_view(odeintr_system_t h, const double*& p, long long& ld, long long& inc) {
+  p = nullptr; ld = 0; inc = 0;
+  if (h->P == 0) return ODEINTR_OK;
+  if (h->par_sets == 0) return fail(ODEINTR_E_STATE, "parameters have not been set");
+  if (h->par_sets == 1) { p = h->pars.p; ld = 1; inc = 0; return ODEINTR_OK; }
+  if (h->par_sets != h->m) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  p = h->pars.p; ld = (long long)h->m; inc = 1;
+  return ODEINTR_OK;
+}
+
+int reserve_out(odeintr_system_t h, size_t rows) {
+  const size_t need = rows * (size_t)h->N * h->m;
+  cudaError_t e = h->out.reserve(need);
+  if (e != cudaSuccess)
+    return fail(ODEINTR_E_CUDA, std::string("cannot allocate observer record (") + std::to_string(need * 8) +
+                                    " bytes): " + cudaGetErrorString(e));
+  return ODEINTR_OK;
+}
+
+struct plain_schedule {
+  std::vector<long long> nfull;
+  std::vector<double> hrem, t;
+  std::vector<unsigned char> obs;
+  bool uniform = false;  // every segment nfull_uniform steps, no remainder, observe every segment
+  long long n_seg = 0, nfull_uniform = 0;
+  int time_rule = ODEINTR_TIME_CONST;
+  long long total_steps = 0;
+};
+
+int run_plain(odeintr_system_t h, const plain_schedule& sc, double t0, double dt, bool record, bool record_final,
+              const std::vector<double>& rec_t) {
+  if (!h->k_plain) return fail(ODEINTR_E_STATE, "system was not compiled with a fixed-step stepper");
+  if (h->m == 0) return fail(ODEINTR_E_STATE, "Invalid initial state");
+  odeintr_plain_args a;
+  std::memset(&a, 0, sizeof(a));
+  int rc = param_view(h, a.pars, a.par_ld, a.par_inc);
+  if (rc) return rc;
+  if (record) {
+    rc = reserve_out(h, rec_t.size());
+    if (rc) return rc;
+  }
+  if (!sc.uniform) {
+    const size_t n = (size_t)sc.n_seg;
+    CU_TRY(h->seg_nfull.reserve(n)); CU_TRY(h->seg_hrem.reserve(n)); CU_TRY(h->seg_t.reserve(n));
+    CU_TRY(h->seg_obs.reserve(n));
+    if ((rc = upload(h, h->seg_nfull.p, sc.nfull.data(), n * sizeof(long long)))) return rc;
+    if ((rc = upload(h, h->seg_hrem.p, sc.hrem.data(), n * sizeof(double)))) return rc;
+    if ((rc = upload(h, h->seg_t.p, sc.t.data(), n * sizeof(double)))) return rc;
+    if ((rc = upload(h, h->seg_obs.p, sc.obs.data(), n))) return rc;
+    // the host vectors die with the caller's frame; pageable copies are staged before returning
+    a.seg_nfull = h->seg_nfull.p; a.seg_hrem = h->seg_hrem.p; a.seg_t = h->seg_t.p; a.seg_obs = h->seg_obs.p;
+  }
+  a.x = h->x.p;
+  a.out = record ? h->out.p : nullptr;
+  a.m = (long long)h->m;
+  a.ld = (long long)h->m;
+  a.t0 = t0;
+  a.dt = dt;
+  a.n_seg = sc.n_seg;
+  a.nfull_uniform = sc.nfull_uniform;
+  a.time_rule = sc.time_rule;
+  a.record_final = record_final ? 1 : 0;
+  if ((rc = begin_timing(h))) return rc;
+  const unsigned block = (unsigned)h->block_plain;
+  const unsigned grid = (unsigned)((h->m + block - 1) / block);
+  if ((rc = launch(h, h->k_plain, grid, block, &a))) return rc;
+  if ((rc = end_timing(h))) return rc;
+  h->last_steps = sc.total_steps;
+  if (record) {
+    h->rec_t = rec_t;
+    h->rows = rec_t.size();
+    h->out_m = h->m;
+    h->ragged = false;
+  }
+  return ODEINTR_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* odeintr_last_error(void) { return g_err.c_str(); }
+
+int odeintr_compile_cubin(const char* cuda_src, unsigned flags, void* cubin, size_t cubin_cap, size_t* cubin_size) {
+  if (!cuda_src) return fail(ODEINTR_E_INVALID, "null source");
+  std::vector<char> image;
+  std::string log;
+  int rc = nvrtc_to_cubin(cuda_src, flags, image, log);
+  if (rc) return rc;
+  if (cubin_size) *cubin_size = image.size();
+  if (cubin && cubin_cap >= image.size()) std::memcpy(cubin, image.data(), image.size());
+  return ODEINTR_OK;
+}
+
+int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_pars, double atol, double rtol,
+                    unsigned flags, odeintr_system_t* out) {
+  if (!cuda_src || !out) return fail(ODEINTR_E_INVALID, "null argument");
+  if (sys_dim < 1) return fail(ODEINTR_E_INVALID, "system dimension must be >= 1");
+  if (n_pars < 0) return fail(ODEINTR_E_INVALID, "negative parameter count");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(ODEINTR_E_CUDA, std::string("no CUDA device available (") +
+                                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                    "); odeintr_b200 has no CPU fallback");
+  odeintr_system_s* h = new odeintr_system_s();
+  h->name = name ? name : "sys";
+  h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
+  std::vector<char> image;
+  int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
+  if (rc) { delete h; return rc; }
+  auto bail = [&](const std::string& what, cudaError_t ce) {
+    std::string msg = what + ": " + cudaGetErrorString(ce);
+    odeintr_destroy(h);
+    return fail(ODEINTR_E_CUDA, msg);
+  };
+  if ((e = cudaGetDevice(&h->device)) != cudaSuccess) return bail("cudaGetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major != 10) {
+    odeintr_destroy(h);
+    return fail(ODEINTR_E_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; this engine is B200-only");
+  }
+  if ((e = cudaLibraryLoadData(&h->lib, image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0)) != cudaSuccess)
+    return bail("cudaLibraryLoadData", e);
+  // whichever stepper kernels the generated TU instantiated
+  if (cudaLibraryGetKernel(&h->k_plain, h->lib, "odeintr_plain_ensemble") != cudaSuccess) h->k_plain = nullptr;
+  if (cudaLibraryGetKernel(&h->k_adaptive, h->lib, "odeintr_adaptive_ensemble") != cudaSuccess) h->k_adaptive = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lattice, h->lib, "odeintr_lattice_stage") != cudaSuccess) h->k_lattice = nullptr;
+  (void)cudaGetLastError();
+  if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
+    odeintr_destroy(h);
+    return fail(ODEINTR_E_COMPILE, "generated translation unit defines no odeintr kernel");
+  }
+  auto max_block = [&](cudaKernel_t k, int& block) {
+    cudaFuncAttributes fa;
+    if (k && cudaFuncGetAttributes(&fa, (const void*)k) == cudaSuccess) block = std::min(block, fa.maxThreadsPerBlock);
+  };
+  max_block(h->k_plain, h->block_plain);
+  max_block(h->k_adaptive, h->block_adaptive);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  h->own_stream = true;
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  *out = h;
+  return ODEINTR_OK;
+}
+
+int odeintr_destroy(odeintr_system_t h) {
+  if (!h) return ODEINTR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->x.release(); h->pars.release(); h->out.release(); h->stage.release(); h->t_rec.release();
+  h->seg_nfull.release(); h->seg_hrem.release(); h->seg_t.release(); h->seg_obs.release(); h->times_dev.release();
+  h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release();
+  h->work_counter.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->lib) cudaLibraryUnload(h->lib);
+  delete h;
+  return ODEINTR_OK;
+}
+
+const char* odeintr_compile_log(odeintr_system_t h) { return h ? h->log.c_str() : ""; }
+
+int odeintr_set_device(int device) {
+  CU_TRY(cudaSetDevice(device));
+  return ODEINTR_OK;
+}
+
+int odeintr_set_stream(odeintr_system_t h, void* cuda_stream) {
+  int rc = activate(h);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  if (cuda_stream) {
+    h->stream = (cudaStream_t)cuda_stream;
+  } else {
+    CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  return ODEINTR_OK;
+}
+
+int odeintr_synchronize(odeintr_system_t h) {
+  int rc = activate(h);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+// ---- state and parameters --------------------------------------------------------------------------
+int odeintr_set_state(odeintr_system_t h, const double* x, size_t n_values, size_t n_inst) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!x || n_inst == 0 || n_values != (size_t)h->N * n_inst) return fail(ODEINTR_E_INVALID, "Invalid initial state");
+  CU_TRY(h->x.reserve(n_values));
+  h->m = n_inst;
+  if ((rc = upload(h, h->x.p, x, n_values * sizeof(double)))) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_state(odeintr_system_t h, double* x, size_t n_values) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!x || h->m == 0 || n_values != (size_t)h->N * h->m) return fail(ODEINTR_E_INVALID, "Invalid state buffer");
+  CU_TRY(cudaMemcpyAsync(x, h->x.p, n_values * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_set_params(odeintr_system_t h, const double* p, size_t n_values, size_t n_inst) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (h->P == 0) return fail(ODEINTR_E_INVALID, "system has no run-time parameters");
+  if (!p || n_inst == 0 || n_values != (size_t)h->P * n_inst) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  CU_TRY(h->pars.reserve(n_values));
+  if ((rc = upload(h, h->pars.p, p, n_values * sizeof(double)))) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->par_sets = n_inst;
+  return ODEINTR_OK;
+}
+
+int odeintr_get_params(odeintr_system_t h, double* p, size_t n_values) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!p || h->par_sets == 0 || n_values != (size_t)h->P * h->par_sets)
+    return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  CU_TRY(cudaMemcpyAsync(p, h->pars.p, n_values * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+size_t odeintr_n_instances(odeintr_system_t h) { return h ? h->m : 0; }
+size_t odeintr_n_param_sets(odeintr_system_t h) { return h ? h->par_sets : 0; }
+
+int odeintr_fill_state_uniform(odeintr_system_t h, size_t n_inst, unsigned long long seed,
+                               unsigned long long first_instance, const double* lo, const double* hi) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!lo || !hi || n_inst == 0) return fail(ODEINTR_E_INVALID, "Invalid initial state");
+  CU_TRY(h->x.reserve((size_t)h->N * n_inst));
+  CU_TRY(h->stage.reserve(2 * (size_t)std::max(h->N, h->P)));
+  std::vector<double> lohi(2 * h->N);
+  for (int v = 0; v < h->N; ++v) { lohi[v] = lo[v]; lohi[h->N + v] = hi[v]; }
+  if ((rc = upload(h, h->stage.p, lohi.data(), lohi.size() * sizeof(double)))) return rc;
+  odeintr_b200::launch_fill_state_uniform(h->x.p, (long long)n_inst, (long long)n_inst, h->N, seed, first_instance,
+                                          h->stage.p, h->stream);
+  g_total_launches += 1;
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->m = n_inst;
+  return ODEINTR_OK;
+}
+
+int odeintr_fill_params_linspace(odeintr_system_t h, size_t n_inst, unsigned long long first_instance,
+                                 unsigned long long total_instances, const double* lo, const double* hi) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (h->P == 0) return fail(ODEINTR_E_INVALID, "system has no run-time parameters");
+  if (!lo || !hi || n_inst == 0) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  CU_TRY(h->pars.reserve((size_t)h->P * n_inst));
+  CU_TRY(h->stage.reserve(2 * (size_t)std::max(h->N, h->P)));
+  std::vector<double> lohi(2 * h->P);
+  for (int k = 0; k < h->P; ++k) { lohi[k] = lo[k]; lohi[h->P + k] = hi[k]; }
+  if ((rc = upload(h, h->stage.p, lohi.data(), lohi.size() * sizeof(double)))) return rc;
+  odeintr_b200::launch_fill_params_linspace(h->pars.p, (long long)n_inst, (long long)n_inst, h->P, first_instance,
+                                            total_instances, h->stage.p, h->stream);
+  g_total_launches += 1;
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->par_sets = n_inst;
+  return ODEINTR_OK;
+}
+
+// ---- integration -----------------------------------------------------------------------------------
+int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt, long long obs_stride, int record) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
+    return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (obs_stride < 1) return fail(ODEINTR_E_INVALID, "obs_stride must be >= 1");
+  if (h->k_plain) {
+    // integrate_const, stepper_tag: obs; do_step; time = t0 + step*dt ... final obs
+    const long long n = const_step_count(t0, t1, dt);
+    plain_schedule sc;
+    sc.time_rule = ODEINTR_TIME_CONST;
+    sc.total_steps = n;
+    std::vector<double> rec_t;
+    if (!record) {
+      sc.uniform = true; sc.n_seg = 1; sc.nfull_uniform = n;
+      return run_plain(h, sc, t0, dt, false, false, rec_t);
+    }
+    const long long k = obs_stride;
+    sc.n_seg = (n + k - 1) / k;
+    if (n % k == 0) {
+      sc.uniform = true; sc.nfull_uniform = k;
+    } else {
+      sc.nfull.assign((size_t)sc.n_seg, k);
+      sc.nfull.back() = n - k * (sc.n_seg - 1);
+      sc.hrem.assign((size_t)sc.n_seg, 0.0);
+      sc.obs.assign((size_t)sc.n_seg, 1);
+      sc.t.resize((size_t)sc.n_seg);
+      for (long long s = 0; s < sc.n_seg; ++s) sc.t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
+    }
+    rec_t.resize((size_t)sc.n_seg + 1);
+    for (long long s = 0; s < sc.n_seg; ++s) rec_t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
+    rec_t[(size_t)sc.n_seg] = t0 + static_cast<double>(n) * dt;
+    return run_plain(h, sc, t0, dt, true, true, rec_t);
+  }
+  return fail(ODEINTR_E_STATE, "integrate_const: no kernel for this stepper family");
+}
+
+int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_times, double dt) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!times || n_times == 0) return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (!(dt != 0.0) || !std::isfinite(dt)) return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (h->k_plain) {
+    // integrate_times, stepper_tag
+    plain_schedule sc;
+    sc.time_rule = ODEINTR_TIME_ACCUM;
+    std::vector<double> rec_t(times, times + n_times);
+    for (size_t k = 0; k + 1 < n_times; ++k) {
+      double t = times[k];
+      const double T = times[k + 1];
+      bool first = true;
+      bool open = false;  // a segment that can still take full steps
+      if (!less_with_sign(t, T, dt)) {  // nothing to integrate, but the observation still happens
+        sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(1);
+        continue;
+      }
+      while (less_with_sign(t, T, dt)) {
+        const double hcur = min_abs(dt, T - t);
+        if (hcur == dt) {
+          if (!open) {
+            sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(first ? 1 : 0);
+            open = true; first = false;
+          }
+          sc.nfull.back() += 1;
+        } else {
+          if (!open) {
+            sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(first ? 1 : 0);
+            first = false;
+          }
+          sc.hrem.back() = hcur;
+          open = false;  // a remainder step closes the segment
+        }
+        sc.total_steps += 1;
+        t += hcur;
+      }
+    }
+    sc.n_seg = (long long)sc.nfull.size();
+    return run_plain(h, sc, times[0], dt, true, true, rec_t);
+  }
+  return fail(ODEINTR_E_STATE, "integrate_times: no kernel for this stepper family");
+}
+
+int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double dt, int record) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
+    return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (h->k_plain) {
+    // integrate_adaptive, stepper_tag: integrate_n_steps + one step onto t1
+    const double q = (t1 - t0) / dt;
+    const long long n = q > 0 ? static_cast<long long>(q) : 0;
+    const double end = t0 + static_cast<double>(n) * dt;
+    const bool rem = less_with_sign(end, t1, dt);
+    plain_schedule sc;
+    sc.time_rule = ODEINTR_TIME_CONST;
+    sc.total_steps = n + (rem ? 1 : 0);
+    std::vector<double> rec_t;
+    if (!record) {
+      sc.n_seg = 1;
+      if (!rem) { sc.uniform = true; sc.nfull_uniform = n; }
+      else { sc.nfull.assign(1, n); sc.hrem.assign(1, t1 - end); sc.t.assign(1, t0); sc.obs.assign(1, 0); }
+      return run_plain(h, sc, t0, dt, false, false, rec_t);
+    }
+    rec_t.resize((size_t)n + 1);
+    for (long long s = 0; s <= n; ++s) rec_t[(size_t)s] = t0 + static_cast<double>(s) * dt;
+    if (!rem) {
+      sc.uniform = true; sc.n_seg = n; sc.nfull_uniform = 1;
+    } else {
+      sc.n_seg = n + 1;
+      sc.nfull.assign((size_t)n + 1, 1); sc.nfull.back() = 0;
+      sc.hrem.assign((size_t)n + 1, 0.0); sc.hrem.back() = t1 - end;
+      sc.obs.assign((size_t)n + 1, 1);
+      sc.t = rec_t;
+      rec_t.push_back(t1);
+    }
+    return run_plain(h, sc, t0, dt, true, true, rec_t);
+  }
+  return fail(ODEINTR_E_STATE, "integrate_adaptive: no kernel for this stepper family");
+}
+
+// ---- observer record -------------------------------------------------------------------------------
+int odeintr_reset_observer(odeintr_system_t h) {
+  if (!h) return fail(ODEINTR_E_INVALID, "null system handle");
+  h->rec_t.clear();
+  h->rows = 0;
+  h->ragged = false;
+  return ODEINTR_OK;
+}
+
+size_t odeintr_output_rows(odeintr_system_t h) { return h ? h->rows : 0; }
+
+int odeintr_get_output_times(odeintr_system_t h, double* t, size_t n_values) {
+  if (!h) return fail(ODEINTR_E_INVALID, "null system handle");
+  if (h->ragged) return fail(ODEINTR_E_STATE, "record is ragged; use odeintr_get_output_times_per_instance");
+  if (n_values != h->rec_t.size() || (!t && n_values)) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (n_values) std::memcpy(t, h->rec_t.data(), n_values * sizeof(double));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_output(odeintr_system_t h, double* x, size_t n_values, size_t inst_begin, size_t inst_count) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (inst_begin + inst_count > h->out_m) return fail(ODEINTR_E_INVALID, "instance range outside the record");
+  const size_t rows = h->ragged ? (size_t)h->max_rows : h->rows;
+  const size_t need = rows * (size_t)h->N * inst_count;
+  if (n_values != need || (!x && need)) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (need == 0) return ODEINTR_OK;
+  CU_TRY(h->stage.reserve(need));
+  odeintr_b200::launch_gather_output(h->out.p, h->stage.p, (long long)rows, h->N, (long long)h->out_m,
+                                     (long long)inst_begin, (long long)inst_count, h->stream);
+  g_total_launches += 1;
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(x, h->stage.p, need * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_output_soa(odeintr_system_t h, double* out, size_t n_values) {
+  int rc = activate(h);
+  if (rc) return rc;
+  const size_t rows = h->ragged ? (size_t)h->max_rows : h->rows;
+  const size_t need = rows * (size_t)h->N * h->out_m;
+  if (n_values != need || (!out && need)) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (need == 0) return ODEINTR_OK;
+  CU_TRY(cudaMemcpyAsync(out, h->out.p, need * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_output_rows_per_instance(odeintr_system_t h, int* rows, size_t n_values) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!rows || n_values != h->out_m) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (!h->ragged) {
+    for (size_t i = 0; i < n_values; ++i) rows[i] = (int)h->rows;
+    return ODEINTR_OK;
+  }
+  CU_TRY(cudaMemcpyAsync(rows, h->rows_inst.p, n_values * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_output_times_per_instance(odeintr_system_t h, double* t, size_t n_values, size_t inst) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->ragged) return odeintr_get_output_times(h, t, n_values);
+  if (!t || inst >= h->out_m || n_values != (size_t)h->max_rows) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  CU_TRY(cudaMemcpy2DAsync(t, sizeof(double), h->t_rec.p + inst, h->out_m * sizeof(double), sizeof(double), n_values,
+                           cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+int odeintr_get_stats(odeintr_system_t h, long long* accepted, long long* rejected, int* status, size_t n_inst) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (n_inst != h->m || h->accepted.cap < h->m) return fail(ODEINTR_E_STATE, "no adaptive statistics recorded");
+  if (accepted) CU_TRY(cudaMemcpyAsync(accepted, h->accepted.p, n_inst * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  if (rejected) CU_TRY(cudaMemcpyAsync(rejected, h->rejected.p, n_inst * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  if (status) CU_TRY(cudaMemcpyAsync(status, h->status.p, n_inst * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return ODEINTR_OK;
+}
+
+long long odeintr_last_steps(odeintr_system_t h) { return h ? h->last_steps : 0; }
+
+// ---- device-resident access and measurement ----------------------------------------------------------
+double* odeintr_state_device_ptr(odeintr_system_t h) { return h ? h->x.p : nullptr; }
+double* odeintr_output_device_ptr(odeintr_system_t h) { return h ? h->out.p : nullptr; }
+double* odeintr_params_device_ptr(odeintr_system_t h) { return h ? h->pars.p : nullptr; }
+
+double odeintr_last_kernel_ms(odeintr_system_t h) {
+  if (!h || !h->timed) return -1.0;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+long long odeintr_last_launches(odeintr_system_t h) { return h ? h->last_launches : 0; }
+long long odeintr_total_launches(void) { return g_total_launches.load(); }
+
+int odeintr_kernel_attributes(odeintr_system_t h, const char* kernel, int* regs, int* local_bytes, int* shared_bytes,
+                              int* max_threads) {
+  int rc = activate(h);
+  if (rc) return rc;
+  cudaKernel_t k = nullptr;
+  if (!kernel || cudaLibraryGetKernel(&k, h->lib, kernel) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(ODEINTR_E_INVALID, "no such kernel in this system");
+  }
+  cudaFuncAttributes fa;
+  CU_TRY(cudaFuncGetAttributes(&fa, (const void*)k));
+  if (regs) *regs = fa.numRegs;
+  if (local_bytes) *local_bytes = (int)fa.localSizeBytes;
+  if (shared_bytes) *shared_bytes = (int)fa.sharedSizeBytes;
+  if (max_threads) *max_threads = fa.maxThreadsPerBlock;
+  return ODEINTR_OK;
+}
+
+void* odeintr_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    g_err = "cudaHostAlloc failed";
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+int odeintr_host_free(void* p) {
+  if (p) CU_TRY(cudaFreeHost(p));
+  return ODEINTR_OK;
+}
+
+int odeintr_fp64_probe(int kind, int device, double* dp_instr_per_s, double* ms_out) {
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  double* sink = nullptr;
+  CU_TRY(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+  const unsigned blocks = (unsigned)prop.multiProcessorCount * 8u;
+  const int iters = 4096;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU_TRY(cudaEventRecord(e0, 0));
+    odeintr_b200::launch_fp64_probe(kind, sink, iters, blocks, 0);
+    CU_TRY(cudaEventRecord(e1, 0));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+    g_total_launches += 1;
+  }
+  CU_TRY(cudaGetLastError());
+  const double instr = (double)blocks * 256.0 * (double)iters * 64.0;  // 8 unrolled x 8 chains per iteration
+  if (dp_instr_per_s) *dp_instr_per_s = instr / ((double)best * 1e-3);
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  return ODEINTR_OK;
+}
+
+int odeintr_hbm_probe(int device, size_t bytes, double* bytes_per_s) {
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  bytes = (bytes / 16) * 16;
+  if (bytes == 0) return fail(ODEINTR_E_INVALID, "probe size too small");
+  void *a = nullptr, *b = nullptr;
+  CU_TRY(cudaMalloc(&a, bytes)); CU_TRY(cudaMalloc(&b, bytes));
+  CU_TRY(cudaMemset(a, 1, bytes));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU_TRY(cudaEventRecord(e0, 0));
+    odeintr_b200::launch_copy_probe(a, b, (long long)bytes, (unsigned)prop.multiProcessorCount * 16u, 0);
+    CU_TRY(cudaEventRecord(e1, 0));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+    g_total_launches += 1;
+  }
+  CU_TRY(cudaGetLastError());
+  if (bytes_per_s) *bytes_per_s = 2.0 * (double)bytes / ((double)best * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+  return ODEINTR_OK;
+}
+
+int odeintr_device_info(int device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                        size_t* total_mem) {
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (name && name_cap) { std::strncpy(name, prop.name, name_cap - 1); name[name_cap - 1] = '\0'; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  return ODEINTR_OK;
+}
+
+}  // extern "C"

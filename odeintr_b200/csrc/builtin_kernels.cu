@@ -1,0 +1,138 @@
+// odeintr_b200/csrc/builtin_kernels.cu
+// Statically compiled (nvcc, sm_100a) helper kernels that do not depend on the user's system:
+// counter-based ensemble generation, record gather for name_get_output(), state broadcast, and the
+// FP64-pipe / HBM probes that give the roofline denominators.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "builtin_kernels.h"
+
+namespace odeintr_b200 {
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) ------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words
+__host__ __device__ inline double u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void fill_state_uniform_kernel(double* x, long long m, long long ld, int n, unsigned long long seed,
+                                          unsigned long long first, const double* __restrict__ lohi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long g = first + (unsigned long long)i;
+  for (int v0 = 0; v0 < n; v0 += 2) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(v0 / 2), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u0 = u53(r[0], r[1]);
+    x[(long long)v0 * ld + i] = lohi[v0] + (lohi[n + v0] - lohi[v0]) * u0;
+    if (v0 + 1 < n) {
+      const double u1 = u53(r[2], r[3]);
+      x[(long long)(v0 + 1) * ld + i] = lohi[v0 + 1] + (lohi[n + v0 + 1] - lohi[v0 + 1]) * u1;
+    }
+  }
+}
+
+__global__ void fill_params_linspace_kernel(double* p, long long m, long long ld, int n, unsigned long long first,
+                                            unsigned long long total, const double* __restrict__ lohi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double frac = total > 1 ? (double)(first + (unsigned long long)i) / (double)(total - 1) : 0.0;
+  for (int k = 0; k < n; ++k) p[(long long)k * ld + i] = lohi[k] + (lohi[n + k] - lohi[k]) * frac;
+}
+
+// out[(s*n + v)*ld + i]  ->  dst[((j*n) + v)*rows + s],  j = i - inst_begin   (data-frame columns)
+__global__ void gather_output_kernel(const double* __restrict__ out, double* __restrict__ dst, long long rows,
+                                     int n, long long ld, long long inst_begin, long long inst_count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = rows * n * inst_count;
+  if (idx >= total) return;
+  const long long s = idx % rows;
+  const long long v = (idx / rows) % n;
+  const long long j = idx / (rows * n);
+  dst[idx] = out[(s * n + v) * ld + inst_begin + j];
+}
+
+__global__ void broadcast_state_kernel(double* x, long long m, long long ld, int n, const double* __restrict__ src) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  for (int v = 0; v < n; ++v) x[(long long)v * ld + i] = src[v];
+}
+
+// ---- FP64 pipe issue-rate probe ----------------------------------------------------------------
+// 8 independent dependency chains per thread so the pipe, not the latency, is the limit.
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* sink, int iters, double a, double b) {
+  double r0 = a + threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6,
+         r7 = r0 + 7;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (KIND == 0) {
+        r0 = __fma_rn(r0, b, a); r1 = __fma_rn(r1, b, a); r2 = __fma_rn(r2, b, a); r3 = __fma_rn(r3, b, a);
+        r4 = __fma_rn(r4, b, a); r5 = __fma_rn(r5, b, a); r6 = __fma_rn(r6, b, a); r7 = __fma_rn(r7, b, a);
+      } else {
+        r0 = __dmul_rn(r0, b); r1 = __dadd_rn(r1, a); r2 = __dmul_rn(r2, b); r3 = __dadd_rn(r3, a);
+        r4 = __dmul_rn(r4, b); r5 = __dadd_rn(r5, a); r6 = __dmul_rn(r6, b); r7 = __dadd_rn(r7, a);
+      }
+    }
+  }
+  const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  if (s == 123.456) sink[0] = s;  // never true for the probe's inputs; keeps the chains alive
+}
+
+__global__ void copy_probe_kernel(const double2* __restrict__ src, double2* __restrict__ dst, long long n2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) dst[i] = src[i];
+}
+
+static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+void launch_fill_state_uniform(double* x, long long m, long long ld, int n, unsigned long long seed,
+                               unsigned long long first, const double* lohi_dev, cudaStream_t st) {
+  if (m <= 0) return;
+  fill_state_uniform_kernel<<<grid_for(m, 256), 256, 0, st>>>(x, m, ld, n, seed, first, lohi_dev);
+}
+void launch_fill_params_linspace(double* p, long long m, long long ld, int n, unsigned long long first,
+                                 unsigned long long total, const double* lohi_dev, cudaStream_t st) {
+  if (m <= 0) return;
+  fill_params_linspace_kernel<<<grid_for(m, 256), 256, 0, st>>>(p, m, ld, n, first, total, lohi_dev);
+}
+void launch_gather_output(const double* out, double* dst, long long rows, int n, long long ld, long long inst_begin,
+                          long long inst_count, cudaStream_t st) {
+  const long long total = rows * n * inst_count;
+  if (total <= 0) return;
+  gather_output_kernel<<<grid_for(total, 256), 256, 0, st>>>(out, dst, rows, n, ld, inst_begin, inst_count);
+}
+void launch_broadcast_state(double* x, long long m, long long ld, int n, const double* src_dev, cudaStream_t st) {
+  if (m <= 0) return;
+  broadcast_state_kernel<<<grid_for(m, 256), 256, 0, st>>>(x, m, ld, n, src_dev);
+}
+void launch_fp64_probe(int kind, double* sink, int iters, unsigned blocks, cudaStream_t st) {
+  if (kind == 0)
+    fp64_probe_kernel<0><<<blocks, 256, 0, st>>>(sink, iters, 1.0e-9, 0.999999);
+  else
+    fp64_probe_kernel<1><<<blocks, 256, 0, st>>>(sink, iters, 1.0e-9, 0.999999);
+}
+void launch_copy_probe(const void* src, void* dst, long long bytes, unsigned blocks, cudaStream_t st) {
+  copy_probe_kernel<<<blocks, 256, 0, st>>>((const double2*)src, (double2*)dst, bytes / 16);
+}
+
+void philox_host(unsigned long long counter, unsigned block, unsigned long long seed, unsigned out[4]) {
+  philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), block, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+
+}  // namespace odeintr_b200

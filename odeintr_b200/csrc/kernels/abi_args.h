@@ -1,0 +1,105 @@
+// odeintr_b200/csrc/kernels/abi_args.h
+// Plain-old-data launch descriptors shared by the host C-ABI (abi.cu) and the NVRTC-compiled
+// stepper kernels.  Only builtin types: this header is compiled by nvcc (host side) and by
+// NVRTC (device side, no host headers available).
+#pragma once
+
+// How the stepper's time variable advances between steps.
+//   ODEINTR_TIME_CONST : t = t0 + step*dt   (integrate_const, integrate_n_steps)
+//   ODEINTR_TIME_ACCUM : t += h, re-based to the requested time at each observation
+//                        (integrate_times for plain steppers)
+#define ODEINTR_TIME_CONST 0
+#define ODEINTR_TIME_ACCUM 1
+
+// Per-instance status words written by the kernels (failure detection).
+#define ODEINTR_STATUS_OK 0
+#define ODEINTR_STATUS_STEP_OVERFLOW 1   // >500 consecutive rejected tries (Boost step_adjustment_error)
+#define ODEINTR_STATUS_NONFINITE 2       // state became NaN/Inf
+
+// Fixed-step ("plain stepper") ensemble launch: one trajectory per thread.
+// State and samples are structure-of-arrays with the instance index fastest:
+//   x   [v * ld + i]                       v < N, i < m
+//   out [(s * N + v) * ld + i]             s < n_seg + 1 (sample-major SoA; one coalesced row per variable)
+// The step schedule is instance-independent and computed on the host with the reference's own
+// loops (less_eq_with_sign etc.), so every thread executes exactly the reference's step sequence:
+//   for s in [0, n_seg):  t = seg_t[s]; observe if seg_obs[s]; nfull(s) steps of dt;
+//                         optional remainder step hrem(s)
+//   observe (final) if record_final
+struct odeintr_plain_args {
+  double* x;                  // in/out state, N x ld
+  const double* pars;         // P x par_ld (par_inc = 1) or P values broadcast (par_inc = 0)
+  double* out;                // samples or null (no_record)
+  long long m;                // instances handled by this launch
+  long long ld;               // leading dimension of x and out rows (>= m)
+  long long par_ld;
+  long long par_inc;
+  double t0;
+  double dt;
+  long long n_seg;            // schedule segments
+  long long nfull_uniform;    // steps per segment when seg_nfull is null
+  const long long* seg_nfull; // per-segment full-step counts or null
+  const double* seg_hrem;     // per-segment remainder step (0 = none) or null
+  const double* seg_t;        // time at the start of each segment, exactly as the reference's loop
+                              // computes it (null: t follows time_rule from t0)
+  const unsigned char* seg_obs; // observe at the start of segment s? (null: every segment)
+  int time_rule;
+  int record_final;           // store the sample after the last segment
+};
+
+// Adaptive ensemble launch (controlled / dense-output steppers: dopri5, rosenbrock4).
+//   mode 0: integrate_times, dense output      -> n_times samples at times[]
+//   mode 1: integrate_const, dense output (A.3)                -> samples at t0 + k*dt
+//   mode 2: integrate_adaptive, dense stepper, no observer (A.5; name_no_record)
+//   mode 3: integrate_const / integrate_times with a controlled stepper (rk5_a; A.3/A.4)
+#define ODEINTR_MODE_TIMES_DENSE 0
+#define ODEINTR_MODE_CONST_DENSE 1
+#define ODEINTR_MODE_ADAPTIVE_NOREC 2
+#define ODEINTR_MODE_CONST_CONTROLLED 3
+#define ODEINTR_MODE_TIMES_CONTROLLED 4
+#define ODEINTR_MODE_ADAPTIVE_RECORD 5
+
+struct odeintr_adaptive_args {
+  double* x;                  // in/out state, N x ld
+  const double* pars;
+  double* out;                // (s * N + v) * ld + i, or null
+  long long m;
+  long long ld;
+  long long par_ld;
+  long long par_inc;
+  double t0;                  // start time
+  double t1;                  // end time (const / adaptive modes)
+  double dt;                  // initial step / observation step
+  const double* times;        // observation times (times modes)
+  long long n_times;          // number of samples to produce (rows of out)
+  double atol;
+  double rtol;
+  int mode;
+  int max_rows;               // capacity of out in rows (adaptive-record mode)
+  long long* accepted;        // per-instance counters (may be null)
+  long long* rejected;
+  int* status;
+  int* rows;                  // per-instance rows written (adaptive-record mode)
+  double* t_rec;              // per-instance sample times (adaptive-record mode), s * ld + i
+  unsigned long long* work_counter; // dynamic instance queue for lane refill (may be null)
+};
+
+// Large coupled system ("lattice") fused RK4 stage launch, SURVEY.md §8(d) config 5.
+struct odeintr_lattice_args {
+  const double* x;            // state at the start of the step
+  const double* xs;           // stage input (x for stage 1, else previous stage's xt)
+  double* xt;                 // stage output state  x + a*dt*k
+  double* acc;                // running accumulator ((x + b1 k1) + b2 k2) ...
+  const double* acc_in;
+  double* x_out;              // final state (stage 4)
+  const double* pars;
+  long long n;                // cells owned by this launch (without ghost cells)
+  long long n_total;          // global periodic length
+  long long i0;               // global index of local cell 0
+  long long ghost;            // ghost cells on each side of the local slab
+  long long lo;               // first local cell (relative to owned cell 0, may be negative) to compute
+  long long hi;               // one past the last local cell to compute
+  double t;
+  double a_dt;                // stage coefficient * dt for xt
+  double b_dt;                // weight * dt for the accumulator
+  int stage;                  // 1..4
+};

@@ -1,0 +1,878 @@
+// oracle/odeint_restated.hpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// CPU restatement of the Boost.Numeric.Odeint algorithms that odeintr's generated code
+// calls (reference call sites: inst/templates/compile_sys_template.cpp:107,121,123,134,136,
+// 154,168 and inst/templates/compile_implicit_template.cpp:28-33; stepper/ctor strings
+// R/utils.R:22-60).  Boost itself (CRAN package BH, version unpinned in DESCRIPTION:14;
+// contemporaneous release BH 1.62.0-1) is NOT vendored in the reference tree and is not
+// installed in this image, so this file restates its published algorithms:
+//   * integrate_const / integrate_times / integrate_adaptive / integrate_n_steps for the
+//     stepper, controlled-stepper and dense-output-stepper tags (boost/numeric/odeint/
+//     integrate/detail/*.hpp), incl. less_with_sign / less_eq_with_sign (util/detail/
+//     less_with_sign.hpp),
+//   * euler, runge_kutta4 (explicit_generic_rk<4,4>), runge_kutta_cash_karp54,
+//     runge_kutta_dopri5 (+ calc_state dense output), controlled_runge_kutta (default_error_checker +
+//     default_step_adjuster), dense_output_runge_kutta (FSAL specialisation),
+//   * rosenbrock4 / rosenbrock4_controller / rosenbrock4_dense_output with uBLAS
+//     lu_factorize / lu_substitute (partial pivoting, column-oriented solves).
+// The order of every floating-point operation follows Boost's;
+// compile with -ffp-contract=off so no FMA is formed (stock x86-64 R builds are -O2, no -mfma).
+//
+// PARITY STATUS: "parity unpinned".  The reference's tests pin only row counts and first
+// rows (tests/testthat/test_odeintr.R:25-54) and real Boost output cannot be produced here.
+// The restatement is pinned instead against SURVEY.md Appendix B golden bit patterns
+// (tests/golden/lorenz_rk4_golden.json), analytic solutions and the 41-row / 4-row facts.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstddef>
+#include <limits>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+namespace restated {
+
+typedef std::vector<double> state_type;
+
+// ---- util/detail/less_with_sign.hpp -------------------------------------------------
+inline bool less_with_sign(double t1, double t2, double dt) {
+  if (dt > 0) return t2 - t1 > std::numeric_limits<double>::epsilon();
+  return t1 - t2 > std::numeric_limits<double>::epsilon();
+}
+inline bool less_eq_with_sign(double t1, double t2, double dt) {
+  if (dt > 0) return t1 - t2 <= std::numeric_limits<double>::epsilon();
+  return t2 - t1 <= std::numeric_limits<double>::epsilon();
+}
+inline double min_abs(double t1, double t2) {
+  if (t1 > 0) return std::min(t1, t2);
+  return std::max(t1, t2);
+}
+inline double max_abs(double t1, double t2) {
+  if (t1 > 0) return std::max(t1, t2);
+  return std::min(t1, t2);
+}
+
+struct step_overflow : std::runtime_error {
+  step_overflow() : std::runtime_error("Max number of iterations exceeded (500). A new step size was not found.") {}
+};
+// failed_step_checker: throws after 500 consecutive failed try_steps
+struct failed_step_checker {
+  int n = 0;
+  void operator()() { if (n++ >= 500) throw step_overflow(); }
+  void reset() { n = 0; }
+};
+
+struct counters { long accepted = 0, rejected = 0, rhs = 0; };
+
+enum controlled_step_result { success, fail };
+
+// =====================================================================================
+// Plain steppers.  All have do_step(sys, x, t, dt) in place, like explicit_stepper_base.
+// =====================================================================================
+struct euler {
+  static const int order_value = 1;
+  state_type dxdt;
+  template <class Sys> void do_step(Sys& sys, state_type& x, double t, double dt) {
+    const std::size_t n = x.size();
+    dxdt.resize(n);
+    sys(x, dxdt, t);
+    for (std::size_t i = 0; i < n; ++i) x[i] = 1.0 * x[i] + dt * dxdt[i];  // scale_sum2(1, dt)
+  }
+};
+
+// explicit_generic_rk<4,4> with rk4 tableau; scale_sumN( 1 , a0*dt , a1*dt , ... ) evaluated
+// left to right, zero coefficients kept.
+struct runge_kutta4 {
+  static const int order_value = 4;
+  state_type dxdt, xt, k2, k3, k4;
+  template <class Sys> void do_step(Sys& sys, state_type& x, double t, double dt) {
+    const std::size_t n = x.size();
+    dxdt.resize(n); xt.resize(n); k2.resize(n); k3.resize(n); k4.resize(n);
+    const double one = 1.0;
+    const double half = 1.0 / 2.0, zero = 0.0;
+    const double b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
+    sys(x, dxdt, t);
+    {
+      const double a0 = half * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i];
+    }
+    sys(xt, k2, t + half * dt);
+    {
+      const double a0 = zero * dt, a1 = half * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i] + a1 * k2[i];
+    }
+    sys(xt, k3, t + half * dt);
+    {
+      const double a0 = zero * dt, a1 = zero * dt, a2 = one * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i] + a1 * k2[i] + a2 * k3[i];
+    }
+    sys(xt, k4, t + one * dt);
+    {
+      const double c0 = b1 * dt, c1 = b2 * dt, c2 = b2 * dt, c3 = b1 * dt;
+      for (std::size_t i = 0; i < n; ++i)
+        x[i] = one * x[i] + c0 * dxdt[i] + c1 * k2[i] + c2 * k3[i] + c3 * k4[i];
+    }
+  }
+};
+
+// runge_kutta_cash_karp54 = explicit_error_generic_rk<6,5,5,4>
+struct runge_kutta_cash_karp54 {
+  static const int order_value = 5, stepper_order_value = 5, error_order_value = 4;
+  state_type dxdt, xt, k2, k3, k4, k5, k6;
+  void resize(std::size_t n) {
+    dxdt.resize(n); xt.resize(n); k2.resize(n); k3.resize(n); k4.resize(n); k5.resize(n); k6.resize(n);
+  }
+  // generic algorithm: x_out = x + dt*sum b_i k_i ; xerr = dt * sum (b_i - b2_i) k_i
+  template <class Sys>
+  void do_step_impl(Sys& sys, const state_type& in, const state_type& dxdt_in, double t, state_type& out,
+                    double dt, state_type* xerr) {
+    const std::size_t n = in.size();
+    resize(n);
+    const double a21 = 1.0 / 5.0;
+    const double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+    const double a41 = 3.0 / 10.0, a42 = -9.0 / 10.0, a43 = 6.0 / 5.0;
+    const double a51 = -11.0 / 54.0, a52 = 5.0 / 2.0, a53 = -70.0 / 27.0, a54 = 35.0 / 27.0;
+    const double a61 = 1631.0 / 55296.0, a62 = 175.0 / 512.0, a63 = 575.0 / 13824.0,
+                 a64 = 44275.0 / 110592.0, a65 = 253.0 / 4096.0;
+    const double b1 = 37.0 / 378.0, b2 = 0.0, b3 = 250.0 / 621.0, b4 = 125.0 / 594.0, b5 = 0.0,
+                 b6 = 512.0 / 1771.0;
+    const double db1 = b1 - 2825.0 / 27648.0, db2 = 0.0, db3 = b3 - 18575.0 / 48384.0,
+                 db4 = b4 - 13525.0 / 55296.0, db5 = -277.0 / 14336.0, db6 = b6 - 1.0 / 4.0;
+    const double c2 = 1.0 / 5.0, c3 = 3.0 / 10.0, c4 = 3.0 / 5.0, c5 = 1.0, c6 = 7.0 / 8.0;
+    const state_type& k1 = dxdt_in;
+    { const double e1 = a21 * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = 1.0 * in[i] + e1 * k1[i]; }
+    sys(xt, k2, t + c2 * dt);
+    { const double e1 = a31 * dt, e2 = a32 * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = 1.0 * in[i] + e1 * k1[i] + e2 * k2[i]; }
+    sys(xt, k3, t + c3 * dt);
+    { const double e1 = a41 * dt, e2 = a42 * dt, e3 = a43 * dt;
+      for (std::size_t i = 0; i < n; ++i) xt[i] = 1.0 * in[i] + e1 * k1[i] + e2 * k2[i] + e3 * k3[i]; }
+    sys(xt, k4, t + c4 * dt);
+    { const double e1 = a51 * dt, e2 = a52 * dt, e3 = a53 * dt, e4 = a54 * dt;
+      for (std::size_t i = 0; i < n; ++i)
+        xt[i] = 1.0 * in[i] + e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i]; }
+    sys(xt, k5, t + c5 * dt);
+    { const double e1 = a61 * dt, e2 = a62 * dt, e3 = a63 * dt, e4 = a64 * dt, e5 = a65 * dt;
+      for (std::size_t i = 0; i < n; ++i)
+        xt[i] = 1.0 * in[i] + e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i]; }
+    sys(xt, k6, t + c6 * dt);
+    { const double e1 = b1 * dt, e2 = b2 * dt, e3 = b3 * dt, e4 = b4 * dt, e5 = b5 * dt, e6 = b6 * dt;
+      // out may alias in: compute into xt first, like Boost does when in==out? Boost writes
+      // x_out directly from x (element-wise, so aliasing is safe).
+      if (xerr) {
+        const double f1 = db1 * dt, f2 = db2 * dt, f3 = db3 * dt, f4 = db4 * dt, f5 = db5 * dt, f6 = db6 * dt;
+        for (std::size_t i = 0; i < n; ++i)
+          (*xerr)[i] = f1 * k1[i] + f2 * k2[i] + f3 * k3[i] + f4 * k4[i] + f5 * k5[i] + f6 * k6[i];
+      }
+      for (std::size_t i = 0; i < n; ++i)
+        out[i] = 1.0 * in[i] + e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i]; }
+  }
+  template <class Sys> void do_step(Sys& sys, state_type& x, double t, double dt) {
+    dxdt.resize(x.size());
+    sys(x, dxdt, t);
+    state_type d = dxdt;
+    do_step_impl(sys, x, d, t, x, dt, nullptr);
+  }
+};
+
+// runge_kutta_dopri5 (explicit_error_stepper_fsal_base), SURVEY.md A.2
+struct runge_kutta_dopri5 {
+  static const int order_value = 5, stepper_order_value = 5, error_order_value = 4;
+  state_type x_tmp, k2, k3, k4, k5, k6;
+  // plain-stepper use (method "rk5"): FSAL base keeps m_dxdt and a first-call flag
+  state_type m_dxdt, m_dxdt_new;
+  bool m_first_call = true;
+
+  void resize(std::size_t n) {
+    x_tmp.resize(n); k2.resize(n); k3.resize(n); k4.resize(n); k5.resize(n); k6.resize(n);
+  }
+  template <class Sys>
+  void do_step_impl(Sys& sys, const state_type& in, const state_type& dxdt_in, double t, state_type& out,
+                    state_type& dxdt_out, double dt) {
+    const std::size_t n = in.size();
+    resize(n);
+    const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+    const double b21 = 1.0 / 5.0;
+    const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+    const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+    const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+    const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
+                 b65 = -5103.0 / 18656.0;
+    const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0,
+                 c6 = 11.0 / 84.0;
+    { const double e1 = dt * b21;
+      for (std::size_t i = 0; i < n; ++i) x_tmp[i] = 1.0 * in[i] + e1 * dxdt_in[i]; }
+    sys(x_tmp, k2, t + dt * a2);
+    { const double e1 = dt * b31, e2 = dt * b32;
+      for (std::size_t i = 0; i < n; ++i) x_tmp[i] = 1.0 * in[i] + e1 * dxdt_in[i] + e2 * k2[i]; }
+    sys(x_tmp, k3, t + dt * a3);
+    { const double e1 = dt * b41, e2 = dt * b42, e3 = dt * b43;
+      for (std::size_t i = 0; i < n; ++i) x_tmp[i] = 1.0 * in[i] + e1 * dxdt_in[i] + e2 * k2[i] + e3 * k3[i]; }
+    sys(x_tmp, k4, t + dt * a4);
+    { const double e1 = dt * b51, e2 = dt * b52, e3 = dt * b53, e4 = dt * b54;
+      for (std::size_t i = 0; i < n; ++i)
+        x_tmp[i] = 1.0 * in[i] + e1 * dxdt_in[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i]; }
+    sys(x_tmp, k5, t + dt * a5);
+    { const double e1 = dt * b61, e2 = dt * b62, e3 = dt * b63, e4 = dt * b64, e5 = dt * b65;
+      for (std::size_t i = 0; i < n; ++i)
+        x_tmp[i] = 1.0 * in[i] + e1 * dxdt_in[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i]; }
+    sys(x_tmp, k6, t + dt);
+    { const double e1 = dt * c1, e3 = dt * c3, e4 = dt * c4, e5 = dt * c5, e6 = dt * c6;
+      for (std::size_t i = 0; i < n; ++i)
+        out[i] = 1.0 * in[i] + e1 * dxdt_in[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i]; }
+    sys(out, dxdt_out, t + dt);
+  }
+  // with error estimate; dxdt_in must not alias dxdt_out here (callers keep them apart)
+  template <class Sys>
+  void do_step_impl(Sys& sys, const state_type& in, const state_type& dxdt_in, double t, state_type& out,
+                    state_type& dxdt_out, double dt, state_type& xerr) {
+    const std::size_t n = in.size();
+    const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0,
+                 c6 = 11.0 / 84.0;
+    const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
+                 dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+    do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt);
+    xerr.resize(n);
+    const double e1 = dt * dc1, e3 = dt * dc3, e4 = dt * dc4, e5 = dt * dc5, e6 = dt * dc6, e7 = dt * dc7;
+    for (std::size_t i = 0; i < n; ++i)
+      xerr[i] = e1 * dxdt_in[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * dxdt_out[i];
+  }
+  // plain in-place stepping (method "rk5"), explicit_error_stepper_fsal_base::do_step_v1
+  template <class Sys> void do_step(Sys& sys, state_type& x, double t, double dt) {
+    const std::size_t n = x.size();
+    if (m_first_call || m_dxdt.size() != n) {
+      m_dxdt.resize(n);
+      sys(x, m_dxdt, t);
+      m_first_call = false;
+    }
+    m_dxdt_new.resize(n);
+    state_type in = x;
+    do_step_impl(sys, in, m_dxdt, t, x, m_dxdt_new, dt);
+    m_dxdt.swap(m_dxdt_new);
+  }
+  // dense output, calc_state
+  void calc_state(double t, state_type& x, const state_type& x_old, const state_type& deriv_old, double t_old,
+                  const state_type& /*x_new*/, const state_type& deriv_new, double t_new) const {
+    const double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0,
+                 b6 = 11.0 / 84.0;
+    const double dt = (t_new - t_old);
+    const double theta = (t - t_old) / dt;
+    const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
+    const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
+    const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
+    const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
+    const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
+    const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
+    const double theta_m_1 = theta - 1.0;
+    const double theta_sq = theta * theta;
+    const double A = theta_sq * (3.0 - 2.0 * theta);
+    const double B = theta_sq * theta_m_1;
+    const double C = theta_sq * theta_m_1 * theta_m_1;
+    const double D = theta * theta_m_1 * theta_m_1;
+    const double b1_theta = A * b1 - C * X1 + D;
+    const double b3_theta = A * b3 + C * X3;
+    const double b4_theta = A * b4 - C * X4;
+    const double b5_theta = A * b5 + C * X5;
+    const double b6_theta = A * b6 - C * X6;
+    const double b7_theta = B + C * X7;
+    const std::size_t n = x_old.size();
+    x.resize(n);
+    const double e1 = dt * b1_theta, e3 = dt * b3_theta, e4 = dt * b4_theta, e5 = dt * b5_theta,
+                 e6 = dt * b6_theta, e7 = dt * b7_theta;
+    for (std::size_t i = 0; i < n; ++i)
+      x[i] = 1.0 * x_old[i] + e1 * deriv_old[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] +
+             e7 * deriv_new[i];
+  }
+};
+
+// default_error_checker<double>::error + default_step_adjuster (max_dt = 0)
+struct error_checker {
+  double eps_abs, eps_rel, a_x, a_dxdt;
+  error_checker(double ea = 1e-6, double er = 1e-6, double ax = 1.0, double adxdt = 1.0)
+      : eps_abs(ea), eps_rel(er), a_x(ax), a_dxdt(adxdt) {}
+  double error(const state_type& x_old, const state_type& dxdt_old, state_type& x_err, double dt) const {
+    const double adt = a_dxdt * std::abs(dt);
+    double m = 0.0;
+    for (std::size_t i = 0; i < x_err.size(); ++i) {
+      x_err[i] = std::abs(x_err[i]) / (eps_abs + eps_rel * (a_x * std::abs(x_old[i]) + adt * std::abs(dxdt_old[i])));
+      m = std::max(m, x_err[i]);  // norm_inf
+    }
+    return m;
+  }
+};
+inline double decrease_step(double dt, double error, int error_order) {
+  dt *= std::max(9.0 / 10.0 * std::pow(error, -1.0 / (error_order - 1)), 1.0 / 5.0);
+  return dt;
+}
+inline double increase_step(double dt, double error, int stepper_order) {
+  if (error < 0.5) {
+    error = std::max(std::pow(5.0, -static_cast<double>(stepper_order)), error);
+    dt *= 9.0 / 10.0 * std::pow(error, -1.0 / stepper_order);
+  }
+  return dt;
+}
+
+// controlled_runge_kutta< runge_kutta_cash_karp54 > (explicit_error_stepper_tag)
+struct controlled_cash_karp54 {
+  runge_kutta_cash_karp54 st;
+  error_checker chk;
+  state_type dxdt, xnew, xerr;
+  counters* cnt = nullptr;
+  controlled_cash_karp54(double atol, double rtol) : chk(atol, rtol) {}
+  template <class Sys> controlled_step_result try_step(Sys& sys, state_type& x, double& t, double& dt) {
+    const std::size_t n = x.size();
+    dxdt.resize(n); xnew.resize(n); xerr.resize(n);
+    sys(x, dxdt, t);
+    st.do_step_impl(sys, x, dxdt, t, xnew, dt, &xerr);
+    double err = chk.error(x, dxdt, xerr, dt);
+    if (err > 1.0) {
+      dt = decrease_step(dt, err, st.error_order_value);
+      if (cnt) cnt->rejected++;
+      return fail;
+    }
+    t += dt;
+    dt = increase_step(dt, err, st.stepper_order_value);
+    x = xnew;
+    if (cnt) cnt->accepted++;
+    return success;
+  }
+};
+
+// controlled_runge_kutta< runge_kutta_dopri5 > (explicit_error_stepper_fsal_tag)
+struct controlled_dopri5 {
+  runge_kutta_dopri5 st;
+  error_checker chk;
+  state_type m_dxdt, m_xnew, m_dxdtnew, m_xerr;
+  bool m_first_call = true;
+  counters* cnt = nullptr;
+  controlled_dopri5(double atol = 1e-6, double rtol = 1e-6) : chk(atol, rtol) {}
+
+  // try_step( sys , in , dxdt_in , t , out , dxdt_out , dt )
+  template <class Sys>
+  controlled_step_result try_step(Sys& sys, const state_type& in, const state_type& dxdt_in, double& t,
+                                  state_type& out, state_type& dxdt_out, double& dt) {
+    st.do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt, m_xerr);
+    double max_rel_err = chk.error(in, dxdt_in, m_xerr, dt);
+    if (max_rel_err > 1.0) {
+      dt = decrease_step(dt, max_rel_err, st.error_order_value);
+      if (cnt) cnt->rejected++;
+      return fail;
+    }
+    t += dt;
+    dt = increase_step(dt, max_rel_err, st.stepper_order_value);
+    if (cnt) cnt->accepted++;
+    return success;
+  }
+  // try_step( sys , x , t , dt ) — keeps its own dxdt (FSAL), first call computes it
+  template <class Sys> controlled_step_result try_step(Sys& sys, state_type& x, double& t, double& dt) {
+    const std::size_t n = x.size();
+    if (m_first_call || m_dxdt.size() != n) {
+      m_dxdt.resize(n);
+      sys(x, m_dxdt, t);
+      m_first_call = false;
+    }
+    m_xnew.resize(n); m_dxdtnew.resize(n);
+    controlled_step_result res = try_step(sys, x, m_dxdt, t, m_xnew, m_dxdtnew, dt);
+    if (res == success) { x = m_xnew; m_dxdt = m_dxdtnew; }
+    return res;
+  }
+};
+
+// dense_output_runge_kutta< controlled_runge_kutta< dopri5 > , explicit_controlled_stepper_fsal_tag >
+struct dense_dopri5 {
+  controlled_dopri5 m_stepper;
+  state_type m_x1, m_x2, m_dxdt1, m_dxdt2;
+  bool m_current1 = true, m_is_deriv_initialized = false;
+  double m_t = 0, m_t_old = 0, m_dt = 0;
+  dense_dopri5(double atol = 1e-6, double rtol = 1e-6) : m_stepper(atol, rtol) {}
+  state_type& cur_x() { return m_current1 ? m_x1 : m_x2; }
+  state_type& old_x() { return m_current1 ? m_x2 : m_x1; }
+  state_type& cur_d() { return m_current1 ? m_dxdt1 : m_dxdt2; }
+  state_type& old_d() { return m_current1 ? m_dxdt2 : m_dxdt1; }
+  const state_type& current_state() { return cur_x(); }
+  double current_time() const { return m_t; }
+  double current_time_step() const { return m_dt; }
+  void initialize(const state_type& x0, double t0, double dt0) {
+    const std::size_t n = x0.size();
+    state_type x0c = x0;  // x0 may alias the current state
+    m_x1.resize(n); m_x2.resize(n); m_dxdt1.resize(n); m_dxdt2.resize(n);
+    cur_x() = x0c;
+    m_t = t0; m_dt = dt0;
+    m_is_deriv_initialized = false;
+  }
+  template <class Sys> std::pair<double, double> do_step(Sys& sys) {
+    if (!m_is_deriv_initialized) {
+      sys(cur_x(), cur_d(), m_t);
+      m_is_deriv_initialized = true;
+    }
+    failed_step_checker fail_checker;
+    controlled_step_result res = fail;
+    m_t_old = m_t;
+    do {
+      res = m_stepper.try_step(sys, cur_x(), cur_d(), m_t, old_x(), old_d(), m_dt);
+      fail_checker();
+    } while (res == fail);
+    m_current1 = !m_current1;
+    return std::make_pair(m_t_old, m_t);
+  }
+  void calc_state(double t, state_type& x) {
+    m_stepper.st.calc_state(t, x, old_x(), old_d(), m_t_old, cur_x(), cur_d(), m_t);
+  }
+};
+
+// =====================================================================================
+// rosenbrock4<double> + controller + dense output (SURVEY.md A.6–A.8), dense row-major
+// uBLAS matrix, lu_factorize with partial pivoting, lu_substitute = swap_rows + unit-lower
+// forward solve + upper backward solve (column-oriented axpy form).
+// =====================================================================================
+struct matrix {
+  std::size_t n = 0;
+  std::vector<double> a;
+  void resize(std::size_t n_) { n = n_; a.assign(n * n, 0.0); }
+  double& operator()(std::size_t i, std::size_t j) { return a[i * n + j]; }
+  double operator()(std::size_t i, std::size_t j) const { return a[i * n + j]; }
+};
+
+inline std::size_t lu_factorize(matrix& m, std::vector<std::size_t>& pm) {
+  const std::size_t size = m.n;
+  std::size_t singular = 0;
+  for (std::size_t i = 0; i < size; ++i) {
+    // index_norm_inf of column i, rows i..size-1: first index of the largest |.|
+    std::size_t i_norm_inf = i;
+    double best = -1.0;
+    for (std::size_t r = i; r < size; ++r) {
+      double v = std::abs(m(r, i));
+      if (v > best) { best = v; i_norm_inf = r; }
+    }
+    if (m(i_norm_inf, i) != 0.0) {
+      if (i_norm_inf != i) {
+        pm[i] = i_norm_inf;
+        for (std::size_t c = 0; c < size; ++c) std::swap(m(i_norm_inf, c), m(i, c));
+      }
+      const double inv = 1.0 / m(i, i);
+      for (std::size_t r = i + 1; r < size; ++r) m(r, i) *= inv;
+    } else if (singular == 0) {
+      singular = i + 1;
+    }
+    for (std::size_t r = i + 1; r < size; ++r)
+      for (std::size_t c = i + 1; c < size; ++c) m(r, c) -= m(r, i) * m(i, c);
+  }
+  return singular;
+}
+inline void lu_substitute(const matrix& m, const std::vector<std::size_t>& pm, state_type& v) {
+  const std::size_t size = m.n;
+  for (std::size_t i = 0; i < size; ++i)
+    if (i != pm[i]) std::swap(v[i], v[pm[i]]);
+  // inplace_solve(m, v, unit_lower_tag): column-oriented
+  for (std::size_t n = 0; n < size; ++n) {
+    const double t = v[n];
+    if (t != 0.0)
+      for (std::size_t r = n + 1; r < size; ++r) v[r] -= t * m(r, n);
+  }
+  // inplace_solve(m, v, upper_tag): column-oriented, from the last row up
+  for (std::size_t nn = size; nn-- > 0;) {
+    const double t = v[nn] /= m(nn, nn);
+    if (t != 0.0)
+      for (std::size_t r = 0; r < nn; ++r) v[r] -= t * m(r, nn);
+  }
+}
+
+struct rosenbrock4 {
+  static const int stepper_order = 4, error_order = 3;
+  // default_rosenbrock_coefficients<double>
+  const double gamma = 0.25;
+  const double d1 = 0.25, d2 = -0.1043, d3 = 0.1035, d4 = -0.3620000000000023e-01;
+  const double c2 = 0.386, c3 = 0.21, c4 = 0.63;
+  const double c21 = -0.5668800000000000e+01, a21 = 0.1544000000000000e+01;
+  const double c31 = -0.2430093356833875e+01, c32 = -0.2063599157091915e+00;
+  const double a31 = 0.9466785280815826e+00, a32 = 0.2557011698983284e+00;
+  const double c41 = -0.1073529058151375e+00, c42 = -0.9594562251023355e+01, c43 = -0.2047028614809616e+02;
+  const double a41 = 0.3314825187068521e+01, a42 = 0.2896124015972201e+01, a43 = 0.9986419139977817e+00;
+  const double c51 = 0.7496443313967647e+01, c52 = -0.1024680431464352e+02, c53 = -0.3399990352819905e+02,
+               c54 = 0.1170890893206160e+02;
+  const double a51 = 0.1221224509226641e+01, a52 = 0.6019134481288629e+01, a53 = 0.1253708332932087e+02,
+               a54 = -0.6878860361058950e+00;
+  const double c61 = 0.8083246795921522e+01, c62 = -0.7981132988064893e+01, c63 = -0.3152159432874371e+02,
+               c64 = 0.1631930543123136e+02, c65 = -0.6058818238834054e+01;
+  const double d21 = 0.1012623508344586e+02, d22 = -0.7487995877610167e+01, d23 = -0.3480091861555747e+02,
+               d24 = -0.7992771707568823e+01, d25 = 0.1025137723295662e+01;
+  const double d31 = -0.6762803392801253e+00, d32 = 0.6087714651680015e+01, d33 = 0.1643084320892478e+02,
+               d34 = 0.2476722511418386e+02, d35 = -0.6594389125716872e+01;
+
+  state_type dxdt, dfdt, dxdtnew, xtmp, g1, g2, g3, g4, g5, cont3, cont4;
+  matrix jac;
+  std::vector<std::size_t> pm;
+  void resize(std::size_t n) {
+    dxdt.resize(n); dfdt.resize(n); dxdtnew.resize(n); xtmp.resize(n);
+    g1.resize(n); g2.resize(n); g3.resize(n); g4.resize(n); g5.resize(n); cont3.resize(n); cont4.resize(n);
+    if (jac.n != n) jac.resize(n);
+    pm.resize(n);
+  }
+  // sys.first(x, dxdt, t), sys.second(x, J, t, dfdt)
+  template <class Sys>
+  void do_step(Sys& sys, const state_type& x, double t, state_type& xout, double dt, state_type& xerr) {
+    const std::size_t n = x.size();
+    resize(n);
+    xout.resize(n); xerr.resize(n);
+    for (std::size_t i = 0; i < n; ++i) pm[i] = i;
+    sys.first(x, dxdt, t);
+    sys.second(x, jac, t, dfdt);
+    for (std::size_t i = 0; i < n * n; ++i) jac.a[i] *= -1.0;
+    const double diag = 1.0 / gamma / dt;
+    for (std::size_t i = 0; i < n; ++i) jac(i, i) += diag * 1.0;
+    lu_factorize(jac, pm);
+
+    for (std::size_t i = 0; i < n; ++i) g1[i] = dxdt[i] + dt * d1 * dfdt[i];
+    lu_substitute(jac, pm, g1);
+
+    for (std::size_t i = 0; i < n; ++i) xtmp[i] = x[i] + a21 * g1[i];
+    sys.first(xtmp, dxdtnew, t + c2 * dt);
+    for (std::size_t i = 0; i < n; ++i) g2[i] = dxdtnew[i] + dt * d2 * dfdt[i] + c21 * g1[i] / dt;
+    lu_substitute(jac, pm, g2);
+
+    for (std::size_t i = 0; i < n; ++i) xtmp[i] = x[i] + a31 * g1[i] + a32 * g2[i];
+    sys.first(xtmp, dxdtnew, t + c3 * dt);
+    for (std::size_t i = 0; i < n; ++i) g3[i] = dxdtnew[i] + dt * d3 * dfdt[i] + (c31 * g1[i] + c32 * g2[i]) / dt;
+    lu_substitute(jac, pm, g3);
+
+    for (std::size_t i = 0; i < n; ++i) xtmp[i] = x[i] + a41 * g1[i] + a42 * g2[i] + a43 * g3[i];
+    sys.first(xtmp, dxdtnew, t + c4 * dt);
+    for (std::size_t i = 0; i < n; ++i)
+      g4[i] = dxdtnew[i] + dt * d4 * dfdt[i] + (c41 * g1[i] + c42 * g2[i] + c43 * g3[i]) / dt;
+    lu_substitute(jac, pm, g4);
+
+    for (std::size_t i = 0; i < n; ++i) xtmp[i] = x[i] + a51 * g1[i] + a52 * g2[i] + a53 * g3[i] + a54 * g4[i];
+    sys.first(xtmp, dxdtnew, t + dt);
+    for (std::size_t i = 0; i < n; ++i)
+      g5[i] = dxdtnew[i] + (c51 * g1[i] + c52 * g2[i] + c53 * g3[i] + c54 * g4[i]) / dt;
+    lu_substitute(jac, pm, g5);
+
+    for (std::size_t i = 0; i < n; ++i) xtmp[i] += g5[i];
+    sys.first(xtmp, dxdtnew, t + dt);
+    for (std::size_t i = 0; i < n; ++i)
+      xerr[i] = dxdtnew[i] + (c61 * g1[i] + c62 * g2[i] + c63 * g3[i] + c64 * g4[i] + c65 * g5[i]) / dt;
+    lu_substitute(jac, pm, xerr);
+
+    for (std::size_t i = 0; i < n; ++i) xout[i] = xtmp[i] + xerr[i];
+  }
+  void prepare_dense_output() {
+    const std::size_t n = g1.size();
+    for (std::size_t i = 0; i < n; ++i) {
+      cont3[i] = d21 * g1[i] + d22 * g2[i] + d23 * g3[i] + d24 * g4[i] + d25 * g5[i];
+      cont4[i] = d31 * g1[i] + d32 * g2[i] + d33 * g3[i] + d34 * g4[i] + d35 * g5[i];
+    }
+  }
+  void calc_state(double t, state_type& x, const state_type& x_old, double t_old, const state_type& x_new,
+                  double t_new) const {
+    const std::size_t n = g1.size();
+    x.resize(n);
+    const double dt = t_new - t_old;
+    const double s = (t - t_old) / dt;
+    const double s1 = 1.0 - s;
+    for (std::size_t i = 0; i < n; ++i) x[i] = x_old[i] * s1 + s * (x_new[i] + s1 * (cont3[i] + s * cont4[i]));
+  }
+};
+
+struct rosenbrock4_controller {
+  rosenbrock4 m_stepper;
+  double m_atol, m_rtol;
+  bool m_first_step = true, m_last_rejected = false;
+  double m_err_old = 0.0, m_dt_old = 0.0;
+  state_type m_xerr, m_xnew;
+  counters* cnt = nullptr;
+  rosenbrock4_controller(double atol = 1e-6, double rtol = 1e-6) : m_atol(atol), m_rtol(rtol) {}
+  double error(const state_type& x, const state_type& xold, const state_type& xerr) const {
+    const std::size_t n = x.size();
+    double err = 0.0, sk = 0.0;
+    for (std::size_t i = 0; i < n; ++i) {
+      sk = m_atol + m_rtol * std::max(std::abs(xold[i]), std::abs(x[i]));
+      err += xerr[i] * xerr[i] / sk / sk;
+    }
+    return std::sqrt(err / double(n));
+  }
+  template <class Sys>
+  controlled_step_result try_step(Sys& sys, const state_type& x, double& t, state_type& xout, double& dt) {
+    static const double safe = 0.9, fac1 = 5.0, fac2 = 1.0 / 6.0;
+    m_stepper.do_step(sys, x, t, xout, dt, m_xerr);
+    double err = error(xout, x, m_xerr);
+    double fac = std::max(fac2, std::min(fac1, std::pow(err, 0.25) / safe));
+    double dt_new = dt / fac;
+    if (err <= 1.0) {
+      if (m_first_step) {
+        m_first_step = false;
+      } else {
+        double fac_pred = (m_dt_old / dt) * std::pow(err * err / m_err_old, 0.25) / safe;
+        fac_pred = std::max(fac2, std::min(fac1, fac_pred));
+        fac = std::max(fac, fac_pred);
+        dt_new = dt / fac;
+      }
+      m_dt_old = dt;
+      m_err_old = std::max(0.01, err);
+      if (m_last_rejected) dt_new = (dt >= 0.0 ? std::min(dt_new, dt) : std::max(dt_new, dt));
+      t += dt;
+      dt = dt_new;
+      m_last_rejected = false;
+      if (cnt) cnt->accepted++;
+      return success;
+    } else {
+      dt = dt_new;
+      m_last_rejected = true;
+      if (cnt) cnt->rejected++;
+      return fail;
+    }
+  }
+};
+
+struct rosenbrock4_dense_output {
+  rosenbrock4_controller m_stepper;
+  state_type m_x1, m_x2;
+  bool m_current1 = true;
+  double m_t = 0, m_t_old = 0, m_dt = 0;
+  rosenbrock4_dense_output(double atol = 1e-6, double rtol = 1e-6) : m_stepper(atol, rtol) {}
+  state_type& cur_x() { return m_current1 ? m_x1 : m_x2; }
+  state_type& old_x() { return m_current1 ? m_x2 : m_x1; }
+  const state_type& current_state() { return cur_x(); }
+  double current_time() const { return m_t; }
+  double current_time_step() const { return m_dt; }
+  void initialize(const state_type& x0, double t0, double dt0) {
+    state_type x0c = x0;
+    m_x1.resize(x0c.size()); m_x2.resize(x0c.size());
+    cur_x() = x0c;
+    m_t = t0; m_dt = dt0;
+  }
+  template <class Sys> std::pair<double, double> do_step(Sys& sys) {
+    failed_step_checker fail_checker;
+    controlled_step_result res = fail;
+    m_t_old = m_t;
+    do {
+      res = m_stepper.try_step(sys, cur_x(), m_t, old_x(), m_dt);
+      fail_checker();
+    } while (res == fail);
+    m_stepper.m_stepper.prepare_dense_output();
+    m_current1 = !m_current1;
+    return std::make_pair(m_t_old, m_t);
+  }
+  void calc_state(double t, state_type& x) {
+    m_stepper.m_stepper.calc_state(t, x, old_x(), m_t_old, cur_x(), m_t);
+  }
+};
+
+// =====================================================================================
+// integrate_* loops.  Tag dispatch is by overload on the stepper family:
+//   plain steppers: anything with do_step(sys,x,t,dt)
+//   controlled:     anything with try_step(sys,x,t,dt)
+//   dense:          anything with initialize/do_step(sys)/calc_state
+// Selected explicitly by the *_plain / *_controlled / *_dense suffix.
+// =====================================================================================
+struct null_observer { void operator()(const state_type&, double) const {} };
+
+template <class St, class Sys, class Obs>
+std::size_t integrate_n_steps_plain(St& st, Sys& sys, state_type& x, double start_time, double dt,
+                                    std::size_t num_of_steps, Obs& obs, double* end_time = nullptr) {
+  double time = start_time;
+  for (std::size_t step = 0; step < num_of_steps; ++step) {
+    obs(x, time);
+    st.do_step(sys, x, time, dt);
+    time = start_time + static_cast<double>(step + 1) * dt;
+  }
+  obs(x, time);
+  if (end_time) *end_time = time;
+  return num_of_steps;
+}
+
+// ---- integrate_adaptive ----
+template <class St, class Sys, class Obs>
+std::size_t integrate_adaptive_plain(St& st, Sys& sys, state_type& x, double start_time, double end_time,
+                                     double dt, Obs& obs) {
+  std::size_t steps = static_cast<std::size_t>((end_time - start_time) / dt);
+  double end = 0;
+  integrate_n_steps_plain(st, sys, x, start_time, dt, steps, obs, &end);
+  if (less_with_sign(end, end_time, dt)) {  // make a last step to end exactly at end_time
+    st.do_step(sys, x, end, end_time - end);
+    steps++;
+    obs(x, end_time);
+  }
+  return steps;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_adaptive_controlled(St& st, Sys& sys, state_type& x, double& start_time, double end_time,
+                                          double& dt, Obs& obs) {
+  failed_step_checker fail_checker;
+  std::size_t count = 0;
+  while (less_with_sign(start_time, end_time, dt)) {
+    obs(x, start_time);
+    if (less_with_sign(end_time, start_time + dt, dt)) dt = end_time - start_time;
+    controlled_step_result res;
+    do {
+      res = st.try_step(sys, x, start_time, dt);
+      fail_checker();
+    } while (res == fail);
+    fail_checker.reset();
+    ++count;
+  }
+  obs(x, start_time);
+  return count;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_adaptive_dense(St& st, Sys& sys, state_type& x, double start_time, double end_time,
+                                     double dt, Obs& obs) {
+  std::size_t count = 0;
+  st.initialize(x, start_time, dt);
+  while (less_with_sign(st.current_time(), end_time, st.current_time_step())) {
+    while (less_eq_with_sign(st.current_time() + st.current_time_step(), end_time, st.current_time_step())) {
+      obs(st.current_state(), st.current_time());
+      st.do_step(sys);
+      ++count;
+    }
+    // calculate time step to arrive exactly at end time
+    st.initialize(st.current_state(), st.current_time(), end_time - st.current_time());
+  }
+  obs(st.current_state(), st.current_time());
+  x = st.current_state();
+  return count;
+}
+
+// ---- integrate_const ----
+template <class St, class Sys, class Obs>
+std::size_t integrate_const_plain(St& st, Sys& sys, state_type& x, double start_time, double end_time,
+                                  double dt, Obs& obs) {
+  double time = start_time;
+  int step = 0;
+  while (less_eq_with_sign(time + dt, end_time, dt)) {
+    obs(x, time);
+    st.do_step(sys, x, time, dt);
+    ++step;
+    time = start_time + static_cast<double>(step) * dt;
+  }
+  obs(x, time);
+  return step;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_const_controlled(St& st, Sys& sys, state_type& x, double start_time, double end_time,
+                                       double dt, Obs& obs) {
+  double time = start_time;
+  const double time_step = dt;
+  int real_steps = 0, step = 0;
+  null_observer nobs;
+  while (less_eq_with_sign(time + time_step, end_time, dt)) {
+    obs(x, time);
+    real_steps += integrate_adaptive_controlled(st, sys, x, time, time + time_step, dt, nobs);
+    step++;
+    time = start_time + static_cast<double>(step) * time_step;
+  }
+  obs(x, time);
+  return real_steps;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_const_dense(St& st, Sys& sys, state_type& x, double start_time, double end_time,
+                                  double dt, Obs& obs) {
+  double time = start_time;
+  st.initialize(x, time, dt);
+  obs(x, time);
+  time += dt;
+  int obs_step = 1, real_step = 0;
+  while (less_eq_with_sign(time + dt, end_time, dt)) {
+    while (less_eq_with_sign(time, st.current_time(), dt)) {
+      st.calc_state(time, x);
+      obs(x, time);
+      ++obs_step;
+      time = start_time + static_cast<double>(obs_step) * dt;
+    }
+    // we have not reached the end, do another real step
+    if (less_with_sign(st.current_time() + st.current_time_step(), end_time, st.current_time_step())) {
+      while (less_eq_with_sign(st.current_time(), time, dt)) {
+        st.do_step(sys);
+        ++real_step;
+      }
+    } else if (less_with_sign(st.current_time(), end_time, st.current_time_step())) {
+      // do the last step ending exactly on the end point
+      st.initialize(st.current_state(), st.current_time(), end_time - st.current_time());
+      st.do_step(sys);
+      ++real_step;
+    }
+  }
+  // last observation, if we are still in observation interval
+  if (less_eq_with_sign(time, end_time, dt)) {
+    st.calc_state(time, x);
+    obs(x, time);
+  }
+  return real_step;
+}
+
+// ---- integrate_times ----
+template <class St, class Sys, class Obs>
+std::size_t integrate_times_plain(St& st, Sys& sys, state_type& x, const double* it, const double* end,
+                                  double dt, Obs& obs) {
+  std::size_t steps = 0;
+  if (it == end) return 0;
+  while (true) {
+    double current_time = *it++;
+    obs(x, current_time);
+    if (it == end) break;
+    while (less_with_sign(current_time, *it, dt)) {
+      double current_dt = min_abs(dt, *it - current_time);
+      st.do_step(sys, x, current_time, current_dt);
+      ++steps;
+      current_time += current_dt;
+    }
+  }
+  return steps;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_times_controlled(St& st, Sys& sys, state_type& x, const double* it, const double* end,
+                                       double dt, Obs& obs) {
+  failed_step_checker fail_checker;
+  std::size_t steps = 0;
+  if (it == end) return 0;
+  while (true) {
+    double current_time = *it++;
+    obs(x, current_time);
+    if (it == end) break;
+    while (less_with_sign(current_time, *it, dt)) {
+      // we want to get as fast as possible to the end time
+      double current_dt = min_abs(dt, *it - current_time);
+      if (st.try_step(sys, x, current_time, current_dt) == success) {
+        ++steps;
+        fail_checker.reset();
+        // continue with the original step size if dt was reduced due to observation
+        dt = max_abs(dt, current_dt);
+      } else {
+        fail_checker();
+        dt = current_dt;
+      }
+    }
+  }
+  return steps;
+}
+template <class St, class Sys, class Obs>
+std::size_t integrate_times_dense(St& st, Sys& sys, state_type& x, const double* it, const double* end,
+                                  double dt, Obs& obs) {
+  if (it == end) return 0;
+  const double last_time_point = *(end - 1);
+  st.initialize(x, *it, dt);
+  obs(x, *it++);
+  std::size_t count = 0;
+  while (it != end) {
+    while ((it != end) && less_eq_with_sign(*it, st.current_time(), st.current_time_step())) {
+      st.calc_state(*it, x);
+      obs(x, *it);
+      it++;
+    }
+    // we have not reached the end, do another real step
+    if (less_eq_with_sign(st.current_time() + st.current_time_step(), last_time_point, st.current_time_step())) {
+      st.do_step(sys);
+      ++count;
+    } else if (it != end) {
+      // do the last step ending exactly on the end point
+      st.initialize(st.current_state(), st.current_time(), last_time_point - st.current_time());
+      st.do_step(sys);
+      ++count;
+    }
+  }
+  return count;
+}
+
+}  // namespace restated

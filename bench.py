@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json configs[1]).
+
+Workload: Lorenz ensemble, 100 M random initial conditions PER GPU (weak scaling; Philox4x32-10, seed
+20260101, instance index = counter, so rank r regenerates instances [r*M, (r+1)*M) of one global
+ensemble), fixed-step rk4 in exact (no-FMA, Boost operation order) mode, dt = 0.001, T = 1.0 (1 000
+steps), observer every 0.1 time units (every 100 steps, 11 samples per trajectory, sample-major SoA).
+One "step" of the benchmark = one integrate_const pass over the rank's whole ensemble.
+
+  value     trajectory-steps/s with the state resident in HBM (device-timed, CUDA events)
+  e2e       the same metric through the host-buffer C-ABI call: initial states in pinned host memory,
+            observer record and final states back in pinned host memory, copies inside the timed region
+  roofline  FP64-pipe issue roofline of the rk4 kernel: 78 DP instructions per trajectory-step
+            (4 x 9 RHS + 3 x 14 stage algebra) against the DP issue rate measured live by
+            a DADD/DMUL probe kernel (MEASURED_PEAKS.json carries no FP64 figure)
+  cpu_baseline  the oracle port of the reference's algorithm on all host cores, bounded sample
+
+`--impl reference` times only the CPU oracle port (the reference itself cannot be built here: no R, Rcpp
+or Boost in the image).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import statistics
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LORENZ = """
+  dxdt[0] = sigma * (x[1] - x[0]);
+  dxdt[1] = R * x[0] - x[1] - x[0] * x[2];
+  dxdt[2] = -b * x[2] + x[0] * x[1];
+"""
+PARS = {"sigma": 10, "R": 28, "b": 8 / 3}
+SEED = 20260101
+LO = (-20.0, -25.0, 5.0)
+HI = (20.0, 25.0, 45.0)
+T_END, DT, STRIDE = 1.0, 0.001, 100
+DP_INSTR_PER_STEP = 78.0      # exact mode: 4 RHS x 9 + 3 components x 14 (mul and add issue separately)
+METRIC = "lorenz_rk4_ensemble_trajectory_steps_per_s"
+UNIT = "trajectory-steps/s"
+
+
+def workload_config(instances, n_gpus):
+    return {
+        "workload": "BASELINE.json configs[1]: Lorenz ensemble, rk4 fixed step (exact no-FMA mode, Boost operation "
+                    "order), dt=0.001, T=1.0 (1000 steps), observer every 100 steps (11 samples), "
+                    "x0 ~ U(-20,20)xU(-25,25)xU(5,45) Philox4x32-10 seed 20260101",
+        "instances_per_gpu": instances,
+        "instances_total": instances * n_gpus,
+        "sharding": "instance-index ranges, one process per GPU, no data-path collective",
+        "l2_policy": "inputs (2.4 GB state) and outputs (26.4 GB record) per step exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "power_w_max": max(self.power) if self.power else None,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(instances, threads, reps=1):
+    """Oracle port of the reference algorithm (restated Boost odeint rk4 + integrate_const with the observer
+    every step kept every 100th, as the reference's name() would record) over `instances` trajectories."""
+    import numpy as np
+
+    from oracle import build_oracle
+
+    ora = build_oracle.build(LORENZ, PARS, True, "rk4")
+    rng = np.random.default_rng(SEED)
+    x0 = np.stack([rng.uniform(LO[v], HI[v], instances) for v in range(3)])
+    best = None
+    steps = int(round(T_END / DT))
+    for _ in range(reps):
+        x = x0.copy()
+        t0 = time.perf_counter()
+        ora.ensemble(0, x, None, 0.0, T_END, DT, obs_stride=STRIDE, out_rows=steps // STRIDE + 1, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return instances * steps / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # calibrate, then size each step's sample so the whole run stays within ~2 minutes
+    rate, _ = cpu_port_throughput(20_000, threads)
+    budget_s = 100.0 / max(1, args.steps + args.warmup)
+    inst = int(min(2_000_000, max(50_000, rate * budget_s / 1000.0)))
+    for _ in range(args.warmup):
+        cpu_port_throughput(inst, threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_port_throughput(inst, threads)
+        t_total += dt
+    value = inst * 1000.0 * args.steps / t_total
+    sample = "%d instances x 1000 rk4 steps per step (of the 100 M-instance workload), OpenMP over instances" % inst
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(100_000_000, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle port of the reference's Boost-odeint path (oracle/); the reference itself needs R, "
+                "Rcpp and Boost, none of which exist in this image",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=100_000_000, help="instances per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    lib = _abi.load()
+    assert lib.odeintr_set_device(local_rank) == 0, _abi.last_error()
+    code = odeintr_b200.compile_sys("lorenz", LORENZ, PARS, True, method="rk4")
+    system = code.system
+    h = system._h
+    M = args.instances
+    steps_per_pass = 1000
+    lo = (C.c_double * 3)(*LO)
+    hi = (C.c_double * 3)(*HI)
+
+    # roofline denominators measured live on this device
+    dp_peak, probe_ms = C.c_double(), C.c_double()
+    assert lib.odeintr_fp64_probe(1, local_rank, C.byref(dp_peak), C.byref(probe_ms)) == 0, _abi.last_error()
+    dp_peak_fma = C.c_double()
+    assert lib.odeintr_fp64_probe(0, local_rank, C.byref(dp_peak_fma), C.byref(probe_ms)) == 0, _abi.last_error()
+
+    # ---- device-resident arm -------------------------------------------------------------------------
+    assert lib.odeintr_fill_state_uniform(h, M, SEED, rank * M, lo, hi) == 0, _abi.last_error()
+
+    def one_pass():
+        rc = lib.odeintr_integrate_const(h, 0.0, T_END, DT, STRIDE, 1)
+        if rc != 0:
+            raise RuntimeError(_abi.last_error())
+
+    for _ in range(args.warmup):
+        one_pass()
+    lib.odeintr_synchronize(h)
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.odeintr_total_launches()
+    barrier()
+    sampler.start()
+    kernel_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+        kernel_ms.append(system.last_kernel_ms())  # CUDA events on the launching stream (syncs on the stop event)
+    lib.odeintr_synchronize(h)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = lib.odeintr_total_launches() - launches0
+    assert system.last_steps() == steps_per_pass and lib.odeintr_output_rows(h) == 11
+    dev_s = max_over_ranks(sum(kernel_ms) * 1e-3)
+    wall = max_over_ranks(wall)
+    value = world * M * steps_per_pass * args.steps / dev_s
+    kern_avg_ms = statistics.mean(kernel_ms)
+    achieved_dp = M * steps_per_pass * DP_INSTR_PER_STEP / (kern_avg_ms * 1e-3)  # this rank's kernel
+    attrs = system.kernel_attributes("odeintr_plain_ensemble")
+
+    # ---- end-to-end arm: host buffers through odeintr_integrate_const_host --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        bytes_per_inst = (11 * 3 + 3 + 3) * 8
+        try:
+            avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
+        except Exception:
+            avail = 64 << 30
+        m_e2e = int(min(M, (0.55 * avail / max(world, 1)) // bytes_per_inst))
+        m_e2e -= m_e2e % 128
+        lib.odeintr_release_record(h)
+        n_x, n_out = 3 * m_e2e, 11 * 3 * m_e2e
+        px = lib.odeintr_host_alloc(n_x * 8)
+        pf = lib.odeintr_host_alloc(n_x * 8)
+        po = lib.odeintr_host_alloc(n_out * 8)
+        assert px and pf and po, "pinned allocation failed: " + _abi.last_error()
+        x_host = np.ctypeslib.as_array(C.cast(px, _abi.c_dbl_p), shape=(3, m_e2e))
+        xf_host = np.ctypeslib.as_array(C.cast(pf, _abi.c_dbl_p), shape=(3, m_e2e))
+        out_host = np.ctypeslib.as_array(C.cast(po, _abi.c_dbl_p), shape=(11, 3, m_e2e))
+        # synthetic initial states: generated once on the device (same Philox stream), copied to the host buffer
+        assert lib.odeintr_fill_state_uniform(h, m_e2e, SEED, rank * M, lo, hi) == 0, _abi.last_error()
+        assert lib.odeintr_get_state(h, C.cast(px, _abi.c_dbl_p), n_x) == 0, _abi.last_error()
+        out_host[...] = 0.0  # touch the pages
+
+        def e2e_pass():
+            rc = lib.odeintr_integrate_const_host(h, C.cast(px, _abi.c_dbl_p), m_e2e, None, 0, 0.0, T_END, DT, STRIDE,
+                                                  C.cast(po, _abi.c_dbl_p), n_out, C.cast(pf, _abi.c_dbl_p), 0)
+            if rc != 0:
+                raise RuntimeError(_abi.last_error())
+
+        k_e2e = args.e2e_steps if args.e2e_steps else max(3, min(args.steps, 5))
+        for _ in range(3):
+            e2e_pass()
+        barrier()
+        t_e2e = 0.0
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_pass()  # returns when the record and the final state are complete in host memory
+            t_e2e += system.last_kernel_ms() * 1e-3
+        barrier()
+        wall_e2e = max_over_ranks(time.perf_counter() - t0)
+        t_e2e = max_over_ranks(t_e2e)
+        # spot check: the record of the last pass starts at the inputs and ends at the returned final state
+        assert np.array_equal(out_host[0, :, :4096], x_host[:, :4096])
+        assert np.array_equal(out_host[10, :, :4096], xf_host[:, :4096])
+        e2e = {
+            "value": world * m_e2e * steps_per_pass * k_e2e / wall_e2e, "unit": UNIT,
+            "h2d_bytes_per_step": n_x * 8, "d2h_bytes_per_step": (n_out + n_x) * 8,
+            "instances_per_gpu": m_e2e, "steps": k_e2e, "ms_per_step": 1e3 * wall_e2e / k_e2e,
+            "device_ms_per_step": 1e3 * t_e2e / k_e2e,
+            "api": "odeintr_integrate_const_host (pinned host buffers, chunked 3-stream copy/compute overlap)",
+        }
+        lib.odeintr_host_free(px); lib.odeintr_host_free(pf); lib.odeintr_host_free(po)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, _ = cpu_port_throughput(20_000, threads)
+        inst = int(min(4_000_000, max(50_000, rate * 12.0 / 1000.0)))
+        v, secs = cpu_port_throughput(inst, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d of the 100 M instances x 1000 rk4 steps, observer every 100 steps, OpenMP over instances "
+                         "(%.1f s)" % (inst, secs)}
+
+    traffic = None
+    tfile = ROOT / "profiles" / "rk4_ensemble_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch_100M")
+            if traffic is not None and M != 100_000_000:
+                traffic = traffic * M / 100_000_000
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(M, world),
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_dp / 1e12, "peak": dp_peak.value / 1e12, "unit": "TFLOP/s",
+                "frac": achieved_dp / dp_peak.value, "traffic": traffic,
+                "kernel": "odeintr_plain_ensemble<rk4_stepper, N=3>",
+                "kernel_ms": kern_avg_ms,
+                "note": "compute-bound on the FP64 pipe (north_star: FP64 pipe utilisation). achieved = 78 DP "
+                        "instructions (= flops: exact mode issues no FMA) per trajectory-step x trajectory-steps per "
+                        "launch / CUDA-event launch time; peak = DADD/DMUL issue rate measured live by "
+                        "odeintr_fp64_probe (MEASURED_PEAKS.json has no FP64 entry); the DFMA rate is the same "
+                        "%.2f T instr/s = %.1f TFLOP/s if every instruction were an FMA" %
+                        (dp_peak_fma.value / 1e12, 2 * dp_peak_fma.value / 1e12),
+                "hbm": {"bytes_per_launch": M * (3 + 3 + 33) * 8,
+                        "achieved_GBps": M * (3 + 3 + 33) * 8 / (kern_avg_ms * 1e-3) / 1e9,
+                        "peak_GBps": _measured_hbm()},
+                "registers": attrs["registers"], "local_bytes": attrs["local_bytes"],
+            },
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _measured_hbm():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -47,6 +47,7 @@ enum {
 /* compile flags */
 #define ODEINTR_FLAG_FMAD 1u            /* allow FMA contraction (fast mode; NOT bit-compatible with the reference) */
 #define ODEINTR_FLAG_KEEP_ZERO_TERMS 2u /* also add Boost's zero tableau entries (x + 0*dt*k) */
+#define ODEINTR_FLAG_DENSE_OUTPUT 4u    /* the TU instantiates a dense-output stepper (rk5_i, rosenbrock4): set by the generator */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 
@@ -113,10 +114,24 @@ int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_ti
 /* odeint::integrate_adaptive(stepper, sys, state, t0, t1, dt[, obs]) — :107 (record) and :168 */
 int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double dt, int record);
 
+/* Host-buffer form of odeintr_integrate_const: x (sys_dim x n_inst), pars (n_pars x par_sets, par_sets in
+ * {1, n_inst}; null when the system has no run-time parameters) and the results live in caller memory
+ * (pinned memory makes the copies asynchronous).  The ensemble is streamed through the GPU in chunks of
+ * `chunk` instances (0 = automatic) with copies and kernels overlapped; out (rows x sys_dim x n_inst,
+ * null = no observer) and x_final (sys_dim x n_inst, may be null) are complete when the call returns.
+ * Nothing stays resident on the device.  rows = odeintr_const_rows(t0, t1, dt, obs_stride). */
+int odeintr_integrate_const_host(odeintr_system_t h, const double* x, size_t n_inst, const double* pars,
+                                 size_t par_sets, double t0, double t1, double dt, long long obs_stride,
+                                 double* out, size_t out_values, double* x_final, size_t chunk);
+/* rows integrate_const records for (t0, t1, dt, obs_stride) with a fixed-step stepper */
+size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride);
+
 /* ---- observer record ------------------------------------------------------------------------ */
 
 /* name_reset_observer(), compile_sys_template.cpp:92-97 */
 int odeintr_reset_observer(odeintr_system_t h);
+/* free the device memory of the observer record and scratch buffers (the record is dropped) */
+int odeintr_release_record(odeintr_system_t h);
 /* rows currently recorded (length of rec_t) */
 size_t odeintr_output_rows(odeintr_system_t h);
 /* rec_t: the Time column (instance independent for const/times integration) */
@@ -126,6 +141,10 @@ int odeintr_get_output_times(odeintr_system_t h, double* t, size_t n_values);
 int odeintr_get_output(odeintr_system_t h, double* x, size_t n_values, size_t inst_begin, size_t inst_count);
 /* the whole record in device layout out[(s * sys_dim + v) * m + i] (rows * sys_dim * m doubles) */
 int odeintr_get_output_soa(odeintr_system_t h, double* out, size_t n_values);
+/* 1 when the record is ragged: integrate_adaptive with a controlled / dense stepper observes once per
+ * accepted step, so every instance has its own row count and Time column; odeintr_output_rows() is then
+ * the maximum over instances and shorter instances are padded (unspecified values) */
+int odeintr_output_is_ragged(odeintr_system_t h);
 /* per-instance row counts / times for ragged records (integrate_adaptive with adaptive steppers) */
 int odeintr_get_output_rows_per_instance(odeintr_system_t h, int* rows, size_t n_values);
 int odeintr_get_output_times_per_instance(odeintr_system_t h, double* t, size_t n_values, size_t inst);

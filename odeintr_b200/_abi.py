@@ -38,11 +38,17 @@ SIGNATURES = {
     "odeintr_integrate_const": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_longlong, C.c_int]),
     "odeintr_integrate_times": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, C.c_double]),
     "odeintr_integrate_adaptive": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "odeintr_integrate_const_host": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, c_dbl_p, C.c_size_t, C.c_double,
+                                               C.c_double, C.c_double, C.c_longlong, c_dbl_p, C.c_size_t, c_dbl_p,
+                                               C.c_size_t]),
+    "odeintr_const_rows": (C.c_size_t, [C.c_double, C.c_double, C.c_double, C.c_longlong]),
     "odeintr_reset_observer": (C.c_int, [C.c_void_p]),
+    "odeintr_release_record": (C.c_int, [C.c_void_p]),
     "odeintr_output_rows": (C.c_size_t, [C.c_void_p]),
     "odeintr_get_output_times": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t]),
     "odeintr_get_output": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "odeintr_get_output_soa": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t]),
+    "odeintr_output_is_ragged": (C.c_int, [C.c_void_p]),
     "odeintr_get_output_rows_per_instance": (C.c_int, [C.c_void_p, c_int_p, C.c_size_t]),
     "odeintr_get_output_times_per_instance": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, C.c_size_t]),
     "odeintr_get_stats": (C.c_int, [C.c_void_p, c_ll_p, c_ll_p, c_int_p, C.c_size_t]),
@@ -64,6 +70,7 @@ SIGNATURES = {
 
 FLAG_FMAD = 1
 FLAG_KEEP_ZERO_TERMS = 2
+FLAG_DENSE_OUTPUT = 4
 
 _lib = None
 

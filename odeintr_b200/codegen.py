@@ -187,6 +187,9 @@ def handle_pars(pars, const: bool = False) -> ParsSpec:
             raise OdeintrError("All parameters must be named")
         vals = list(pars.values())
         decl = "double " + ", ".join("%s = %s" % (n, r_num(v)) for n, v in zip(names, vals)) + ";"
+        # the run-time default of a parameter is what the pasted text compiles to (15 significant digits),
+        # e.g. b = 8/3 defaults to 2.66666666666667 until name_set_params(b = 8/3) stores the exact double
+        vals = [float(r_num(v)) for v in vals]
         if const:
             # compile-time constants: R/utils.R:181-187 with const = TRUE; no setter / getter
             return ParsSpec("named", names, [float(v) for v in vals], True, "const " + decl, "", True)
@@ -212,6 +215,10 @@ def handle_pars(pars, const: bool = False) -> ParsSpec:
 # --------------------------------------------------------------------------------------------------
 # symbolic Jacobian (R/utils.R:123-154, R/odeintr.R:613-627) -- sympy instead of stats::D
 # --------------------------------------------------------------------------------------------------
+_MATH_FUNCS = {"exp", "log", "sin", "cos", "tan", "sinh", "cosh", "tanh", "sqrt", "asin", "acos", "atan", "pow",
+               "fabs"}
+
+
 def Jacobian2(code: Union[str, Sequence[str]], sys_dim: int = -1) -> str:
     import sympy
     from sympy.parsing.sympy_parser import parse_expr
@@ -241,7 +248,13 @@ def Jacobian2(code: Union[str, Sequence[str]], sys_dim: int = -1) -> str:
             raise OdeintrError("no expression for dxdt[%d]" % i)
         rhs = re.sub(r"\bstd::", "", rows[i])
         rhs = re.sub(r"\bx\s*\[\s*(\d+)\s*\]", r"x__\1", rhs)
-        expr = parse_expr(rhs, local_dict=dict(local), evaluate=True)
+        # every identifier that is not a math function is a parameter (R's D() treats them the same way);
+        # without this sympy would read names such as beta / gamma as its own special functions
+        names = dict(local)
+        for ident in set(re.findall(r"[A-Za-z_]\w*", rhs)):
+            if ident not in names and ident not in _MATH_FUNCS:
+                names[ident] = sympy.Symbol(ident, real=True)
+        expr = parse_expr(rhs, local_dict=names, evaluate=True)
         for j in range(sys_dim):
             d = sympy.diff(expr, xs[j])
             txt = sympy.ccode(sympy.nsimplify(d, rational=False) if d.is_number else d)

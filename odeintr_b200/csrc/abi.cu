@@ -135,7 +135,8 @@ struct odeintr_system_s {
   dev_buf<long long> seg_nfull, accepted, rejected;
   dev_buf<double> seg_hrem, seg_t, times_dev;
   dev_buf<unsigned char> seg_obs;
-  dev_buf<int> status, rows_inst;
+  dev_buf<int> status, rows_inst, fail_flags;
+  bool dense = false;    // the adaptive kernel wraps a dense-output stepper (rk5_i, rosenbrock4)
   dev_buf<unsigned long long> work_counter;
   size_t m = 0;          // resident instances
   size_t par_sets = 0;   // 0 (none set), 1 (broadcast) or m
@@ -145,6 +146,11 @@ struct odeintr_system_s {
   bool ragged = false;   // per-instance row counts (adaptive record)
   int max_rows = 0;
   long long last_steps = 0, last_launches = 0;
+  // host-streaming pipeline (odeintr_integrate_*_host)
+  bool pipe_ready = false;
+  cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+  dev_buf<double> pipe_x[3], pipe_out[3], pipe_pars[3];
 };
 
 namespace {
@@ -166,9 +172,9 @@ int end_timing(odeintr_system_t h) {
   return ODEINTR_OK;
 }
 
-int launch(odeintr_system_t h, cudaKernel_t k, unsigned grid, unsigned block, void* args_struct) {
+int launch(odeintr_system_t h, cudaKernel_t k, cudaStream_t st, unsigned grid, unsigned block, void* args_struct) {
   void* params[1] = {args_struct};
-  CU_TRY(cudaLaunchKernel((const void*)k, dim3(grid), dim3(block), params, 0, h->stream));
+  CU_TRY(cudaLaunchKernel((const void*)k, dim3(grid), dim3(block), params, 0, st));
   h->last_launches += 1;
   g_total_launches += 1;
   return ODEINTR_OK;
@@ -208,53 +214,332 @@ struct plain_schedule {
   long long n_seg = 0, nfull_uniform = 0;
   int time_rule = ODEINTR_TIME_CONST;
   long long total_steps = 0;
+  double t0 = 0.0, dt = 0.0;
+  bool record = false, record_final = false;
+  std::vector<double> rec_t;  // the Time column the observer would have recorded
 };
 
-int run_plain(odeintr_system_t h, const plain_schedule& sc, double t0, double dt, bool record, bool record_final,
-              const std::vector<double>& rec_t) {
+// integrate_const, stepper_tag: obs; do_step; time = t0 + step*dt ... final obs
+void schedule_const(plain_schedule& sc, double t0, double t1, double dt, long long k, bool record) {
+  const long long n = const_step_count(t0, t1, dt);
+  sc.time_rule = ODEINTR_TIME_CONST;
+  sc.total_steps = n;
+  sc.t0 = t0; sc.dt = dt;
+  sc.record = record; sc.record_final = record;
+  if (!record) {
+    sc.uniform = true; sc.n_seg = 1; sc.nfull_uniform = n;
+    return;
+  }
+  sc.n_seg = (n + k - 1) / k;
+  if (n % k == 0) {
+    sc.uniform = true; sc.nfull_uniform = k;
+  } else {
+    sc.nfull.assign((size_t)sc.n_seg, k);
+    sc.nfull.back() = n - k * (sc.n_seg - 1);
+    sc.hrem.assign((size_t)sc.n_seg, 0.0);
+    sc.obs.assign((size_t)sc.n_seg, 1);
+    sc.t.resize((size_t)sc.n_seg);
+    for (long long s = 0; s < sc.n_seg; ++s) sc.t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
+  }
+  sc.rec_t.resize((size_t)sc.n_seg + 1);
+  for (long long s = 0; s < sc.n_seg; ++s) sc.rec_t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
+  sc.rec_t[(size_t)sc.n_seg] = t0 + static_cast<double>(n) * dt;
+}
+
+// integrate_times, stepper_tag: per interval, steps of dt then min_abs(dt, T - t) remainders
+void schedule_times(plain_schedule& sc, const double* times, size_t n_times, double dt) {
+  sc.time_rule = ODEINTR_TIME_ACCUM;
+  sc.t0 = times[0]; sc.dt = dt;
+  sc.record = true; sc.record_final = true;
+  sc.rec_t.assign(times, times + n_times);
+  auto open_segment = [&](double t, bool observe) {
+    sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(observe ? 1 : 0);
+  };
+  for (size_t k = 0; k + 1 < n_times; ++k) {
+    double t = times[k];
+    const double T = times[k + 1];
+    bool first = true;
+    bool open = false;  // the current segment can still take full steps
+    if (!less_with_sign(t, T, dt)) {  // nothing to integrate, but the observation still happens
+      open_segment(t, true);
+      continue;
+    }
+    while (less_with_sign(t, T, dt)) {
+      const double hcur = min_abs(dt, T - t);
+      if (!open) { open_segment(t, first); first = false; open = true; }
+      if (hcur == dt) {
+        sc.nfull.back() += 1;
+      } else {
+        sc.hrem.back() = hcur;
+        open = false;  // a remainder step closes the segment
+      }
+      sc.total_steps += 1;
+      t += hcur;
+    }
+  }
+  sc.n_seg = (long long)sc.nfull.size();
+}
+
+// integrate_adaptive, stepper_tag: integrate_n_steps + one step onto t1
+void schedule_adaptive(plain_schedule& sc, double t0, double t1, double dt, bool record) {
+  const double q = (t1 - t0) / dt;
+  const long long n = q > 0 ? static_cast<long long>(q) : 0;
+  const double end = t0 + static_cast<double>(n) * dt;
+  const bool rem = less_with_sign(end, t1, dt);
+  sc.time_rule = ODEINTR_TIME_CONST;
+  sc.total_steps = n + (rem ? 1 : 0);
+  sc.t0 = t0; sc.dt = dt;
+  sc.record = record; sc.record_final = record;
+  if (!record) {
+    sc.n_seg = 1;
+    if (!rem) { sc.uniform = true; sc.nfull_uniform = n; }
+    else { sc.nfull.assign(1, n); sc.hrem.assign(1, t1 - end); sc.t.assign(1, t0); sc.obs.assign(1, 0); }
+    return;
+  }
+  sc.rec_t.resize((size_t)n + 1);
+  for (long long s = 0; s <= n; ++s) sc.rec_t[(size_t)s] = t0 + static_cast<double>(s) * dt;
+  if (!rem) {
+    sc.uniform = true; sc.n_seg = n; sc.nfull_uniform = 1;
+  } else {
+    sc.n_seg = n + 1;
+    sc.nfull.assign((size_t)n + 1, 1); sc.nfull.back() = 0;
+    sc.hrem.assign((size_t)n + 1, 0.0); sc.hrem.back() = t1 - end;
+    sc.obs.assign((size_t)n + 1, 1);
+    sc.t = sc.rec_t;
+    sc.rec_t.push_back(t1);
+  }
+}
+
+int upload_schedule(odeintr_system_t h, const plain_schedule& sc, odeintr_plain_args& a) {
+  int rc;
+  a.t0 = sc.t0;
+  a.dt = sc.dt;
+  a.n_seg = sc.n_seg;
+  a.nfull_uniform = sc.nfull_uniform;
+  a.time_rule = sc.time_rule;
+  a.record_final = sc.record_final ? 1 : 0;
+  if (sc.uniform) return ODEINTR_OK;
+  const size_t n = (size_t)sc.n_seg;
+  CU_TRY(h->seg_nfull.reserve(n)); CU_TRY(h->seg_hrem.reserve(n)); CU_TRY(h->seg_t.reserve(n));
+  CU_TRY(h->seg_obs.reserve(n));
+  // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die afterwards
+  if ((rc = upload(h, h->seg_nfull.p, sc.nfull.data(), n * sizeof(long long)))) return rc;
+  if ((rc = upload(h, h->seg_hrem.p, sc.hrem.data(), n * sizeof(double)))) return rc;
+  if ((rc = upload(h, h->seg_t.p, sc.t.data(), n * sizeof(double)))) return rc;
+  if ((rc = upload(h, h->seg_obs.p, sc.obs.data(), n))) return rc;
+  a.seg_nfull = h->seg_nfull.p; a.seg_hrem = h->seg_hrem.p; a.seg_t = h->seg_t.p; a.seg_obs = h->seg_obs.p;
+  return ODEINTR_OK;
+}
+
+// Device-resident run: the whole ensemble in one launch.
+int run_plain(odeintr_system_t h, const plain_schedule& sc) {
   if (!h->k_plain) return fail(ODEINTR_E_STATE, "system was not compiled with a fixed-step stepper");
   if (h->m == 0) return fail(ODEINTR_E_STATE, "Invalid initial state");
   odeintr_plain_args a;
   std::memset(&a, 0, sizeof(a));
   int rc = param_view(h, a.pars, a.par_ld, a.par_inc);
   if (rc) return rc;
-  if (record) {
-    rc = reserve_out(h, rec_t.size());
-    if (rc) return rc;
-  }
-  if (!sc.uniform) {
-    const size_t n = (size_t)sc.n_seg;
-    CU_TRY(h->seg_nfull.reserve(n)); CU_TRY(h->seg_hrem.reserve(n)); CU_TRY(h->seg_t.reserve(n));
-    CU_TRY(h->seg_obs.reserve(n));
-    if ((rc = upload(h, h->seg_nfull.p, sc.nfull.data(), n * sizeof(long long)))) return rc;
-    if ((rc = upload(h, h->seg_hrem.p, sc.hrem.data(), n * sizeof(double)))) return rc;
-    if ((rc = upload(h, h->seg_t.p, sc.t.data(), n * sizeof(double)))) return rc;
-    if ((rc = upload(h, h->seg_obs.p, sc.obs.data(), n))) return rc;
-    // the host vectors die with the caller's frame; pageable copies are staged before returning
-    a.seg_nfull = h->seg_nfull.p; a.seg_hrem = h->seg_hrem.p; a.seg_t = h->seg_t.p; a.seg_obs = h->seg_obs.p;
-  }
+  if (sc.record && (rc = reserve_out(h, sc.rec_t.size()))) return rc;
+  if ((rc = upload_schedule(h, sc, a))) return rc;
   a.x = h->x.p;
-  a.out = record ? h->out.p : nullptr;
+  a.out = sc.record ? h->out.p : nullptr;
   a.m = (long long)h->m;
   a.ld = (long long)h->m;
-  a.t0 = t0;
-  a.dt = dt;
-  a.n_seg = sc.n_seg;
-  a.nfull_uniform = sc.nfull_uniform;
-  a.time_rule = sc.time_rule;
-  a.record_final = record_final ? 1 : 0;
   if ((rc = begin_timing(h))) return rc;
   const unsigned block = (unsigned)h->block_plain;
   const unsigned grid = (unsigned)((h->m + block - 1) / block);
-  if ((rc = launch(h, h->k_plain, grid, block, &a))) return rc;
+  if ((rc = launch(h, h->k_plain, h->stream, grid, block, &a))) return rc;
   if ((rc = end_timing(h))) return rc;
   h->last_steps = sc.total_steps;
-  if (record) {
-    h->rec_t = rec_t;
-    h->rows = rec_t.size();
+  if (sc.record) {
+    h->rec_t = sc.rec_t;
+    h->rows = sc.rec_t.size();
     h->out_m = h->m;
     h->ragged = false;
   }
+  return ODEINTR_OK;
+}
+
+// Host-buffer run: the ensemble is streamed through the GPU in chunks of instances on three streams
+// so the host->device copy of chunk j+1, the kernel of chunk j and the device->host copy of chunk j-1
+// overlap (full-duplex PCIe + compute).  Host layouts are the C-ABI's SoA layouts with leading
+// dimension n_inst; the device works on dense chunk-local copies.
+int run_plain_host(odeintr_system_t h, const plain_schedule& sc, const double* x_host, size_t n_inst,
+                   const double* pars_host, size_t par_sets, double* out_host, double* x_final_host, size_t chunk) {
+  if (!h->k_plain) return fail(ODEINTR_E_STATE, "system was not compiled with a fixed-step stepper");
+  if (!x_host || n_inst == 0) return fail(ODEINTR_E_INVALID, "Invalid initial state");
+  if (h->P && (!pars_host || (par_sets != 1 && par_sets != n_inst))) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  const size_t N = (size_t)h->N, P = (size_t)h->P;
+  const size_t rows = sc.record ? sc.rec_t.size() : 0;
+  if (sc.record && !out_host) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (chunk == 0) {
+    // ~1 GiB of record per chunk, at least 64 Ki instances, a multiple of the block size
+    const size_t per_inst = (rows * N + 2 * N + P) * sizeof(double);
+    chunk = std::max<size_t>((size_t)1 << 16, ((size_t)1 << 30) / std::max<size_t>(per_inst, 1));
+  }
+  chunk = std::min(chunk, n_inst);
+  chunk = ((chunk + 127) / 128) * 128;
+  constexpr int kSlots = 3;
+  if (!h->pipe_ready) {
+    for (int s = 0; s < kSlots; ++s) {
+      CU_TRY(cudaStreamCreateWithFlags(&h->pipe_stream[s], cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreateWithFlags(&h->pipe_done[s], cudaEventDisableTiming));
+    }
+    h->pipe_ready = true;
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    CU_TRY(h->pipe_x[s].reserve(N * chunk));
+    if (rows) CU_TRY(h->pipe_out[s].reserve(rows * N * chunk));
+    if (P && par_sets == n_inst) CU_TRY(h->pipe_pars[s].reserve(P * chunk));
+  }
+  odeintr_plain_args base;
+  std::memset(&base, 0, sizeof(base));
+  int rc = upload_schedule(h, sc, base);
+  if (rc) return rc;
+  if (P && par_sets == 1) {
+    CU_TRY(h->pars.reserve(P));
+    if ((rc = upload(h, h->pars.p, pars_host, P * sizeof(double)))) return rc;
+  }
+  if ((rc = begin_timing(h))) return rc;
+  // the chunk streams start after the schedule / broadcast-parameter uploads on the main stream
+  cudaEvent_t start_ev = h->pipe_done[0];
+  CU_TRY(cudaEventRecord(start_ev, h->stream));
+  for (int s = 0; s < kSlots; ++s) CU_TRY(cudaStreamWaitEvent(h->pipe_stream[s], start_ev, 0));
+  const unsigned block = (unsigned)h->block_plain;
+  size_t j = 0;
+  for (size_t i0 = 0; i0 < n_inst; i0 += chunk, ++j) {
+    const int s = (int)(j % kSlots);
+    cudaStream_t st = h->pipe_stream[s];
+    const size_t c = std::min(chunk, n_inst - i0);
+    CU_TRY(cudaMemcpy2DAsync(h->pipe_x[s].p, c * sizeof(double), x_host + i0, n_inst * sizeof(double), c * sizeof(double),
+                             N, cudaMemcpyHostToDevice, st));
+    odeintr_plain_args a = base;
+    if (P) {
+      if (par_sets == 1) { a.pars = h->pars.p; a.par_ld = 1; a.par_inc = 0; }
+      else {
+        CU_TRY(cudaMemcpy2DAsync(h->pipe_pars[s].p, c * sizeof(double), pars_host + i0, n_inst * sizeof(double),
+                                 c * sizeof(double), P, cudaMemcpyHostToDevice, st));
+        a.pars = h->pipe_pars[s].p; a.par_ld = (long long)c; a.par_inc = 1;
+      }
+    }
+    a.x = h->pipe_x[s].p;
+    a.out = rows ? h->pipe_out[s].p : nullptr;
+    a.m = (long long)c;
+    a.ld = (long long)c;
+    if ((rc = launch(h, h->k_plain, st, (unsigned)((c + block - 1) / block), block, &a))) return rc;
+    if (rows)
+      CU_TRY(cudaMemcpy2DAsync(out_host + i0, n_inst * sizeof(double), h->pipe_out[s].p, c * sizeof(double),
+                               c * sizeof(double), rows * N, cudaMemcpyDeviceToHost, st));
+    if (x_final_host)
+      CU_TRY(cudaMemcpy2DAsync(x_final_host + i0, n_inst * sizeof(double), h->pipe_x[s].p, c * sizeof(double),
+                               c * sizeof(double), N, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    CU_TRY(cudaEventRecord(h->pipe_done[s], h->pipe_stream[s]));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->pipe_done[s], 0));
+  }
+  if ((rc = end_timing(h))) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->last_steps = sc.total_steps;
+  h->rec_t = sc.rec_t;
+  h->rows = 0;  // the record lives in the caller's buffer, not on the device
+  h->out_m = 0;
+  return ODEINTR_OK;
+}
+
+// Time column integrate_const records with a dense-output stepper: instance independent.
+std::vector<double> dense_const_times(double t0, double t1, double dt) {
+  std::vector<double> rec;
+  double time = t0;
+  rec.push_back(time);
+  time += dt;
+  long long k = 1;
+  while (less_eq_with_sign(time + dt, t1, dt)) {
+    rec.push_back(time);
+    ++k;
+    time = t0 + static_cast<double>(k) * dt;
+  }
+  if (less_eq_with_sign(time, t1, dt)) rec.push_back(time);
+  return rec;
+}
+
+// Controlled / dense-output steppers: one launch, per-instance step control inside the kernel.
+int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times, size_t n_times,
+                 bool record) {
+  if (!h->k_adaptive) return fail(ODEINTR_E_STATE, "system was not compiled with an adaptive stepper");
+  if (h->m == 0) return fail(ODEINTR_E_STATE, "Invalid initial state");
+  const size_t m = h->m, N = (size_t)h->N;
+  odeintr_adaptive_args a;
+  std::memset(&a, 0, sizeof(a));
+  int rc = param_view(h, a.pars, a.par_ld, a.par_inc);
+  if (rc) return rc;
+  CU_TRY(h->accepted.reserve(m)); CU_TRY(h->rejected.reserve(m)); CU_TRY(h->status.reserve(m));
+  CU_TRY(h->rows_inst.reserve(m)); CU_TRY(h->fail_flags.reserve(1));
+  std::vector<double> rec_t;
+  if (mode == ODEINTR_MODE_TIMES) {
+    CU_TRY(h->times_dev.reserve(n_times));
+    if ((rc = upload(h, h->times_dev.p, times, n_times * sizeof(double)))) return rc;
+    a.times = h->times_dev.p;
+    a.n_times = (long long)n_times;
+    rec_t.assign(times, times + n_times);
+  } else if (mode == ODEINTR_MODE_CONST && record) {
+    if (h->dense) rec_t = dense_const_times(t0, t1, dt);
+    else {
+      const long long n = const_step_count(t0, t1, dt);
+      rec_t.resize((size_t)n + 1);
+      for (long long s = 0; s <= n; ++s) rec_t[(size_t)s] = t0 + static_cast<double>(s) * dt;
+    }
+  }
+  a.x = h->x.p;
+  a.m = (long long)m; a.ld = (long long)m;
+  a.t0 = t0; a.t1 = t1; a.dt = dt;
+  a.atol = h->atol; a.rtol = h->rtol;
+  a.mode = mode;
+  a.accepted = h->accepted.p; a.rejected = h->rejected.p; a.status = h->status.p; a.rows = h->rows_inst.p;
+  a.fail_flags = h->fail_flags.p;
+  const unsigned block = (unsigned)h->block_adaptive;
+  const unsigned grid = (unsigned)((m + block - 1) / block);
+  CU_TRY(cudaMemsetAsync(h->fail_flags.p, 0, sizeof(int), h->stream));
+  if ((rc = begin_timing(h))) return rc;
+  bool ragged = false;
+  int max_rows = 0;
+  if (mode == ODEINTR_MODE_ADAPTIVE && record) {
+    // Ragged record (one row per accepted step): a dry run on a copy of the state counts the rows of every
+    // instance; the arithmetic is deterministic, so the recording run below takes exactly the same steps.
+    CU_TRY(h->stage.reserve(N * m));
+    CU_TRY(cudaMemcpyAsync(h->stage.p, h->x.p, N * m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    odeintr_adaptive_args dry = a;
+    dry.x = h->stage.p;
+    if ((rc = launch(h, h->k_adaptive, h->stream, grid, block, &dry))) return rc;
+    std::vector<int> rows_host(m);
+    CU_TRY(cudaMemcpyAsync(rows_host.data(), h->rows_inst.p, m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < m; ++i) max_rows = std::max(max_rows, rows_host[i]);
+    if ((rc = reserve_out(h, (size_t)max_rows))) return rc;
+    CU_TRY(h->t_rec.reserve((size_t)max_rows * m));
+    a.out = h->out.p; a.t_rec = h->t_rec.p; a.max_rows = max_rows;
+    CU_TRY(cudaMemsetAsync(h->fail_flags.p, 0, sizeof(int), h->stream));
+    ragged = true;
+  } else if (record) {
+    if ((rc = reserve_out(h, rec_t.size()))) return rc;
+    a.out = h->out.p;
+    a.max_rows = (int)rec_t.size();
+  }
+  if ((rc = launch(h, h->k_adaptive, h->stream, grid, block, &a))) return rc;
+  if ((rc = end_timing(h))) return rc;
+  int flags = 0;
+  CU_TRY(cudaMemcpyAsync(&flags, h->fail_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->last_steps = 0;
+  if (record) {
+    h->rec_t = rec_t;
+    h->rows = ragged ? (size_t)max_rows : rec_t.size();
+    h->out_m = m;
+    h->ragged = ragged;
+    h->max_rows = max_rows;
+  }
+  if (flags & ODEINTR_STATUS_STEP_OVERFLOW)
+    return fail(ODEINTR_E_STEP, "Max number of iterations exceeded (500). A new step size was not found.");
   return ODEINTR_OK;
 }
 
@@ -291,6 +576,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   odeintr_system_s* h = new odeintr_system_s();
   h->name = name ? name : "sys";
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
+  h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }
@@ -337,8 +623,13 @@ int odeintr_destroy(odeintr_system_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->x.release(); h->pars.release(); h->out.release(); h->stage.release(); h->t_rec.release();
   h->seg_nfull.release(); h->seg_hrem.release(); h->seg_t.release(); h->seg_obs.release(); h->times_dev.release();
-  h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release();
+  h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release();
   h->work_counter.release();
+  for (int s = 0; s < 3; ++s) {
+    h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
+    if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
+    if (h->pipe_stream[s]) cudaStreamDestroy(h->pipe_stream[s]);
+  }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -468,32 +759,13 @@ int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt,
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (obs_stride < 1) return fail(ODEINTR_E_INVALID, "obs_stride must be >= 1");
   if (h->k_plain) {
-    // integrate_const, stepper_tag: obs; do_step; time = t0 + step*dt ... final obs
-    const long long n = const_step_count(t0, t1, dt);
     plain_schedule sc;
-    sc.time_rule = ODEINTR_TIME_CONST;
-    sc.total_steps = n;
-    std::vector<double> rec_t;
-    if (!record) {
-      sc.uniform = true; sc.n_seg = 1; sc.nfull_uniform = n;
-      return run_plain(h, sc, t0, dt, false, false, rec_t);
-    }
-    const long long k = obs_stride;
-    sc.n_seg = (n + k - 1) / k;
-    if (n % k == 0) {
-      sc.uniform = true; sc.nfull_uniform = k;
-    } else {
-      sc.nfull.assign((size_t)sc.n_seg, k);
-      sc.nfull.back() = n - k * (sc.n_seg - 1);
-      sc.hrem.assign((size_t)sc.n_seg, 0.0);
-      sc.obs.assign((size_t)sc.n_seg, 1);
-      sc.t.resize((size_t)sc.n_seg);
-      for (long long s = 0; s < sc.n_seg; ++s) sc.t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
-    }
-    rec_t.resize((size_t)sc.n_seg + 1);
-    for (long long s = 0; s < sc.n_seg; ++s) rec_t[(size_t)s] = t0 + static_cast<double>(s * k) * dt;
-    rec_t[(size_t)sc.n_seg] = t0 + static_cast<double>(n) * dt;
-    return run_plain(h, sc, t0, dt, true, true, rec_t);
+    schedule_const(sc, t0, t1, dt, obs_stride, record != 0);
+    return run_plain(h, sc);
+  }
+  if (h->k_adaptive) {
+    if (obs_stride != 1) return fail(ODEINTR_E_INVALID, "obs_stride applies to fixed-step steppers only");
+    return run_adaptive(h, ODEINTR_MODE_CONST, t0, t1, dt, nullptr, 0, record != 0);
   }
   return fail(ODEINTR_E_STATE, "integrate_const: no kernel for this stepper family");
 }
@@ -504,42 +776,11 @@ int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_ti
   if (!times || n_times == 0) return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (!(dt != 0.0) || !std::isfinite(dt)) return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (h->k_plain) {
-    // integrate_times, stepper_tag
     plain_schedule sc;
-    sc.time_rule = ODEINTR_TIME_ACCUM;
-    std::vector<double> rec_t(times, times + n_times);
-    for (size_t k = 0; k + 1 < n_times; ++k) {
-      double t = times[k];
-      const double T = times[k + 1];
-      bool first = true;
-      bool open = false;  // a segment that can still take full steps
-      if (!less_with_sign(t, T, dt)) {  // nothing to integrate, but the observation still happens
-        sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(1);
-        continue;
-      }
-      while (less_with_sign(t, T, dt)) {
-        const double hcur = min_abs(dt, T - t);
-        if (hcur == dt) {
-          if (!open) {
-            sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(first ? 1 : 0);
-            open = true; first = false;
-          }
-          sc.nfull.back() += 1;
-        } else {
-          if (!open) {
-            sc.nfull.push_back(0); sc.hrem.push_back(0.0); sc.t.push_back(t); sc.obs.push_back(first ? 1 : 0);
-            first = false;
-          }
-          sc.hrem.back() = hcur;
-          open = false;  // a remainder step closes the segment
-        }
-        sc.total_steps += 1;
-        t += hcur;
-      }
-    }
-    sc.n_seg = (long long)sc.nfull.size();
-    return run_plain(h, sc, times[0], dt, true, true, rec_t);
+    schedule_times(sc, times, n_times, dt);
+    return run_plain(h, sc);
   }
+  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_TIMES, times[0], times[n_times - 1], dt, times, n_times, true);
   return fail(ODEINTR_E_STATE, "integrate_times: no kernel for this stepper family");
 }
 
@@ -549,41 +790,49 @@ int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double 
   if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (h->k_plain) {
-    // integrate_adaptive, stepper_tag: integrate_n_steps + one step onto t1
-    const double q = (t1 - t0) / dt;
-    const long long n = q > 0 ? static_cast<long long>(q) : 0;
-    const double end = t0 + static_cast<double>(n) * dt;
-    const bool rem = less_with_sign(end, t1, dt);
     plain_schedule sc;
-    sc.time_rule = ODEINTR_TIME_CONST;
-    sc.total_steps = n + (rem ? 1 : 0);
-    std::vector<double> rec_t;
-    if (!record) {
-      sc.n_seg = 1;
-      if (!rem) { sc.uniform = true; sc.nfull_uniform = n; }
-      else { sc.nfull.assign(1, n); sc.hrem.assign(1, t1 - end); sc.t.assign(1, t0); sc.obs.assign(1, 0); }
-      return run_plain(h, sc, t0, dt, false, false, rec_t);
-    }
-    rec_t.resize((size_t)n + 1);
-    for (long long s = 0; s <= n; ++s) rec_t[(size_t)s] = t0 + static_cast<double>(s) * dt;
-    if (!rem) {
-      sc.uniform = true; sc.n_seg = n; sc.nfull_uniform = 1;
-    } else {
-      sc.n_seg = n + 1;
-      sc.nfull.assign((size_t)n + 1, 1); sc.nfull.back() = 0;
-      sc.hrem.assign((size_t)n + 1, 0.0); sc.hrem.back() = t1 - end;
-      sc.obs.assign((size_t)n + 1, 1);
-      sc.t = rec_t;
-      rec_t.push_back(t1);
-    }
-    return run_plain(h, sc, t0, dt, true, true, rec_t);
+    schedule_adaptive(sc, t0, t1, dt, record != 0);
+    return run_plain(h, sc);
   }
+  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_ADAPTIVE, t0, t1, dt, nullptr, 0, record != 0);
   return fail(ODEINTR_E_STATE, "integrate_adaptive: no kernel for this stepper family");
+}
+
+int odeintr_integrate_const_host(odeintr_system_t h, const double* x, size_t n_inst, const double* pars,
+                                 size_t par_sets, double t0, double t1, double dt, long long obs_stride,
+                                 double* out, size_t out_values, double* x_final, size_t chunk) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
+    return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (obs_stride < 1) return fail(ODEINTR_E_INVALID, "obs_stride must be >= 1");
+  if (!h->k_plain) return fail(ODEINTR_E_STATE, "integrate_const_host: no kernel for this stepper family");
+  plain_schedule sc;
+  schedule_const(sc, t0, t1, dt, obs_stride, out != nullptr);
+  if (out && out_values != sc.rec_t.size() * (size_t)h->N * n_inst) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  return run_plain_host(h, sc, x, n_inst, pars, par_sets, out, x_final, chunk);
+}
+
+size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride) {
+  if (!(dt != 0.0) || obs_stride < 1) return 0;
+  const long long n = const_step_count(t0, t1, dt);
+  return (size_t)((n + obs_stride - 1) / obs_stride) + 1;
 }
 
 // ---- observer record -------------------------------------------------------------------------------
 int odeintr_reset_observer(odeintr_system_t h) {
   if (!h) return fail(ODEINTR_E_INVALID, "null system handle");
+  h->rec_t.clear();
+  h->rows = 0;
+  h->ragged = false;
+  return ODEINTR_OK;
+}
+
+int odeintr_release_record(odeintr_system_t h) {
+  int rc = activate(h);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->out.release(); h->stage.release(); h->t_rec.release();
   h->rec_t.clear();
   h->rows = 0;
   h->ragged = false;
@@ -629,6 +878,8 @@ int odeintr_get_output_soa(odeintr_system_t h, double* out, size_t n_values) {
   CU_TRY(cudaStreamSynchronize(h->stream));
   return ODEINTR_OK;
 }
+
+int odeintr_output_is_ragged(odeintr_system_t h) { return (h && h->ragged) ? 1 : 0; }
 
 int odeintr_get_output_rows_per_instance(odeintr_system_t h, int* rows, size_t n_values) {
   int rc = activate(h);

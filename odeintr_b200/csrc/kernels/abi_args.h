@@ -46,41 +46,36 @@ struct odeintr_plain_args {
   int record_final;           // store the sample after the last segment
 };
 
-// Adaptive ensemble launch (controlled / dense-output steppers: dopri5, rosenbrock4).
-//   mode 0: integrate_times, dense output      -> n_times samples at times[]
-//   mode 1: integrate_const, dense output (A.3)                -> samples at t0 + k*dt
-//   mode 2: integrate_adaptive, dense stepper, no observer (A.5; name_no_record)
-//   mode 3: integrate_const / integrate_times with a controlled stepper (rk5_a; A.3/A.4)
-#define ODEINTR_MODE_TIMES_DENSE 0
-#define ODEINTR_MODE_CONST_DENSE 1
-#define ODEINTR_MODE_ADAPTIVE_NOREC 2
-#define ODEINTR_MODE_CONST_CONTROLLED 3
-#define ODEINTR_MODE_TIMES_CONTROLLED 4
-#define ODEINTR_MODE_ADAPTIVE_RECORD 5
+// Adaptive ensemble launch (controlled / dense-output steppers: dopri5, cash-karp, rosenbrock4).
+// The stepper family (controlled vs dense) is fixed at compile time by ODEINTR_STEPPER; `mode` picks the
+// integrate_* loop.  A null `out` is Boost's null_observer.
+#define ODEINTR_MODE_CONST 0     // integrate_const:    samples at t0 + k*dt up to t1
+#define ODEINTR_MODE_TIMES 1     // integrate_times:    samples at times[0..n_times)
+#define ODEINTR_MODE_ADAPTIVE 2  // integrate_adaptive: one sample per accepted step (ragged) + the end point
 
 struct odeintr_adaptive_args {
   double* x;                  // in/out state, N x ld
   const double* pars;
   double* out;                // (s * N + v) * ld + i, or null
+  double* t_rec;              // per-instance sample times s * ld + i (ragged records) or null
   long long m;
   long long ld;
   long long par_ld;
   long long par_inc;
-  double t0;                  // start time
-  double t1;                  // end time (const / adaptive modes)
-  double dt;                  // initial step / observation step
-  const double* times;        // observation times (times modes)
-  long long n_times;          // number of samples to produce (rows of out)
+  double t0;
+  double t1;
+  double dt;                  // initial step (adaptive) / observation step (const)
+  const double* times;        // observation times (times mode)
+  long long n_times;
   double atol;
   double rtol;
   int mode;
-  int max_rows;               // capacity of out in rows (adaptive-record mode)
+  int max_rows;               // capacity of out in rows
   long long* accepted;        // per-instance counters (may be null)
   long long* rejected;
   int* status;
-  int* rows;                  // per-instance rows written (adaptive-record mode)
-  double* t_rec;              // per-instance sample times (adaptive-record mode), s * ld + i
-  unsigned long long* work_counter; // dynamic instance queue for lane refill (may be null)
+  int* rows;                  // per-instance observer calls (may be null)
+  int* fail_flags;            // one word: OR of every instance's non-zero status (may be null)
 };
 
 // Large coupled system ("lattice") fused RK4 stage launch, SURVEY.md §8(d) config 5.

@@ -1,0 +1,68 @@
+// odeintr_b200/csrc/kernels/ensemble_adaptive.cuh
+// K2: adaptive ensemble kernel — the device replacement for integrate_const / integrate_times /
+// integrate_adaptive (compile_sys_template.cpp:107,121,123,134,136,154,168) when the stepper is a
+// controlled or dense-output stepper: rk5_a, rk5_i (the reference's default method), rk54_a, and the
+// rosenbrock4 dense-output stepper of compile_implicit.
+//
+// One trajectory per thread.  Step size, error estimate, accepted / rejected counters and the dense-output
+// interpolant are per instance and live in registers; the only global traffic is the initial state, the
+// requested samples (SoA rows, instance index fastest) and the final state + counters.
+//
+// Included at the end of the generated translation unit with ODEINTR_SYS_SIZE and
+// ODEINTR_STEPPER (dopri5_dense | dopri5_controlled | rk54_controlled | rosenbrock4_dense).
+#pragma once
+#include "odeintr_b200/integrate_device.cuh"
+
+extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK)
+odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
+  constexpr int N = ODEINTR_SYS_SIZE;
+  typedef odeintr::system_type Sys;
+  typedef odeintr_b200::ODEINTR_STEPPER<Sys, N> Stepper;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.m) return;
+
+  Sys sys;
+  sys.load_params(a.pars, a.par_ld, i * a.par_inc);
+  Stepper st;
+  st.setup(a.atol, a.rtol);
+
+  odeintr_b200::vec<N> x;
+#pragma unroll
+  for (int v = 0; v < N; ++v) x[v] = a.x[v * a.ld + i];
+
+  odeintr_b200::sample_writer<N> obs;
+  obs.out = a.out ? a.out + i : nullptr;
+  obs.t_rec = a.t_rec ? a.t_rec + i : nullptr;
+  obs.ld = a.ld;
+  obs.rows = 0;
+  obs.max_rows = a.max_rows;
+
+  bool ok;
+  if constexpr (Stepper::is_dense) {
+    if (a.mode == ODEINTR_MODE_TIMES) ok = odeintr_b200::integrate_times_dense(st, sys, x, a.times, a.n_times, a.dt, obs);
+    else if (a.mode == ODEINTR_MODE_CONST) ok = odeintr_b200::integrate_const_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+    else ok = odeintr_b200::integrate_adaptive_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+  } else {
+    double dt = a.dt;
+    if (a.mode == ODEINTR_MODE_TIMES) ok = odeintr_b200::integrate_times_controlled(st, sys, x, a.times, a.n_times, dt, obs);
+    else if (a.mode == ODEINTR_MODE_CONST) ok = odeintr_b200::integrate_const_controlled(st, sys, x, a.t0, a.t1, dt, obs);
+    else {
+      double t = a.t0;
+      ok = odeintr_b200::integrate_adaptive_controlled(st, sys, x, t, a.t1, dt, obs);
+    }
+  }
+  (void)ok;  // the status word carries the failure
+#pragma unroll
+  for (int v = 0; v < N; ++v) a.x[v * a.ld + i] = x[v];
+  odeintr_b200::step_counters& c = st.counters();
+  if (a.accepted) a.accepted[i] = c.accepted;
+  if (a.rejected) a.rejected[i] = c.rejected;
+  if (a.status) {
+    int status = c.status;
+#pragma unroll
+    for (int v = 0; v < N; ++v) if (!isfinite(x[v]) && status == ODEINTR_STATUS_OK) status = ODEINTR_STATUS_NONFINITE;
+    a.status[i] = status;
+    if (status != ODEINTR_STATUS_OK && a.fail_flags) atomicOr(a.fail_flags, status);
+  }
+  if (a.rows) a.rows[i] = obs.rows;
+}

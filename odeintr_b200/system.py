@@ -60,6 +60,8 @@ class CompiledSystem:
         self.P = gen.pars.n_runtime
         self._lib = _abi.load()
         handle = C.c_void_p()
+        if gen.stepper is None or gen.stepper.mode == "dense":
+            flags |= _abi.FLAG_DENSE_OUTPUT
         rc = self._lib.odeintr_compile(gen.code.encode(), gen.name.encode(), self.N, self.P, gen.atol, gen.rtol,
                                        flags, C.byref(handle))
         if rc != 0:
@@ -124,6 +126,9 @@ class CompiledSystem:
     def get_output(self):
         rows = int(self._lib.odeintr_output_rows(self._h))
         m = self.n_instances
+        ragged = bool(self._lib.odeintr_output_is_ragged(self._h))
+        if ragged:
+            return self._get_ragged_output(rows, m)
         t = np.empty(rows, dtype=np.float64)
         self._check(self._lib.odeintr_get_output_times(self._h, _dptr(t), rows))
         if m <= 1:
@@ -135,6 +140,23 @@ class CompiledSystem:
         if rows:
             self._check(self._lib.odeintr_get_output_soa(self._h, _dptr(x), x.size))
         return EnsembleRecord(t, x)
+
+    def _get_ragged_output(self, rows, m):
+        """integrate_adaptive with an adaptive stepper: one row per accepted step, per instance."""
+        counts = np.empty(m, dtype=np.int32)
+        self._check(self._lib.odeintr_get_output_rows_per_instance(self._h, counts.ctypes.data_as(_abi.c_int_p), m))
+        x = np.empty((rows, self.N, m), dtype=np.float64)
+        self._check(self._lib.odeintr_get_output_soa(self._h, _dptr(x), x.size))
+        times = np.empty((m, rows), dtype=np.float64)
+        for i in range(m if m <= 64 else 0):
+            self._check(self._lib.odeintr_get_output_times_per_instance(self._h, _dptr(times[i]), rows, i))
+        if m == 1:
+            n = int(counts[0])
+            return _frame(times[0, :n], x[:n, :, 0])
+        rec = EnsembleRecord(times[0] if m <= 64 else None, x)
+        rec.rows_per_instance = counts
+        rec.times_per_instance = times if m <= 64 else None
+        return rec
 
     # -- parameters (pars_setter_template.cpp, pars_vec_setter_template.cpp) --------------------------
     def set_params(self, *args, **kw):
@@ -228,6 +250,35 @@ class CompiledSystem:
         self.set_state(init)
         self._check(self._lib.odeintr_integrate_adaptive(self._h, start, start + duration, step_size, 0))
         return self.get_state()
+
+    def run_host(self, init, duration, step_size=1.0, start=0.0, obs_stride=1, out=None, x_final=None, pars=None,
+                 chunk=0, record=True):
+        """NAME() for ensembles that live in host memory (and may exceed device memory): the instances are
+        streamed through the GPU in chunks with copies and kernels overlapped (odeintr_integrate_const_host).
+        ``init`` is (N, M); ``out`` / ``x_final`` may be preallocated (pinned) arrays.  Returns
+        (EnsembleRecord or None, x_final)."""
+        x = np.ascontiguousarray(np.asarray(init, dtype=np.float64))
+        if x.ndim != 2 or x.shape[0] != self.N or x.shape[1] == 0:
+            raise OdeintrError("Invalid initial state")
+        m = x.shape[1]
+        rows = int(self._lib.odeintr_const_rows(start, start + duration, step_size, obs_stride)) if record else 0
+        if record and out is None:
+            out = np.empty((rows, self.N, m), dtype=np.float64)
+        if x_final is None:
+            x_final = np.empty((self.N, m), dtype=np.float64)
+        p = None
+        par_sets = 0
+        if self.P:
+            p = np.ascontiguousarray(self._par_values if pars is None else np.asarray(pars, dtype=np.float64))
+            par_sets = p.shape[1]
+        self._check(self._lib.odeintr_integrate_const_host(
+            self._h, _dptr(x), m, None if p is None else _dptr(p), par_sets, start, start + duration, step_size,
+            obs_stride, None if not record else _dptr(out), out.size if record else 0, _dptr(x_final), chunk))
+        if not record:
+            return None, x_final
+        t = np.array([start + (s * obs_stride) * step_size for s in range(rows - 1)] +
+                     [start + self.last_steps() * step_size])
+        return EnsembleRecord(t, out), x_final
 
     # -- measurement ----------------------------------------------------------------------------------
     def last_kernel_ms(self) -> float:

@@ -759,7 +759,10 @@ std::size_t integrate_const_controlled(St& st, Sys& sys, state_type& x, double s
   null_observer nobs;
   while (less_eq_with_sign(time + time_step, end_time, dt)) {
     obs(x, time);
-    real_steps += integrate_adaptive_controlled(st, sys, x, time, time + time_step, dt, nobs);
+    // detail::integrate_adaptive takes the stepper by value: every interval starts from a copy of the
+    // caller's (never mutated) stepper, so an FSAL stepper re-evaluates its first derivative
+    St st_interval = st;
+    real_steps += integrate_adaptive_controlled(st_interval, sys, x, time, time + time_step, dt, nobs);
     step++;
     time = start_time + static_cast<double>(step) * time_step;
   }

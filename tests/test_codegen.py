@@ -1,0 +1,103 @@
+"""Host generator (mirror of R/odeintr.R + R/utils.R of the reference): text-level behaviour."""
+import ctypes as C
+import re
+
+import pytest
+
+import odeintr_b200
+from odeintr_b200 import _abi, codegen
+from odeintr_b200.codegen import OdeintrError
+from systems import LOGISTIC, LORENZ, LORENZ_PARS, ROBERTSON, ROBERTSON_PARS, STIFF, VDP
+
+
+def test_r_number_formatting():
+    # R/utils.R:181-187 pastes doubles with 15 significant digits; README.md:259 shows the 1e-06 style
+    cases = {8 / 3: "2.66666666666667", 10: "10", 28.0: "28", 1e-6: "1e-06", 1e5: "1e+05", 1e4: "10000",
+             0.0001: "1e-04", 0.001: "0.001", 3e7: "3e+07", 0.04: "0.04", 1 / 3: "0.333333333333333", -0.5: "-0.5",
+             0.1 + 0.2: "0.3", 1234567.0: "1234567", 0.5: "0.5", 100.0: "100", 1e-15: "1e-15"}
+    for v, txt in cases.items():
+        assert codegen.r_num(v) == txt
+
+
+def test_parameter_declarations():
+    p = codegen.handle_pars(LORENZ_PARS, const=True)
+    assert p.globals == "const double sigma = 10, R = 28, b = 2.66666666666667;"
+    assert p.n_runtime == 0
+    p = codegen.handle_pars(LORENZ_PARS)
+    assert p.globals == "double sigma = 10, R = 28, b = 2.66666666666667;" and p.n_runtime == 3
+    p = codegen.handle_pars("mu")
+    assert p.globals == "double mu;" and p.names == ["mu"]
+    p = codegen.handle_pars(["a", "b"])
+    assert p.globals == "double a, b;"
+    p = codegen.handle_pars(3)
+    assert p.kind == "vector" and p.n_runtime == 3
+    with pytest.raises(OdeintrError, match="All parameters must be named"):
+        codegen.handle_pars({"a": 1, "": 2})
+    with pytest.raises(OdeintrError, match="Invalid parameter specification"):
+        codegen.handle_pars(object())
+
+
+def test_sys_dim_and_vectorisation():
+    assert codegen.get_sys_dim(LORENZ) == 3
+    assert codegen.get_sys_dim("dxdt[ 7 ] = 1") == 8
+    assert codegen.get_sys_dim(LOGISTIC) is None
+    assert codegen.vectorize_1d_sys(LOGISTIC) == "dxdt[0] = x[0] * (1 - x[0])"
+    g = codegen.generate_sys("logistic", LOGISTIC)
+    assert g.sys_dim == 1 and "dxdt[0] = x[0] * (1 - x[0])" in g.code
+    assert g.stepper.method == "rk5_i"  # the reference's default (R/odeintr.R:296)
+
+
+def test_method_table_and_invalid_methods():
+    assert codegen.make_stepper_type("rk4") == "runge_kutta4<state_type>"
+    assert codegen.make_stepper_type("rk5_i") == "runge_kutta_dopri5<state_type>"
+    assert codegen.make_stepper_constr("rk5_i", 1e-6, 1e-6) == "odeint::make_dense_output(1e-06, 1e-06, stepper_type())"
+    assert codegen.make_stepper_constr("rk54_a", 1e-8, 1e-6) == "odeint::make_controlled(1e-08, 1e-06, stepper_type())"
+    for bad in ("euler_a", "rk4_i", "rk4_a", "rk54_i", "rk78_i", "bs_a", "bsd_i"):
+        with pytest.raises(OdeintrError, match="Invalid integration method"):
+            codegen.stepper_spec(bad)
+    with pytest.raises(OdeintrError):
+        codegen.stepper_spec("nonsense")
+
+
+def test_symbolic_jacobian_matches_readme_golden_text():
+    # /root/reference/README.md:180-187
+    assert codegen.JacobianCpp(STIFF) == ("J(0, 0) = -101;\nJ(0, 1) = -100;\nJ(1, 0) = 1;\nJ(1, 1) = 0;\n"
+                                          "dfdt[0] = 0.0;\ndfdt[1] = 0.0;")
+    rob = codegen.JacobianCpp(ROBERTSON)
+    assert "J(1, 1) = -beta*x[2] - 2*gamma*x[1];" in rob and rob.count("J(") == 9 and rob.count("dfdt[") == 3
+
+
+def _cubin(code: str, flags: int = 0) -> int:
+    lib = _abi.load()
+    size = C.c_size_t()
+    rc = lib.odeintr_compile_cubin(code.encode(), flags, None, 0, C.byref(size))
+    assert rc == 0, _abi.last_error()
+    return size.value
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5"])
+def test_generated_code_compiles_for_sm100a_without_a_device(method):
+    g = codegen.generate_sys("lorenz", LORENZ, LORENZ_PARS, False, method)
+    assert "__SYS__" not in g.code and "__GLOBALS__" not in g.code
+    assert _cubin(g.code) > 1000
+    assert _cubin(g.code, _abi.FLAG_FMAD | _abi.FLAG_KEEP_ZERO_TERMS) > 1000
+
+
+def test_snippets_may_use_std_math_globals_and_vector_pars():
+    g = codegen.generate_sys("osc", "dxdt[0] = x[1]; dxdt[1] = -pars[0] * std::sin(x[0]) - damp(x[1]) + std::pow(t, 2.0)",
+                             pars=2, method="rk4", globals="double damp(double v) { return pars[1] * std::abs(v) * v; }")
+    assert g.pars.n_runtime == 2
+    assert _cubin(g.code) > 1000
+
+
+def test_bad_snippet_reports_nvrtc_log():
+    g = codegen.generate_sys("bad", "dxdt[0] = undefined_symbol * x[0]", method="rk4")
+    lib = _abi.load()
+    size = C.c_size_t()
+    rc = lib.odeintr_compile_cubin(g.code.encode(), 0, None, 0, C.byref(size))
+    assert rc == 2 and "undefined_symbol" in _abi.last_error()
+
+
+def test_compile_false_returns_code_without_touching_the_gpu():
+    code = odeintr_b200.compile_sys("logitest", LOGISTIC, compile=False, method="rk4")
+    assert isinstance(code, str) and "logitest" in code and code.system is None

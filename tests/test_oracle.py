@@ -1,0 +1,145 @@
+"""The oracle (CPU restatement of Boost odeint) against everything that pins it: SURVEY.md Appendix B
+golden bit patterns, the reference's own test facts (tests/testthat/test_odeintr.R:25-54: 41 rows, 4 rows,
+first row == initial state), analytic solutions and convergence orders."""
+import json
+import math
+import pathlib
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import build_oracle as bo
+from systems import LOGISTIC, LORENZ, LORENZ_PARS, ROBERTSON, ROBERTSON_PARS, STIFF, VDP
+
+GOLDEN = json.loads((pathlib.Path(__file__).parent / "golden" / "lorenz_rk4_golden.json").read_text())
+
+
+def hexd(v):
+    return struct.pack(">d", float(v)).hex()
+
+
+def test_lorenz_rk4_golden_bits():
+    const = bo.build(LORENZ, LORENZ_PARS, True, "rk4")
+    dyn = bo.build(LORENZ, LORENZ_PARS, False, "rk4")
+    runs = {"const_text": const.integrate_const([1, 1, 1], 0, 100, 0.001),
+            "exact_8_3": dyn.integrate_const([1, 1, 1], 0, 100, 0.001, pars=[10, 28, 8 / 3])}
+    for case in GOLDEN["cases"]:
+        r = runs[case["pars"]]
+        assert r["rows"] == 100001
+        for n, bits in case["steps"].items():
+            assert [hexd(v) for v in r["rec"][int(n)]] == bits, (case["pars"], n)
+
+
+def test_const_step_counts_follow_boost_loop():
+    # absolute-epsilon comparison drops the last step for some (t1, dt)
+    o = bo.build(LOGISTIC, method="rk4")
+    for t1, dt, rows in [(100, 0.001, 100001), (40, 1, 41), (40, 40 / 3, 4), (15, 0.01, 1501), (100, 0.01, 10000),
+                         (7, 0.001, 7000), (20, 0.01, 2000)]:
+        r = o.integrate_const([0.01], 0, t1, dt)
+        assert r["rows"] == rows, (t1, dt)
+
+
+def logistic(t, x0=0.01):
+    return x0 * math.exp(t) / (1 + x0 * (math.exp(t) - 1))
+
+
+def test_reference_test_facts_default_method():
+    # test_odeintr.R:32-46: compile_sys("logistic", "dxdt = x * (1 - x)"); logistic(0.01, 40) -> 41 x 2
+    o = bo.build(LOGISTIC, method="rk5_i")
+    r = o.integrate_const([0.01], 0, 40, 1.0)
+    assert r["rows"] == 41 and r["rec"][0, 0] == 0.01 and r["t"][0] == 0.0
+    assert r["accepted"] == 33 and r["rejected"] == 6  # SURVEY.md A.3 re-simulation
+    for t, x in zip(r["t"], r["rec"][:, 0]):
+        assert abs(x - logistic(t)) < 2e-5
+    # large step: the host guard turns step 100 into 40/3 -> 4 rows
+    r = o.integrate_const([0.01], 0, 40, 40 / 3)
+    assert r["rows"] == 4 and r["rec"][0, 0] == 0.01
+
+
+def test_reference_test_facts_implicit():
+    # test_odeintr.R:48-54 through rosenbrock4
+    o = bo.build("dxdt[0] = x[0] * (1 - x[0])", method="rosenbrock4")
+    r = o.integrate_const([0.01], 0, 40, 1.0)
+    assert r["rows"] == 41 and r["rec"][0, 0] == 0.01
+    for t, x in zip(r["t"], r["rec"][:, 0]):
+        assert abs(x - logistic(t)) < 5e-5
+    r = o.integrate_const([0.01], 0, 40, 40 / 3)
+    assert r["rows"] == 4
+
+
+@pytest.mark.parametrize("method,order", [("euler", 1), ("rk4", 4), ("rk54", 5), ("rk5", 5)])
+def test_convergence_order(method, order):
+    o = bo.build("dxdt[0] = x[1]; dxdt[1] = -x[0]", method=method)
+    errs = []
+    for n in (50, 100):
+        r = o.integrate_const([1.0, 0.0], 0, 1.0, 1.0 / n, record=False)
+        errs.append(math.hypot(r["x"][0] - math.cos(1.0), r["x"][1] + math.sin(1.0)))
+    assert abs(math.log2(errs[0] / errs[1]) - order) < 0.35
+
+
+def test_stiff_linear_system_analytic():
+    # README.md:173-176: eigenvalues -1 and -100; x0 = (2, 1) -> x1(t) = e^-t-ish combination
+    o = bo.build(STIFF, method="rosenbrock4")
+    r = o.integrate_const([2.0, 1.0], 0, 5, 0.001)
+    assert r["rows"] == 5001
+    # exact solution via eigen-decomposition
+    A = np.array([[-101.0, -100.0], [1.0, 0.0]])
+    w, V = np.linalg.eig(A)
+    c = np.linalg.solve(V, np.array([2.0, 1.0]))
+    for k in (0, 1, 10, 1000, 5000):
+        t = r["t"][k]
+        exact = (V * np.exp(w * t)) @ c
+        assert np.allclose(r["rec"][k], exact.real, rtol=0, atol=2e-5)
+
+
+def test_robertson_conservation_and_times():
+    o = bo.build(ROBERTSON, ROBERTSON_PARS, True, "rosenbrock4")
+    times = 10 ** np.linspace(-5, 5, 41)
+    r = o.integrate_times([1.0, 0.0, 0.0], times, 1.0)
+    assert r["rows"] == 41
+    assert np.allclose(r["rec"].sum(axis=1), 1.0, atol=1e-4)
+    assert np.all(r["rec"] >= -1e-6)
+    # SciPy cross-check
+    from scipy.integrate import solve_ivp
+
+    def f(t, y):
+        a, b, g = 0.04, 1e4, 3e7
+        return [-a * y[0] + b * y[1] * y[2], a * y[0] - b * y[1] * y[2] - g * y[1] ** 2, g * y[1] ** 2]
+
+    s = solve_ivp(f, (0, times[-1]), [1, 0, 0], method="Radau", t_eval=times[times > 0], rtol=1e-10, atol=1e-12)
+    assert np.allclose(r["rec"][:, 0], s.y[0], rtol=0, atol=5e-5)
+    assert np.allclose(r["rec"][:, 2], s.y[2], rtol=0, atol=5e-5)
+
+
+def test_vdp_dense_times_against_scipy():
+    from scipy.integrate import solve_ivp
+
+    o = bo.build(VDP, "mu", False, "rk5_i", atol=1e-8, rtol=1e-8)
+    times = np.arange(0, 20.0001, 0.2)
+    r = o.integrate_times([2.0, 0.0], times, 0.01, pars=[1.5])
+    assert r["rows"] == len(times)
+    s = solve_ivp(lambda t, y: [y[1], 1.5 * (1 - y[0] ** 2) * y[1] - y[0]], (0, 20), [2.0, 0.0], method="DOP853",
+                  t_eval=times, rtol=1e-13, atol=1e-13)
+    assert np.max(np.abs(r["rec"] - s.y.T)) < 1e-5
+
+
+def test_integrate_adaptive_variants_reach_t1():
+    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a"):
+        o = bo.build(LOGISTIC, method=method)
+        r = o.integrate_adaptive([0.01], 0, 7.3, 0.25, record=True)
+        assert r["t"][-1] == 7.3
+        assert abs(r["x"][0] - logistic(7.3)) < 1e-4, method
+
+
+def test_ensemble_matches_single_runs():
+    o = bo.build(LORENZ, LORENZ_PARS, False, "rk4")
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-5, 5, (3, 7))
+    P = np.stack([np.full(7, 10.0), np.linspace(20, 30, 7), np.full(7, 8 / 3)])
+    e = o.ensemble(0, X.copy(), P, 0, 0.5, 0.01, obs_stride=10, out_rows=6, threads=2)
+    assert e["rows"] == 6
+    for i in range(7):
+        r = o.integrate_const(X[:, i], 0, 0.5, 0.01, pars=P[:, i])
+        assert np.array_equal(e["out"][:, :, i], r["rec"][::10])
+        assert np.array_equal(e["x"][:, i], r["x"])

@@ -75,6 +75,11 @@ int odeintr_set_device(int device);
 /* Use an existing CUDA stream (cudaStream_t / CUstream) for all work of this system; 0 = own stream. */
 int odeintr_set_stream(odeintr_system_t h, void* cuda_stream);
 int odeintr_synchronize(odeintr_system_t h);
+/* Per-instance budget of step attempts (accepted + rejected) in one integrate call with an adaptive stepper
+ * (default 20 000 000).  Boost has no such limit and can loop forever, e.g. when the step size underflows
+ * at a finite-time blow-up; on a GPU that would hang the device, so the kernels stop the instance, set
+ * ODEINTR_STATUS_STEP_BUDGET and the call returns ODEINTR_E_STEP. */
+int odeintr_set_max_tries(odeintr_system_t h, long long max_tries);
 
 /* ---- state and parameters ------------------------------------------------------------------- */
 

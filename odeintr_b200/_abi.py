@@ -25,6 +25,7 @@ SIGNATURES = {
     "odeintr_compile_log": (C.c_char_p, [C.c_void_p]),
     "odeintr_set_device": (C.c_int, [C.c_int]),
     "odeintr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "odeintr_set_max_tries": (C.c_int, [C.c_void_p, C.c_longlong]),
     "odeintr_synchronize": (C.c_int, [C.c_void_p]),
     "odeintr_set_state": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, C.c_size_t]),
     "odeintr_get_state": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t]),

@@ -340,3 +340,35 @@ def generate_sys(name: str, sys, pars=None, const: bool = False, method: str = "
     })
     family = "plain" if spec.mode == "plain" else "adaptive"
     return Generated(code, name, sys_dim, p, spec, family, float(atol), float(rtol))
+
+
+def generate_implicit(name: str, sys, pars=None, const: bool = False, sys_dim: int = -1, jacobian=None,
+                      atol: float = 1e-6, rtol: float = 1e-6, globals: str = "", headers: str = "",
+                      footers: str = "") -> Generated:
+    """Text generation half of compile_implicit (R/odeintr.R:573-599).  ``jacobian`` defaults to the
+    symbolic JacobianCpp(sys, sys_dim), as the reference's default argument does (R/odeintr.R:563)."""
+    p = handle_pars(pars, const)
+    sys = _join(sys)
+    if jacobian is None:
+        jacobian = JacobianCpp(sys, sys_dim)
+    jacobian = _join(jacobian)
+    if sys_dim is None or math.ceil(sys_dim) < 1:
+        sys_dim = get_sys_dim(sys)
+    if sys_dim is None:
+        sys = vectorize_1d_sys(sys)
+        sys_dim = 1
+    sys_dim = int(math.ceil(sys_dim))
+    code = _fill(read_template("compile_implicit_template"), {
+        "__FUNCNAME__": name,
+        "__SYS_SIZE__": str(sys_dim),
+        "__NPARS__": str(p.n_runtime),
+        "__ATOL__": r_num(atol),
+        "__RTOL__": r_num(rtol),
+        "__HEADERS__": headers,
+        "__GLOBALS__": p.globals + globals,
+        "__LOAD_PARS__": p.load,
+        "__JACOBIAN__": jacobian,
+        "__SYS__": sys,
+        "__FOOTERS__": footers,
+    })
+    return Generated(code, name, sys_dim, p, None, "implicit", float(atol), float(rtol))

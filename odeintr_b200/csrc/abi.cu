@@ -136,6 +136,7 @@ struct odeintr_system_s {
   dev_buf<double> seg_hrem, seg_t, times_dev;
   dev_buf<unsigned char> seg_obs;
   dev_buf<int> status, rows_inst, fail_flags;
+  long long max_tries = 20000000;  // per-instance step-attempt budget per call
   bool dense = false;    // the adaptive kernel wraps a dense-output stepper (rk5_i, rosenbrock4)
   dev_buf<unsigned long long> work_counter;
   size_t m = 0;          // resident instances
@@ -495,6 +496,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   a.t0 = t0; a.t1 = t1; a.dt = dt;
   a.atol = h->atol; a.rtol = h->rtol;
   a.mode = mode;
+  a.max_tries = h->max_tries;
   a.accepted = h->accepted.p; a.rejected = h->rejected.p; a.status = h->status.p; a.rows = h->rows_inst.p;
   a.fail_flags = h->fail_flags.p;
   const unsigned block = (unsigned)h->block_adaptive;
@@ -540,6 +542,9 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   }
   if (flags & ODEINTR_STATUS_STEP_OVERFLOW)
     return fail(ODEINTR_E_STEP, "Max number of iterations exceeded (500). A new step size was not found.");
+  if (flags & ODEINTR_STATUS_STEP_BUDGET)
+    return fail(ODEINTR_E_STEP, "step budget exceeded: an instance needed more than " + std::to_string(h->max_tries) +
+                                    " step attempts in one call (see odeintr_set_max_tries)");
   return ODEINTR_OK;
 }
 
@@ -656,6 +661,12 @@ int odeintr_set_stream(odeintr_system_t h, void* cuda_stream) {
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
   }
+  return ODEINTR_OK;
+}
+
+int odeintr_set_max_tries(odeintr_system_t h, long long max_tries) {
+  if (!h || max_tries < 1) return fail(ODEINTR_E_INVALID, "max_tries must be >= 1");
+  h->max_tries = max_tries;
   return ODEINTR_OK;
 }
 

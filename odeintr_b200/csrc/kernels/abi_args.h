@@ -15,6 +15,8 @@
 #define ODEINTR_STATUS_OK 0
 #define ODEINTR_STATUS_STEP_OVERFLOW 1   // >500 consecutive rejected tries (Boost step_adjustment_error)
 #define ODEINTR_STATUS_NONFINITE 2       // state became NaN/Inf
+#define ODEINTR_STATUS_STEP_BUDGET 4     // more than max_tries step attempts in one call (guards the GPU against
+                                         // the endless loops Boost itself can enter, e.g. dt underflow at a blow-up)
 
 // Fixed-step ("plain stepper") ensemble launch: one trajectory per thread.
 // State and samples are structure-of-arrays with the instance index fastest:
@@ -71,6 +73,7 @@ struct odeintr_adaptive_args {
   double rtol;
   int mode;
   int max_rows;               // capacity of out in rows
+  long long max_tries;        // per-instance budget of step attempts (accepted + rejected) per call
   long long* accepted;        // per-instance counters (may be null)
   long long* rejected;
   int* status;

@@ -13,9 +13,15 @@ namespace odeintr_b200 {
 #define ODEINTR_MAX_FAILED_STEPS 500  // Boost failed_step_checker
 
 struct step_counters {
-  long long accepted, rejected;
+  long long accepted, rejected, budget;
   int status;
-  ODEINTR_DEV void reset() { accepted = 0; rejected = 0; status = ODEINTR_STATUS_OK; }
+  ODEINTR_DEV void reset() { accepted = 0; rejected = 0; status = ODEINTR_STATUS_OK; budget = 0x7fffffffffffffffLL; }
+  // true (and the status is set) once the instance has used up its step-attempt budget
+  ODEINTR_DEV bool exhausted() {
+    if (accepted + rejected < budget) return false;
+    status |= ODEINTR_STATUS_STEP_BUDGET;
+    return true;
+  }
 };
 
 // controlled_runge_kutta< runge_kutta_dopri5 > (FSAL): method "rk5_a"
@@ -143,8 +149,9 @@ struct dopri5_dense {
     t_old = t;
     vec<N> xn, dn;
     int fails = 0;
+    if (ctl.cnt.exhausted()) return false;
     while (!ctl.try_step_full(sys, x_cur, d_cur, t, xn, dn, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status = ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
     }
     x_old = x_cur; d_old = d_cur;
     x_cur = xn; d_cur = dn;

@@ -25,6 +25,7 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
   sys.load_params(a.pars, a.par_ld, i * a.par_inc);
   Stepper st;
   st.setup(a.atol, a.rtol);
+  st.counters().budget = a.max_tries;
 
   odeintr_b200::vec<N> x;
 #pragma unroll

@@ -35,8 +35,9 @@ ODEINTR_DEV bool integrate_adaptive_controlled(St& st, Sys& sys, vec<N>& x, doub
   while (less_with_sign(t, t1, dt)) {
     obs(x, t);
     if (less_with_sign(t1, t + dt, dt)) dt = t1 - t;
+    if (st.cnt.exhausted()) return false;
     while (!st.try_step(sys, x, t, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { st.cnt.status = ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails > ODEINTR_MAX_FAILED_STEPS) { st.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
     }
     fails = 0;
   }
@@ -89,19 +90,28 @@ ODEINTR_DEV bool integrate_const_dense(St& st, Sys& sys, vec<N>& x, const double
   time += dt;
   long long obs_step = 1;
   while (less_eq_with_sign(time + dt, t1, dt)) {
+    bool progressed = false;
     while (less_eq_with_sign(time, st.t, dt)) {  // every sample the last real step already covers
       st.calc_state(time, x);
       obs(x, time);
       ++obs_step;
       time = t0 + static_cast<double>(obs_step) * dt;
+      progressed = true;
     }
     if (less_with_sign(st.t + st.dt, t1, st.dt)) {
       while (less_eq_with_sign(st.t, time, dt)) {
         if (!st.do_step(sys)) return false;
+        progressed = true;
       }
     } else if (less_with_sign(st.t, t1, st.dt)) {
       st.initialize(st.current_state(), st.t, t1 - st.t);
       if (!st.do_step(sys)) return false;
+      progressed = true;
+    }
+    if (!progressed) {
+      // st.t is NaN (or the step collapsed): Boost's loop would spin here forever; stop this instance
+      st.counters().status |= ODEINTR_STATUS_NONFINITE;
+      return false;
     }
   }
   if (less_eq_with_sign(time, t1, dt)) {
@@ -125,11 +135,12 @@ ODEINTR_DEV bool integrate_times_controlled(St& st, Sys& sys, vec<N>& x, const d
     const double next = times[it];
     while (less_with_sign(current_time, next, dt)) {
       double current_dt = dt > 0 ? fmin(dt, next - current_time) : fmax(dt, next - current_time);  // min_abs
+      if (st.cnt.exhausted()) return false;
       if (st.try_step(sys, x, current_time, current_dt)) {
         fails = 0;
         dt = dt > 0 ? fmax(dt, current_dt) : fmin(dt, current_dt);  // max_abs: keep the larger step
       } else {
-        if (++fails > ODEINTR_MAX_FAILED_STEPS) { st.cnt.status = ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+        if (++fails > ODEINTR_MAX_FAILED_STEPS) { st.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
         dt = current_dt;
       }
     }

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q "$@" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -40 gpurun_out/pytest_gpu.log

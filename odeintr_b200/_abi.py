@@ -43,6 +43,10 @@ SIGNATURES = {
                                                C.c_double, C.c_double, C.c_longlong, c_dbl_p, C.c_size_t, c_dbl_p,
                                                C.c_size_t]),
     "odeintr_const_rows": (C.c_size_t, [C.c_double, C.c_double, C.c_double, C.c_longlong]),
+    "odeintr_lattice_shard": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                        C.c_void_p]),
+    "odeintr_lattice_ghost_width": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "odeintr_lattice_shard_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "odeintr_reset_observer": (C.c_int, [C.c_void_p]),
     "odeintr_release_record": (C.c_int, [C.c_void_p]),
     "odeintr_output_rows": (C.c_size_t, [C.c_void_p]),
@@ -72,6 +76,7 @@ SIGNATURES = {
 FLAG_FMAD = 1
 FLAG_KEEP_ZERO_TERMS = 2
 FLAG_DENSE_OUTPUT = 4
+FLAG_LATTICE_EULER = 8
 
 _lib = None
 

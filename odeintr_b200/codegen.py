@@ -372,3 +372,158 @@ def generate_implicit(name: str, sys, pars=None, const: bool = False, sys_dim: i
         "__FOOTERS__": footers,
     })
     return Generated(code, name, sys_dim, p, None, "implicit", float(atol), float(rtol))
+
+
+# --------------------------------------------------------------------------------------------------
+# large systems (compile_sys_openmp, R/odeintr.R:418-470): the snippet is a sequence of loops over the
+# cells of the state, `for (int i = 0; i < BOUND; ++i) BODY`, optionally under `#pragma omp` lines
+# (R/odeintr.R:396-401).  On the GPU every loop iteration becomes one thread's work item: the loop
+# header is stripped and BODY becomes a per-cell __device__ function.
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class CellLoops:
+    var_type: str
+    start: str
+    bound: str
+    bodies: List[str]            # per-cell bodies, dxdt[...] replaced by odeintr_k[slot]
+    var_names: List[str]
+    offsets: List[str]           # index expression of every distinct dxdt[...] target (slot order)
+
+
+def _strip_comments(src: str) -> str:
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    return re.sub(r"//[^\n]*", " ", src)
+
+
+def _match(src: str, pos: int, open_ch: str, close_ch: str) -> int:
+    depth = 0
+    for k in range(pos, len(src)):
+        if src[k] == open_ch:
+            depth += 1
+        elif src[k] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return k
+    raise OdeintrError("unbalanced '%s' in system definition" % open_ch)
+
+
+def parse_cell_loops(sys_src: str) -> CellLoops:
+    src = _strip_comments(sys_src)
+    src = "\n".join(l for l in src.split("\n") if not l.strip().startswith("#pragma"))
+    # the reference joins snippet lines with "; " (R/odeintr.R:317): drop the empty statements that leaves
+    pos, n = 0, len(src)
+    loops = []
+    while True:
+        while pos < n and (src[pos].isspace() or src[pos] == ";"):
+            pos += 1
+        if pos >= n:
+            break
+        m = re.match(r"for\s*\(", src[pos:])
+        if not m:
+            raise OdeintrError("large-system snippets must be loops over the cells of the state "
+                               "(`for (int i = 0; i < N; ++i) ...`); found: " + src[pos:pos + 40].strip())
+        p_open = pos + m.end() - 1
+        p_close = _match(src, p_open, "(", ")")
+        header = src[p_open + 1:p_close]
+        parts = header.split(";")
+        if len(parts) != 3:
+            raise OdeintrError("cannot parse loop header: for (" + header + ")")
+        mi = re.match(r"\s*((?:unsigned\s+|const\s+|std::)?[A-Za-z_][\w:]*(?:\s+long)?)\s+([A-Za-z_]\w*)\s*=\s*(.+?)\s*$",
+                      parts[0], flags=re.S)
+        if not mi:
+            raise OdeintrError("cannot parse loop initialiser: " + parts[0])
+        vtype, var, start = mi.group(1), mi.group(2), mi.group(3)
+        mc = re.match(r"\s*%s\s*(<|!=)\s*(.+?)\s*$" % re.escape(var), parts[1], flags=re.S)
+        if not mc:
+            raise OdeintrError("loop condition must be `%s < bound`: %s" % (var, parts[1]))
+        bound = mc.group(2)
+        if not re.match(r"\s*(\+\+\s*%s|%s\s*\+\+|%s\s*\+=\s*1)\s*$" % ((re.escape(var),) * 3), parts[2]):
+            raise OdeintrError("loop increment must be ++%s: %s" % (var, parts[2]))
+        pos = p_close + 1
+        while pos < n and src[pos].isspace():
+            pos += 1
+        if pos < n and src[pos] == "{":
+            b_close = _match(src, pos, "{", "}")
+            body = src[pos + 1:b_close]
+            pos = b_close + 1
+        else:
+            b_end = src.find(";", pos)
+            if b_end < 0:
+                b_end = n
+            body = src[pos:b_end] + ";"
+            pos = b_end + 1
+        loops.append((vtype, var, start, bound, body))
+    if not loops:
+        raise OdeintrError("empty system definition")
+    vtype, _, start, bound, _ = loops[0]
+    norm = lambda s: re.sub(r"\s+", "", s)
+    for l in loops[1:]:
+        if norm(l[2]) != norm(start) or norm(l[3]) != norm(bound):
+            raise OdeintrError("all cell loops of a large system must run over the same range")
+    offsets: List[str] = []
+    keys: List[str] = []
+    bodies, names = [], []
+    for (_, var, _, _, body) in loops:
+        out, k = [], 0
+        while True:
+            m = re.search(r"\bdxdt\s*\[", body[k:])
+            if not m:
+                out.append(body[k:])
+                break
+            i_open = k + m.end() - 1
+            i_close = _match(body, i_open, "[", "]")
+            expr = body[i_open + 1:i_close]
+            # canonical key: the index expression with the loop variable renamed, whitespace removed
+            key = norm(re.sub(r"\b%s\b" % re.escape(var), "odeintr_c", expr))
+            if key not in keys:
+                keys.append(key)
+                offsets.append(re.sub(r"\b%s\b" % re.escape(var), "odeintr_c", expr))
+            out.append(body[k:k + m.start()] + "odeintr_k[%d]" % keys.index(key))
+            k = i_close + 1
+        bodies.append("".join(out))
+        names.append(var)
+    return CellLoops(vtype, start, bound, bodies, names, offsets)
+
+
+_LATTICE_STEPPERS = {"rk4": "4", "euler": "1"}
+
+
+def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: str = "rk5_i", sys_dim: int = -1,
+                        atol: float = 1e-6, rtol: float = 1e-6, globals: str = "", headers: str = "",
+                        footers: str = "") -> Generated:
+    """Text generation half of compile_sys_openmp (R/odeintr.R:433-456)."""
+    p = handle_pars(pars, const)
+    make_stepper_constr(method, atol, rtol)  # same validity errors as the reference
+    boost_type = make_stepper_type(method)
+    base = re.sub(r"_i$|_a$", "", method)
+    if method not in _LATTICE_STEPPERS:
+        raise OdeintrError("method '%s' is not yet provided for large systems by odeintr_b200 "
+                           "(fixed-step rk4 and euler are)" % method)
+    sys = _join(sys)
+    if sys_dim is None or math.ceil(sys_dim) < 1:
+        sys_dim = get_sys_dim(sys)
+    if sys_dim is None:
+        raise OdeintrError("large systems must pass sys_dim (loop-indexed dxdt has no literal index; "
+                           "R/odeintr.R:403)")
+    sys_dim = int(math.ceil(sys_dim))
+    loops = parse_cell_loops(sys)
+    cell = []
+    for var, body in zip(loops.var_names, loops.bodies):
+        cell.append("{ const %s %s = static_cast<%s>(odeintr_c); %s }" % (loops.var_type, var, loops.var_type, body))
+    offs = ", ".join("static_cast<long long>(%s)" % o for o in loops.offsets)
+    code = _fill(read_template("compile_sys_openmp_template"), {
+        "__FUNCNAME__": name,
+        "__SYS_SIZE__": str(sys_dim),
+        "__NPARS__": str(p.n_runtime),
+        "__STEPPER_TYPE__": _LATTICE_STEPPERS[method],
+        "__HEADERS__": headers,
+        "__GLOBALS__": p.globals + globals,
+        "__LOAD_PARS__": p.load,
+        "__SYS__": "\n      ".join(cell),
+        "__FOOTERS__": footers,
+    })
+    code = code.replace("__NFIELDS__", str(len(loops.offsets)))
+    code = code.replace("__CELL_START__", loops.start).replace("__CELL_BOUND__", loops.bound)
+    code = code.replace("__FIELD_OFFSETS__", offs)
+    spec = StepperSpec(method, base, "plain", boost_type, "stepper_type()", "lattice_rk.cuh", "lattice_" + base)
+    return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol))

@@ -136,6 +136,14 @@ struct odeintr_system_s {
   dev_buf<double> seg_hrem, seg_t, times_dev;
   dev_buf<unsigned char> seg_obs;
   dev_buf<int> status, rows_inst, fail_flags;
+  // large-system (lattice) path
+  int lattice_stages = 4, sm_count = 148;
+  dev_buf<double> lat_buf_a, lat_buf_b, lat_buf_acc;
+  double *lat_x = nullptr, *lat_a = nullptr, *lat_b = nullptr, *lat_acc = nullptr;
+  bool sharded = false, sh_primed = false;
+  long long sh_total = 0, sh_c0 = 0, sh_n = 0, sh_ghost = 0, sh_pitch = 0;
+  int sh_fields = 1, sh_halo = 1;
+  double* sh_x = nullptr;
   long long max_tries = 20000000;  // per-instance step-attempt budget per call
   bool dense = false;    // the adaptive kernel wraps a dense-output stepper (rk5_i, rosenbrock4)
   dev_buf<unsigned long long> work_counter;
@@ -448,6 +456,109 @@ int run_plain_host(odeintr_system_t h, const plain_schedule& sc, const double* x
   return ODEINTR_OK;
 }
 
+// Large systems (compile_sys_openmp): one trajectory of N states; every Runge-Kutta stage is one fused
+// launch of odeintr_lattice_stage (RHS + stage algebra), the observer is a device-to-device row copy.
+struct lattice_window {      // which cells a launch computes and how local buffers map to global cells
+  long long n, n_total, c0, ghost, pitch;
+  int sharded;
+};
+
+int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
+  // sharded runs compute a window that shrinks by the stencil radius `halo` with every stage, so one halo
+  // exchange of width halo * stages per step is enough (redundant work on 2 * halo * stages * (stages-1)/2 cells)
+  odeintr_lattice_args a;
+  std::memset(&a, 0, sizeof(a));
+  a.pars = h->P ? h->pars.p : nullptr;
+  a.n = w.n; a.n_total = w.n_total; a.c0 = w.c0; a.ghost = w.ghost; a.pitch = w.pitch; a.sharded = w.sharded;
+  double* x = h->lat_x;
+  double* A = h->lat_a;
+  double* B = h->lat_b;
+  double* acc = h->lat_acc;
+  const unsigned grid = (unsigned)h->sm_count * 8u, block = 256u;
+  int rc;
+  auto stage = [&](int s, int n_stages, const double* xs, double* xt, const double* acc_in, double* acc_out,
+                   double ts, double a_dt, double b_dt) {
+    a.xs = xs; a.x = x; a.xt = xt; a.acc_in = acc_in; a.acc_out = acc_out; a.t = ts; a.a_dt = a_dt; a.b_dt = b_dt;
+    const long long margin = w.sharded ? (long long)halo * (n_stages - s) : 0;
+    a.lo = w.c0 - margin;
+    a.hi = w.c0 + w.n + margin;
+    return launch(h, h->k_lattice, h->stream, grid, block, &a);
+  };
+  if (h->lattice_stages == 4) {
+    // runge_kutta4 = explicit_generic_rk<4,4>: a = {1/2}, {0,1/2}, {0,0,1}; b = {1/6,1/3,1/3,1/6}
+    const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
+    if ((rc = stage(1, 4, x, A, x, acc, t, half * dt, b1 * dt))) return rc;
+    if ((rc = stage(2, 4, A, B, acc, acc, t + half * dt, half * dt, b2 * dt))) return rc;
+    if ((rc = stage(3, 4, B, A, acc, acc, t + half * dt, 1.0 * dt, b2 * dt))) return rc;
+    if ((rc = stage(4, 4, A, nullptr, acc, x, t + 1.0 * dt, 0.0, b1 * dt))) return rc;
+  } else {
+    // euler: x_new = x + dt * f(x); written to A, then the buffers trade places
+    if ((rc = stage(1, 1, x, nullptr, x, A, t, 0.0, dt))) return rc;
+    std::swap(h->lat_x, h->lat_a);
+  }
+  return ODEINTR_OK;
+}
+
+int lattice_step(odeintr_system_t h, const lattice_window& w, double t, double dt, int) {
+  return lattice_step_halo(h, w, t, dt, 0);
+}
+
+int lattice_prepare(odeintr_system_t h, size_t total) {
+  // work buffers; A and B start as copies of x so cells no loop writes keep their value in every stage
+  CU_TRY(h->lat_buf_a.reserve(total)); CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total));
+  CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return ODEINTR_OK;
+}
+
+int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
+  if (h->m != 1) return fail(ODEINTR_E_STATE, "Invalid initial state");
+  const size_t N = (size_t)h->N;
+  int rc;
+  if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  if ((rc = lattice_prepare(h, N))) return rc;
+  h->lat_x = h->x.p; h->lat_a = h->lat_buf_a.p; h->lat_b = h->lat_buf_b.p; h->lat_acc = h->lat_buf_acc.p;
+  if (sc.record && (rc = reserve_out(h, sc.rec_t.size()))) return rc;
+  lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0};
+  if ((rc = begin_timing(h))) return rc;
+  size_t row = 0;
+  auto observe = [&]() -> int {
+    CU_TRY(cudaMemcpyAsync(h->out.p + row * N, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    ++row;
+    return ODEINTR_OK;
+  };
+  double t = sc.t0;
+  long long step = 0;
+  for (long long s = 0; s < sc.n_seg; ++s) {
+    if (!sc.uniform) t = sc.t[(size_t)s];
+    if (sc.record && (sc.uniform || sc.obs[(size_t)s])) if ((rc = observe())) return rc;
+    const long long nfull = sc.uniform ? sc.nfull_uniform : sc.nfull[(size_t)s];
+    for (long long k = 0; k < nfull; ++k) {
+      if ((rc = lattice_step(h, w, t, sc.dt, 0))) return rc;
+      ++step;
+      t = (sc.time_rule == ODEINTR_TIME_CONST) ? sc.t0 + static_cast<double>(step) * sc.dt : t + sc.dt;
+    }
+    if (!sc.uniform && sc.hrem[(size_t)s] != 0.0) {
+      const double hr = sc.hrem[(size_t)s];
+      if ((rc = lattice_step(h, w, t, hr, 0))) return rc;
+      t += hr;
+    }
+  }
+  if (sc.record && sc.record_final) if ((rc = observe())) return rc;
+  if (h->lat_x != h->x.p)  // euler swapped an odd number of times: bring the state home
+    CU_TRY(cudaMemcpyAsync(h->x.p, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = end_timing(h))) return rc;
+  h->last_steps = sc.total_steps;
+  if (sc.record) {
+    h->rec_t = sc.rec_t;
+    h->rows = sc.rec_t.size();
+    h->out_m = 1;
+    h->ragged = false;
+  }
+  return ODEINTR_OK;
+}
+
 // Time column integrate_const records with a dense-output stepper: instance independent.
 std::vector<double> dense_const_times(double t0, double t1, double dt) {
   std::vector<double> rec;
@@ -582,6 +693,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->name = name ? name : "sys";
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
   h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
+  h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : 4;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }
@@ -593,6 +705,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if ((e = cudaGetDevice(&h->device)) != cudaSuccess) return bail("cudaGetDevice", e);
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  h->sm_count = prop.multiProcessorCount;
   if (prop.major != 10) {
     odeintr_destroy(h);
     return fail(ODEINTR_E_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; this engine is B200-only");
@@ -630,6 +743,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->seg_nfull.release(); h->seg_hrem.release(); h->seg_t.release(); h->seg_obs.release(); h->times_dev.release();
   h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release();
   h->work_counter.release();
+  h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
@@ -769,10 +883,10 @@ int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt,
   if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (obs_stride < 1) return fail(ODEINTR_E_INVALID, "obs_stride must be >= 1");
-  if (h->k_plain) {
+  if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_const(sc, t0, t1, dt, obs_stride, record != 0);
-    return run_plain(h, sc);
+    return h->k_lattice ? run_lattice(h, sc) : run_plain(h, sc);
   }
   if (h->k_adaptive) {
     if (obs_stride != 1) return fail(ODEINTR_E_INVALID, "obs_stride applies to fixed-step steppers only");
@@ -786,10 +900,10 @@ int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_ti
   if (rc) return rc;
   if (!times || n_times == 0) return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (!(dt != 0.0) || !std::isfinite(dt)) return fail(ODEINTR_E_INVALID, "Invalid time specification");
-  if (h->k_plain) {
+  if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_times(sc, times, n_times, dt);
-    return run_plain(h, sc);
+    return h->k_lattice ? run_lattice(h, sc) : run_plain(h, sc);
   }
   if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_TIMES, times[0], times[n_times - 1], dt, times, n_times, true);
   return fail(ODEINTR_E_STATE, "integrate_times: no kernel for this stepper family");
@@ -800,10 +914,10 @@ int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double 
   if (rc) return rc;
   if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
-  if (h->k_plain) {
+  if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_adaptive(sc, t0, t1, dt, record != 0);
-    return run_plain(h, sc);
+    return h->k_lattice ? run_lattice(h, sc) : run_plain(h, sc);
   }
   if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_ADAPTIVE, t0, t1, dt, nullptr, 0, record != 0);
   return fail(ODEINTR_E_STATE, "integrate_adaptive: no kernel for this stepper family");
@@ -828,6 +942,55 @@ size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride)
   if (!(dt != 0.0) || obs_stride < 1) return 0;
   const long long n = const_step_count(t0, t1, dt);
   return (size_t)((n + obs_stride - 1) / obs_stride) + 1;
+}
+
+// ---- slab-sharded large systems (one process per GPU) -------------------------------------------------------
+int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long first_cell, long long n_local,
+                          int fields, int halo, double* x_dev) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->k_lattice) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
+  if (cells_total < 1 || n_local < 1 || first_cell < 0 || first_cell + n_local > cells_total || fields < 1 || halo < 0)
+    return fail(ODEINTR_E_INVALID, "Invalid shard specification");
+  if ((long long)fields * cells_total != (long long)h->N) return fail(ODEINTR_E_INVALID, "fields * cells_total must equal sys_dim");
+  if (!x_dev) return fail(ODEINTR_E_INVALID, "null state pointer");
+  const long long ghost = (long long)halo * h->lattice_stages;
+  if (n_local + 2 * ghost > cells_total && n_local != cells_total)
+    return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
+  h->sh_total = cells_total; h->sh_c0 = first_cell; h->sh_n = n_local; h->sh_fields = fields; h->sh_halo = halo;
+  h->sh_ghost = ghost;
+  h->sh_pitch = n_local + 2 * ghost;
+  h->sh_x = x_dev;
+  const size_t total = (size_t)fields * (size_t)h->sh_pitch;
+  CU_TRY(h->lat_buf_a.reserve(total)); CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total));
+  h->sharded = true;
+  return ODEINTR_OK;
+}
+
+long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo) {
+  return h ? (long long)halo * h->lattice_stages : 0;
+}
+
+int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
+  if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
+  // stage buffers start as copies of the state so that entries no loop writes keep their value
+  if (!h->sh_primed) {
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    h->sh_primed = true;
+  }
+  const long long g = h->sh_ghost;
+  h->lat_x = h->sh_x + g; h->lat_a = h->lat_buf_a.p + g; h->lat_b = h->lat_buf_b.p + g; h->lat_acc = h->lat_buf_acc.p + g;
+  lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1};
+  if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
+  h->last_launches = 0;
+  if ((rc = lattice_step_halo(h, w, t, dt, h->sh_halo))) return rc;
+  return ODEINTR_OK;
 }
 
 // ---- observer record -------------------------------------------------------------------------------

@@ -81,23 +81,26 @@ struct odeintr_adaptive_args {
   int* fail_flags;            // one word: OR of every instance's non-zero status (may be null)
 };
 
-// Large coupled system ("lattice") fused RK4 stage launch, SURVEY.md §8(d) config 5.
+// Large coupled system ("lattice") fused Runge-Kutta stage launch, SURVEY.md §8(d) config 5:
+//   k = f(xs)[cell];  xt = x + a_dt*k (if xt != null);  acc_out = acc_in + b_dt*k
+// All pointers address local cell 0 of field 0; on a sharded run ghost cells sit at negative offsets and
+// the slabs of consecutive fields are `pitch` doubles apart.
 struct odeintr_lattice_args {
-  const double* x;            // state at the start of the step
-  const double* xs;           // stage input (x for stage 1, else previous stage's xt)
-  double* xt;                 // stage output state  x + a*dt*k
-  double* acc;                // running accumulator ((x + b1 k1) + b2 k2) ...
-  const double* acc_in;
-  double* x_out;              // final state (stage 4)
+  const double* xs;           // stage input state (argument of f)
+  const double* x;            // state at the start of the step (base of xt)
+  double* xt;                 // next stage's input state, or null on the last stage
+  const double* acc_in;       // running sum so far (x itself on the first stage)
+  double* acc_out;            // running sum (the new state on the last stage)
   const double* pars;
-  long long n;                // cells owned by this launch (without ghost cells)
-  long long n_total;          // global periodic length
-  long long i0;               // global index of local cell 0
-  long long ghost;            // ghost cells on each side of the local slab
-  long long lo;               // first local cell (relative to owned cell 0, may be negative) to compute
-  long long hi;               // one past the last local cell to compute
+  long long n;                // cells per field owned by this rank
+  long long n_total;          // global cells per field
+  long long c0;               // global cell index of local cell 0
+  long long ghost;            // ghost cells on each side
+  long long pitch;            // doubles between consecutive field slabs (sharded runs)
+  long long lo;               // first global cell to compute (may be < 0: periodic image)
+  long long hi;               // one past the last global cell to compute
   double t;
-  double a_dt;                // stage coefficient * dt for xt
-  double b_dt;                // weight * dt for the accumulator
-  int stage;                  // 1..4
+  double a_dt;
+  double b_dt;
+  int sharded;
 };

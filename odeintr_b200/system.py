@@ -62,6 +62,8 @@ class CompiledSystem:
         handle = C.c_void_p()
         if gen.stepper is None or gen.stepper.mode == "dense":
             flags |= _abi.FLAG_DENSE_OUTPUT
+        if gen.family == "lattice" and gen.stepper.base == "euler":
+            flags |= _abi.FLAG_LATTICE_EULER
         rc = self._lib.odeintr_compile(gen.code.encode(), gen.name.encode(), self.N, self.P, gen.atol, gen.rtol,
                                        flags, C.byref(handle))
         if rc != 0:

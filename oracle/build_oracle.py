@@ -33,16 +33,18 @@ def _dp(a):
     return a.ctypes.data_as(c_dbl_p) if a is not None else None
 
 
-def _pars_text(pars, const):
+def _pars_text(pars, const, shared=False):
+    """shared=True: plain statics (a large-system snippet runs its own `#pragma omp parallel for`, whose worker
+    threads must see the values); otherwise thread_local so the ensemble loop can set them per instance."""
     p = codegen.handle_pars(pars, const)
     if p.kind == "none":
         return "", "", 0
     if p.kind == "vector":
-        decl = "static thread_local std::array<double, %d> pars;" % len(p.names)
+        decl = "static %sstd::array<double, %d> pars;" % ("" if shared else "thread_local ", len(p.names))
     elif p.const:
         decl = "static " + p.globals
     else:
-        decl = "static thread_local " + p.globals
+        decl = "static %s" % ("" if shared else "thread_local ") + p.globals
     return decl, p.load.replace("\n      ", "\n  "), p.n_runtime
 
 
@@ -56,7 +58,7 @@ def generate(sys_src, pars=None, const=False, method="rk4", sys_dim=-1, atol=1e-
         sys_dim = 1
     if method == "rosenbrock4" and jacobian is None:
         jacobian = codegen.JacobianCpp(sys_src, sys_dim)
-    decl, setp, npars = _pars_text(pars, const)
+    decl, setp, npars = _pars_text(pars, const, shared="#pragma omp" in sys_src)
     text = (_HERE / "oracle_template.cpp").read_text()
     subs = {
         "@SYS_SIZE@": str(int(sys_dim)),

@@ -30,3 +30,35 @@ ROBERTSON_PARS = {"alpha": 0.04, "beta": 1e4, "gamma": 3e7}
 
 # /root/reference/tests/testthat/test_odeintr.R:33
 LOGISTIC = "dxdt = x * (1 - x)"
+
+# 1-D periodic bistable reaction-diffusion chain: the reference's own large-system example
+# (/root/reference/R/odeintr.R:396-401) with the Laplacian written out (its laplace4 helper does not exist)
+BISTABLE_1D = """
+#pragma omp parallel for
+for (int i = 0; i < N; ++i)
+  dxdt[i] = D * (x[(i + N - 1) % N] + x[(i + 1) % N] - 2.0 * x[i]) + a * x[i] * (1 - x[i]) * (x[i] - b);
+"""
+BISTABLE_PARS = {"D": 0.1, "a": 1.0, "b": 0.5}
+
+# the same on the periodic M x M lattice through the reference's laplace2D helper (inst/include/utils.h:29-31),
+# written as two loops like the reference's example (Laplacian first, reaction term added by a second loop)
+BISTABLE_2D = """
+#pragma omp parallel for
+for (int i = 0; i < N; ++i)
+  dxdt[i] = D * laplace2D(x, i / M, i % M);
+#pragma omp parallel for
+for (int i = 0; i < N; ++i)
+  dxdt[i] += a * x[i] * (1 - x[i]) * (x[i] - b);
+"""
+
+# SURVEY.md §8(d) config 5: periodic chain of L = N/2 anharmonic oscillators, SoA state [q_0..q_{L-1}, p_0..p_{L-1}]
+CHAIN = """
+#pragma omp parallel for
+for (int i = 0; i < L; ++i) {
+  const double q = x[i];
+  dxdt[i] = x[L + i];
+  dxdt[L + i] = -q - beta * q * q * q + K * (x[(i + L - 1) % L] - 2.0 * q + x[(i + 1) % L]);
+}
+"""
+CHAIN_PARS = {"beta": 1.0, "K": 0.5}
+CHAIN_GLOBALS = "static const int L = N / 2;"

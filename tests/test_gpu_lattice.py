@@ -1,0 +1,84 @@
+"""GPU parity for large coupled systems (K4, compile_sys_openmp, BASELINE.json configs[4]): fused
+Runge-Kutta stage kernels against the oracle running the same loops on the CPU.  Fixed-step arithmetic in
+Boost's order without FMA -> bit-exact."""
+import numpy as np
+import pytest
+
+import odeintr_b200
+from oracle import build_oracle as bo
+from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def cols(df):
+    return df.iloc[:, 1:].to_numpy()
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler"])
+def test_bistable_chain_bit_exact(method):
+    n = 4099  # not a multiple of anything: ragged last block, `% N` wrap at both ends
+    env = {}
+    odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=n)
+    rng = np.random.default_rng(11)
+    x0 = rng.integers(0, 2, n).astype(np.float64)  # inic = rbinom(M * M, 1, 1/2) in the reference's example
+    df = env["bistable"](x0, 5.0, 0.1)
+    ref = ora.integrate_const(x0, 0, 5.0, 0.1)
+    assert df.shape == (ref["rows"], n + 1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"])) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    # bistable_at(inic, at) of the example
+    at = np.array([1.0, 2.5, 10.0 ** 0.5, 7.0])
+    df = env["bistable_at"](x0, at, 0.25)
+    adv = ora.integrate_const(x0, 0.0, at[0], 0.25, record=False)
+    ref = ora.integrate_times(adv["x"], at, 0.25)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["bistable_no_record"](x0, 3.3, 0.25)
+    ref = ora.integrate_adaptive(x0, 0, 3.3, 0.25)
+    assert np.array_equal(bits(fin), bits(ref["x"]))
+    assert np.array_equal(bits(env["bistable_get_state"]()), bits(ref["x"]))
+
+
+def test_two_loops_and_laplace2d_helper():
+    m = 48
+    env = {}
+    odeintr_b200.compile_sys_openmp("b2d", BISTABLE_2D, BISTABLE_PARS, True, method="rk4", sys_dim=m * m, env=env)
+    ora = bo.build(BISTABLE_2D, BISTABLE_PARS, True, "rk4", sys_dim=m * m)
+    rng = np.random.default_rng(12)
+    x0 = rng.integers(0, 2, m * m).astype(np.float64)
+    df = env["b2d"](x0, 4.0, 0.2)
+    ref = ora.integrate_const(x0, 0, 4.0, 0.2)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+
+
+def test_oscillator_chain_two_fields_runtime_parameters():
+    n = 2 * 3001
+    env = {}
+    odeintr_b200.compile_sys_openmp("chain", CHAIN, CHAIN_PARS, False, method="rk4", sys_dim=n, globals=CHAIN_GLOBALS,
+                                    env=env)
+    ora = bo.build(CHAIN, CHAIN_PARS, False, "rk4", sys_dim=n, globals=CHAIN_GLOBALS)
+    L = n // 2
+    x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(L) / L), np.zeros(L)])
+    env["chain_set_params"](beta=0.7, K=0.45)
+    df = env["chain"](x0, 2.0, 0.01)
+    ref = ora.integrate_const(x0, 0, 2.0, 0.01, pars=[0.7, 0.45])
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    # the symplectic-ish energy drifts only slightly over 200 rk4 steps: a size-independent sanity property
+    def energy(s):
+        q, p = s[:L], s[L:]
+        return np.sum(0.5 * p * p + 0.5 * q * q + 0.7 * q ** 4 / 4 + 0.45 * 0.5 * (np.roll(q, -1) - q) ** 2)
+    e0, e1 = energy(x0), energy(cols(df)[-1])
+    assert abs(e1 - e0) / e0 < 1e-8
+
+
+def test_large_system_errors():
+    with pytest.raises(odeintr_b200.OdeintrError, match="sys_dim"):
+        odeintr_b200.compile_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method="rk4")
+    with pytest.raises(odeintr_b200.OdeintrError, match="loops over the cells"):
+        odeintr_b200.compile_sys_openmp("b", "dxdt[0] = x[1]; dxdt[1] = -x[0];", method="rk4", sys_dim=2)
+    with pytest.raises(odeintr_b200.OdeintrError, match="Invalid integration method"):
+        odeintr_b200.compile_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method="rk4_a", sys_dim=64)

@@ -1,0 +1,134 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on GPUs, gloo on CPU for
+the host-logic tests).
+
+* Ensembles (parameter sweeps, initial-condition batches) shard by instance index -- contiguous ranges, no
+  data-path collective.  ``shard_range`` / ``EnsembleShard`` only compute who owns what.
+* Large lattices shard spatially into slabs.  Every rank keeps ``ghost = halo * stages`` extra cells on both
+  sides of its slab and refreshes them ONCE per Runge-Kutta step from its ring neighbours
+  (``exchange_halos``: batched isend/irecv, i.e. ncclSend/ncclRecv inside one group on NCCL); the fused stage
+  kernels then recompute a window that shrinks by the stencil radius per stage
+  (``odeintr_lattice_shard_step``), so no communication happens between stages.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from .codegen import OdeintrError
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of `total` units owned by `rank`: sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise OdeintrError("invalid rank / world size")
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def exchange_halos(x, ghost: int, rank: int, world: int, group=None):
+    """Periodic ring exchange of the ghost cells of a slab-sharded lattice.
+
+    x: torch tensor [fields, ghost + n_local + ghost] (CPU with gloo, CUDA with NCCL), updated in place:
+    the left ghost cells receive the left neighbour's last `ghost` owned cells, the right ghost cells the right
+    neighbour's first `ghost` owned cells.  With one rank the lattice wraps onto itself."""
+    import torch
+    import torch.distributed as dist
+
+    if ghost == 0:
+        return
+    n_local = x.shape[1] - 2 * ghost
+    if n_local < ghost:
+        raise OdeintrError("slab too small for the halo width")
+    if world == 1:
+        x[:, :ghost] = x[:, n_local:n_local + ghost]
+        x[:, ghost + n_local:] = x[:, ghost:2 * ghost]
+        return
+    left, right = (rank - 1) % world, (rank + 1) % world
+    send_l = x[:, ghost:2 * ghost].contiguous()
+    send_r = x[:, n_local:n_local + ghost].contiguous()
+    recv_l = torch.empty_like(send_l)
+    recv_r = torch.empty_like(send_r)
+    ops = [dist.P2POp(dist.isend, send_r, right, group), dist.P2POp(dist.irecv, recv_l, left, group),
+           dist.P2POp(dist.isend, send_l, left, group), dist.P2POp(dist.irecv, recv_r, right, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    x[:, :ghost] = recv_l
+    x[:, ghost + n_local:] = recv_r
+
+
+class ShardedLattice:
+    """A compile_sys_openmp system whose cells are split into one slab per rank (GPU).
+
+    The state buffer is a torch CUDA tensor (torch owns the memory and talks NCCL); the stepping is done by the
+    C-ABI on that memory.  Fixed-step rk4, periodic lattice, stencil radius `halo`."""
+
+    def __init__(self, system, cells_total: int, fields: int = 1, halo: int = 1, rank: int = 0, world: int = 1,
+                 group=None, device=None):
+        import torch
+
+        if system.gen.family != "lattice":
+            raise OdeintrError("ShardedLattice needs a system compiled with compile_sys_openmp")
+        self.system, self.fields, self.halo = system, fields, halo
+        self.rank, self.world, self.group = rank, world, group
+        self.cells_total = cells_total
+        self.begin, self.end = shard_range(cells_total, rank, world)
+        self.n_local = self.end - self.begin
+        self.lib = _abi.load()
+        self.ghost = int(self.lib.odeintr_lattice_ghost_width(system._h, halo))
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.x = torch.zeros((fields, self.n_local + 2 * self.ghost), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # kernels and NCCL traffic are ordered on torch's current stream
+        if self.lib.odeintr_set_stream(system._h, C.c_void_p(stream)) != 0:
+            raise OdeintrError(_abi.last_error())
+        rc = self.lib.odeintr_lattice_shard(system._h, cells_total, self.begin, self.n_local, fields, halo,
+                                            C.c_void_p(self.x.data_ptr()))
+        if rc != 0:
+            raise OdeintrError(_abi.last_error())
+        self.t = 0.0
+        self.steps = 0
+
+    def set_state_from(self, fn):
+        """fn(field, global_cell_indices: np.ndarray) -> values; every rank fills only its own slab."""
+        import torch
+
+        cells = np.arange(self.begin, self.end)
+        for f in range(self.fields):
+            vals = np.asarray(fn(f, cells), dtype=np.float64)
+            self.x[f, self.ghost:self.ghost + self.n_local] = torch.from_numpy(vals).to(self.device)
+
+    def step(self, n_steps: int, dt: float, t0: Optional[float] = None):
+        if t0 is not None:
+            self.t, self.steps = t0, 0
+            self._t0 = t0
+        t0 = getattr(self, "_t0", 0.0)
+        for _ in range(n_steps):
+            exchange_halos(self.x, self.ghost, self.rank, self.world, self.group)
+            rc = self.lib.odeintr_lattice_shard_step(self.system._h, self.t, dt)
+            if rc != 0:
+                raise OdeintrError(_abi.last_error())
+            self.steps += 1
+            self.t = t0 + self.steps * dt  # integrate_const time rule
+
+    def local_state(self):
+        return self.x[:, self.ghost:self.ghost + self.n_local]
+
+    def gather_state(self):
+        """Full state [fields, cells_total] on every rank (for checks; not part of the timed path)."""
+        import torch
+        import torch.distributed as dist
+
+        loc = self.local_state().contiguous()
+        if self.world == 1:
+            return loc.clone()
+        sizes = [shard_range(self.cells_total, r, self.world) for r in range(self.world)]
+        widest = max(e - b for b, e in sizes)  # all_gather needs equal shapes: pad the short slabs
+        padded = torch.zeros((self.fields, widest), dtype=loc.dtype, device=loc.device)
+        padded[:, :loc.shape[1]] = loc
+        parts = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(parts, padded, group=self.group)
+        return torch.cat([p[:, :e - b] for p, (b, e) in zip(parts, sizes)], dim=1)

@@ -82,3 +82,33 @@ def test_large_system_errors():
         odeintr_b200.compile_sys_openmp("b", "dxdt[0] = x[1]; dxdt[1] = -x[0];", method="rk4", sys_dim=2)
     with pytest.raises(odeintr_b200.OdeintrError, match="Invalid integration method"):
         odeintr_b200.compile_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method="rk4_a", sys_dim=64)
+
+
+@pytest.mark.parametrize("case", ["bistable", "chain"])
+def test_sharded_stepping_single_rank_matches_unsharded(case):
+    # odeintr_lattice_shard_step with world = 1: ghost cells wrap onto the same slab; the shrinking-window
+    # schedule must give the bits of the plain single-GPU path (and hence of the oracle)
+    import torch
+
+    from odeintr_b200.distributed import ShardedLattice
+
+    if case == "bistable":
+        n_cells, fields = 5003, 1
+        code = odeintr_b200.compile_sys_openmp("bs", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells)
+        code2 = odeintr_b200.compile_sys_openmp("bs2", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells)
+        rng = np.random.default_rng(31)
+        x0 = rng.integers(0, 2, n_cells).astype(np.float64)
+    else:
+        n_cells, fields = 4001, 2
+        code = odeintr_b200.compile_sys_openmp("ch", CHAIN, CHAIN_PARS, True, method="rk4", sys_dim=2 * n_cells,
+                                               globals=CHAIN_GLOBALS)
+        code2 = odeintr_b200.compile_sys_openmp("ch2", CHAIN, CHAIN_PARS, True, method="rk4", sys_dim=2 * n_cells,
+                                                globals=CHAIN_GLOBALS)
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n_cells) / n_cells), np.zeros(n_cells)])
+    ref = code.system.no_record(x0, 2.0, 0.1)  # 20 rk4 steps on the unsharded path
+    lat = ShardedLattice(code2.system, n_cells, fields=fields, halo=1, rank=0, world=1)
+    lat.set_state_from(lambda f, cells: x0[f * n_cells + cells])
+    lat.step(20, 0.1, t0=0.0)
+    torch.cuda.synchronize()
+    got = lat.gather_state().cpu().numpy().reshape(-1)
+    assert np.array_equal(bits(got), bits(ref))

@@ -124,7 +124,7 @@ struct odeintr_system_s {
   double atol = 1e-6, rtol = 1e-6;
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr;
+  cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr;
   int block_plain = 128, block_adaptive = 128;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -469,7 +469,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   odeintr_lattice_args a;
   std::memset(&a, 0, sizeof(a));
   a.pars = h->P ? h->pars.p : nullptr;
-  a.n = w.n; a.n_total = w.n_total; a.c0 = w.c0; a.ghost = w.ghost; a.pitch = w.pitch; a.sharded = w.sharded;
+  a.n = w.n; a.n_total = w.n_total; a.c0 = w.c0; a.ghost = w.ghost; a.pitch = w.pitch;
   double* x = h->lat_x;
   double* A = h->lat_a;
   double* B = h->lat_b;
@@ -482,7 +482,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     const long long margin = w.sharded ? (long long)halo * (n_stages - s) : 0;
     a.lo = w.c0 - margin;
     a.hi = w.c0 + w.n + margin;
-    return launch(h, h->k_lattice, h->stream, grid, block, &a);
+    return launch(h, w.sharded ? h->k_lattice_sharded : h->k_lattice, h->stream, grid, block, &a);
   };
   if (h->lattice_stages == 4) {
     // runge_kutta4 = explicit_generic_rk<4,4>: a = {1/2}, {0,1/2}, {0,0,1}; b = {1/6,1/3,1/3,1/6}
@@ -716,6 +716,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_plain, h->lib, "odeintr_plain_ensemble") != cudaSuccess) h->k_plain = nullptr;
   if (cudaLibraryGetKernel(&h->k_adaptive, h->lib, "odeintr_adaptive_ensemble") != cudaSuccess) h->k_adaptive = nullptr;
   if (cudaLibraryGetKernel(&h->k_lattice, h->lib, "odeintr_lattice_stage") != cudaSuccess) h->k_lattice = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lattice_sharded, h->lib, "odeintr_lattice_stage_sharded") != cudaSuccess)
+    h->k_lattice_sharded = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);

@@ -102,5 +102,4 @@ struct odeintr_lattice_args {
   double t;
   double a_dt;
   double b_dt;
-  int sharded;
 };

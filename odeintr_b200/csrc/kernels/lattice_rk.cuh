@@ -12,45 +12,70 @@
 // instead of 208 B (+64 B of by-value vector copies), SURVEY.md §8(d).
 //
 // Memory-bound: every thread reads 8-24 B and writes 8-16 B per cell, fully coalesced (consecutive threads
-// own consecutive cells); stencil neighbours are served by L1/L2 through the read-only path.
+// own consecutive cells).  Every block owns one contiguous chunk of cells (page / TLB locality: an SM touches
+// 1/gridDim of each array instead of striding over all of it); stencil neighbours are served by L1/L2
+// through the read-only path.  Two entry points: the single-GPU kernel indexes the arrays directly, the
+// sharded one maps global indices into the rank's slab + ghost window.
 #pragma once
 #include "odeintr_b200/lattice_view.cuh"
 
-extern "C" __global__ void __launch_bounds__(256)
-odeintr_lattice_stage(const odeintr_lattice_args a) {
-  typedef odeintr::system_type Sys;
+namespace odeintr_b200 {
+
+template <bool SHARDED, bool HAS_XT>
+ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
+  typedef odeintr::system_type_t<lattice_view_t<SHARDED> > Sys;
   constexpr int F = ODEINTR_NFIELDS;
   Sys sys;
   sys.load_params(a.pars, 1, 0);
   long long off[F];
   sys.field_offsets(off);
 
-  odeintr_b200::lattice_view xs;
+  lattice_view_t<SHARDED> xs;
   xs.p = a.xs; xs.n_total = a.n_total; xs.n_local = a.n; xs.c0 = a.c0; xs.ghost = a.ghost; xs.pitch = a.pitch;
-  xs.sharded = a.sharded != 0;
 
-  // cells this launch computes: the user loop's range, clipped to this rank's window [lo, hi) (global cells)
   // local position of entry (field f, cell c) is base[f] + c: fields are `pitch` apart, cell c sits at c - c0
   long long base[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) base[f] = a.sharded ? (off[f] / a.n_total) * a.pitch - a.c0 : off[f];
+  for (int f = 0; f < F; ++f) base[f] = SHARDED ? (off[f] / a.n_total) * a.pitch - a.c0 : off[f];
 
+  // cells this launch computes: the user loop's range, clipped to this rank's window [lo, hi) (global cells),
+  // split into one contiguous chunk per block (a multiple of the block size, so rows stay aligned)
   const long long first = sys.cell_start() > a.lo ? sys.cell_start() : a.lo;
   const long long last = sys.cell_bound() < a.hi ? sys.cell_bound() : a.hi;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < last; c += stride) {
+  if (last <= first) return;
+  long long chunk = (last - first + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + blockDim.x - 1) / blockDim.x * blockDim.x;
+  const long long c_lo = first + (long long)blockIdx.x * chunk;
+  long long c_hi = c_lo + chunk;
+  if (c_hi > last) c_hi = last;
+  for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
     double k[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) k[f] = 0.0;
-    // periodic images: on a sharded run the window may start below 0 or end above n_total
     long long cg = c;
-    if (cg < 0) cg += a.n_total; else if (cg >= a.n_total) cg -= a.n_total;
+    if (SHARDED) {  // periodic images: the window may start below 0 or end above n_total
+      if (cg < 0) cg += a.n_total; else if (cg >= a.n_total) cg -= a.n_total;
+    }
     sys.cell(xs, k, cg, a.t);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
       const long long idx = base[f] + c;
-      if (a.xt) a.xt[idx] = a.x[idx] + a.a_dt * k[f];
+      if (HAS_XT) a.xt[idx] = a.x[idx] + a.a_dt * k[f];
       a.acc_out[idx] = a.acc_in[idx] + a.b_dt * k[f];
     }
   }
+}
+
+}  // namespace odeintr_b200
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_stage(const odeintr_lattice_args a) {
+  if (a.xt) odeintr_b200::lattice_stage_body<false, true>(a);
+  else odeintr_b200::lattice_stage_body<false, false>(a);
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_stage_sharded(const odeintr_lattice_args a) {
+  if (a.xt) odeintr_b200::lattice_stage_body<true, true>(a);
+  else odeintr_b200::lattice_stage_body<true, false>(a);
 }

@@ -1,25 +1,25 @@
 // odeintr_b200/csrc/kernels/lattice_view.cuh
 // Read-only view of a large state vector in HBM, indexed by GLOBAL state index exactly as the user's
 // snippet indexes the reference's std::vector (x[i - 1], x[(i + 1) % N], laplace2D(x, i, j), ...).
-// On one GPU it is a plain pointer.  On a slab-sharded run (one process per GPU) the local
-// buffer holds, per field, the rank's owned cells plus `ghost` cells on each side; a global index is
-// wrapped periodically into that window.
+// On one GPU it is a plain pointer (SHARDED = false: no index arithmetic at all).  On a slab-sharded run
+// (one process per GPU) the local buffer holds, per field, the rank's owned cells plus
+// `ghost` cells on each side; a global index is wrapped periodically into that window.
 #pragma once
 #include "odeintr_b200/prelude.cuh"
 
 namespace odeintr_b200 {
 
-struct lattice_view {
+template <bool SHARDED>
+struct lattice_view_t {
   const double* p;       // local cell 0 of field 0 (ghost cells sit at negative offsets)
   long long n_total;     // global cells per field (L)
   long long n_local;     // cells per field owned by this rank
   long long c0;          // global index of local cell 0
   long long ghost;       // ghost cells on each side
   long long pitch;       // distance between the local slabs of consecutive fields
-  bool sharded;
 
   ODEINTR_DEV double operator[](const long long g) const {
-    if (!sharded) return __ldg(p + g);
+    if (!SHARDED) return __ldg(p + g);
     // field and cell of the global index, then the periodic distance from the slab origin
 #if defined(ODEINTR_NFIELDS) && ODEINTR_NFIELDS == 1
     const long long f = 0;

@@ -81,9 +81,11 @@ class ShardedLattice:
         self.ghost = int(self.lib.odeintr_lattice_ghost_width(system._h, halo))
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.x = torch.zeros((fields, self.n_local + 2 * self.ghost), dtype=torch.float64, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        # kernels and NCCL traffic are ordered on torch's current stream
-        if self.lib.odeintr_set_stream(system._h, C.c_void_p(stream)) != 0:
+        # One dedicated stream orders everything: the halo copies and NCCL send/recv are issued by torch with this
+        # stream current, the stage kernels are launched on the same stream by the C-ABI.
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.lib.odeintr_set_stream(system._h, C.c_void_p(self.stream.cuda_stream)) != 0:
             raise OdeintrError(_abi.last_error())
         rc = self.lib.odeintr_lattice_shard(system._h, cells_total, self.begin, self.n_local, fields, halo,
                                             C.c_void_p(self.x.data_ptr()))
@@ -97,22 +99,26 @@ class ShardedLattice:
         import torch
 
         cells = np.arange(self.begin, self.end)
-        for f in range(self.fields):
-            vals = np.asarray(fn(f, cells), dtype=np.float64)
-            self.x[f, self.ghost:self.ghost + self.n_local] = torch.from_numpy(vals).to(self.device)
+        with torch.cuda.stream(self.stream):
+            for f in range(self.fields):
+                vals = np.asarray(fn(f, cells), dtype=np.float64)
+                self.x[f, self.ghost:self.ghost + self.n_local] = torch.from_numpy(vals).to(self.device)
 
     def step(self, n_steps: int, dt: float, t0: Optional[float] = None):
         if t0 is not None:
             self.t, self.steps = t0, 0
             self._t0 = t0
+        import torch
+
         t0 = getattr(self, "_t0", 0.0)
-        for _ in range(n_steps):
-            exchange_halos(self.x, self.ghost, self.rank, self.world, self.group)
-            rc = self.lib.odeintr_lattice_shard_step(self.system._h, self.t, dt)
-            if rc != 0:
-                raise OdeintrError(_abi.last_error())
-            self.steps += 1
-            self.t = t0 + self.steps * dt  # integrate_const time rule
+        with torch.cuda.stream(self.stream):
+            for _ in range(n_steps):
+                exchange_halos(self.x, self.ghost, self.rank, self.world, self.group)
+                rc = self.lib.odeintr_lattice_shard_step(self.system._h, self.t, dt)
+                if rc != 0:
+                    raise OdeintrError(_abi.last_error())
+                self.steps += 1
+                self.t = t0 + self.steps * dt  # integrate_const time rule
 
     def local_state(self):
         return self.x[:, self.ghost:self.ghost + self.n_local]
@@ -122,6 +128,7 @@ class ShardedLattice:
         import torch
         import torch.distributed as dist
 
+        self.stream.synchronize()
         loc = self.local_state().contiguous()
         if self.world == 1:
             return loc.clone()

@@ -48,9 +48,9 @@ lat.step(5, 0.01, t0=0.0)
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
+e0.record(lat.stream)
 lat.step(steps, 0.01)
-e1.record(); torch.cuda.synchronize()
+e1.record(lat.stream); torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
 if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:

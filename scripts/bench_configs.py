@@ -1,0 +1,136 @@
+#!/usr/bin/env python3
+"""Secondary measurements for BASELINE.json configs[2..4] (the headline, configs[1], is bench.py):
+  config 3  Van der Pol mu-sweep, 10 M instances, adaptive dopri5 (rk5_i, atol = rtol = 1e-8), name_at dense output
+  config 4  Robertson, 10 M instances (alpha sweep), compile_implicit rosenbrock4, log-spaced name_at
+  config 5  1-D lattice of 2^28 states, rk4 (fused stage kernels), single GPU
+Each prints one JSON line: device-timed value, a parity spot check against the oracle, and the oracle's CPU
+throughput on a bounded sample (all host cores).  Usage: python scripts/bench_configs.py [3] [4] [5]"""
+import ctypes as C, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import odeintr_b200
+from odeintr_b200 import _abi
+from oracle import build_oracle as bo
+from systems import *
+lib = _abi.load()
+which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
+threads = os.cpu_count() or 1
+dp_peak = C.c_double(); ms = C.c_double()
+lib.odeintr_fp64_probe(1, 0, C.byref(dp_peak), C.byref(ms))
+try:
+    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    hbm_peak = 6650.0
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / (1.0 + np.abs(b))))
+
+if 3 in which:
+    m, rtol = 10_000_000, 1e-8
+    code = odeintr_b200.compile_sys("vpol", VDP, "mu", method="rk5_i", atol=rtol, rtol=rtol)
+    s = code.system
+    lo = (C.c_double * 1)(0.5); hi = (C.c_double * 1)(2.0)
+    assert lib.odeintr_fill_params_linspace(s._h, m, 0, m, lo, hi) == 0
+    times = np.arange(0, 20.0001, 0.2)
+    X = np.repeat(np.array([2.0, 0.0])[:, None], m, axis=1)
+    best = None
+    for rep in range(3):
+        s.set_state(X)
+        assert lib.odeintr_integrate_times(s._h, times.ctypes.data_as(_abi.c_dbl_p), times.size, 0.01) == 0, _abi.last_error()
+        best = s.last_kernel_ms() if best is None else min(best, s.last_kernel_ms())
+    st = s.stats()
+    acc, rej = int(st["accepted"].sum()), int(st["rejected"].sum())
+    # parity: 2 048 instances spread over the sweep vs the oracle
+    ora = bo.build(VDP, "mu", False, "rk5_i", atol=rtol, rtol=rtol)
+    idx = np.linspace(0, m - 1, 2048).astype(np.int64)
+    mus = 0.5 + 1.5 * idx / (m - 1)
+    sub = np.empty((1, 2, len(times)))
+    got = np.empty((len(times), 2, len(idx)))
+    for j, i in enumerate(idx):
+        assert lib.odeintr_get_output(s._h, sub.ctypes.data_as(_abi.c_dbl_p), sub.size, int(i), 1) == 0
+        got[:, :, j] = sub[0].T
+    e = ora.ensemble(1, np.repeat(np.array([2.0, 0.0])[:, None], len(idx), axis=1), mus[None, :], times=times, dt=0.01,
+                     out_rows=len(times), threads=threads)
+    err = relerr(got, e["out"])
+    cnt_equal = float(np.mean(st["accepted"][idx] == e["accepted"]))
+    # CPU baseline
+    mc = 100_000
+    Xc = np.repeat(np.array([2.0, 0.0])[:, None], mc, axis=1); muc = (0.5 + 1.5 * np.arange(mc) / (mc - 1))[None, :]
+    t0 = time.perf_counter(); ec = ora.ensemble(1, Xc, muc, times=times, dt=0.01, out_rows=len(times), threads=threads); tc = time.perf_counter() - t0
+    print(json.dumps({"config": 3, "metric": "vdp_dopri5_dense_accepted_steps_per_s", "value": acc / best * 1e3, "unit": "accepted steps/s",
+        "instances": m, "kernel_ms": best, "accepted": acc, "rejected": rej, "tries_per_s": (acc + rej) / best * 1e3,
+        "samples_per_instance": len(times), "record_bytes": int(len(times) * 2 * m * 8),
+        "parity": {"instances_checked": len(idx), "max_err_over_1_plus_abs": err, "tolerance_10_rtol": 10 * rtol, "ok": err <= 10 * rtol,
+                   "accepted_count_equal_fraction": cnt_equal},
+        "cpu_baseline": {"value": float(ec["accepted"].sum()) / tc, "unit": "accepted steps/s", "cores": threads, "kind": "port", "sample": "%d instances" % mc},
+        "registers": s.kernel_attributes("odeintr_adaptive_ensemble")["registers"], "fp64_issue_peak_T_per_s": dp_peak.value / 1e12}), flush=True)
+    s.close()
+
+if 4 in which:
+    m, rtol = 10_000_000, 1e-6
+    code = odeintr_b200.compile_implicit("rob", ROBERTSON, ROBERTSON_PARS)
+    s = code.system
+    lo = (C.c_double * 3)(0.02, 1e4, 3e7); hi = (C.c_double * 3)(0.08, 1e4, 3e7)
+    assert lib.odeintr_fill_params_linspace(s._h, m, 0, m, lo, hi) == 0
+    times = 10 ** np.linspace(-5, 5, 41)
+    X = np.repeat(np.array([1.0, 0.0, 0.0])[:, None], m, axis=1)
+    best = None
+    for rep in range(3):
+        s.set_state(X)
+        assert lib.odeintr_integrate_times(s._h, times.ctypes.data_as(_abi.c_dbl_p), times.size, 1e-6) == 0, _abi.last_error()
+        best = s.last_kernel_ms() if best is None else min(best, s.last_kernel_ms())
+    st = s.stats()
+    acc, rej = int(st["accepted"].sum()), int(st["rejected"].sum())
+    ora = bo.build(ROBERTSON, ROBERTSON_PARS, False, "rosenbrock4")
+    idx = np.linspace(0, m - 1, 2048).astype(np.int64)
+    P = np.stack([0.02 + 0.06 * idx / (m - 1), np.full(len(idx), 1e4), np.full(len(idx), 3e7)])
+    sub = np.empty((1, 3, len(times))); got = np.empty((len(times), 3, len(idx)))
+    for j, i in enumerate(idx):
+        assert lib.odeintr_get_output(s._h, sub.ctypes.data_as(_abi.c_dbl_p), sub.size, int(i), 1) == 0
+        got[:, :, j] = sub[0].T
+    e = ora.ensemble(1, np.repeat(np.array([1.0, 0.0, 0.0])[:, None], len(idx), axis=1), P, times=times, dt=1e-6, out_rows=len(times), threads=threads)
+    err = relerr(got, e["out"])
+    mc = 100_000
+    Pc = np.stack([np.linspace(0.02, 0.08, mc), np.full(mc, 1e4), np.full(mc, 3e7)])
+    t0 = time.perf_counter(); ec = ora.ensemble(1, np.repeat(np.array([1.0, 0.0, 0.0])[:, None], mc, axis=1), Pc, times=times, dt=1e-6, out_rows=len(times), threads=threads); tc = time.perf_counter() - t0
+    print(json.dumps({"config": 4, "metric": "robertson_rosenbrock4_accepted_steps_per_s", "value": acc / best * 1e3, "unit": "accepted steps/s",
+        "instances": m, "kernel_ms": best, "accepted": acc, "rejected": rej,
+        "parity": {"instances_checked": len(idx), "max_err_over_1_plus_abs": err, "tolerance_10_rtol": 10 * rtol, "ok": err <= 10 * rtol,
+                   "accepted_count_equal_fraction": float(np.mean(st["accepted"][idx] == e["accepted"]))},
+        "cpu_baseline": {"value": float(ec["accepted"].sum()) / tc, "unit": "accepted steps/s", "cores": threads, "kind": "port", "sample": "%d instances" % mc},
+        "registers": s.kernel_attributes("odeintr_adaptive_ensemble")["registers"]}), flush=True)
+    s.close()
+
+if 5 in which:
+    n, steps = 1 << 28, 100
+    code = odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n)
+    s = code.system
+    x0 = (np.arange(n) % 7 < 3).astype(np.float64)
+    s.set_state(x0)
+    best = None
+    for rep in range(3):
+        assert lib.odeintr_integrate_const(s._h, 0.0, steps * 0.01, 0.01, 1, 0) == 0, _abi.last_error()
+        best = s.last_kernel_ms() if best is None else min(best, s.last_kernel_ms())
+    nsteps = s.last_steps()
+    # parity at 2^20 cells (the oracle finishes in seconds), same system and initial pattern
+    ns = 1 << 20
+    code_s = odeintr_b200.compile_sys_openmp("bistable_s", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=ns)
+    xs0 = (np.arange(ns) % 7 < 3).astype(np.float64)
+    got = code_s.system.no_record(xs0, 0.2, 0.01)
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, "rk4", sys_dim=ns)
+    t0 = time.perf_counter(); ref = ora.integrate_adaptive(xs0, 0.0, 0.2, 0.01); tc = time.perf_counter() - t0
+    exact = bool(np.array_equal(got.view(np.uint64), ref["x"].view(np.uint64)))
+    # size-independent property at full size: the initial pattern has period 7, and 2^28 = 7 * 38347922 + 2, so the
+    # state is not periodic at the wrap; away from it every cell must equal the cell 7 places on (translation symmetry)
+    fin = s.get_state()
+    sym = bool(np.array_equal(fin[1000:100000], fin[1007:100007]))
+    gbs = 128.0 * n * nsteps / best / 1e6
+    print(json.dumps({"config": 5, "metric": "lattice_rk4_cell_steps_per_s", "value": n * nsteps / best * 1e3, "unit": "cell-steps/s",
+        "cells": n, "steps": nsteps, "ms_per_step": best / nsteps,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                     "algorithmic_bytes_per_cell_step": 128},
+        "parity": {"bit_exact_vs_oracle_2^20_cells_20_steps": exact, "translation_symmetry_full_size": sym},
+        "cpu_baseline": {"value": ns * 20 / tc, "unit": "cell-steps/s", "cores": threads, "kind": "port",
+                         "sample": "2^20 cells x 20 rk4 steps, user loop under #pragma omp parallel for"}}), flush=True)
+    s.close()

@@ -105,7 +105,8 @@ _BOOST_TYPES = {
     "bs": "bulirsch_stoer<state_type>",
     "bsd": "bulirsch_stoer_dense_out<state_type>",
 }
-_PLAIN_DEVICE = {"euler": "euler_stepper", "rk4": "rk4_stepper", "rk54": "rk54_stepper", "rk5": "rk5_stepper"}
+_PLAIN_DEVICE = {"euler": "euler_stepper", "rk4": "rk4_stepper", "rk54": "rk54_stepper", "rk5": "rk5_stepper",
+                 "rk78": "rk78_stepper"}
 
 
 def make_stepper_constr(method: str, atol, rtol) -> str:
@@ -151,6 +152,8 @@ def stepper_spec(method: str, atol=1e-6, rtol=1e-6) -> StepperSpec:
         return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", dev)
     if base == "rk54" and mode == "controlled":
         return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "rk54_controlled")
+    if base == "rk78" and mode == "controlled":
+        return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "rk78_controlled")
     raise OdeintrError("method '%s' is not yet provided by odeintr_b200" % method)
 
 

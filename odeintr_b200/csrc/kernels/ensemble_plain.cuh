@@ -12,10 +12,11 @@
 // 256-byte segment of a structure-of-arrays row (no shared-memory transpose needed in this layout).
 //
 // Included at the end of the generated translation unit, after `odeintr::system_type`, with
-//   ODEINTR_SYS_SIZE, ODEINTR_STEPPER (euler_stepper | rk4_stepper | rk54_stepper | rk5_stepper)
+//   ODEINTR_SYS_SIZE, ODEINTR_STEPPER (euler_stepper | rk4_stepper | rk54_stepper | rk5_stepper | rk78_stepper)
 #pragma once
 #include "odeintr_b200/steppers_plain.cuh"
 #include "odeintr_b200/dopri5.cuh"
+#include "odeintr_b200/rk78.cuh"
 
 extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK)
 odeintr_plain_ensemble(const odeintr_plain_args a) {

@@ -6,6 +6,7 @@
 // All loops return false when the stepper reported Boost's 500-failed-steps overflow.
 #pragma once
 #include "odeintr_b200/adaptive_steppers.cuh"
+#include "odeintr_b200/rk78.cuh"
 
 namespace odeintr_b200 {
 

@@ -38,10 +38,12 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
 #pragma unroll
   for (int f = 0; f < F; ++f) base[f] = SHARDED ? (off[f] / a.n_total) * a.pitch - a.c0 : off[f];
 
-  // cells this launch computes: the user loop's range, clipped to this rank's window [lo, hi) (global cells),
-  // split into one contiguous chunk per block (a multiple of the block size, so rows stay aligned)
-  const long long first = sys.cell_start() > a.lo ? sys.cell_start() : a.lo;
-  const long long last = sys.cell_bound() < a.hi ? sys.cell_bound() : a.hi;
+  // cells this launch computes: the user loop's range (unsharded) or this rank's window [lo, hi) of global
+  // cells, which may reach below 0 / above n_total: those are periodic images and are computed too (they are
+  // the ghost cells the next stage reads); split into one contiguous chunk per block (a multiple of the
+  // block size, so rows stay aligned)
+  const long long first = SHARDED ? a.lo : (sys.cell_start() > a.lo ? sys.cell_start() : a.lo);
+  const long long last = SHARDED ? a.hi : (sys.cell_bound() < a.hi ? sys.cell_bound() : a.hi);
   if (last <= first) return;
   long long chunk = (last - first + gridDim.x - 1) / gridDim.x;
   chunk = (chunk + blockDim.x - 1) / blockDim.x * blockDim.x;
@@ -53,8 +55,9 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
 #pragma unroll
     for (int f = 0; f < F; ++f) k[f] = 0.0;
     long long cg = c;
-    if (SHARDED) {  // periodic images: the window may start below 0 or end above n_total
+    if (SHARDED) {
       if (cg < 0) cg += a.n_total; else if (cg >= a.n_total) cg -= a.n_total;
+      if (cg < sys.cell_start() || cg >= sys.cell_bound()) continue;  // not a cell of the user's loop
     }
     sys.cell(xs, k, cg, a.t);
 #pragma unroll

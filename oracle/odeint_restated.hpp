@@ -10,7 +10,7 @@
 //     stepper, controlled-stepper and dense-output-stepper tags (boost/numeric/odeint/
 //     integrate/detail/*.hpp), incl. less_with_sign / less_eq_with_sign (util/detail/
 //     less_with_sign.hpp),
-//   * euler, runge_kutta4 (explicit_generic_rk<4,4>), runge_kutta_cash_karp54,
+//   * euler, runge_kutta4 (explicit_generic_rk<4,4>), runge_kutta_cash_karp54, runge_kutta_fehlberg78,
 //     runge_kutta_dopri5 (+ calc_state dense output), controlled_runge_kutta (default_error_checker +
 //     default_step_adjuster), dense_output_runge_kutta (FSAL specialisation),
 //   * rosenbrock4 / rosenbrock4_controller / rosenbrock4_dense_output with uBLAS
@@ -178,6 +178,75 @@ struct runge_kutta_cash_karp54 {
   }
 };
 
+// runge_kutta_fehlberg78 = explicit_error_generic_rk<13,8,8,7>: generic algorithm, zero entries kept,
+// x_out = x + dt * sum b_i k_i (8th order), xerr = dt * sum (b_i - b7_i) k_i
+struct runge_kutta_fehlberg78 {
+  static const int order_value = 8, stepper_order_value = 8, error_order_value = 7;
+  static const int S = 13;
+  state_type k[13], xt, dxdt;
+  static const double* A(int s) {
+    static const double a[13][12] = {
+        {0},
+        {2.0 / 27.0},
+        {1.0 / 36.0, 1.0 / 12.0},
+        {1.0 / 24.0, 0.0, 1.0 / 8.0},
+        {5.0 / 12.0, 0.0, -25.0 / 16.0, 25.0 / 16.0},
+        {1.0 / 20.0, 0.0, 0.0, 1.0 / 4.0, 1.0 / 5.0},
+        {-25.0 / 108.0, 0.0, 0.0, 125.0 / 108.0, -65.0 / 27.0, 125.0 / 54.0},
+        {31.0 / 300.0, 0.0, 0.0, 0.0, 61.0 / 225.0, -2.0 / 9.0, 13.0 / 900.0},
+        {2.0, 0.0, 0.0, -53.0 / 6.0, 704.0 / 45.0, -107.0 / 9.0, 67.0 / 90.0, 3.0},
+        {-91.0 / 108.0, 0.0, 0.0, 23.0 / 108.0, -976.0 / 135.0, 311.0 / 54.0, -19.0 / 60.0, 17.0 / 6.0, -1.0 / 12.0},
+        {2383.0 / 4100.0, 0.0, 0.0, -341.0 / 164.0, 4496.0 / 1025.0, -301.0 / 82.0, 2133.0 / 4100.0, 45.0 / 82.0,
+         45.0 / 164.0, 18.0 / 41.0},
+        {3.0 / 205.0, 0.0, 0.0, 0.0, 0.0, -6.0 / 41.0, -3.0 / 205.0, -3.0 / 41.0, 3.0 / 41.0, 6.0 / 41.0, 0.0},
+        {-1777.0 / 4100.0, 0.0, 0.0, -341.0 / 164.0, 4496.0 / 1025.0, -289.0 / 82.0, 2193.0 / 4100.0, 51.0 / 82.0,
+         33.0 / 164.0, 12.0 / 41.0, 0.0, 1.0}};
+    return a[s];
+  }
+  template <class Sys>
+  void do_step_impl(Sys& sys, const state_type& in, const state_type& dxdt_in, double t, state_type& out, double dt,
+                    state_type* xerr) {
+    static const double c[13] = {0.0, 2.0 / 27.0, 1.0 / 9.0, 1.0 / 6.0, 5.0 / 12.0, 1.0 / 2.0, 5.0 / 6.0,
+                                 1.0 / 6.0, 2.0 / 3.0, 1.0 / 3.0, 1.0, 0.0, 1.0};
+    static const double b[13] = {0.0, 0.0, 0.0, 0.0, 0.0, 34.0 / 105.0, 9.0 / 35.0, 9.0 / 35.0, 9.0 / 280.0,
+                                 9.0 / 280.0, 0.0, 41.0 / 840.0, 41.0 / 840.0};
+    static const double db[13] = {0.0 - 41.0 / 840.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                                  0.0 - 41.0 / 840.0, 41.0 / 840.0, 41.0 / 840.0};
+    const std::size_t n = in.size();
+    for (int s = 0; s < S; ++s) k[s].resize(n);
+    xt.resize(n);
+    k[0] = dxdt_in;
+    for (int s = 1; s < S; ++s) {
+      const double* a = A(s);
+      for (std::size_t i = 0; i < n; ++i) {
+        double v = 1.0 * in[i];
+        for (int j = 0; j < s; ++j) v = v + (a[j] * dt) * k[j][i];
+        xt[i] = v;
+      }
+      sys(xt, k[s], t + c[s] * dt);
+    }
+    if (xerr) {
+      xerr->resize(n);
+      for (std::size_t i = 0; i < n; ++i) {
+        double v = (db[0] * dt) * k[0][i];
+        for (int j = 1; j < S; ++j) v = v + (db[j] * dt) * k[j][i];
+        (*xerr)[i] = v;
+      }
+    }
+    for (std::size_t i = 0; i < n; ++i) {
+      double v = 1.0 * in[i];
+      for (int j = 0; j < S; ++j) v = v + (b[j] * dt) * k[j][i];
+      out[i] = v;
+    }
+  }
+  template <class Sys> void do_step(Sys& sys, state_type& x, double t, double dt) {
+    dxdt.resize(x.size());
+    sys(x, dxdt, t);
+    state_type d = dxdt, in = x;
+    do_step_impl(sys, in, d, t, x, dt, nullptr);
+  }
+};
+
 // runge_kutta_dopri5 (explicit_error_stepper_fsal_base), SURVEY.md A.2
 struct runge_kutta_dopri5 {
   static const int order_value = 5, stepper_order_value = 5, error_order_value = 4;
@@ -322,6 +391,32 @@ struct controlled_cash_karp54 {
   state_type dxdt, xnew, xerr;
   counters* cnt = nullptr;
   controlled_cash_karp54(double atol, double rtol) : chk(atol, rtol) {}
+  template <class Sys> controlled_step_result try_step(Sys& sys, state_type& x, double& t, double& dt) {
+    const std::size_t n = x.size();
+    dxdt.resize(n); xnew.resize(n); xerr.resize(n);
+    sys(x, dxdt, t);
+    st.do_step_impl(sys, x, dxdt, t, xnew, dt, &xerr);
+    double err = chk.error(x, dxdt, xerr, dt);
+    if (err > 1.0) {
+      dt = decrease_step(dt, err, st.error_order_value);
+      if (cnt) cnt->rejected++;
+      return fail;
+    }
+    t += dt;
+    dt = increase_step(dt, err, st.stepper_order_value);
+    x = xnew;
+    if (cnt) cnt->accepted++;
+    return success;
+  }
+};
+
+// controlled_runge_kutta< runge_kutta_fehlberg78 > (explicit_error_stepper_tag)
+struct controlled_fehlberg78 {
+  runge_kutta_fehlberg78 st;
+  error_checker chk;
+  state_type dxdt, xnew, xerr;
+  counters* cnt = nullptr;
+  controlled_fehlberg78(double atol, double rtol) : chk(atol, rtol) {}
   template <class Sys> controlled_step_result try_step(Sys& sys, state_type& x, double& t, double& dt) {
     const std::size_t n = x.size();
     dxdt.resize(n); xnew.resize(n); xerr.resize(n);

@@ -22,9 +22,11 @@
 #define ORACLE_RK4 1
 #define ORACLE_RK54 2
 #define ORACLE_RK5 3
+#define ORACLE_RK78 4
 #define ORACLE_RK5_A 10
 #define ORACLE_RK5_I 11
 #define ORACLE_RK54_A 12
+#define ORACLE_RK78_A 13
 #define ORACLE_ROSENBROCK4 20
 #define ORACLE_METHOD @METHOD@
 
@@ -99,6 +101,14 @@ static stepper_t make_stepper(restated::counters*) { return stepper_t(); }
 typedef restated::runge_kutta_dopri5 stepper_t;
 #define ORACLE_FAMILY_PLAIN 1
 static stepper_t make_stepper(restated::counters*) { return stepper_t(); }
+#elif ORACLE_METHOD == ORACLE_RK78
+typedef restated::runge_kutta_fehlberg78 stepper_t;
+#define ORACLE_FAMILY_PLAIN 1
+static stepper_t make_stepper(restated::counters*) { return stepper_t(); }
+#elif ORACLE_METHOD == ORACLE_RK78_A
+typedef restated::controlled_fehlberg78 stepper_t;
+#define ORACLE_FAMILY_CONTROLLED 1
+static stepper_t make_stepper(restated::counters* c) { stepper_t s(atol, rtol); s.cnt = c; return s; }
 #elif ORACLE_METHOD == ORACLE_RK5_A
 typedef restated::controlled_dopri5 stepper_t;
 #define ORACLE_FAMILY_CONTROLLED 1

@@ -75,7 +75,7 @@ def _cubin(code: str, flags: int = 0) -> int:
     return size.value
 
 
-@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5"])
+@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5", "rk78", "rk5_a", "rk5_i", "rk54_a", "rk78_a"])
 def test_generated_code_compiles_for_sm100a_without_a_device(method):
     g = codegen.generate_sys("lorenz", LORENZ, LORENZ_PARS, False, method)
     assert "__SYS__" not in g.code and "__GLOBALS__" not in g.code
@@ -101,3 +101,27 @@ def test_bad_snippet_reports_nvrtc_log():
 def test_compile_false_returns_code_without_touching_the_gpu():
     code = odeintr_b200.compile_sys("logitest", LOGISTIC, compile=False, method="rk4")
     assert isinstance(code, str) and "logitest" in code and code.system is None
+
+
+def test_implicit_and_large_system_code_compiles_without_a_device():
+    from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
+    assert _cubin(codegen.generate_implicit("stiff", STIFF).code) > 1000
+    assert _cubin(codegen.generate_implicit("rob", ROBERTSON, ROBERTSON_PARS).code) > 1000
+    for method in ("rk4", "euler"):
+        assert _cubin(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code) > 1000
+    assert _cubin(codegen.generate_sys_openmp("b2", BISTABLE_2D, BISTABLE_PARS, False, "rk4", sys_dim=64 * 64).code) > 1000
+    g = codegen.generate_sys_openmp("c", CHAIN, CHAIN_PARS, True, "rk4", sys_dim=1 << 20, globals=CHAIN_GLOBALS)
+    assert "odeintr_k[1]" in g.code and _cubin(g.code) > 1000
+
+
+def test_cell_loop_parser():
+    from systems import BISTABLE_2D, CHAIN
+    loops = codegen.parse_cell_loops(CHAIN)
+    assert loops.bound == "L" and loops.start == "0" and loops.var_type == "int"
+    assert [o.replace(" ", "") for o in loops.offsets] == ["odeintr_c", "L+odeintr_c"]
+    loops = codegen.parse_cell_loops(BISTABLE_2D)
+    assert len(loops.bodies) == 2 and len(loops.offsets) == 1 and "odeintr_k[0] +=" in loops.bodies[1]
+    with pytest.raises(OdeintrError, match="same range"):
+        codegen.parse_cell_loops("for (int i = 0; i < N; ++i) dxdt[i] = 1; for (int i = 1; i < N; ++i) dxdt[i] += 1;")
+    with pytest.raises(OdeintrError, match="not yet provided for large systems"):
+        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i

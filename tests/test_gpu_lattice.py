@@ -112,3 +112,39 @@ def test_sharded_stepping_single_rank_matches_unsharded(case):
     torch.cuda.synchronize()
     got = lat.gather_state().cpu().numpy().reshape(-1)
     assert np.array_equal(bits(got), bits(ref))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_stepping_emulated_ranks_on_one_gpu(world):
+    # several slabs of one lattice inside one process: the halo exchange is done by hand between the slabs'
+    # tensors, the kernels are the multi-GPU ones (window below 0 / above n_total = periodic images)
+    import torch
+
+    from odeintr_b200.distributed import ShardedLattice
+
+    n_cells = 3001
+    rng = np.random.default_rng(41)
+    x0 = rng.integers(0, 2, n_cells).astype(np.float64)
+    ref_sys = odeintr_b200.compile_sys_openmp("ref", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells).system
+    ref = ref_sys.no_record(x0, 1.5, 0.1)  # 15 steps
+    lats = []
+    for r in range(world):
+        sysr = odeintr_b200.compile_sys_openmp("r%d" % r, BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells).system
+        lat = ShardedLattice(sysr, n_cells, rank=r, world=world)
+        lat.set_state_from(lambda f, cells: x0[cells])
+        lats.append(lat)
+    g = lats[0].ghost
+    for step in range(15):
+        for lat in lats:
+            lat.stream.synchronize()
+        for r, lat in enumerate(lats):
+            left, right = lats[(r - 1) % world], lats[(r + 1) % world]
+            lat.x[:, :g] = left.x[:, left.n_local:left.n_local + g]
+            lat.x[:, g + lat.n_local:] = right.x[:, g:2 * g]
+        torch.cuda.synchronize()
+        for lat in lats:
+            lat.step(1, 0.1, t0=0.0 if step == 0 else None, exchange=False)
+    for lat in lats:
+        lat.stream.synchronize()
+    got = torch.cat([lat.local_state() for lat in lats], dim=1).cpu().numpy().reshape(-1)
+    assert np.array_equal(bits(got), bits(ref))

@@ -112,7 +112,7 @@ def test_parameter_sweep_per_instance(lorenz_dyn):
     env["lorenz2_set_params"]()
 
 
-@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5"])
+@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5", "rk78"])
 @pytest.mark.parametrize("flags", [0, _abi.FLAG_KEEP_ZERO_TERMS])
 def test_every_fixed_step_method_bit_exact(method, flags):
     sys_t = "dxdt[0] = x[1] + 0.1 * t; dxdt[1] = -k * x[0] - 0.05 * x[1] * x[1] * x[1] + std::sqrt(t + 1.0) / (2.0 + x[0] * x[0])"

@@ -68,11 +68,11 @@ def test_reference_test_facts_implicit():
     assert r["rows"] == 4
 
 
-@pytest.mark.parametrize("method,order", [("euler", 1), ("rk4", 4), ("rk54", 5), ("rk5", 5)])
+@pytest.mark.parametrize("method,order", [("euler", 1), ("rk4", 4), ("rk54", 5), ("rk5", 5), ("rk78", 8)])
 def test_convergence_order(method, order):
     o = bo.build("dxdt[0] = x[1]; dxdt[1] = -x[0]", method=method)
     errs = []
-    for n in (50, 100):
+    for n in ((4, 8) if order == 8 else (50, 100)):
         r = o.integrate_const([1.0, 0.0], 0, 1.0, 1.0 / n, record=False)
         errs.append(math.hypot(r["x"][0] - math.cos(1.0), r["x"][1] + math.sin(1.0)))
     assert abs(math.log2(errs[0] / errs[1]) - order) < 0.35
@@ -125,7 +125,7 @@ def test_vdp_dense_times_against_scipy():
 
 
 def test_integrate_adaptive_variants_reach_t1():
-    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a"):
+    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a", "rk78_a"):
         o = bo.build(LOGISTIC, method=method)
         r = o.integrate_adaptive([0.01], 0, 7.3, 0.25, record=True)
         assert r["t"][-1] == 7.3

@@ -136,15 +136,29 @@ size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride)
  * The state of a compile_sys_openmp system is `fields` arrays of `cells_total` cells (sys_dim = fields *
  * cells_total; entry (f, c) is x[f * cells_total + c]).  A rank owns the cells [first_cell, first_cell +
  * n_local) of every field.  Its local buffer x_dev (device memory owned by the caller, e.g. a torch tensor, so
- * the caller can exchange halos with NCCL) is laid out [field][ghost + n_local + ghost] with
- * ghost = halo * stages (odeintr_lattice_ghost_width): one halo exchange per step is enough because every
- * Runge-Kutta stage recomputes a window that shrinks by the stencil radius `halo`.
+ * the caller may also exchange halos itself) is laid out [field][pitch] with the owned cells of a field at
+ * [pad, pad + n_local) and the ghost cells directly around them: [pad - ghost, pad) and [pad + n_local,
+ * pad + n_local + ghost), ghost = halo * stages (odeintr_lattice_ghost_width).  pad = ghost rounded up to 16
+ * doubles and pitch = pad + n_local + pad rounded up to 16 (odeintr_lattice_pad_width / _pitch) keep local
+ * cell 0 of every field 128-byte aligned.  One halo exchange per step is enough because every Runge-Kutta stage
+ * recomputes a window that shrinks by the stencil radius `halo`.
  * odeintr_lattice_shard_step() advances the owned cells by one step of size dt from time t; the ghost cells of
  * x_dev must hold the neighbours' current values on entry (periodic ring) and are stale on return. */
 int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long first_cell, long long n_local,
                           int fields, int halo, double* x_dev);
 long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo);
+long long odeintr_lattice_pad_width(odeintr_system_t h, int halo);
+long long odeintr_lattice_pitch(odeintr_system_t h, int halo, long long n_local);
 int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt);
+/* Native multi-GPU loop: the library owns an NCCL communicator over the ranks' GPUs (NVLink / NVSwitch).
+ * Rank 0 creates a 128-byte unique id (odeintr_nccl_unique_id) and hands it to every rank out of band
+ * (torch.distributed broadcast, MPI, a file ...); every rank then calls odeintr_lattice_comm_init (collective).
+ * odeintr_lattice_shard_run() does n_steps of { ring halo exchange (ncclSend / ncclRecv to both neighbours in one
+ * group, on the system's stream), rk4 step at t0 + (first_step + s)*dt } without returning to the host language.
+ * world == 1 needs no id: the slab's ghost cells are filled from its own far ends. */
+int odeintr_nccl_unique_id(void* id_out, size_t cap);
+int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const void* id_bytes, size_t id_size);
+int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long long n_steps, double t0, double dt);
 
 /* ---- observer record ------------------------------------------------------------------------ */
 

@@ -46,7 +46,12 @@ SIGNATURES = {
     "odeintr_lattice_shard": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                         C.c_void_p]),
     "odeintr_lattice_ghost_width": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "odeintr_lattice_pad_width": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "odeintr_lattice_pitch": (C.c_longlong, [C.c_void_p, C.c_int, C.c_longlong]),
     "odeintr_lattice_shard_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "odeintr_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "odeintr_lattice_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "odeintr_lattice_shard_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_double, C.c_double]),
     "odeintr_reset_observer": (C.c_int, [C.c_void_p]),
     "odeintr_release_record": (C.c_int, [C.c_void_p]),
     "odeintr_output_rows": (C.c_size_t, [C.c_void_p]),

@@ -10,6 +10,8 @@
 //
 // There is deliberately no CPU path: without a device every compute entry point fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -35,6 +37,52 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+
+// NCCL is bound at run time (dlopen) so that the library also loads where NCCL is absent; inside a process that
+// already imported torch this resolves to the libnccl torch loaded.  Only the halo exchange of sharded lattices
+// uses it (ncclSend / ncclRecv to the two ring neighbours inside one group).
+struct nccl_api {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+nccl_api g_nccl;
+
+int load_nccl() {
+  if (g_nccl.ok) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(3, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define ODEINTR_NCCL_SYM(field, name)                                                   \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                                   \
+  if (!g_nccl.field) return fail(3, std::string("libnccl is missing ") + name);
+  ODEINTR_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  ODEINTR_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  ODEINTR_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  ODEINTR_NCCL_SYM(GroupStart, "ncclGroupStart")
+  ODEINTR_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  ODEINTR_NCCL_SYM(Send, "ncclSend")
+  ODEINTR_NCCL_SYM(Recv, "ncclRecv")
+  ODEINTR_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef ODEINTR_NCCL_SYM
+  g_nccl.ok = true;
+  return 0;
+}
+#define NCCL_TRY(expr)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r_ = (expr);                                                                   \
+    if (r_ != ncclSuccess) return fail(ODEINTR_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r_)); \
+  } while (0)
 #define CU_TRY(expr)                                                                        \
   do {                                                                                      \
     cudaError_t e_ = (expr);                                                                \
@@ -140,8 +188,10 @@ struct odeintr_system_s {
   int lattice_stages = 4, sm_count = 148;
   dev_buf<double> lat_buf_a, lat_buf_b, lat_buf_acc;
   double *lat_x = nullptr, *lat_a = nullptr, *lat_b = nullptr, *lat_acc = nullptr;
+  ncclComm_t comm = nullptr;
+  int comm_world = 1, comm_rank = 0;
   bool sharded = false, sh_primed = false;
-  long long sh_total = 0, sh_c0 = 0, sh_n = 0, sh_ghost = 0, sh_pitch = 0;
+  long long sh_total = 0, sh_c0 = 0, sh_n = 0, sh_ghost = 0, sh_pitch = 0, sh_pad = 0;
   int sh_fields = 1, sh_halo = 1;
   double* sh_x = nullptr;
   long long max_tries = 20000000;  // per-instance step-attempt budget per call
@@ -751,6 +801,7 @@ int odeintr_destroy(odeintr_system_t h) {
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
     if (h->pipe_stream[s]) cudaStreamDestroy(h->pipe_stream[s]);
   }
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -959,9 +1010,11 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
   const long long ghost = (long long)halo * h->lattice_stages;
   if (n_local + 2 * ghost > cells_total && n_local != cells_total)
     return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
+  if (n_local < ghost) return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
   h->sh_total = cells_total; h->sh_c0 = first_cell; h->sh_n = n_local; h->sh_fields = fields; h->sh_halo = halo;
   h->sh_ghost = ghost;
-  h->sh_pitch = n_local + 2 * ghost;
+  h->sh_pad = odeintr_lattice_pad_width(h, halo);
+  h->sh_pitch = odeintr_lattice_pitch(h, halo, n_local);
   h->sh_x = x_dev;
   const size_t total = (size_t)fields * (size_t)h->sh_pitch;
   CU_TRY(h->lat_buf_a.reserve(total)); CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total));
@@ -971,6 +1024,19 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
 
 long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo) {
   return h ? (long long)halo * h->lattice_stages : 0;
+}
+
+// cells reserved in front of (and behind) the owned cells of every field: the ghost width rounded up to a
+// multiple of 16 doubles so that local cell 0 of every field is 128-byte aligned
+long long odeintr_lattice_pad_width(odeintr_system_t h, int halo) {
+  const long long g = odeintr_lattice_ghost_width(h, halo);
+  return (g + 15) / 16 * 16;
+}
+
+// doubles per field in the caller's state buffer: pad + n_local + pad, rounded up to a multiple of 16
+long long odeintr_lattice_pitch(odeintr_system_t h, int halo, long long n_local) {
+  const long long pad = odeintr_lattice_pad_width(h, halo);
+  return (pad + n_local + pad + 15) / 16 * 16;
 }
 
 int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
@@ -986,12 +1052,86 @@ int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
     CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     h->sh_primed = true;
   }
-  const long long g = h->sh_ghost;
-  h->lat_x = h->sh_x + g; h->lat_a = h->lat_buf_a.p + g; h->lat_b = h->lat_buf_b.p + g; h->lat_acc = h->lat_buf_acc.p + g;
+  const long long g = h->sh_ghost, pad = h->sh_pad;
+  h->lat_x = h->sh_x + pad; h->lat_a = h->lat_buf_a.p + pad; h->lat_b = h->lat_buf_b.p + pad;
+  h->lat_acc = h->lat_buf_acc.p + pad;
   lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1};
   if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
   h->last_launches = 0;
   if ((rc = lattice_step_halo(h, w, t, dt, h->sh_halo))) return rc;
+  return ODEINTR_OK;
+}
+
+int odeintr_nccl_unique_id(void* id_out, size_t cap) {
+  if (!id_out || cap < sizeof(ncclUniqueId)) return fail(ODEINTR_E_INVALID, "unique-id buffer too small (128 bytes)");
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  std::memcpy(id_out, &id, sizeof(id));
+  return ODEINTR_OK;
+}
+
+int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const void* id_bytes, size_t id_size) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ODEINTR_E_INVALID, "invalid rank / world size");
+  h->comm_world = world; h->comm_rank = rank;
+  if (world == 1) return ODEINTR_OK;
+  if (!id_bytes || id_size < sizeof(ncclUniqueId)) return fail(ODEINTR_E_INVALID, "missing NCCL unique id");
+  if ((rc = load_nccl())) return rc;
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, id, rank));
+  return ODEINTR_OK;
+}
+
+namespace {
+// ghost cells <- ring neighbours' boundary cells, every field, one NCCL group (or local copies for one rank)
+int lattice_exchange(odeintr_system_t h) {
+  const long long g = h->sh_ghost, n = h->sh_n, pitch = h->sh_pitch;
+  if (g == 0) return ODEINTR_OK;
+  const int world = h->comm_world, rank = h->comm_rank;
+  const long long pad = h->sh_pad;
+  // per field: owned cells live at [pad, pad + n); ghost cells at [pad - g, pad) and [pad + n, pad + n + g)
+  if (world == 1) {
+    for (int f = 0; f < h->sh_fields; ++f) {
+      double* own = h->sh_x + (long long)f * pitch + pad;
+      CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return ODEINTR_OK;
+  }
+  if (!h->comm) return fail(ODEINTR_E_STATE, "odeintr_lattice_comm_init has not been called");
+  const int left = (rank + world - 1) % world, right = (rank + 1) % world;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int f = 0; f < h->sh_fields; ++f) {
+    double* own = h->sh_x + (long long)f * pitch + pad;
+    // order matters when left == right (two ranks): sends (to right, to left) pair with recvs (from left, from right)
+    NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, h->stream));
+    NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, h->stream));
+    NCCL_TRY(g_nccl.Send(own, (size_t)g, ncclDouble, left, h->comm, h->stream));
+    NCCL_TRY(g_nccl.Recv(own + n, (size_t)g, ncclDouble, right, h->comm, h->stream));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return ODEINTR_OK;
+}
+}  // namespace
+
+int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long long n_steps, double t0, double dt) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
+  if (n_steps < 0) return fail(ODEINTR_E_INVALID, "negative step count");
+  if ((rc = begin_timing(h))) return rc;
+  for (long long s = 0; s < n_steps; ++s) {
+    if ((rc = lattice_exchange(h))) return rc;
+    const long long keep = h->last_launches;
+    if ((rc = odeintr_lattice_shard_step(h, t0 + static_cast<double>(first_step + s) * dt, dt))) return rc;  // integrate_const time rule
+    h->last_launches += keep;
+  }
+  if ((rc = end_timing(h))) return rc;
+  h->last_steps = n_steps;
   return ODEINTR_OK;
 }
 

@@ -45,12 +45,20 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   const long long first = SHARDED ? a.lo : (sys.cell_start() > a.lo ? sys.cell_start() : a.lo);
   const long long last = SHARDED ? a.hi : (sys.cell_bound() < a.hi ? sys.cell_bound() : a.hi);
   if (last <= first) return;
-  long long chunk = (last - first + gridDim.x - 1) / gridDim.x;
+  // chunks start at multiples of 32 cells counted from local cell 0 (which the host keeps 128-byte aligned),
+  // so every warp reads and writes whole 128-byte lines even when the window starts a few ghost cells early
+  long long origin = first;
+  if (SHARDED) {
+    const long long rel = first - a.c0;
+    origin = a.c0 + (rel >= 0 ? rel / 32 : -((-rel + 31) / 32)) * 32;
+  }
+  long long chunk = (last - origin + gridDim.x - 1) / gridDim.x;
   chunk = (chunk + blockDim.x - 1) / blockDim.x * blockDim.x;
-  const long long c_lo = first + (long long)blockIdx.x * chunk;
+  const long long c_lo = origin + (long long)blockIdx.x * chunk;
   long long c_hi = c_lo + chunk;
   if (c_hi > last) c_hi = last;
   for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    if (SHARDED && c < first) continue;
     double k[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) k[f] = 0.0;

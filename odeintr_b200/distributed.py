@@ -29,35 +29,38 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def exchange_halos(x, ghost: int, rank: int, world: int, group=None):
+def exchange_halos(x, ghost: int, rank: int, world: int, group=None, pad: Optional[int] = None, n_local: Optional[int] = None):
     """Periodic ring exchange of the ghost cells of a slab-sharded lattice.
 
-    x: torch tensor [fields, ghost + n_local + ghost] (CPU with gloo, CUDA with NCCL), updated in place:
-    the left ghost cells receive the left neighbour's last `ghost` owned cells, the right ghost cells the right
-    neighbour's first `ghost` owned cells.  With one rank the lattice wraps onto itself."""
+    x: torch tensor [fields, pitch] (CPU with gloo, CUDA with NCCL), updated in place.  The owned cells of a field
+    sit at [pad, pad + n_local), the ghost cells directly around them (pad defaults to ghost, n_local to
+    pitch - 2 * pad).  The left ghost cells receive the left neighbour's last `ghost` owned cells, the right ghost
+    cells the right neighbour's first `ghost` owned cells.  With one rank the lattice wraps onto itself."""
     import torch
     import torch.distributed as dist
 
     if ghost == 0:
         return
-    n_local = x.shape[1] - 2 * ghost
+    pad = ghost if pad is None else pad
+    n_local = x.shape[1] - 2 * pad if n_local is None else n_local
     if n_local < ghost:
         raise OdeintrError("slab too small for the halo width")
+    lo, hi = pad, pad + n_local  # owned cells
     if world == 1:
-        x[:, :ghost] = x[:, n_local:n_local + ghost]
-        x[:, ghost + n_local:] = x[:, ghost:2 * ghost]
+        x[:, lo - ghost:lo] = x[:, hi - ghost:hi]
+        x[:, hi:hi + ghost] = x[:, lo:lo + ghost]
         return
     left, right = (rank - 1) % world, (rank + 1) % world
-    send_l = x[:, ghost:2 * ghost].contiguous()
-    send_r = x[:, n_local:n_local + ghost].contiguous()
+    send_l = x[:, lo:lo + ghost].contiguous()
+    send_r = x[:, hi - ghost:hi].contiguous()
     recv_l = torch.empty_like(send_l)
     recv_r = torch.empty_like(send_r)
     ops = [dist.P2POp(dist.isend, send_r, right, group), dist.P2POp(dist.irecv, recv_l, left, group),
            dist.P2POp(dist.isend, send_l, left, group), dist.P2POp(dist.irecv, recv_r, right, group)]
     for req in dist.batch_isend_irecv(ops):
         req.wait()
-    x[:, :ghost] = recv_l
-    x[:, ghost + n_local:] = recv_r
+    x[:, lo - ghost:lo] = recv_l
+    x[:, hi:hi + ghost] = recv_r
 
 
 class ShardedLattice:
@@ -67,7 +70,10 @@ class ShardedLattice:
     C-ABI on that memory.  Fixed-step rk4, periodic lattice, stencil radius `halo`."""
 
     def __init__(self, system, cells_total: int, fields: int = 1, halo: int = 1, rank: int = 0, world: int = 1,
-                 group=None, device=None):
+                 group=None, device=None, native: bool = True):
+        """native=True: the C-ABI owns an NCCL communicator and runs exchange + step loops itself
+        (odeintr_lattice_shard_run); torch.distributed only ships the 128-byte NCCL unique id.
+        native=False: halos are exchanged by torch.distributed P2P ops between the C-ABI's steps."""
         import torch
 
         if system.gen.family != "lattice":
@@ -79,8 +85,10 @@ class ShardedLattice:
         self.n_local = self.end - self.begin
         self.lib = _abi.load()
         self.ghost = int(self.lib.odeintr_lattice_ghost_width(system._h, halo))
+        self.pad = int(self.lib.odeintr_lattice_pad_width(system._h, halo))
+        self.pitch = int(self.lib.odeintr_lattice_pitch(system._h, halo, self.n_local))
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.x = torch.zeros((fields, self.n_local + 2 * self.ghost), dtype=torch.float64, device=self.device)
+        self.x = torch.zeros((fields, self.pitch), dtype=torch.float64, device=self.device)
         # One dedicated stream orders everything: the halo copies and NCCL send/recv are issued by torch with this
         # stream current, the stage kernels are launched on the same stream by the C-ABI.
         self.stream = torch.cuda.Stream(device=self.device)
@@ -93,6 +101,25 @@ class ShardedLattice:
             raise OdeintrError(_abi.last_error())
         self.t = 0.0
         self.steps = 0
+        self.native = native
+        if native:
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if world > 1:
+                import torch.distributed as dist
+
+                if rank == 0:
+                    buf = (C.c_ubyte * 128)()
+                    if self.lib.odeintr_nccl_unique_id(buf, 128) != 0:
+                        raise OdeintrError(_abi.last_error())
+                    ident = torch.tensor(list(buf), dtype=torch.uint8)
+                # the id travels over whatever backend the group has (NCCL needs a device tensor)
+                backend = dist.get_backend(group)
+                ident = ident.to(self.device) if backend == "nccl" else ident
+                dist.broadcast(ident, src=0, group=group)
+                ident = ident.cpu()
+            raw = (C.c_ubyte * 128)(*ident.tolist())
+            if self.lib.odeintr_lattice_comm_init(system._h, world, rank, raw, 128) != 0:
+                raise OdeintrError(_abi.last_error())
 
     def set_state_from(self, fn):
         """fn(field, global_cell_indices: np.ndarray) -> values; every rank fills only its own slab."""
@@ -102,7 +129,7 @@ class ShardedLattice:
         with torch.cuda.stream(self.stream):
             for f in range(self.fields):
                 vals = np.asarray(fn(f, cells), dtype=np.float64)
-                self.x[f, self.ghost:self.ghost + self.n_local] = torch.from_numpy(vals).to(self.device)
+                self.x[f, self.pad:self.pad + self.n_local] = torch.from_numpy(vals).to(self.device)
 
     def step(self, n_steps: int, dt: float, t0: Optional[float] = None, exchange: bool = True):
         """n_steps rk4 steps.  exchange=False leaves the ghost cells to the caller (tests emulate several ranks
@@ -113,10 +140,17 @@ class ShardedLattice:
         import torch
 
         t0 = getattr(self, "_t0", 0.0)
+        if self.native and exchange:
+            rc = self.lib.odeintr_lattice_shard_run(self.system._h, self.steps, n_steps, t0, dt)
+            if rc != 0:
+                raise OdeintrError(_abi.last_error())
+            self.steps += n_steps
+            self.t = t0 + self.steps * dt
+            return
         with torch.cuda.stream(self.stream):
             for _ in range(n_steps):
                 if exchange:
-                    exchange_halos(self.x, self.ghost, self.rank, self.world, self.group)
+                    exchange_halos(self.x, self.ghost, self.rank, self.world, self.group, self.pad, self.n_local)
                 rc = self.lib.odeintr_lattice_shard_step(self.system._h, self.t, dt)
                 if rc != 0:
                     raise OdeintrError(_abi.last_error())
@@ -124,7 +158,7 @@ class ShardedLattice:
                 self.t = t0 + self.steps * dt  # integrate_const time rule
 
     def local_state(self):
-        return self.x[:, self.ghost:self.ghost + self.n_local]
+        return self.x[:, self.pad:self.pad + self.n_local]
 
     def gather_state(self):
         """Full state [fields, cells_total] on every rank (for checks; not part of the timed path)."""

@@ -532,6 +532,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     const long long margin = w.sharded ? (long long)halo * (n_stages - s) : 0;
     a.lo = w.c0 - margin;
     a.hi = w.c0 + w.n + margin;
+    a.halo = halo;
     return launch(h, w.sharded ? h->k_lattice_sharded : h->k_lattice, h->stream, grid, block, &a);
   };
   if (h->lattice_stages == 4) {

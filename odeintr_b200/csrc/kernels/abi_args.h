@@ -99,6 +99,7 @@ struct odeintr_lattice_args {
   long long pitch;            // doubles between consecutive field slabs (sharded runs)
   long long lo;               // first global cell to compute (may be < 0: periodic image)
   long long hi;               // one past the last global cell to compute
+  long long halo;             // stencil radius of the user's loop (sharded runs)
   double t;
   double a_dt;
   double b_dt;

@@ -10,14 +10,16 @@
 
 namespace odeintr_b200 {
 
+#ifndef ODEINTR_MAX_FAILED_STEPS
 #define ODEINTR_MAX_FAILED_STEPS 500  // Boost failed_step_checker
+#endif
 
 struct step_counters {
   long long accepted, rejected, budget;
   int status;
-  ODEINTR_DEV void reset() { accepted = 0; rejected = 0; status = ODEINTR_STATUS_OK; budget = 0x7fffffffffffffffLL; }
+  ODEINTR_HD void reset() { accepted = 0; rejected = 0; status = ODEINTR_STATUS_OK; budget = 0x7fffffffffffffffLL; }
   // true (and the status is set) once the instance has used up its step-attempt budget
-  ODEINTR_DEV bool exhausted() {
+  ODEINTR_HD bool exhausted() {
     if (accepted + rejected < budget) return false;
     status |= ODEINTR_STATUS_STEP_BUDGET;
     return true;

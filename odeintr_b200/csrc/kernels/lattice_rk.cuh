@@ -21,32 +21,57 @@
 
 namespace odeintr_b200 {
 
-template <bool SHARDED, bool HAS_XT>
-ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
-  typedef odeintr::system_type_t<lattice_view_t<SHARDED> > Sys;
-  constexpr int F = ODEINTR_NFIELDS;
+// cells [c_lo, c_hi) of one block through one view type; entry (f, c) of every array sits at base[f] + c
+template <bool WRAP, bool HAS_XT, int F>
+ODEINTR_DEV void lattice_chunk(const odeintr_lattice_args& a, const lattice_view_t<WRAP>& xs, const long long* base,
+                               const long long c_lo, const long long c_hi, const long long first) {
+  typedef odeintr::system_type_t<lattice_view_t<WRAP> > Sys;
   Sys sys;
   sys.load_params(a.pars, 1, 0);
+  const long long start = sys.cell_start(), bound = sys.cell_bound();
+  for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    if (c < first) continue;
+    double k[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) k[f] = 0.0;
+    long long cg = c;
+    if (WRAP) {  // periodic images of cells across the ring's seam are computed too: they are ghost cells
+      if (cg < 0) cg += a.n_total; else if (cg >= a.n_total) cg -= a.n_total;
+    }
+    if (cg < start || cg >= bound) continue;  // not a cell of the user's loop
+    sys.cell(xs, k, cg, a.t);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const long long idx = base[f] + c;
+      if (HAS_XT) a.xt[idx] = a.x[idx] + a.a_dt * k[f];
+      a.acc_out[idx] = a.acc_in[idx] + a.b_dt * k[f];
+    }
+  }
+}
+
+template <bool SHARDED, bool HAS_XT>
+ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
+  constexpr int F = ODEINTR_NFIELDS;
   long long off[F];
-  sys.field_offsets(off);
-
-  lattice_view_t<SHARDED> xs;
-  xs.p = a.xs; xs.n_total = a.n_total; xs.n_local = a.n; xs.c0 = a.c0; xs.ghost = a.ghost; xs.pitch = a.pitch;
-
+  {
+    odeintr::system_type_t<lattice_view_t<false> > sys;
+    sys.field_offsets(off);
+  }
   // local position of entry (field f, cell c) is base[f] + c: fields are `pitch` apart, cell c sits at c - c0
   long long base[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) base[f] = SHARDED ? (off[f] / a.n_total) * a.pitch - a.c0 : off[f];
 
-  // cells this launch computes: the user loop's range (unsharded) or this rank's window [lo, hi) of global
-  // cells, which may reach below 0 / above n_total: those are periodic images and are computed too (they are
-  // the ghost cells the next stage reads); split into one contiguous chunk per block (a multiple of the
-  // block size, so rows stay aligned)
-  const long long first = SHARDED ? a.lo : (sys.cell_start() > a.lo ? sys.cell_start() : a.lo);
-  const long long last = SHARDED ? a.hi : (sys.cell_bound() < a.hi ? sys.cell_bound() : a.hi);
+  // The launch computes the window [lo, hi) of global cells (on a sharded run it may reach below 0 / above
+  // n_total), split into one contiguous chunk per block.  Chunks start at multiples of 32 cells counted from
+  // local cell 0 (which the host keeps 128-byte aligned), so every warp reads and writes whole lines.
+  long long first = a.lo, last = a.hi;
+  if (!SHARDED) {  // one GPU: exactly the user loop's range
+    odeintr::system_type_t<lattice_view_t<false> > sys;
+    if (sys.cell_start() > first) first = sys.cell_start();
+    if (sys.cell_bound() < last) last = sys.cell_bound();
+  }
   if (last <= first) return;
-  // chunks start at multiples of 32 cells counted from local cell 0 (which the host keeps 128-byte aligned),
-  // so every warp reads and writes whole 128-byte lines even when the window starts a few ghost cells early
   long long origin = first;
   if (SHARDED) {
     const long long rel = first - a.c0;
@@ -57,23 +82,27 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   const long long c_lo = origin + (long long)blockIdx.x * chunk;
   long long c_hi = c_lo + chunk;
   if (c_hi > last) c_hi = last;
-  for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
-    if (SHARDED && c < first) continue;
-    double k[F];
-#pragma unroll
-    for (int f = 0; f < F; ++f) k[f] = 0.0;
-    long long cg = c;
-    if (SHARDED) {
-      if (cg < 0) cg += a.n_total; else if (cg >= a.n_total) cg -= a.n_total;
-      if (cg < sys.cell_start() || cg >= sys.cell_bound()) continue;  // not a cell of the user's loop
+  if (c_lo >= c_hi) return;
+
+  if (SHARDED) {
+    // A chunk whose cells and stencil neighbours (radius a.halo) stay inside [0, n_total) never wraps: the
+    // snippet's global indices then differ from local positions by the constant c0, so the plain-pointer view on
+    // a shifted base serves it at full speed.  Only the (at most two) chunks at the ring's seam take the
+    // wrapping view.  (One field only: with several fields the shift differs per field.)
+    const bool interior = F == 1 && c_lo - a.halo >= 0 && c_hi + a.halo <= a.n_total && c_lo >= first;
+    if (interior) {
+      lattice_view_t<false> v;
+      v.p = a.xs - a.c0; v.n_total = a.n_total; v.n_local = a.n; v.c0 = a.c0; v.ghost = a.ghost; v.pitch = a.pitch;
+      lattice_chunk<false, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+      return;
     }
-    sys.cell(xs, k, cg, a.t);
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
-      const long long idx = base[f] + c;
-      if (HAS_XT) a.xt[idx] = a.x[idx] + a.a_dt * k[f];
-      a.acc_out[idx] = a.acc_in[idx] + a.b_dt * k[f];
-    }
+    lattice_view_t<true> v;
+    v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = a.c0; v.ghost = a.ghost; v.pitch = a.pitch;
+    lattice_chunk<true, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+  } else {
+    lattice_view_t<false> v;
+    v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = 0; v.ghost = 0; v.pitch = 0;
+    lattice_chunk<false, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
   }
 }
 

@@ -6,6 +6,7 @@
 // so nothing here includes one.
 #pragma once
 #include "odeintr_b200/abi_args.h"
+#include "odeintr_b200/time_compare.cuh"
 
 #ifndef ODEINTR_BLOCK
 #define ODEINTR_BLOCK 128
@@ -53,15 +54,6 @@ constexpr int isqrt(unsigned long n) {
   unsigned long r = 0;
   while ((r + 1) * (r + 1) <= n) ++r;
   return static_cast<int>(r);
-}
-
-// util/detail/less_with_sign.hpp (Boost), SURVEY.md Appendix A: absolute epsilon.
-#define ODEINTR_EPS 2.220446049250313e-16
-ODEINTR_DEV bool less_with_sign(double t1, double t2, double dt) {
-  return dt > 0 ? (t2 - t1 > ODEINTR_EPS) : (t1 - t2 > ODEINTR_EPS);
-}
-ODEINTR_DEV bool less_eq_with_sign(double t1, double t2, double dt) {
-  return dt > 0 ? (t1 - t2 <= ODEINTR_EPS) : (t2 - t1 <= ODEINTR_EPS);
 }
 
 // streaming (evict-first) stores for observer samples: they are written once and never re-read

@@ -131,7 +131,7 @@ def test_sharded_stepping_emulated_ranks_on_one_gpu(world):
     lats = []
     for r in range(world):
         sysr = odeintr_b200.compile_sys_openmp("r%d" % r, BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells).system
-        lat = ShardedLattice(sysr, n_cells, rank=r, world=world)
+        lat = ShardedLattice(sysr, n_cells, rank=r, world=world, native=False)  # no process group: halos by hand
         lat.set_state_from(lambda f, cells: x0[cells])
         lats.append(lat)
     g, pad = lats[0].ghost, lats[0].pad

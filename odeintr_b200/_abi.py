@@ -82,6 +82,7 @@ FLAG_FMAD = 1
 FLAG_KEEP_ZERO_TERMS = 2
 FLAG_DENSE_OUTPUT = 4
 FLAG_LATTICE_EULER = 8
+FLAG_LATTICE_ADAPTIVE = 16
 
 _lib = None
 

@@ -488,7 +488,7 @@ def parse_cell_loops(sys_src: str) -> CellLoops:
     return CellLoops(vtype, start, bound, bodies, names, offsets)
 
 
-_LATTICE_STEPPERS = {"rk4": "4", "euler": "1"}
+_LATTICE_STEPPERS = {"rk4": "4", "euler": "1", "rk5_a": "7", "rk5_i": "7"}
 
 
 def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: str = "rk5_i", sys_dim: int = -1,
@@ -501,7 +501,7 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     base = re.sub(r"_i$|_a$", "", method)
     if method not in _LATTICE_STEPPERS:
         raise OdeintrError("method '%s' is not yet provided for large systems by odeintr_b200 "
-                           "(fixed-step rk4 and euler are)" % method)
+                           "(rk4, euler, rk5_a and the default rk5_i are)" % method)
     sys = _join(sys)
     if sys_dim is None or math.ceil(sys_dim) < 1:
         sys_dim = get_sys_dim(sys)
@@ -528,5 +528,7 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     code = code.replace("__NFIELDS__", str(len(loops.offsets)))
     code = code.replace("__CELL_START__", loops.start).replace("__CELL_BOUND__", loops.bound)
     code = code.replace("__FIELD_OFFSETS__", offs)
-    spec = StepperSpec(method, base, "plain", boost_type, "stepper_type()", "lattice_rk.cuh", "lattice_" + base)
+    mode = "dense" if method.endswith("_i") else ("controlled" if method.endswith("_a") else "plain")
+    spec = StepperSpec(method, base, mode, boost_type, make_stepper_constr(method, atol, rtol), "lattice_rk.cuh",
+                       "lattice_" + base)
     return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol))

@@ -26,6 +26,7 @@
 #include "../../include/odeintr_b200.h"
 #include "builtin_kernels.h"
 #include "kernels/abi_args.h"
+#include "kernels/integrate_loops.cuh"
 #include "embedded_headers.inc"  // generated: k_header_names[], k_header_srcs[], k_num_headers
 
 namespace {
@@ -172,7 +173,11 @@ struct odeintr_system_s {
   double atol = 1e-6, rtol = 1e-6;
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr;
+  cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
+               k_combo = nullptr;
+  int lattice_method = 0;  // 0 = fixed step (rk4 / euler), 1 = rk5_a, 2 = rk5_i
+  dev_buf<double> lat_work;
+  dev_buf<unsigned long long> lat_err;
   int block_plain = 128, block_adaptive = 128;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -610,6 +615,110 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   return ODEINTR_OK;
 }
 
+#include "lattice_adaptive.h"
+
+// Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
+int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
+                         size_t n_times, bool record) {
+  if (!h->k_combo) return fail(ODEINTR_E_STATE, "system was not compiled for adaptive stepping of a large system");
+  if (h->m != 1) return fail(ODEINTR_E_STATE, "Invalid initial state");
+  if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  const size_t N = (size_t)h->N;
+  CU_TRY(h->lat_work.reserve(13 * N));
+  CU_TRY(h->lat_err.reserve(1));
+  double* w = h->lat_work.p;
+  // state-like vectors start as copies of x, derivative-like ones as zeros: entries no user loop writes keep
+  // their value / a zero derivative through every stage
+  double* state_like[5];
+  for (int j = 0; j < 5; ++j) {
+    state_like[j] = w + (size_t)j * N;
+    CU_TRY(cudaMemcpyAsync(state_like[j], h->x.p, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CU_TRY(cudaMemsetAsync(w + 5 * N, 0, 8 * N * sizeof(double), h->stream));
+  double* deriv_like[8];
+  for (int j = 0; j < 8; ++j) deriv_like[j] = w + (size_t)(5 + j) * N;
+
+  lattice_dopri5 core;
+  core.h = h;
+  core.xtA = state_like[0]; core.xtB = state_like[1];
+  core.k2 = deriv_like[0]; core.k3 = deriv_like[1]; core.k4 = deriv_like[2]; core.k5 = deriv_like[3];
+  core.k6 = deriv_like[4];
+  std::vector<double> rec_t;
+  size_t cap_rows = 0;
+  if (record) {
+    size_t guess = mode == ODEINTR_MODE_TIMES ? n_times : 16;
+    if (mode == ODEINTR_MODE_CONST) guess = (size_t)const_step_count(t0, t1, dt) + 2;
+    int rc = reserve_out(h, guess);
+    if (rc) return rc;
+    cap_rows = h->out.cap / N;
+  }
+  lattice_observer obs{h, &rec_t, cap_rows};
+  odeintr_b200::null_observer nobs;
+  lat_sys sys;
+  lat_state x(h, h->x.p);
+  int rc;
+  if ((rc = begin_timing(h))) return rc;
+  bool ok = true;  // failures are carried by the counters' status word
+  lat_counters cnt;
+  if (h->lattice_method == 2) {
+    lattice_dopri5_dense st;
+    st.ctl.core = core;
+    st.ctl.cnt.budget = h->max_tries;
+    st.x_cur = lat_state(h, state_like[2]); st.x_old = lat_state(h, state_like[3]);
+    st.d_cur = deriv_like[5]; st.d_old = deriv_like[6];
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_dense(st, sys, x, times, (long long)n_times, dt, obs)
+                  : odeintr_b200::integrate_times_dense(st, sys, x, times, (long long)n_times, dt, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_dense(st, sys, x, t0, t1, dt, obs)
+                  : odeintr_b200::integrate_const_dense(st, sys, x, t0, t1, dt, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, obs)
+                  : odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, nobs);
+    cnt = st.ctl.cnt;
+    if (st.ctl.core.rc) return st.ctl.core.rc;
+  } else {
+    lattice_dopri5_controlled st;
+    st.core = core;
+    st.cnt.budget = h->max_tries;
+    st.dxdt = deriv_like[5]; st.dnew = deriv_like[6]; st.xnew = state_like[2];
+    double dtc = dt, tc = t0;
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, obs)
+                  : odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, obs)
+                  : odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, obs)
+                  : odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, nobs);
+    cnt = st.cnt;
+    if (st.core.rc) return st.core.rc;
+  }
+  if (!ok && cnt.status == ODEINTR_STATUS_OK) cnt.status = ODEINTR_STATUS_NONFINITE;
+  if ((rc = end_timing(h))) return rc;
+  if (obs.rc) return fail(ODEINTR_E_CUDA, "cannot grow the observer record");
+  CU_TRY(h->accepted.reserve(1)); CU_TRY(h->rejected.reserve(1)); CU_TRY(h->status.reserve(1));
+  CU_TRY(cudaMemcpyAsync(h->accepted.p, &cnt.accepted, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->rejected.p, &cnt.rejected, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->status.p, &cnt.status, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->last_steps = cnt.accepted;
+  if (record) {
+    h->rec_t = rec_t;
+    h->rows = rec_t.size();
+    h->out_m = 1;
+    h->ragged = false;
+  }
+  if (cnt.status & ODEINTR_STATUS_STEP_OVERFLOW)
+    return fail(ODEINTR_E_STEP, "Max number of iterations exceeded (500). A new step size was not found.");
+  if (cnt.status & ODEINTR_STATUS_STEP_BUDGET)
+    return fail(ODEINTR_E_STEP, "step budget exceeded: more than " + std::to_string(h->max_tries) +
+                                    " step attempts in one call (see odeintr_set_max_tries)");
+  if (cnt.status & ODEINTR_STATUS_NONFINITE) return fail(ODEINTR_E_STEP, "integration stopped making progress (non-finite time)");
+  return ODEINTR_OK;
+}
+
 // Time column integrate_const records with a dense-output stepper: instance independent.
 std::vector<double> dense_const_times(double t0, double t1, double dt) {
   std::vector<double> rec;
@@ -745,6 +854,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
   h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
   h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : 4;
+  h->lattice_method = (flags & ODEINTR_FLAG_LATTICE_ADAPTIVE) ? ((flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 2 : 1) : 0;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }
@@ -769,6 +879,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_lattice, h->lib, "odeintr_lattice_stage") != cudaSuccess) h->k_lattice = nullptr;
   if (cudaLibraryGetKernel(&h->k_lattice_sharded, h->lib, "odeintr_lattice_stage_sharded") != cudaSuccess)
     h->k_lattice_sharded = nullptr;
+  if (cudaLibraryGetKernel(&h->k_combo, h->lib, "odeintr_lattice_combo") != cudaSuccess) h->k_combo = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);
@@ -797,6 +908,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release();
   h->work_counter.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
+  h->lat_work.release(); h->lat_err.release();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
@@ -937,6 +1049,7 @@ int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt,
   if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (obs_stride < 1) return fail(ODEINTR_E_INVALID, "obs_stride must be >= 1");
+  if (h->k_lattice && h->lattice_method) return run_lattice_adaptive(h, ODEINTR_MODE_CONST, t0, t1, dt, nullptr, 0, record != 0);
   if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_const(sc, t0, t1, dt, obs_stride, record != 0);
@@ -954,6 +1067,8 @@ int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_ti
   if (rc) return rc;
   if (!times || n_times == 0) return fail(ODEINTR_E_INVALID, "Invalid time specification");
   if (!(dt != 0.0) || !std::isfinite(dt)) return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (h->k_lattice && h->lattice_method)
+    return run_lattice_adaptive(h, ODEINTR_MODE_TIMES, times[0], times[n_times - 1], dt, times, n_times, true);
   if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_times(sc, times, n_times, dt);
@@ -968,6 +1083,7 @@ int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double 
   if (rc) return rc;
   if (!(dt != 0.0) || !std::isfinite(dt) || !std::isfinite(t0) || !std::isfinite(t1))
     return fail(ODEINTR_E_INVALID, "Invalid time specification");
+  if (h->k_lattice && h->lattice_method) return run_lattice_adaptive(h, ODEINTR_MODE_ADAPTIVE, t0, t1, dt, nullptr, 0, record != 0);
   if (h->k_plain || h->k_lattice) {
     plain_schedule sc;
     schedule_adaptive(sc, t0, t1, dt, record != 0);

@@ -104,3 +104,24 @@ struct odeintr_lattice_args {
   double a_dt;
   double b_dt;
 };
+
+// Generic fused stage for large systems under adaptive steppers (lattice_combo.cuh), one GPU:
+//   k = f(xs)[cell] (if xs);  v = base + sum c[j]*in[j] (+ ck*k);  out = v;  k_out = k;
+//   err_max = max |v| / (eps_abs + eps_rel*(|err_x| + adt*|err_d|))  (if err_max)
+struct odeintr_lattice_combo_args {
+  const double* xs;
+  const double* base;
+  const double* in[7];
+  double c[7];
+  int nin;
+  double ck;
+  double* out;
+  double* k_out;
+  const double* err_x;
+  const double* err_d;
+  double eps_abs, eps_rel, adt;
+  unsigned long long* err_max;
+  const double* pars;
+  long long n_total;
+  double t;
+};

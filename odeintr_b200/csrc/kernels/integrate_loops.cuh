@@ -19,6 +19,7 @@ struct null_observer {
 };
 
 // ---- integrate_adaptive --------------------------------------------------------------------------------
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_adaptive_controlled(St& st, Sys& sys, State& x, double& t, const double t1, double& dt,
                                                Obs& obs) {
@@ -36,6 +37,7 @@ ODEINTR_HD bool integrate_adaptive_controlled(St& st, Sys& sys, State& x, double
   return true;
 }
 
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_adaptive_dense(St& st, Sys& sys, State& x, const double t0, const double t1,
                                           const double dt, Obs& obs) {
@@ -53,6 +55,7 @@ ODEINTR_HD bool integrate_adaptive_dense(St& st, Sys& sys, State& x, const doubl
 }
 
 // ---- integrate_const -----------------------------------------------------------------------------------
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_const_controlled(St& st, Sys& sys, State& x, const double t0, const double t1, double dt,
                                             Obs& obs) {
@@ -72,6 +75,7 @@ ODEINTR_HD bool integrate_const_controlled(St& st, Sys& sys, State& x, const dou
   return true;
 }
 
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_const_dense(St& st, Sys& sys, State& x, const double t0, const double t1, const double dt,
                                        Obs& obs) {
@@ -113,6 +117,7 @@ ODEINTR_HD bool integrate_const_dense(St& st, Sys& sys, State& x, const double t
 }
 
 // ---- integrate_times -----------------------------------------------------------------------------------
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_times_controlled(St& st, Sys& sys, State& x, const double* times, const long long n,
                                             double dt, Obs& obs) {
@@ -139,6 +144,7 @@ ODEINTR_HD bool integrate_times_controlled(St& st, Sys& sys, State& x, const dou
   return true;
 }
 
+#pragma nv_exec_check_disable
 template <class St, class Sys, class State, class Obs>
 ODEINTR_HD bool integrate_times_dense(St& st, Sys& sys, State& x, const double* times, const long long n,
                                        const double dt, Obs& obs) {

@@ -1,0 +1,253 @@
+// odeintr_b200/csrc/lattice_adaptive.h — included by abi.cu (inside its anonymous namespace).
+//
+// Adaptive Dormand-Prince 5(4) for large systems (compile_sys_openmp with the reference's default method
+// rk5_i, or rk5_a): the state and every stage derivative are device-resident vectors of N doubles; each
+// Runge-Kutta stage is one launch of odeintr_lattice_combo (RHS + Boost-ordered vector algebra, the last one
+// also reducing default_error_checker's max norm).  The stepper classes below expose the interfaces the shared
+// integrate loops expect (kernels/integrate_loops.cuh), so the control flow is the same code that every GPU
+// thread runs for ensembles; the controller arithmetic (pow) runs on the host.
+// Reference semantics: controlled_runge_kutta / dense_output_runge_kutta over runge_kutta_dopri5 with
+// openmp_range_algebra (R/utils.R:34-38,52), SURVEY.md Appendix A.2-A.5.
+#pragma once
+
+struct lat_sys {};  // the system lives in the NVRTC module; the loops only pass it through
+
+// handle of one device-resident vector; assignment copies the values (like std::vector assignment does)
+struct lat_state {
+  odeintr_system_t h = nullptr;
+  double* p = nullptr;
+  lat_state() {}
+  lat_state(odeintr_system_t h_, double* p_) : h(h_), p(p_) {}
+  lat_state(const lat_state&) = default;
+  lat_state& operator=(const lat_state& o) {
+    if (p != o.p && p && o.p)
+      cudaMemcpyAsync(p, o.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    return *this;
+  }
+};
+
+struct lat_counters {
+  long long accepted = 0, rejected = 0, budget = 0x7fffffffffffffffLL;
+  int status = ODEINTR_STATUS_OK;
+  bool exhausted() {
+    if (accepted + rejected < budget) return false;
+    status |= ODEINTR_STATUS_STEP_BUDGET;
+    return true;
+  }
+};
+
+struct lattice_dopri5 {
+  odeintr_system_t h;
+  double *k2, *k3, *k4, *k5, *k6, *xtA, *xtB;
+  int rc = 0;  // first launch error, reported by the caller
+
+  int combo(const double* xs, const double* base, int nin, const double* const* in, const double* c, double ck,
+            double* out, double* k_out, double t, const double* err_x = nullptr, const double* err_d = nullptr,
+            double adt = 0.0) {
+    odeintr_lattice_combo_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.xs = xs; a.base = base; a.nin = nin;
+    for (int j = 0; j < nin; ++j) { a.in[j] = in[j]; a.c[j] = c[j]; }
+    a.ck = ck; a.out = out; a.k_out = k_out;
+    a.err_x = err_x; a.err_d = err_d; a.eps_abs = h->atol; a.eps_rel = h->rtol; a.adt = adt;
+    a.err_max = err_x ? h->lat_err.p : nullptr;
+    a.pars = h->P ? h->pars.p : nullptr;
+    a.n_total = h->N;
+    a.t = t;
+    const int r = launch(h, h->k_combo, h->stream, (unsigned)h->sm_count * 8u, 256u, &a);
+    if (r && !rc) rc = r;
+    return r;
+  }
+
+  // runge_kutta_dopri5::do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt, xerr) + default_error_checker::error
+  // returns the max-norm error (A.2); out / dxdt_out must not alias in / dxdt_in
+  double step_with_error(const double* in, const double* d_in, double t, double* out, double* d_out, double dt) {
+    const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+    const double b21 = 1.0 / 5.0;
+    const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+    const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+    const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+    const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
+                 b65 = -5103.0 / 18656.0;
+    const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+    const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
+                 dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+    {  // x_tmp = in + dt*b21*dxdt
+      const double* v[] = {d_in};
+      const double c[] = {dt * b21};
+      combo(nullptr, in, 1, v, c, 0.0, xtA, nullptr, t);
+    }
+    {  // k2 = f(x_tmp, t + dt*a2);  x_tmp = in + dt*b31*dxdt + dt*b32*k2
+      const double* v[] = {d_in};
+      const double c[] = {dt * b31};
+      combo(xtA, in, 1, v, c, dt * b32, xtB, k2, t + dt * a2);
+    }
+    {  // k3
+      const double* v[] = {d_in, k2};
+      const double c[] = {dt * b41, dt * b42};
+      combo(xtB, in, 2, v, c, dt * b43, xtA, k3, t + dt * a3);
+    }
+    {  // k4
+      const double* v[] = {d_in, k2, k3};
+      const double c[] = {dt * b51, dt * b52, dt * b53};
+      combo(xtA, in, 3, v, c, dt * b54, xtB, k4, t + dt * a4);
+    }
+    {  // k5
+      const double* v[] = {d_in, k2, k3, k4};
+      const double c[] = {dt * b61, dt * b62, dt * b63, dt * b64};
+      combo(xtB, in, 4, v, c, dt * b65, xtA, k5, t + dt * a5);
+    }
+    {  // k6 = f(x_tmp, t + dt);  out = in + dt*c1*dxdt + dt*c3*k3 + dt*c4*k4 + dt*c5*k5 + dt*c6*k6
+      const double* v[] = {d_in, k3, k4, k5};
+      const double c[] = {dt * c1, dt * c3, dt * c4, dt * c5};
+      combo(xtA, in, 4, v, c, dt * c6, out, k6, t + dt);
+    }
+    cudaMemsetAsync(h->lat_err.p, 0, sizeof(unsigned long long), h->stream);
+    {  // dxdt_out = f(out, t + dt);  xerr = dt*dc1*dxdt + dt*dc3*k3 + ... + dt*dc6*k6 + dt*dc7*dxdt_out, and its norm
+      const double* v[] = {d_in, k3, k4, k5, k6};
+      const double c[] = {dt * dc1, dt * dc3, dt * dc4, dt * dc5, dt * dc6};
+      combo(out, nullptr, 5, v, c, dt * dc7, nullptr, d_out, t + dt, in, d_in, 1.0 * std::fabs(dt));
+    }
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(&bits, h->lat_err.p, sizeof(bits), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    double err;
+    std::memcpy(&err, &bits, sizeof(err));
+    return err;
+  }
+
+  // dense output (A.2) between (t_old, x_old, d_old) and (t_new, ., d_new) with the k3..k6 of the last step
+  void calc_state(double t, double* x, const double* x_old, const double* d_old, double t_old, const double* d_new,
+                  double t_new) {
+    const double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+    const double dt = (t_new - t_old);
+    const double theta = (t - t_old) / dt;
+    const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
+    const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
+    const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
+    const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
+    const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
+    const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
+    const double theta_m_1 = theta - 1.0;
+    const double theta_sq = theta * theta;
+    const double A = theta_sq * (3.0 - 2.0 * theta);
+    const double B = theta_sq * theta_m_1;
+    const double C = theta_sq * theta_m_1 * theta_m_1;
+    const double D = theta * theta_m_1 * theta_m_1;
+    const double b1_theta = A * b1 - C * X1 + D;
+    const double b3_theta = A * b3 + C * X3;
+    const double b4_theta = A * b4 - C * X4;
+    const double b5_theta = A * b5 + C * X5;
+    const double b6_theta = A * b6 - C * X6;
+    const double b7_theta = B + C * X7;
+    const double* v[] = {d_old, k3, k4, k5, k6, d_new};
+    const double c[] = {dt * b1_theta, dt * b3_theta, dt * b4_theta, dt * b5_theta, dt * b6_theta, dt * b7_theta};
+    combo(nullptr, x_old, 6, v, c, 0.0, x, nullptr, t);
+  }
+
+  // dxdt = f(x, t)
+  void rhs(const double* x, double* dxdt, double t) { combo(x, nullptr, 0, nullptr, nullptr, 1.0, nullptr, dxdt, t); }
+};
+
+// default_step_adjuster on the host: glibc pow, i.e. exactly what the CPU reference evaluates
+inline double lat_decrease_step(double dt, double error, int error_order) {
+  dt *= std::max(9.0 / 10.0 * std::pow(error, -1.0 / (error_order - 1)), 1.0 / 5.0);
+  return dt;
+}
+inline double lat_increase_step(double dt, double error, int stepper_order) {
+  if (error < 0.5) {
+    error = std::max(std::pow(5.0, -static_cast<double>(stepper_order)), error);
+    dt *= 9.0 / 10.0 * std::pow(error, -1.0 / stepper_order);
+  }
+  return dt;
+}
+
+// controlled_runge_kutta< runge_kutta_dopri5 > over device vectors (method "rk5_a")
+struct lattice_dopri5_controlled {
+  static constexpr bool is_dense = false;
+  lattice_dopri5 core;
+  double *dxdt, *xnew, *dnew;
+  bool first = true;
+  lat_counters cnt;
+  lat_counters& counters() { return cnt; }
+  void restart() { first = true; }
+
+  bool try_step_full(const double* in, const double* d_in, double& t, double* out, double* d_out, double& dt) {
+    const double err = core.step_with_error(in, d_in, t, out, d_out, dt);
+    if (err > 1.0) {
+      dt = lat_decrease_step(dt, err, 4);
+      cnt.rejected++;
+      return false;
+    }
+    t += dt;
+    dt = lat_increase_step(dt, err, 5);
+    cnt.accepted++;
+    return true;
+  }
+  bool try_step(lat_sys&, lat_state& x, double& t, double& dt) {
+    if (first) { core.rhs(x.p, dxdt, t); first = false; }
+    const bool ok = try_step_full(x.p, dxdt, t, xnew, dnew, dt);
+    if (ok) {
+      const size_t bytes = (size_t)core.h->N * sizeof(double);
+      cudaMemcpyAsync(x.p, xnew, bytes, cudaMemcpyDeviceToDevice, core.h->stream);
+      std::swap(dxdt, dnew);
+    }
+    return ok;
+  }
+};
+
+// dense_output_runge_kutta< controlled_runge_kutta< runge_kutta_dopri5 > > over device vectors (method "rk5_i")
+struct lattice_dopri5_dense {
+  static constexpr bool is_dense = true;
+  lattice_dopri5_controlled ctl;
+  lat_state x_cur, x_old;
+  double *d_cur, *d_old;
+  double t = 0, t_old = 0, dt = 0;
+  bool deriv_ready = false;
+  lat_counters& counters() { return ctl.cnt; }
+  void initialize(const lat_state& x0, double t0, double dt0) {
+    x_cur = x0;  // value copy (no-op when x0 is the current state itself)
+    t = t0; dt = dt0; deriv_ready = false;
+  }
+  const lat_state& current_state() const { return x_cur; }
+  bool do_step(lat_sys&) {
+    if (!deriv_ready) { ctl.core.rhs(x_cur.p, d_cur, t); deriv_ready = true; }
+    t_old = t;
+    int fails = 0;
+    if (ctl.cnt.exhausted()) return false;
+    while (!ctl.try_step_full(x_cur.p, d_cur, t, x_old.p, d_old, dt)) {
+      if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (ctl.core.rc) return false;
+    }
+    std::swap(x_cur.p, x_old.p);  // toggle current / old like Boost's m_current_state_x1 flag
+    std::swap(d_cur, d_old);
+    return ctl.core.rc == 0;
+  }
+  void calc_state(double tq, lat_state& x) {
+    ctl.core.calc_state(tq, x.p, x_old.p, d_old, t_old, d_cur, t);
+  }
+};
+
+// observer of a large system: one record row = the whole state
+struct lattice_observer {
+  odeintr_system_t h;
+  std::vector<double>* rec_t;
+  size_t cap_rows;
+  int rc = 0;
+  void operator()(const lat_state& x, double t) {
+    const size_t N = (size_t)h->N, row = rec_t->size();
+    if (row >= cap_rows) {  // grow the record, keeping what is there
+      const size_t new_cap = std::max<size_t>(16, cap_rows * 2);
+      double* bigger = nullptr;
+      if (cudaMalloc(&bigger, new_cap * N * sizeof(double)) != cudaSuccess) { rc = ODEINTR_E_CUDA; return; }
+      if (h->out.p && row)
+        cudaMemcpyAsync(bigger, h->out.p, row * N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (h->out.p) cudaFree(h->out.p);
+      h->out.p = bigger; h->out.cap = new_cap * N;
+      cap_rows = new_cap;
+    }
+    cudaMemcpyAsync(h->out.p + row * N, x.p, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    rec_t->push_back(t);
+  }
+};

@@ -123,5 +123,7 @@ def test_cell_loop_parser():
     assert len(loops.bodies) == 2 and len(loops.offsets) == 1 and "odeintr_k[0] +=" in loops.bodies[1]
     with pytest.raises(OdeintrError, match="same range"):
         codegen.parse_cell_loops("for (int i = 0; i < N; ++i) dxdt[i] = 1; for (int i = 1; i < N; ++i) dxdt[i] += 1;")
+    g = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i
+    assert g.stepper.method == "rk5_i" and g.stepper.mode == "dense" and _cubin(g.code) > 1000
     with pytest.raises(OdeintrError, match="not yet provided for large systems"):
-        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i
+        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method="rk54_a")

@@ -149,3 +149,38 @@ def test_sharded_stepping_emulated_ranks_on_one_gpu(world):
         lat.stream.synchronize()
     got = torch.cat([lat.local_state() for lat in lats], dim=1).cpu().numpy().reshape(-1)
     assert np.array_equal(bits(got), bits(ref))
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a"])
+def test_large_system_adaptive_dopri5(method):
+    # compile_sys_openmp's default method is rk5_i (R/odeintr.R:421): dopri5 with the error norm taken over the
+    # whole lattice.  Stage algebra runs on the GPU in Boost's order without FMA and the controller's pow() on the
+    # host (glibc), so the run follows the oracle step for step; asserted at the stated 10 x rtol tolerance.
+    n = 2053
+    kw = {} if method == "rk5_i" else {"method": method}
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("bis", BISTABLE_1D, BISTABLE_PARS, True, sys_dim=n, env=env, **kw)
+    assert code.system.gen.stepper.method == method
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=n)
+    rng = np.random.default_rng(51)
+    x0 = rng.uniform(0, 1, n)
+    df = env["bis"](x0, 6.0, 0.5)
+    ref = ora.integrate_const(x0, 0, 6.0, 0.5)
+    assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    err = np.max(np.abs(cols(df) - ref["rec"]) / (1 + np.abs(ref["rec"])))
+    assert err <= 10 * 1e-6, err
+    st = code.system.stats()
+    assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
+    # bistable_at(inic, at) of the reference's example, then the other generated functions
+    at = np.array([0.0, 1.0, 10.0 ** 0.5, 10.0])
+    df = env["bis_at"](x0, at)
+    ref = ora.integrate_times(x0, at, 1.0)
+    assert np.max(np.abs(cols(df) - ref["rec"]) / (1 + np.abs(ref["rec"]))) <= 1e-5
+    fin = env["bis_no_record"](x0, 4.2, 0.3)
+    ref = ora.integrate_adaptive(x0, 0, 4.2, 0.3)
+    assert np.max(np.abs(fin - ref["x"])) <= 1e-5
+    df = env["bis_adap"](x0, 4.2, 0.3)
+    ref = ora.integrate_adaptive(x0, 0, 4.2, 0.3, record=True)
+    assert len(df) == ref["rows"] and df["Time"].iloc[-1] == 4.2
+    assert np.max(np.abs(df["Time"].to_numpy() - ref["t"])) <= 1e-9
+    assert np.max(np.abs(cols(df) - ref["rec"])) <= 1e-5

@@ -664,7 +664,8 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
     lattice_dopri5_dense st;
     st.ctl.core = core;
     st.ctl.cnt.budget = h->max_tries;
-    st.x_cur = lat_state(h, state_like[2]); st.x_old = lat_state(h, state_like[3]);
+    st.x_cur.h = h; st.x_cur.p = state_like[2];  // (assignment of lat_state copies values, not handles)
+    st.x_old.h = h; st.x_old.p = state_like[3];
     st.d_cur = deriv_like[5]; st.d_old = deriv_like[6];
     if (mode == ODEINTR_MODE_TIMES)
       ok = record ? odeintr_b200::integrate_times_dense(st, sys, x, times, (long long)n_times, dt, obs)

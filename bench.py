@@ -131,11 +131,11 @@ def cpu_port_throughput(instances, threads, reps=1):
     return instances * steps / best, best
 
 
-def run_reference(args):
+def run_reference(args, saved_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     # calibrate, then size each step's sample so the whole run stays within ~2 minutes
     rate, _ = cpu_port_throughput(20_000, threads)
     budget_s = 100.0 / max(1, args.steps + args.warmup)
@@ -158,12 +158,49 @@ def run_reference(args):
         "note": "CPU oracle port of the reference's Boost-odeint path (oracle/); the reference itself needs R, "
                 "Rcpp and Boost, none of which exist in this image",
     }
-    print(json.dumps(line), flush=True)
+    _emit(saved_stdout, line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------
+_ALL_CPUS = os.sched_getaffinity(0)
+
+
+def _bind_to_gpu_numa_node(index):
+    """Run this rank's host threads (and hence first-touch its pinned buffers) on the CPUs NVML reports as local
+    to its GPU: with 8 ranks streaming 29 GB per step each, host buffers on the wrong socket turn the end-to-end
+    path into an inter-socket-link benchmark."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {w * 64 + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1, so fd 1 is
+    pointed at stderr for the duration of the run and the line goes to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -177,7 +214,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, saved_stdout)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,6 +223,7 @@ def main():
     import torch
 
     torch.cuda.set_device(local_rank)
+    _bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -314,7 +352,8 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        os.sched_setaffinity(0, _ALL_CPUS)  # the CPU baseline gets every host core again
+        threads = len(_ALL_CPUS)
         rate, _ = cpu_port_throughput(20_000, threads)
         inst = int(min(4_000_000, max(50_000, rate * 12.0 / 1000.0)))
         v, secs = cpu_port_throughput(inst, threads)
@@ -360,7 +399,7 @@ def main():
             },
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(saved_stdout, line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

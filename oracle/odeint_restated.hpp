@@ -519,6 +519,194 @@ struct dense_dopri5 {
 };
 
 // =====================================================================================
+// modified_midpoint + bulirsch_stoer (controlled stepper; method "bs", R/utils.R:57).  The reference constructs
+// it with stepper_type(): eps_abs = eps_rel = 1e-6 whatever atol / rtol the user passed (R/utils.R:22-32).
+// =====================================================================================
+struct modified_midpoint {
+  unsigned short m_steps = 2;
+  state_type m_x0, m_x1, m_dxdt;
+  void set_steps(unsigned short steps) { m_steps = steps; }
+  template <class Sys>
+  void do_step(Sys& sys, const state_type& in, const state_type& dxdt, double t, state_type& out, double dt) {
+    const std::size_t n = in.size();
+    m_x0.resize(n); m_x1.resize(n); m_dxdt.resize(n); out.resize(n);
+    const double val1 = 1.0, val05 = 1.0 / 2.0;
+    const double h = dt / static_cast<double>(m_steps);
+    const double h2 = 2.0 * h;
+    double th = t + h;
+    for (std::size_t i = 0; i < n; ++i) m_x1[i] = val1 * in[i] + h * dxdt[i];
+    sys(m_x1, m_dxdt, th);
+    m_x0 = in;
+    unsigned short i = 1;
+    while (i != m_steps) {
+      for (std::size_t j = 0; j < n; ++j) {  // scale_sum_swap2: tmp = x1; x1 = x0 + h2*dxdt; x0 = tmp
+        const double tmp = m_x1[j];
+        m_x1[j] = val1 * m_x0[j] + h2 * m_dxdt[j];
+        m_x0[j] = tmp;
+      }
+      th += h;
+      sys(m_x1, m_dxdt, th);
+      i++;
+    }
+    const double c3 = val05 * h;
+    for (std::size_t j = 0; j < n; ++j) out[j] = val05 * m_x0[j] + val05 * m_x1[j] + c3 * m_dxdt[j];
+  }
+};
+
+struct bulirsch_stoer {
+  static const std::size_t m_k_max = 8;
+  error_checker m_error_checker;
+  modified_midpoint m_midpoint;
+  bool m_last_step_rejected = false, m_first = true;
+  double m_dt_last = 0.0;
+  std::size_t m_current_k_opt = 4;
+  std::size_t m_interval_sequence[m_k_max + 1];
+  double m_coeff[m_k_max + 1][m_k_max + 1];
+  std::size_t m_cost[m_k_max + 1];
+  double m_facmin_table[m_k_max + 1];
+  state_type m_table[m_k_max], m_err, m_dxdt, m_xnew;
+  const double STEPFAC1 = 0.65, STEPFAC2 = 0.94, STEPFAC3 = 0.02, STEPFAC4 = 4.0, KFAC1 = 0.8, KFAC2 = 0.9;
+  counters* cnt = nullptr;
+
+  bulirsch_stoer(double eps_abs = 1e-6, double eps_rel = 1e-6) : m_error_checker(eps_abs, eps_rel) {
+    for (unsigned short i = 0; i < m_k_max + 1; i++) {
+      m_interval_sequence[i] = 2 * (i + 1);
+      m_cost[i] = i == 0 ? m_interval_sequence[i] : m_cost[i - 1] + m_interval_sequence[i];
+      for (std::size_t k = 0; k < i; ++k) {
+        const double r = static_cast<double>(m_interval_sequence[i]) / static_cast<double>(m_interval_sequence[k]);
+        m_coeff[i][k] = 1.0 / (r * r - 1.0);
+      }
+      m_facmin_table[i] = std::pow(STEPFAC3, 1.0 / static_cast<double>(2 * i + 1));
+    }
+  }
+  void reset() { m_first = true; m_last_step_rejected = false; m_current_k_opt = 4; }
+
+  void extrapolate(std::size_t k, state_type& xest) {
+    const std::size_t n = xest.size();
+    for (int j = static_cast<int>(k) - 1; j > 0; --j) {
+      const double a1 = 1.0 + m_coeff[k][j], a2 = -m_coeff[k][j];
+      for (std::size_t i = 0; i < n; ++i) m_table[j - 1][i] = a1 * m_table[j][i] + a2 * m_table[j - 1][i];
+    }
+    const double a1 = 1.0 + m_coeff[k][0], a2 = -m_coeff[k][0];
+    for (std::size_t i = 0; i < n; ++i) xest[i] = a1 * m_table[0][i] + a2 * xest[i];
+  }
+  double calc_h_opt(double h, double error, std::size_t k) const {
+    const double expo = 1.0 / (2 * k + 1);
+    const double facmin = m_facmin_table[k];
+    double fac;
+    if (error == 0.0) fac = 1.0 / facmin;
+    else {
+      fac = STEPFAC2 / std::pow(error / STEPFAC1, expo);
+      fac = std::max(facmin / STEPFAC4, std::min(1.0 / facmin, fac));
+    }
+    return h * fac;
+  }
+  bool should_reject(double error, std::size_t k) const {
+    if (k == m_current_k_opt - 1) {
+      const double d = m_interval_sequence[m_current_k_opt] * m_interval_sequence[m_current_k_opt + 1] /
+                       (m_interval_sequence[0] * m_interval_sequence[0]);
+      return error > d * d;  // criterion 17.3.17 in NR
+    } else if (k == m_current_k_opt) {
+      const double d = m_interval_sequence[m_current_k_opt] / m_interval_sequence[0];
+      return error > d * d;
+    }
+    return error > 1.0;
+  }
+
+  template <class Sys>
+  controlled_step_result try_step(Sys& sys, const state_type& in, const state_type& dxdt, double& t, state_type& out,
+                                  double& dt) {
+    const std::size_t n = in.size();
+    for (std::size_t i = 0; i < m_k_max; ++i) m_table[i].resize(n);
+    m_err.resize(n); out.resize(n);
+    if (dt != m_dt_last) reset();  // step size changed from outside -> reset
+    bool reject = true;
+    double h_opt[m_k_max + 1], work[m_k_max + 1];
+    double new_h = dt;
+    for (std::size_t k = 0; k <= m_current_k_opt + 1; k++) {
+      m_midpoint.set_steps(static_cast<unsigned short>(m_interval_sequence[k]));
+      if (k == 0) {
+        m_midpoint.do_step(sys, in, dxdt, t, out, dt);
+      } else {
+        m_midpoint.do_step(sys, in, dxdt, t, m_table[k - 1], dt);
+        extrapolate(k, out);
+        for (std::size_t i = 0; i < n; ++i) m_err[i] = 1.0 * out[i] + (-1.0) * m_table[0][i];
+        const double error = m_error_checker.error(in, dxdt, m_err, dt);
+        h_opt[k] = calc_h_opt(dt, error, k);
+        work[k] = static_cast<double>(m_cost[k]) / h_opt[k];
+        if ((k == m_current_k_opt - 1) || m_first) {  // convergence before k_opt
+          if (error < 1.0) {
+            reject = false;
+            if ((work[k] < KFAC2 * work[k - 1]) || (m_current_k_opt <= 2)) {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, std::max(2, static_cast<int>(k) + 1));
+              new_h = h_opt[k];
+              new_h *= static_cast<double>(m_cost[k + 1]) / static_cast<double>(m_cost[k]);
+            } else {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, std::max(2, static_cast<int>(k)));
+              new_h = h_opt[k];
+            }
+            break;
+          } else if (should_reject(error, k) && !m_first) {
+            reject = true;
+            new_h = h_opt[k];
+            break;
+          }
+        }
+        if (k == m_current_k_opt) {  // convergence at k_opt
+          if (error < 1.0) {
+            reject = false;
+            if (work[k - 1] < KFAC2 * work[k]) {
+              m_current_k_opt = std::max(2, static_cast<int>(m_current_k_opt) - 1);
+              new_h = h_opt[m_current_k_opt];
+            } else if ((work[k] < KFAC2 * work[k - 1]) && !m_last_step_rejected) {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max - 1), static_cast<int>(m_current_k_opt) + 1);
+              new_h = h_opt[k];
+              new_h *= static_cast<double>(m_cost[m_current_k_opt]) / static_cast<double>(m_cost[k]);
+            } else
+              new_h = h_opt[m_current_k_opt];
+            break;
+          } else if (should_reject(error, k)) {
+            reject = true;
+            new_h = h_opt[m_current_k_opt];
+            break;
+          }
+        }
+        if (k == m_current_k_opt + 1) {  // convergence at k_opt+1
+          if (error < 1.0) {
+            reject = false;
+            if (work[k - 2] < KFAC2 * work[k - 1])
+              m_current_k_opt = std::max(2, static_cast<int>(m_current_k_opt) - 1);
+            if ((work[k] < KFAC2 * work[m_current_k_opt]) && !m_last_step_rejected)
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, static_cast<int>(k));
+            new_h = h_opt[m_current_k_opt];
+          } else {
+            reject = true;
+            new_h = h_opt[m_current_k_opt];
+          }
+          break;
+        }
+      }
+    }
+    if (!reject) t += dt;
+    if (!m_last_step_rejected || less_with_sign(new_h, dt, dt)) {
+      m_dt_last = new_h;
+      dt = new_h;
+    }
+    m_last_step_rejected = reject;
+    m_first = false;
+    if (cnt) { if (reject) cnt->rejected++; else cnt->accepted++; }
+    return reject ? fail : success;
+  }
+  template <class Sys> controlled_step_result try_step(Sys& sys, state_type& x, double& t, double& dt) {
+    m_dxdt.resize(x.size());
+    sys(x, m_dxdt, t);
+    controlled_step_result res = try_step(sys, x, m_dxdt, t, m_xnew, dt);
+    if (res == success) x = m_xnew;
+    return res;
+  }
+};
+
+// =====================================================================================
 // rosenbrock4<double> + controller + dense output (SURVEY.md A.6–A.8), dense row-major
 // uBLAS matrix, lu_factorize with partial pivoting, lu_substitute = swap_rows + unit-lower
 // forward solve + upper backward solve (column-oriented axpy form).

@@ -5,6 +5,7 @@
 #pragma once
 #include "odeintr_b200/adaptive_steppers.cuh"
 #include "odeintr_b200/rk78.cuh"
+#include "odeintr_b200/bulirsch_stoer.cuh"
 #include "odeintr_b200/integrate_loops.cuh"
 
 namespace odeintr_b200 {

@@ -125,7 +125,7 @@ def test_vdp_dense_times_against_scipy():
 
 
 def test_integrate_adaptive_variants_reach_t1():
-    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a", "rk78_a"):
+    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a", "rk78_a", "bs"):
         o = bo.build(LOGISTIC, method=method)
         r = o.integrate_adaptive([0.01], 0, 7.3, 0.25, record=True)
         assert r["t"][-1] == 7.3

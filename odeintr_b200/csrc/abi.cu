@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -134,6 +135,9 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   o.push_back("-lineinfo");
   o.push_back((flags & ODEINTR_FLAG_FMAD) ? "--fmad=true" : "--fmad=false");
   if (flags & ODEINTR_FLAG_KEEP_ZERO_TERMS) o.push_back("-DODEINTR_KEEP_ZERO_TERMS=1");
+  // tuning knobs for experiments (scripts/explore_*.py): register cap and block size of the ensemble kernels
+  if (const char* r = std::getenv("ODEINTR_MAXRREGCOUNT")) o.push_back(std::string("--maxrregcount=") + r);
+  if (const char* b = std::getenv("ODEINTR_BLOCK")) o.push_back(std::string("-DODEINTR_BLOCK=") + b);
   return o;
 }
 
@@ -890,6 +894,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     cudaFuncAttributes fa;
     if (k && cudaFuncGetAttributes(&fa, (const void*)k) == cudaSuccess) block = std::min(block, fa.maxThreadsPerBlock);
   };
+  if (const char* b = std::getenv("ODEINTR_BLOCK")) { h->block_plain = std::atoi(b); h->block_adaptive = std::atoi(b); }
   max_block(h->k_plain, h->block_plain);
   max_block(h->k_adaptive, h->block_adaptive);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);

@@ -138,6 +138,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   // tuning knobs for experiments (scripts/explore_*.py): register cap and block size of the ensemble kernels
   if (const char* r = std::getenv("ODEINTR_MAXRREGCOUNT")) o.push_back(std::string("--maxrregcount=") + r);
   if (const char* b = std::getenv("ODEINTR_BLOCK")) o.push_back(std::string("-DODEINTR_BLOCK=") + b);
+  if (const char* b = std::getenv("ODEINTR_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_MIN_BLOCKS=") + b);
   return o;
 }
 

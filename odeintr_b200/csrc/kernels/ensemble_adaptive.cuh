@@ -13,7 +13,14 @@
 #pragma once
 #include "odeintr_b200/integrate_device.cuh"
 
-extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK)
+// Register budget: measured on a B200 (scripts/explore_regs.py, 10 M instances) 5 resident blocks of 128 threads
+// per SM (<= 96 registers, a few spilled words in L1) beats the uncapped build by 3 % (dopri5, 104 registers) to
+// 12 % (rosenbrock4, 156 registers); tighter caps lose again.
+#ifndef ODEINTR_ADAPTIVE_MIN_BLOCKS
+#define ODEINTR_ADAPTIVE_MIN_BLOCKS ((ODEINTR_MIN_BLOCKS) > 1 ? (ODEINTR_MIN_BLOCKS) : (ODEINTR_BLOCK == 128 ? 5 : 1))
+#endif
+
+extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK, ODEINTR_ADAPTIVE_MIN_BLOCKS)
 odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
   constexpr int N = ODEINTR_SYS_SIZE;
   typedef odeintr::system_type Sys;

@@ -18,7 +18,7 @@
 #include "odeintr_b200/dopri5.cuh"
 #include "odeintr_b200/rk78.cuh"
 
-extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK)
+extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK, ODEINTR_MIN_BLOCKS)
 odeintr_plain_ensemble(const odeintr_plain_args a) {
   constexpr int N = ODEINTR_SYS_SIZE;
   typedef odeintr::system_type Sys;

@@ -11,6 +11,9 @@
 #ifndef ODEINTR_BLOCK
 #define ODEINTR_BLOCK 128
 #endif
+#ifndef ODEINTR_MIN_BLOCKS   // resident blocks per SM the ensemble kernels are compiled for (register cap)
+#define ODEINTR_MIN_BLOCKS 1
+#endif
 
 #define ODEINTR_DEV __device__ __forceinline__
 

@@ -28,12 +28,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     a = s.kernel_attributes("odeintr_adaptive_ensemble")
     st = s.stats()
     print(json.dumps({"which": which, "regs": a["registers"], "local": a["local_bytes"], "ms": best, "acc": int(st["accepted"].sum()),
-                      "maxr": os.environ.get("ODEINTR_MAXRREGCOUNT"), "block": os.environ.get("ODEINTR_BLOCK")}), flush=True)
+                      "minblocks": os.environ.get("ODEINTR_MIN_BLOCKS"), "block": os.environ.get("ODEINTR_BLOCK")}), flush=True)
     sys.exit(0)
 for which in ("vdp", "rob"):
-    for maxr, block in ((None, None), ("96", None), ("80", None), ("64", None), (None, "64"), (None, "256"), ("80", "256"), ("128", None)):
+    for maxr, block in ((None, None), ("5", None), ("6", None), ("8", None), ("10", None), ("2", "256"), ("3", "256"), ("4", "256"), ("12", "64"), ("16", "64")):
         env = dict(os.environ)
-        if maxr: env["ODEINTR_MAXRREGCOUNT"] = maxr
+        if maxr: env["ODEINTR_MIN_BLOCKS"] = maxr
         if block: env["ODEINTR_BLOCK"] = block
         r = subprocess.run([sys.executable, __file__, "child", which], env=env, capture_output=True, text=True, timeout=300)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ("FAIL " + r.stderr[-300:]), flush=True)

@@ -527,6 +527,9 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
         "__SYS__": "\n      ".join(cell),
         "__FOOTERS__": footers,
     })
+    # an M x M lattice (laplace2D & friends, or M itself) is walked in column strips by the stage kernel
+    if re.search(r"\b(laplace2D|d_left|d_right|d_up|d_down|M)\b", _strip_comments(sys + " " + globals)):
+        code = code.replace("#define ODEINTR_NFIELDS", "#define ODEINTR_LATTICE_2D 1\n#define ODEINTR_NFIELDS", 1)
     code = code.replace("__NFIELDS__", str(len(loops.offsets)))
     code = code.replace("__CELL_START__", loops.start).replace("__CELL_BOUND__", loops.bound)
     code = code.replace("__FIELD_OFFSETS__", offs)

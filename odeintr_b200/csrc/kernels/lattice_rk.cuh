@@ -102,6 +102,32 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   } else {
     lattice_view_t<false> v;
     v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = 0; v.ghost = 0; v.pitch = 0;
+#ifdef ODEINTR_LATTICE_2D
+    // M x M lattice (the snippet uses laplace2D / M): walk it in column strips of one block width, row after row,
+    // so the rows above and below the current one are L1 hits instead of lines 8*M bytes away that come back
+    // from DRAM (measured 64 % -> see profiles/ of the HBM peak with the flat order at M = 16384)
+    constexpr long long MM = odeintr_b200::isqrt(ODEINTR_SYS_SIZE);
+    if (F == 1 && first == 0 && last == MM * MM && MM % 256 == 0 && blockDim.x == 256) {
+      typedef odeintr::system_type_t<lattice_view_t<false> > Sys;
+      Sys sys;
+      sys.load_params(a.pars, 1, 0);
+      const long long strips = MM / 256, total = strips * MM;  // (strip, row) pairs, strip-major
+      const long long per_block = (total + gridDim.x - 1) / gridDim.x;
+      const long long q_lo = (long long)blockIdx.x * per_block;
+      const long long q_hi = q_lo + per_block < total ? q_lo + per_block : total;
+      for (long long q = q_lo; q < q_hi; ++q) {
+        const long long strip = q / MM, row = q - strip * MM;
+        const long long c = row * MM + strip * 256 + threadIdx.x;
+        double k[F];
+        k[0] = 0.0;
+        sys.cell(v, k, c, a.t);
+        const long long idx = base[0] + c;
+        if (HAS_XT) a.xt[idx] = a.x[idx] + a.a_dt * k[0];
+        a.acc_out[idx] = a.acc_in[idx] + a.b_dt * k[0];
+      }
+      return;
+    }
+#endif
     lattice_chunk<false, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
   }
 }

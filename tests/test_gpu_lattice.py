@@ -186,3 +186,17 @@ def test_large_system_adaptive_dopri5(method):
     assert len(df) == ref["rows"] and df["Time"].iloc[-1] == 4.2
     assert np.max(np.abs(df["Time"].to_numpy() - ref["t"])) <= 1e-9
     assert np.max(np.abs(cols(df) - ref["rec"])) <= 1e-5
+
+
+def test_2d_lattice_strip_traversal_bit_exact():
+    # M a multiple of the block width: the stage kernel walks the lattice in column strips (L1 reuse of the rows
+    # above / below); the visiting order must not change a single bit
+    m = 512
+    env = {}
+    odeintr_b200.compile_sys_openmp("b2s", BISTABLE_2D, BISTABLE_PARS, True, method="rk4", sys_dim=m * m, env=env)
+    ora = bo.build(BISTABLE_2D, BISTABLE_PARS, True, "rk4", sys_dim=m * m)
+    rng = np.random.default_rng(71)
+    x0 = rng.integers(0, 2, m * m).astype(np.float64)
+    fin = env["b2s_no_record"](x0, 1.0, 0.1)
+    ref = ora.integrate_adaptive(x0, 0.0, 1.0, 0.1)
+    assert np.array_equal(bits(fin), bits(ref["x"]))

@@ -13,13 +13,13 @@
 
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_combo(const odeintr_lattice_combo_args a) {
-  typedef odeintr::system_type_t<odeintr_b200::lattice_view_t<false> > Sys;
+  typedef odeintr::system_type_t<odeintr_b200::lattice_view_t<odeintr_b200::LATTICE_PLAIN> > Sys;
   constexpr int F = ODEINTR_NFIELDS;
   Sys sys;
   sys.load_params(a.pars, 1, 0);
   long long off[F];
   sys.field_offsets(off);
-  odeintr_b200::lattice_view_t<false> xs;
+  odeintr_b200::lattice_view_t<odeintr_b200::LATTICE_PLAIN> xs;
   xs.p = a.xs; xs.n_total = a.n_total; xs.n_local = a.n_total; xs.c0 = 0; xs.ghost = 0; xs.pitch = 0;
 
   const long long first = sys.cell_start(), last = sys.cell_bound();

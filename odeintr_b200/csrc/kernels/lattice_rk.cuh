@@ -22,10 +22,11 @@
 namespace odeintr_b200 {
 
 // cells [c_lo, c_hi) of one block through one view type; entry (f, c) of every array sits at base[f] + c
-template <bool WRAP, bool HAS_XT, int F>
-ODEINTR_DEV void lattice_chunk(const odeintr_lattice_args& a, const lattice_view_t<WRAP>& xs, const long long* base,
+template <int MODE, bool HAS_XT, int F>
+ODEINTR_DEV void lattice_chunk(const odeintr_lattice_args& a, const lattice_view_t<MODE>& xs, const long long* base,
                                const long long c_lo, const long long c_hi, const long long first) {
-  typedef odeintr::system_type_t<lattice_view_t<WRAP> > Sys;
+  typedef odeintr::system_type_t<lattice_view_t<MODE> > Sys;
+  constexpr bool WRAP = MODE == LATTICE_WRAP;
   Sys sys;
   sys.load_params(a.pars, 1, 0);
   const long long start = sys.cell_start(), bound = sys.cell_bound();
@@ -54,7 +55,7 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   constexpr int F = ODEINTR_NFIELDS;
   long long off[F];
   {
-    odeintr::system_type_t<lattice_view_t<false> > sys;
+    odeintr::system_type_t<lattice_view_t<LATTICE_PLAIN> > sys;
     sys.field_offsets(off);
   }
   // local position of entry (field f, cell c) is base[f] + c: fields are `pitch` apart, cell c sits at c - c0
@@ -67,7 +68,7 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   // local cell 0 (which the host keeps 128-byte aligned), so every warp reads and writes whole lines.
   long long first = a.lo, last = a.hi;
   if (!SHARDED) {  // one GPU: exactly the user loop's range
-    odeintr::system_type_t<lattice_view_t<false> > sys;
+    odeintr::system_type_t<lattice_view_t<LATTICE_PLAIN> > sys;
     if (sys.cell_start() > first) first = sys.cell_start();
     if (sys.cell_bound() < last) last = sys.cell_bound();
   }
@@ -86,21 +87,27 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
 
   if (SHARDED) {
     // A chunk whose cells and stencil neighbours (radius a.halo) stay inside [0, n_total) never wraps: the
-    // snippet's global indices then differ from local positions by the constant c0, so the plain-pointer view on
-    // a shifted base serves it at full speed.  Only the (at most two) chunks at the ring's seam take the
-    // wrapping view.  (One field only: with several fields the shift differs per field.)
-    const bool interior = F == 1 && c_lo - a.halo >= 0 && c_hi + a.halo <= a.n_total && c_lo >= first;
-    if (interior) {
-      lattice_view_t<false> v;
+    // snippet's global indices then differ from local positions by a constant (one per field), so a plain pointer
+    // on a shifted base serves it at full speed.  Only the (at most two) chunks at the ring's seam take the
+    // wrapping view.
+    const bool interior = c_lo - a.halo >= 0 && c_hi + a.halo <= a.n_total && c_lo >= first;
+    if (interior && F == 1) {
+      lattice_view_t<LATTICE_PLAIN> v;
       v.p = a.xs - a.c0; v.n_total = a.n_total; v.n_local = a.n; v.c0 = a.c0; v.ghost = a.ghost; v.pitch = a.pitch;
-      lattice_chunk<false, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+      lattice_chunk<LATTICE_PLAIN, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
       return;
     }
-    lattice_view_t<true> v;
+    if (interior) {
+      lattice_view_t<LATTICE_FIELDS> v;
+      v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = a.c0; v.ghost = a.ghost; v.pitch = a.pitch;
+      lattice_chunk<LATTICE_FIELDS, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+      return;
+    }
+    lattice_view_t<LATTICE_WRAP> v;
     v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = a.c0; v.ghost = a.ghost; v.pitch = a.pitch;
-    lattice_chunk<true, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+    lattice_chunk<LATTICE_WRAP, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
   } else {
-    lattice_view_t<false> v;
+    lattice_view_t<LATTICE_PLAIN> v;
     v.p = a.xs; v.n_total = a.n_total; v.n_local = a.n; v.c0 = 0; v.ghost = 0; v.pitch = 0;
 #ifdef ODEINTR_LATTICE_2D
     // M x M lattice (the snippet uses laplace2D / M): walk it in column strips of one block width, row after row,
@@ -108,7 +115,7 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
     // from DRAM (measured 64 % -> see profiles/ of the HBM peak with the flat order at M = 16384)
     constexpr long long MM = odeintr_b200::isqrt(ODEINTR_SYS_SIZE);
     if (F == 1 && first == 0 && last == MM * MM && MM % 256 == 0 && blockDim.x == 256) {
-      typedef odeintr::system_type_t<lattice_view_t<false> > Sys;
+      typedef odeintr::system_type_t<lattice_view_t<LATTICE_PLAIN> > Sys;
       Sys sys;
       sys.load_params(a.pars, 1, 0);
       const long long strips = MM / 256, total = strips * MM;  // (strip, row) pairs, strip-major
@@ -128,7 +135,7 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
       return;
     }
 #endif
-    lattice_chunk<false, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
+    lattice_chunk<LATTICE_PLAIN, HAS_XT, F>(a, v, base, c_lo, c_hi, first);
   }
 }
 

@@ -115,24 +115,31 @@ def test_sharded_stepping_single_rank_matches_unsharded(case):
     assert np.array_equal(bits(got), bits(ref))
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_stepping_emulated_ranks_on_one_gpu(world):
+@pytest.mark.parametrize("world,case", [(2, "bistable"), (3, "bistable"), (2, "chain"), (4, "chain")])
+def test_sharded_stepping_emulated_ranks_on_one_gpu(world, case):
     # several slabs of one lattice inside one process: the halo exchange is done by hand between the slabs'
-    # tensors, the kernels are the multi-GPU ones (window below 0 / above n_total = periodic images)
+    # tensors, the kernels are the multi-GPU ones (window below 0 / above n_total = periodic images; interior
+    # chunks on shifted plain pointers, one shift per field)
     import torch
 
     from odeintr_b200.distributed import ShardedLattice
 
-    n_cells = 3001
-    rng = np.random.default_rng(41)
-    x0 = rng.integers(0, 2, n_cells).astype(np.float64)
-    ref_sys = odeintr_b200.compile_sys_openmp("ref", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells).system
-    ref = ref_sys.no_record(x0, 1.5, 0.1)  # 15 steps
+    if case == "bistable":
+        n_cells, fields = 3001, 1
+        rng = np.random.default_rng(41)
+        x0 = rng.integers(0, 2, n_cells).astype(np.float64)
+        build = lambda name: odeintr_b200.compile_sys_openmp(name, BISTABLE_1D, BISTABLE_PARS, True, method="rk4",
+                                                             sys_dim=n_cells).system
+    else:
+        n_cells, fields = 2 * 4099, 2  # cells per field; enough for several chunks per slab
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n_cells) / n_cells), np.zeros(n_cells)])
+        build = lambda name: odeintr_b200.compile_sys_openmp(name, CHAIN, CHAIN_PARS, True, method="rk4",
+                                                             sys_dim=2 * n_cells, globals=CHAIN_GLOBALS).system
+    ref = build("ref").no_record(x0, 1.5, 0.1)  # 15 steps
     lats = []
     for r in range(world):
-        sysr = odeintr_b200.compile_sys_openmp("r%d" % r, BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n_cells).system
-        lat = ShardedLattice(sysr, n_cells, rank=r, world=world, native=False)  # no process group: halos by hand
-        lat.set_state_from(lambda f, cells: x0[cells])
+        lat = ShardedLattice(build("r%d" % r), n_cells, fields=fields, rank=r, world=world, native=False)
+        lat.set_state_from(lambda f, cells: x0[f * n_cells + cells])
         lats.append(lat)
     g, pad = lats[0].ghost, lats[0].pad
     for step in range(15):

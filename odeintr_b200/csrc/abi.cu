@@ -139,6 +139,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* r = std::getenv("ODEINTR_MAXRREGCOUNT")) o.push_back(std::string("--maxrregcount=") + r);
   if (const char* b = std::getenv("ODEINTR_BLOCK")) o.push_back(std::string("-DODEINTR_BLOCK=") + b);
   if (const char* b = std::getenv("ODEINTR_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_MIN_BLOCKS=") + b);
+  if (std::getenv("ODEINTR_NESTED_LOOPS")) o.push_back("-DODEINTR_NESTED_LOOPS=1");
   return o;
 }
 

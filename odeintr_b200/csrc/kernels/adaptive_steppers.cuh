@@ -162,6 +162,28 @@ struct dopri5_dense {
   ODEINTR_DEV void calc_state(const double tq, vec<N>& x) const {
     ctl.core.calc_state(tq, x, x_old, d_old, t_old, d_cur, t);
   }
+
+  // do_step split into "start a step" + "one attempt", for the warp-synchronous loops of integrate_device.cuh:
+  // a lane whose attempt was rejected retries in the warp's next iteration together with the lanes that start
+  // their next step, instead of making the whole warp wait inside a retry loop.
+  int fails;
+  ODEINTR_DEV void begin_step(Sys& sys) {
+    if (!deriv_ready) { sys.sys(x_cur, d_cur, t); deriv_ready = true; }
+    t_old = t;
+    fails = 0;
+  }
+  // 1 = step accepted, 0 = rejected (dt was reduced; call again), -1 = failed (status says why)
+  ODEINTR_DEV int try_once(Sys& sys) {
+    if (ctl.cnt.exhausted()) return -1;
+    vec<N> xn, dn;
+    if (ctl.try_step_full(sys, x_cur, d_cur, t, xn, dn, dt)) {
+      x_old = x_cur; d_old = d_cur;
+      x_cur = xn; d_cur = dn;
+      return 1;
+    }
+    if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
+    return 0;
+  }
 };
 
 }  // namespace odeintr_b200

@@ -47,9 +47,15 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
 
   bool ok;
   if constexpr (Stepper::is_dense) {
+#ifdef ODEINTR_NESTED_LOOPS  // Boost's literal loop nesting (kept for A/B measurements)
     if (a.mode == ODEINTR_MODE_TIMES) ok = odeintr_b200::integrate_times_dense(st, sys, x, a.times, a.n_times, a.dt, obs);
     else if (a.mode == ODEINTR_MODE_CONST) ok = odeintr_b200::integrate_const_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
     else ok = odeintr_b200::integrate_adaptive_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+#else
+    if (a.mode == ODEINTR_MODE_TIMES) ok = odeintr_b200::flat_times_dense(st, sys, x, a.times, a.n_times, a.dt, obs);
+    else if (a.mode == ODEINTR_MODE_CONST) ok = odeintr_b200::flat_const_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+    else ok = odeintr_b200::flat_adaptive_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+#endif
   } else {
     double dt = a.dt;
     if (a.mode == ODEINTR_MODE_TIMES) ok = odeintr_b200::integrate_times_controlled(st, sys, x, a.times, a.n_times, dt, obs);

@@ -232,6 +232,26 @@ struct rosenbrock4_dense {
     x_cur = xn;
     return true;
   }
+  // do_step split into "start a step" + "one attempt" (see dopri5_dense::try_once)
+  int fails;
+  ODEINTR_DEV void begin_step(Sys&) { t_old = t; fails = 0; }
+  ODEINTR_DEV int try_once(Sys& sys) {
+    if (cnt.exhausted()) return -1;
+    vec<N> xn;
+    if (try_step(sys, x_cur, t, xn, dt)) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {  // prepare_dense_output
+        cont3[i] = K::d21 * g1[i] + K::d22 * g2[i] + K::d23 * g3[i] + K::d24 * g4[i] + K::d25 * g5[i];
+        cont4[i] = K::d31 * g1[i] + K::d32 * g2[i] + K::d33 * g3[i] + K::d34 * g4[i] + K::d35 * g5[i];
+      }
+      x_old = x_cur;
+      x_cur = xn;
+      return 1;
+    }
+    if (++fails > ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
+    return 0;
+  }
+
   ODEINTR_DEV void calc_state(const double tq, vec<N>& x) const {
     const double h = t - t_old;
     const double s = (tq - t_old) / h;

@@ -154,6 +154,8 @@ def stepper_spec(method: str, atol=1e-6, rtol=1e-6) -> StepperSpec:
         return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "rk54_controlled")
     if base == "bs":
         return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "bs_controlled")
+    if base == "bsd":
+        return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "bsd_dense")
     if base == "rk78" and mode == "controlled":
         return StepperSpec(method, base, mode, boost_type, constr, "ensemble_adaptive.cuh", "rk78_controlled")
     raise OdeintrError("method '%s' is not yet provided by odeintr_b200" % method)

@@ -6,6 +6,7 @@
 #include "odeintr_b200/adaptive_steppers.cuh"
 #include "odeintr_b200/rk78.cuh"
 #include "odeintr_b200/bulirsch_stoer.cuh"
+#include "odeintr_b200/bulirsch_stoer_dense.cuh"
 #include "odeintr_b200/integrate_loops.cuh"
 
 namespace odeintr_b200 {

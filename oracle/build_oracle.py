@@ -23,7 +23,7 @@ _BUILD = _HERE / "_build"
 sys.path.insert(0, str(_HERE.parent))
 from odeintr_b200 import codegen  # noqa: E402  (text helpers only: number formatting, sys_dim inference)
 
-METHOD_IDS = {"euler": 0, "rk4": 1, "rk54": 2, "rk5": 3, "rk78": 4, "rk78_a": 13, "bs": 14, "rk5_a": 10, "rk5_i": 11, "rk54_a": 12, "rosenbrock4": 20}
+METHOD_IDS = {"euler": 0, "rk4": 1, "rk54": 2, "rk5": 3, "rk78": 4, "rk78_a": 13, "bs": 14, "bsd": 15, "rk5_a": 10, "rk5_i": 11, "rk54_a": 12, "rosenbrock4": 20}
 
 c_dbl_p = C.POINTER(C.c_double)
 c_long_p = C.POINTER(C.c_long)

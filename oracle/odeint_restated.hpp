@@ -707,6 +707,307 @@ struct bulirsch_stoer {
 };
 
 // =====================================================================================
+// bulirsch_stoer_dense_out (dense-output stepper; method "bsd", R/utils.R:58) over modified_midpoint_dense_out.
+// Interval sequence 2, 6, 10, ...; the derivatives of every midpoint run are kept, finite differences of them
+// at the interval centre are extrapolated like the states, and the dense output is the Taylor polynomial about
+// the centre (theta in [-1, 1]).  Default-constructed by the reference: eps 1e-6 / 1e-6, no interpolation control.
+// =====================================================================================
+struct bulirsch_stoer_dense_out {
+  static const std::size_t m_k_max = 8;
+  error_checker m_error_checker;
+  bool m_control_interpolation = false;
+  bool m_last_step_rejected = false, m_first = true;
+  double m_t = 0, m_dt = 0, m_t_last = 0;
+  std::size_t m_current_k_opt = 4, m_k_final = 0;
+  state_type m_x1, m_x2, m_dxdt1, m_dxdt2, m_err;
+  bool m_current_state_x1 = true;
+  std::size_t m_interval_sequence[m_k_max + 1];
+  double m_coeff[m_k_max + 1][m_k_max + 1];
+  std::size_t m_cost[m_k_max + 1];
+  double m_facmin_table[m_k_max + 1];
+  state_type m_table[m_k_max];
+  state_type m_mp_states[m_k_max + 1];
+  std::vector<state_type> m_derivs[m_k_max + 1];
+  std::vector<state_type> m_diffs[2 * m_k_max + 2];
+  // modified_midpoint_dense_out work vectors
+  state_type mm_x0, mm_x1;
+  const double STEPFAC1 = 0.65, STEPFAC2 = 0.94, STEPFAC3 = 0.02, STEPFAC4 = 4.0, KFAC1 = 0.8, KFAC2 = 0.9;
+  counters* cnt = nullptr;
+
+  bulirsch_stoer_dense_out(double eps_abs = 1e-6, double eps_rel = 1e-6) : m_error_checker(eps_abs, eps_rel) {
+    for (unsigned short i = 0; i < m_k_max + 1; i++) {
+      m_interval_sequence[i] = 2 + 4 * i;  // only this sequence allows for dense output
+      m_derivs[i].resize(m_interval_sequence[i]);
+      m_cost[i] = i == 0 ? m_interval_sequence[i] : m_cost[i - 1] + m_interval_sequence[i];
+      m_facmin_table[i] = std::pow(STEPFAC3, 1.0 / static_cast<double>(2 * i + 1));
+      for (std::size_t k = 0; k < i; ++k) {
+        const double r = static_cast<double>(m_interval_sequence[i]) / static_cast<double>(m_interval_sequence[k]);
+        m_coeff[i][k] = 1.0 / (r * r - 1.0);
+      }
+    }
+    int num = 1;
+    for (int i = 2 * static_cast<int>(m_k_max) + 1; i >= 0; i--) {
+      m_diffs[i].resize(num);
+      num += (i + 1) % 2;
+    }
+  }
+  state_type& cur_x() { return m_current_state_x1 ? m_x1 : m_x2; }
+  state_type& old_x() { return m_current_state_x1 ? m_x2 : m_x1; }
+  state_type& cur_d() { return m_current_state_x1 ? m_dxdt1 : m_dxdt2; }
+  state_type& old_d() { return m_current_state_x1 ? m_dxdt2 : m_dxdt1; }
+  const state_type& current_state() { return cur_x(); }
+  double current_time() const { return m_t; }
+  double current_time_step() const { return m_dt; }
+  void reset() { m_first = true; m_last_step_rejected = false; }
+  void initialize(const state_type& x0, double t0, double dt0) {
+    state_type c = x0;
+    const std::size_t n = c.size();
+    m_x1.resize(n); m_x2.resize(n); m_dxdt1.resize(n); m_dxdt2.resize(n);
+    cur_x() = c;
+    m_t = t0; m_dt = dt0;
+    reset();
+  }
+
+  template <class Sys>
+  void midpoint(Sys& sys, unsigned short steps, const state_type& in, const state_type& dxdt, double t, state_type& out,
+                double dt, state_type& x_mp, std::vector<state_type>& derivs) {
+    const std::size_t n = in.size();
+    mm_x0.resize(n); mm_x1.resize(n); out.resize(n); x_mp.resize(n);
+    for (auto& d : derivs) d.resize(n);
+    const double val1 = 1.0, val05 = 1.0 / 2.0;
+    const double h = dt / static_cast<double>(steps);
+    const double h2 = 2.0 * h;
+    double th = t + h;
+    for (std::size_t i = 0; i < n; ++i) mm_x1[i] = val1 * in[i] + h * dxdt[i];
+    if (steps == 2) x_mp = mm_x1;  // the first step already approximates the centre of the interval
+    sys(mm_x1, derivs[0], th);
+    mm_x0 = in;
+    unsigned short i = 1;
+    while (i != steps) {
+      for (std::size_t j = 0; j < n; ++j) {
+        const double tmp = mm_x1[j];
+        mm_x1[j] = val1 * mm_x0[j] + h2 * derivs[i - 1][j];
+        mm_x0[j] = tmp;
+      }
+      if (i == steps / 2 - 1) x_mp = mm_x1;  // approximation at the centre of the interval
+      th += h;
+      sys(mm_x1, derivs[i], th);
+      i++;
+    }
+    const double c3 = val05 * h;
+    for (std::size_t j = 0; j < n; ++j) out[j] = val05 * mm_x0[j] + val05 * mm_x1[j] + c3 * derivs[steps - 1][j];
+  }
+  void extrapolate(std::size_t k, state_type& xest) {
+    const std::size_t n = xest.size();
+    for (int j = static_cast<int>(k) - 1; j > 0; --j) {
+      const double a1 = 1.0 + m_coeff[k][j], a2 = -m_coeff[k][j];
+      for (std::size_t i = 0; i < n; ++i) m_table[j - 1][i] = a1 * m_table[j][i] + a2 * m_table[j - 1][i];
+    }
+    const double a1 = 1.0 + m_coeff[k][0], a2 = -m_coeff[k][0];
+    for (std::size_t i = 0; i < n; ++i) xest[i] = a1 * m_table[0][i] + a2 * xest[i];
+  }
+  template <class Table>
+  void extrapolate_dense_out(std::size_t k, Table& table, std::size_t order_start_index = 0) {
+    const std::size_t n = table[0].size();
+    for (int j = static_cast<int>(k); j > 1; --j) {
+      const double cf = m_coeff[k + order_start_index][j + order_start_index - 1];
+      const double a1 = 1.0 + cf, a2 = -cf;
+      for (std::size_t i = 0; i < n; ++i) table[j - 1][i] = a1 * table[j][i] + a2 * table[j - 1][i];
+    }
+    const double cf = m_coeff[k + order_start_index][order_start_index];
+    const double a1 = 1.0 + cf, a2 = -cf;
+    for (std::size_t i = 0; i < n; ++i) table[0][i] = a1 * table[1][i] + a2 * table[0][i];
+  }
+  static double binomial(int n, int k) {
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * static_cast<double>(n - k + i) / static_cast<double>(i);
+    return std::floor(r + 0.5);
+  }
+  void calculate_finite_difference(std::size_t j, std::size_t kappa, double fac, const state_type& dxdt) {
+    const std::size_t n = dxdt.size();
+    const int m = static_cast<int>(m_interval_sequence[j] / 2) - 1;
+    if (kappa == 0) {  // no calculation required for the 0th derivative of f
+      m_diffs[0][j].resize(n);
+      for (std::size_t i = 0; i < n; ++i) m_diffs[0][j][i] = fac * m_derivs[j][m][i];
+    } else {
+      const int j_diffs = static_cast<int>(j) - static_cast<int>(kappa / 2);
+      state_type& d = m_diffs[kappa][j_diffs];
+      d.resize(n);
+      for (std::size_t i = 0; i < n; ++i) d[i] = fac * m_derivs[j][m + kappa][i];
+      double sign = -1.0;
+      int c = 1;
+      for (int i = m + static_cast<int>(kappa) - 2; i >= m - static_cast<int>(kappa); i -= 2) {
+        if (i >= 0) {
+          const double w = sign * fac * binomial(static_cast<int>(kappa), c);
+          for (std::size_t q = 0; q < n; ++q) d[q] = 1.0 * d[q] + w * m_derivs[j][i][q];
+        } else {
+          const double w = sign * fac;
+          for (std::size_t q = 0; q < n; ++q) d[q] = 1.0 * d[q] + w * dxdt[q];
+        }
+        sign *= -1;
+        ++c;
+      }
+    }
+  }
+  double prepare_dense_output(int k, const state_type& x_start, const state_type& dxdt_start, double dt) {
+    for (int j = 0; j <= k; j++) {
+      const double d = m_interval_sequence[j] / (2.0 * dt);
+      double f = 1.0;
+      for (int kappa = 0; kappa <= 2 * j + 1; ++kappa) {
+        calculate_finite_difference(j, kappa, f, dxdt_start);
+        f *= d;
+      }
+      if (j > 0) extrapolate_dense_out(j, m_mp_states);
+    }
+    double d = dt / 2;
+    for (int kappa = 0; kappa <= 2 * k + 1; kappa++) {
+      for (int j = 1; j <= (k - kappa / 2); ++j) extrapolate_dense_out(j, m_diffs[kappa], kappa / 2);
+      for (double& v : m_diffs[kappa][0]) v *= d;  // (dt/2)^(kappa+1) / (kappa+1)!
+      d *= dt / (2 * (kappa + 2));
+    }
+    double error = 0.0;
+    if (m_control_interpolation) {
+      m_err = m_diffs[2 * k + 1][0];
+      error = m_error_checker.error(x_start, dxdt_start, m_err, dt);
+    }
+    return error;
+  }
+  double calc_h_opt(double h, double error, std::size_t k) const {
+    const double expo = 1.0 / (2 * k + 1);
+    const double facmin = m_facmin_table[k];
+    double fac;
+    if (error == 0.0) fac = 1.0 / facmin;
+    else {
+      fac = STEPFAC2 / std::pow(error / STEPFAC1, expo);
+      fac = std::max(facmin / STEPFAC4, std::min(1.0 / facmin, fac));
+    }
+    return h * fac;
+  }
+  bool should_reject(double error, std::size_t k) const {
+    if (k == m_current_k_opt - 1) {
+      const double d = m_interval_sequence[m_current_k_opt] * m_interval_sequence[m_current_k_opt + 1] /
+                       (m_interval_sequence[0] * m_interval_sequence[0]);
+      return error > d * d;
+    } else if (k == m_current_k_opt) {
+      const double d = m_interval_sequence[m_current_k_opt] / m_interval_sequence[0];
+      return error > d * d;
+    }
+    return error > 1.0;
+  }
+
+  template <class Sys>
+  controlled_step_result try_step(Sys& sys, const state_type& in, const state_type& dxdt, double& t, state_type& out,
+                                  state_type& dxdt_new, double& dt) {
+    const std::size_t n = in.size();
+    for (std::size_t i = 0; i < m_k_max; ++i) m_table[i].resize(n);
+    m_err.resize(n); out.resize(n); dxdt_new.resize(n);
+    bool reject = true;
+    double h_opt[m_k_max + 1], work[m_k_max + 1];
+    m_k_final = 0;
+    double new_h = dt;
+    for (std::size_t k = 0; k <= m_current_k_opt + 1; k++) {
+      const unsigned short steps = static_cast<unsigned short>(m_interval_sequence[k]);
+      if (k == 0) {
+        midpoint(sys, steps, in, dxdt, t, out, dt, m_mp_states[k], m_derivs[k]);
+      } else {
+        midpoint(sys, steps, in, dxdt, t, m_table[k - 1], dt, m_mp_states[k], m_derivs[k]);
+        extrapolate(k, out);
+        for (std::size_t i = 0; i < n; ++i) m_err[i] = 1.0 * out[i] + (-1.0) * m_table[0][i];
+        const double error = m_error_checker.error(in, dxdt, m_err, dt);
+        h_opt[k] = calc_h_opt(dt, error, k);
+        work[k] = static_cast<double>(m_cost[k]) / h_opt[k];
+        m_k_final = k;
+        if ((k == m_current_k_opt - 1) || m_first) {  // convergence before k_opt
+          if (error < 1.0) {
+            reject = false;
+            if ((work[k] < KFAC2 * work[k - 1]) || (m_current_k_opt <= 2)) {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, std::max(2, static_cast<int>(k) + 1));
+              new_h = h_opt[k] * static_cast<double>(m_cost[k + 1]) / static_cast<double>(m_cost[k]);
+            } else {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, std::max(2, static_cast<int>(k)));
+              new_h = h_opt[k];
+            }
+            break;
+          } else if (should_reject(error, k) && !m_first) {
+            reject = true;
+            new_h = h_opt[k];
+            break;
+          }
+        }
+        if (k == m_current_k_opt) {  // convergence at k_opt
+          if (error < 1.0) {
+            reject = false;
+            if (work[k - 1] < KFAC2 * work[k]) {
+              m_current_k_opt = std::max(2, static_cast<int>(m_current_k_opt) - 1);
+              new_h = h_opt[m_current_k_opt];
+            } else if ((work[k] < KFAC2 * work[k - 1]) && !m_last_step_rejected) {
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, static_cast<int>(m_current_k_opt) + 1);
+              new_h = h_opt[k] * static_cast<double>(m_cost[m_current_k_opt]) / static_cast<double>(m_cost[k]);
+            } else
+              new_h = h_opt[m_current_k_opt];
+            break;
+          } else if (should_reject(error, k)) {
+            reject = true;
+            new_h = h_opt[m_current_k_opt];
+            break;
+          }
+        }
+        if (k == m_current_k_opt + 1) {  // convergence at k_opt+1
+          if (error < 1.0) {
+            reject = false;
+            if (work[k - 2] < KFAC2 * work[k - 1])
+              m_current_k_opt = std::max(2, static_cast<int>(m_current_k_opt) - 1);
+            if ((work[k] < KFAC2 * work[m_current_k_opt]) && !m_last_step_rejected)
+              m_current_k_opt = std::min(static_cast<int>(m_k_max) - 1, static_cast<int>(k));
+            new_h = h_opt[m_current_k_opt];
+          } else {
+            reject = true;
+            new_h = h_opt[m_current_k_opt];
+          }
+          break;
+        }
+      }
+    }
+    if (!reject) {
+      sys(out, dxdt_new, t + dt);  // dxdt for the next step and the dense output
+      const double error = prepare_dense_output(static_cast<int>(m_k_final), in, dxdt, dt);
+      if (error > 10.0) {  // we are not as accurate for interpolation as for the steps
+        reject = true;
+        new_h = dt * std::pow(error, -1.0 / (2 * m_k_final + 2));
+      } else {
+        t += dt;
+      }
+    }
+    if (!m_last_step_rejected || (new_h < dt)) dt = new_h;
+    m_last_step_rejected = reject;
+    if (cnt) { if (reject) cnt->rejected++; else cnt->accepted++; }
+    return reject ? fail : success;
+  }
+  template <class Sys> std::pair<double, double> do_step(Sys& sys) {
+    if (m_first) sys(cur_x(), cur_d(), m_t);
+    failed_step_checker fail_checker;
+    controlled_step_result res = fail;
+    m_t_last = m_t;
+    while (res == fail) {
+      res = try_step(sys, cur_x(), cur_d(), m_t, old_x(), old_d(), m_dt);
+      m_first = false;
+      fail_checker();
+    }
+    m_current_state_x1 = !m_current_state_x1;
+    return std::make_pair(m_t_last, m_t);
+  }
+  void calc_state(double t, state_type& out) {
+    const double theta = 2 * ((t - m_t_last) / (m_t - m_t_last)) - 1;  // interpolation polynomial on theta = -1 ... 1
+    out = m_mp_states[0];
+    double theta_pow = theta;
+    for (std::size_t i = 0; i <= 2 * m_k_final + 1; ++i) {
+      for (std::size_t q = 0; q < out.size(); ++q) out[q] = 1.0 * out[q] + theta_pow * m_diffs[i][0][q];
+      theta_pow *= theta;
+    }
+  }
+};
+
+// =====================================================================================
 // rosenbrock4<double> + controller + dense output (SURVEY.md A.6–A.8), dense row-major
 // uBLAS matrix, lu_factorize with partial pivoting, lu_substitute = swap_rows + unit-lower
 // forward solve + upper backward solve (column-oriented axpy form).

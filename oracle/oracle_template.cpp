@@ -28,6 +28,7 @@
 #define ORACLE_RK54_A 12
 #define ORACLE_RK78_A 13
 #define ORACLE_BS 14
+#define ORACLE_BSD 15
 #define ORACLE_ROSENBROCK4 20
 #define ORACLE_METHOD @METHOD@
 
@@ -113,6 +114,10 @@ static stepper_t make_stepper(restated::counters* c) { stepper_t s(atol, rtol); 
 #elif ORACLE_METHOD == ORACLE_BS
 typedef restated::bulirsch_stoer stepper_t;
 #define ORACLE_FAMILY_CONTROLLED 1
+static stepper_t make_stepper(restated::counters* c) { stepper_t s; s.cnt = c; return s; }  // default eps: atol/rtol ignored
+#elif ORACLE_METHOD == ORACLE_BSD
+typedef restated::bulirsch_stoer_dense_out stepper_t;
+#define ORACLE_FAMILY_DENSE 1
 static stepper_t make_stepper(restated::counters* c) { stepper_t s; s.cnt = c; return s; }  // default eps: atol/rtol ignored
 #elif ORACLE_METHOD == ORACLE_RK5_A
 typedef restated::controlled_dopri5 stepper_t;

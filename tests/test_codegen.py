@@ -75,7 +75,7 @@ def _cubin(code: str, flags: int = 0) -> int:
     return size.value
 
 
-@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5", "rk78", "rk5_a", "rk5_i", "rk54_a", "rk78_a", "bs"])
+@pytest.mark.parametrize("method", ["euler", "rk4", "rk54", "rk5", "rk78", "rk5_a", "rk5_i", "rk54_a", "rk78_a", "bs", "bsd"])
 def test_generated_code_compiles_for_sm100a_without_a_device(method):
     g = codegen.generate_sys("lorenz", LORENZ, LORENZ_PARS, False, method)
     assert "__SYS__" not in g.code and "__GLOBALS__" not in g.code

@@ -40,7 +40,7 @@ def test_default_method_reference_test_facts():
     assert df.shape == (4, 2) and df.iloc[0, 1] == 0.01
 
 
-@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a", "rk78_a", "bs"])
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a", "rk78_a", "bs", "bsd"])
 def test_config3_vdp_sweep_every_function(method):
     rtol = 1e-8
     env = {}
@@ -89,7 +89,7 @@ def test_config3_vdp_sweep_every_function(method):
     close(rec2.x[:, :, 100], r2["rec"], rtol)
 
 
-@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a", "rk78_a", "bs"])
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk54_a", "rk78_a", "bs", "bsd"])
 def test_adap_ragged_record_single_and_ensemble(method):
     # name_adap: one observer call per accepted step -> every instance has its own Time column
     env = {}

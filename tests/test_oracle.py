@@ -125,7 +125,7 @@ def test_vdp_dense_times_against_scipy():
 
 
 def test_integrate_adaptive_variants_reach_t1():
-    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a", "rk78_a", "bs"):
+    for method in ("rk4", "rk5_a", "rk5_i", "rk54_a", "rk78_a", "bs", "bsd"):
         o = bo.build(LOGISTIC, method=method)
         r = o.integrate_adaptive([0.01], 0, 7.3, 0.25, record=True)
         assert r["t"][-1] == 7.3
@@ -143,3 +143,18 @@ def test_ensemble_matches_single_runs():
         r = o.integrate_const(X[:, i], 0, 0.5, 0.01, pars=P[:, i])
         assert np.array_equal(e["out"][:, :, i], r["rec"][::10])
         assert np.array_equal(e["x"][:, i], r["x"])
+
+
+def test_bulirsch_stoer_dense_output_is_exact_for_polynomial_solutions():
+    # bsd interpolates with the Taylor polynomial about the interval centre built from extrapolated finite
+    # differences: for x(t) = t^3 + 2t every sample between the (5) real steps must be exact to round-off, which
+    # pins the indexing and the (dt/2)^k / k! scaling of the restated prepare_dense_output / calc_state
+    o = bo.build("dxdt[0] = 3.0 * x[1] * x[1] + 2.0; dxdt[1] = 1.0", method="bsd")
+    r = o.integrate_const([0.0, 0.0], 0, 10, 0.1)
+    t = r["t"]
+    assert r["rows"] == 101 and r["accepted"] <= 8
+    assert np.max(np.abs(r["rec"][:, 0] - (t ** 3 + 2 * t))) < 1e-10 and np.max(np.abs(r["rec"][:, 1] - t)) < 1e-12
+    # README.md:125-132: vanderpol(rep(1e-4, 2), 100, 0.01) with bsd -> 10 001 observer calls
+    o = bo.build(VDP, "mu", False, "bsd")
+    r = o.integrate_const([1e-4, 1e-4], 0, 100, 0.01, pars=[1.0])
+    assert r["rows"] == 10001

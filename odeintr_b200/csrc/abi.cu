@@ -194,7 +194,7 @@ struct odeintr_system_s {
   dev_buf<long long> seg_nfull, accepted, rejected;
   dev_buf<double> seg_hrem, seg_t, times_dev;
   dev_buf<unsigned char> seg_obs;
-  dev_buf<int> status, rows_inst, fail_flags;
+  dev_buf<int> status, rows_inst, fail_flags, rows_min;
   // large-system (lattice) path
   int lattice_stages = 4, sm_count = 148;
   dev_buf<double> lat_buf_a, lat_buf_b, lat_buf_acc;
@@ -727,7 +727,8 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
 }
 
 // Time column integrate_const records with a dense-output stepper: instance independent.
-std::vector<double> dense_const_times(double t0, double t1, double dt) {
+std::vector<double> dense_const_times(double t0, double t1, double dt, bool* optional_last = nullptr) {
+  if (optional_last) *optional_last = false;
   std::vector<double> rec;
   double time = t0;
   rec.push_back(time);
@@ -738,7 +739,15 @@ std::vector<double> dense_const_times(double t0, double t1, double dt) {
     ++k;
     time = t0 + static_cast<double>(k) * dt;
   }
-  if (less_eq_with_sign(time, t1, dt)) rec.push_back(time);
+  if (less_eq_with_sign(time, t1, dt)) {
+    rec.push_back(time);
+    // One more sample can appear: when the stepper's last real step (the one landing on t1) is taken while two or
+    // more samples are still ahead, Boost's inner emission loop also delivers the sample after this one, provided
+    // it is not beyond t1.  Whether that happens depends on the step sizes, i.e. on the instance.
+    ++k;
+    const double extra = t0 + static_cast<double>(k) * dt;
+    if (optional_last && less_eq_with_sign(extra, t1, dt)) { rec.push_back(extra); *optional_last = true; }
+  }
   return rec;
 }
 
@@ -755,6 +764,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   CU_TRY(h->accepted.reserve(m)); CU_TRY(h->rejected.reserve(m)); CU_TRY(h->status.reserve(m));
   CU_TRY(h->rows_inst.reserve(m)); CU_TRY(h->fail_flags.reserve(1));
   std::vector<double> rec_t;
+  bool optional_last = false;  // rec_t ends with a sample that only some instances produce
   if (mode == ODEINTR_MODE_TIMES) {
     CU_TRY(h->times_dev.reserve(n_times));
     if ((rc = upload(h, h->times_dev.p, times, n_times * sizeof(double)))) return rc;
@@ -762,7 +772,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
     a.n_times = (long long)n_times;
     rec_t.assign(times, times + n_times);
   } else if (mode == ODEINTR_MODE_CONST && record) {
-    if (h->dense) rec_t = dense_const_times(t0, t1, dt);
+    if (h->dense) rec_t = dense_const_times(t0, t1, dt, &optional_last);
     else {
       const long long n = const_step_count(t0, t1, dt);
       rec_t.resize((size_t)n + 1);
@@ -777,6 +787,12 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   a.max_tries = h->max_tries;
   a.accepted = h->accepted.p; a.rejected = h->rejected.p; a.status = h->status.p; a.rows = h->rows_inst.p;
   a.fail_flags = h->fail_flags.p;
+  CU_TRY(h->rows_min.reserve(1));
+  if (optional_last) {
+    const int big = 0x7fffffff;
+    CU_TRY(cudaMemcpyAsync(h->rows_min.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    a.rows_min = h->rows_min.p;
+  }
   const unsigned block = (unsigned)h->block_adaptive;
   const unsigned grid = (unsigned)((m + block - 1) / block);
   CU_TRY(cudaMemsetAsync(h->fail_flags.p, 0, sizeof(int), h->stream));
@@ -807,9 +823,11 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   }
   if ((rc = launch(h, h->k_adaptive, h->stream, grid, block, &a))) return rc;
   if ((rc = end_timing(h))) return rc;
-  int flags = 0;
+  int flags = 0, rows_min = 0x7fffffff;
   CU_TRY(cudaMemcpyAsync(&flags, h->fail_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (optional_last) CU_TRY(cudaMemcpyAsync(&rows_min, h->rows_min.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  if (optional_last && !flags && rows_min < (int)rec_t.size()) rec_t.resize((size_t)std::max(rows_min, 1));
   h->last_steps = 0;
   if (record) {
     h->rec_t = rec_t;
@@ -913,7 +931,7 @@ int odeintr_destroy(odeintr_system_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->x.release(); h->pars.release(); h->out.release(); h->stage.release(); h->t_rec.release();
   h->seg_nfull.release(); h->seg_hrem.release(); h->seg_t.release(); h->seg_obs.release(); h->times_dev.release();
-  h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release();
+  h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release(); h->rows_min.release();
   h->work_counter.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
   h->lat_work.release(); h->lat_err.release();

@@ -79,6 +79,7 @@ struct odeintr_adaptive_args {
   int* status;
   int* rows;                  // per-instance observer calls (may be null)
   int* fail_flags;            // one word: OR of every instance's non-zero status (may be null)
+  int* rows_min;              // one word: minimum over instances of the observer calls made (may be null)
 };
 
 // Large coupled system ("lattice") fused Runge-Kutta stage launch, SURVEY.md §8(d) config 5:

@@ -27,6 +27,7 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
   typedef odeintr_b200::ODEINTR_STEPPER<Sys, N> Stepper;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.m) return;
+  const unsigned live = __activemask();  // lanes of this warp that own an instance
 
   Sys sys;
   sys.load_params(a.pars, a.par_ld, i * a.par_inc);
@@ -79,4 +80,12 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
     if (status != ODEINTR_STATUS_OK && a.fail_flags) atomicOr(a.fail_flags, status);
   }
   if (a.rows) a.rows[i] = obs.rows;
+  if (a.rows_min) {
+    // integrate_const with a dense-output stepper may or may not emit the sample at the very end of the interval
+    // (it depends on whether the last real step was taken while that sample was still ahead): the host keeps the
+    // rows every instance produced
+    __syncwarp(live);
+    const int least = __reduce_min_sync(live, obs.rows);
+    if ((threadIdx.x & 31) == (__ffs(live) - 1)) atomicMin(a.rows_min, least);
+  }
 }

@@ -79,7 +79,11 @@ def test_config3_vdp_sweep_every_function(method):
     assert rec.rows == e["rows"]
     close(rec.x, e["out"], rtol)
     single = ora.integrate_const(x0, 0, 10.0, 0.05, pars=[mus[5]])
-    assert np.array_equal(rec.time, single["t"])
+    # (dense steppers may or may not deliver the sample at t1 itself, depending on the instance's last real step;
+    #  an ensemble record keeps the rows every instance has)
+    assert rec.rows in (single["rows"], single["rows"] - 1) and np.array_equal(rec.time, single["t"][:rec.rows])
+    df = env["vpol"](x0, 10.0, 0.05)  # the sweep is still set: first instance only?  no: one state x all mu
+    assert df.rows == rec.rows
 
     # name_no_record: integrate_adaptive without observer; state is left for get_state
     fin = env["vpol_no_record"](x0, 7.3, 0.01)
@@ -115,6 +119,23 @@ def test_adap_ragged_record_single_and_ensemble(method):
         assert n == r["rows"]
         close(rec.times_per_instance[i, :n], r["t"], 1e-7)
         close(rec.x[:n, :, i], r["rec"], 1e-7 * 100)
+
+
+@pytest.mark.parametrize("method,rows", [("rk5_i", 200), ("bsd", 201)])
+def test_dense_const_row_count_follows_the_last_real_step(method, rows):
+    # integrate_const(0, 10, 0.05) with a dense-output stepper: fl(199 * 0.05) + 0.05 > 10, so Boost's outer loop
+    # stops at 9.95; the sample at 10.0 appears only if the inner emission loop runs after the stepper has already
+    # reached t1 (Bulirsch-Stoer's big last step does, dopri5 at 1e-8 does not).  A single trajectory must return
+    # exactly the reference's rows.
+    env = {}
+    odeintr_b200.compile_sys("v1", VDP, "mu", method=method, atol=1e-8, rtol=1e-8, env=env)
+    ora = bo.build(VDP, "mu", False, method, atol=1e-8, rtol=1e-8)
+    env["v1_set_params"](mu=0.535)
+    df = env["v1"](np.array([2.0, 0.0]), 10.0, 0.05)
+    ref = ora.integrate_const([2.0, 0.0], 0, 10.0, 0.05, pars=[0.535])
+    assert len(df) == ref["rows"] == rows
+    assert np.array_equal(df["Time"].to_numpy(), ref["t"])
+    close(df[["X1", "X2"]].to_numpy(), ref["rec"], 1e-6)
 
 
 def test_runaway_instances_are_stopped_and_reported():

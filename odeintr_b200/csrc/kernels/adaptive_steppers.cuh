@@ -46,13 +46,12 @@ struct dopri5_controlled {
     core.do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt);
     core.calc_error(dxdt_in, dxdt_out, dt, xerr);
     const double err = error_norm<N>(in, dxdt_in, xerr, dt, eps_abs, eps_rel);
-    if (err > 1.0) {
-      dt = decrease_step(dt, err, 4);
+    const double dt_used = dt;
+    if (!adjust_step(err, dt, 4, 5, 0.00032)) {
       cnt.rejected++;
       return false;
     }
-    t += dt;
-    dt = increase_step(dt, err, 5);
+    t += dt_used;
     cnt.accepted++;
     return true;
   }
@@ -118,13 +117,12 @@ struct rk54_controlled {
       }
     }
     const double err = error_norm<N>(x, k1, xerr, dt, eps_abs, eps_rel);
-    if (err > 1.0) {
-      dt = decrease_step(dt, err, 4);
+    const double dt_used = dt;
+    if (!adjust_step(err, dt, 4, 5, 0.00032)) {
       cnt.rejected++;
       return false;
     }
-    t += dt;
-    dt = increase_step(dt, err, 5);
+    t += dt_used;
     x = xnew;
     cnt.accepted++;
     return true;

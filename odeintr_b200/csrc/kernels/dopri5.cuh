@@ -114,17 +114,22 @@ ODEINTR_DEV double error_norm(const vec<N>& x_old, const vec<N>& dxdt_old, const
   return m;
 }
 
-// default_step_adjuster (max_dt = 0)
-ODEINTR_DEV double decrease_step(double dt, const double error, const int error_order) {
-  dt *= fmax(9.0 / 10.0 * pow(error, -1.0 / (error_order - 1)), 1.0 / 5.0);
-  return dt;
-}
-ODEINTR_DEV double increase_step(double dt, double error, const int stepper_order) {
-  if (error < 0.5) {
-    error = fmax(pow(5.0, -static_cast<double>(stepper_order)), error);
-    dt *= 9.0 / 10.0 * pow(error, -1.0 / stepper_order);
-  }
-  return dt;
+// default_step_adjuster (max_dt = 0): decrease_step on rejection, increase_step on acceptance
+//   reject:  dt *= max(0.9 * pow(err, -1/(error_order-1)), 1/5)
+//   accept:  if err < 0.5:  dt *= 0.9 * pow(max(5^-stepper_order, err), -1/stepper_order)
+// folded into ONE pow call per attempt with per-lane arguments: the values are exactly Boost's, but the lanes of a
+// warp that reject, grow or keep their step no longer execute two serialized pow expansions (~100 instructions
+// each).  5^-stepper_order is passed as the literal glibc's pow returns (5^-5 = 0.00032, 5^-8 = 2.56e-6).
+// Returns true when the step is accepted; the caller advances t with the OLD dt before calling.
+ODEINTR_DEV bool adjust_step(const double err, double& dt, const int error_order, const int stepper_order,
+                             const double pow5_minus_order) {
+  const bool rejected = err > 1.0;
+  const double base = rejected ? err : fmax(pow5_minus_order, err);
+  const double expo = rejected ? -1.0 / (error_order - 1) : -1.0 / stepper_order;
+  const double p = pow(base, expo);
+  if (rejected) dt *= fmax(9.0 / 10.0 * p, 1.0 / 5.0);
+  else if (err < 0.5) dt *= 9.0 / 10.0 * p;
+  return !rejected;
 }
 
 // runge_kutta_dopri5 as a plain stepper (method "rk5"): explicit_error_stepper_fsal_base::do_step keeps

@@ -104,13 +104,12 @@ struct rk78_controlled {
     sys.sys(x, k1, t);
     rkf78_step<Sys, N, true>(sys, x, k1, t, dt, xn, xe);
     const double err = error_norm<N>(x, k1, xe, dt, eps_abs, eps_rel);
-    if (err > 1.0) {
-      dt = decrease_step(dt, err, 7);
+    const double dt_used = dt;
+    if (!adjust_step(err, dt, 7, 8, 2.56e-6)) {
       cnt.rejected++;
       return false;
     }
-    t += dt;
-    dt = increase_step(dt, err, 8);
+    t += dt_used;
     x = xn;
     cnt.accepted++;
     return true;

@@ -126,7 +126,10 @@ ODEINTR_DEV bool adjust_step(const double err, double& dt, const int error_order
   const bool rejected = err > 1.0;
   const double base = rejected ? err : fmax(pow5_minus_order, err);
   const double expo = rejected ? -1.0 / (error_order - 1) : -1.0 / stepper_order;
-  const double p = pow(base, expo);
+  // (no lane of the warp needs it when every error lies in [0.5, 1]: common in smooth, sorted sweeps)
+  const bool needed = rejected || err < 0.5;
+  double p = 1.0;
+  if (__any_sync(__activemask(), needed)) p = pow(base, expo);
   if (rejected) dt *= fmax(9.0 / 10.0 * p, 1.0 / 5.0);
   else if (err < 0.5) dt *= 9.0 / 10.0 * p;
   return !rejected;

@@ -170,6 +170,8 @@ def _bind_to_gpu_numa_node(index):
     """Run this rank's host threads (and hence first-touch its pinned buffers) on the CPUs NVML reports as local
     to its GPU: with 8 ranks streaming 29 GB per step each, host buffers on the wrong socket turn the end-to-end
     path into an inter-socket-link benchmark."""
+    if os.environ.get("ODEINTR_BENCH_NO_BIND"):
+        return
     try:
         import pynvml
 
@@ -298,7 +300,7 @@ def main():
     # ---- end-to-end arm: host buffers through odeintr_integrate_const_host --------------------------------
     e2e = None
     if not args.no_e2e:
-        bytes_per_inst = (11 * 3 + 3 + 3) * 8
+        bytes_per_inst = (11 * 3 + 3) * 8
         try:
             avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
         except Exception:
@@ -308,11 +310,9 @@ def main():
         lib.odeintr_release_record(h)
         n_x, n_out = 3 * m_e2e, 11 * 3 * m_e2e
         px = lib.odeintr_host_alloc(n_x * 8)
-        pf = lib.odeintr_host_alloc(n_x * 8)
         po = lib.odeintr_host_alloc(n_out * 8)
-        assert px and pf and po, "pinned allocation failed: " + _abi.last_error()
+        assert px and po, "pinned allocation failed: " + _abi.last_error()
         x_host = np.ctypeslib.as_array(C.cast(px, _abi.c_dbl_p), shape=(3, m_e2e))
-        xf_host = np.ctypeslib.as_array(C.cast(pf, _abi.c_dbl_p), shape=(3, m_e2e))
         out_host = np.ctypeslib.as_array(C.cast(po, _abi.c_dbl_p), shape=(11, 3, m_e2e))
         # synthetic initial states: generated once on the device (same Philox stream), copied to the host buffer
         assert lib.odeintr_fill_state_uniform(h, m_e2e, SEED, rank * M, lo, hi) == 0, _abi.last_error()
@@ -320,8 +320,10 @@ def main():
         out_host[...] = 0.0  # touch the pages
 
         def e2e_pass():
+            # what NAME(init, duration, step) returns is the observer record; its last row IS the final state, so no
+            # separate final-state copy is requested (x_final = NULL)
             rc = lib.odeintr_integrate_const_host(h, C.cast(px, _abi.c_dbl_p), m_e2e, None, 0, 0.0, T_END, DT, STRIDE,
-                                                  C.cast(po, _abi.c_dbl_p), n_out, C.cast(pf, _abi.c_dbl_p), 0)
+                                                  C.cast(po, _abi.c_dbl_p), n_out, None, 0)
             if rc != 0:
                 raise RuntimeError(_abi.last_error())
 
@@ -337,17 +339,17 @@ def main():
         barrier()
         wall_e2e = max_over_ranks(time.perf_counter() - t0)
         t_e2e = max_over_ranks(t_e2e)
-        # spot check: the record of the last pass starts at the inputs and ends at the returned final state
+        # spot check: the record of the last pass starts at the inputs and its last row is a propagated state
         assert np.array_equal(out_host[0, :, :4096], x_host[:, :4096])
-        assert np.array_equal(out_host[10, :, :4096], xf_host[:, :4096])
+        assert np.all(np.isfinite(out_host[10, :, :4096])) and not np.array_equal(out_host[10, :, :4096], x_host[:, :4096])
         e2e = {
             "value": world * m_e2e * steps_per_pass * k_e2e / wall_e2e, "unit": UNIT,
-            "h2d_bytes_per_step": n_x * 8, "d2h_bytes_per_step": (n_out + n_x) * 8,
+            "h2d_bytes_per_step": n_x * 8, "d2h_bytes_per_step": n_out * 8,
             "instances_per_gpu": m_e2e, "steps": k_e2e, "ms_per_step": 1e3 * wall_e2e / k_e2e,
             "device_ms_per_step": 1e3 * t_e2e / k_e2e,
             "api": "odeintr_integrate_const_host (pinned host buffers, chunked 3-stream copy/compute overlap)",
         }
-        lib.odeintr_host_free(px); lib.odeintr_host_free(pf); lib.odeintr_host_free(po)
+        lib.odeintr_host_free(px); lib.odeintr_host_free(po)
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------
     cpu = None

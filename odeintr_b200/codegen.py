@@ -425,6 +425,17 @@ def parse_cell_loops(sys_src: str) -> CellLoops:
             pos += 1
         if pos >= n:
             break
+        # `laplace4(x, dxdt, D);` -- the helper the reference documents for the method of lines
+        # (R/odeintr.R:383-388,398) but never shipped: dxdt = D * (periodic 4-neighbour Laplacian of x)
+        ml = re.match(r"laplace4\s*\(\s*x\s*,\s*dxdt\s*,", src[pos:])
+        if ml:
+            p_open = pos + src[pos:].index("(")
+            p_close = _match(src, p_open, "(", ")")
+            coeff = src[pos + ml.end():p_close].strip()
+            loops.append(("int", "odeintr_i", "0", "N",
+                          "dxdt[odeintr_i] = (%s) * laplace2D(x, odeintr_i / M, odeintr_i %% M);" % coeff))
+            pos = p_close + 1
+            continue
         m = re.match(r"for\s*\(", src[pos:])
         if not m:
             raise OdeintrError("large-system snippets must be loops over the cells of the state "
@@ -530,7 +541,7 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
         "__FOOTERS__": footers,
     })
     # an M x M lattice (laplace2D & friends, or M itself) is walked in column strips by the stage kernel
-    if re.search(r"\b(laplace2D|d_left|d_right|d_up|d_down|M)\b", _strip_comments(sys + " " + globals)):
+    if re.search(r"\b(laplace4|laplace2D|d_left|d_right|d_up|d_down|M)\b", _strip_comments(sys + " " + globals)):
         code = code.replace("#define ODEINTR_NFIELDS", "#define ODEINTR_LATTICE_2D 1\n#define ODEINTR_NFIELDS", 1)
     code = code.replace("__NFIELDS__", str(len(loops.offsets)))
     code = code.replace("__CELL_START__", loops.start).replace("__CELL_BOUND__", loops.bound)

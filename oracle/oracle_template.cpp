@@ -51,6 +51,11 @@ static inline double laplace2D(const state_type& x, int i, int j) {
          (x[bound(i + 1) * M + j] - c);
 }
 
+// the helper the reference's documentation promises (R/odeintr.R:383-388) but its sources never define
+static inline void laplace4(const state_type& x, state_type& dxdt, double D) {
+  for (std::size_t i = 0; i < N; ++i) dxdt[i] = D * laplace2D(x, static_cast<int>(i) / M, static_cast<int>(i) % M);
+}
+
 struct rhs_t {
   restated::counters* cnt;
   void operator()(const state_type& x, state_type& dxdt, const double t) const {

@@ -62,3 +62,12 @@ for (int i = 0; i < L; ++i) {
 """
 CHAIN_PARS = {"beta": 1.0, "K": 0.5}
 CHAIN_GLOBALS = "static const int L = N / 2;"
+
+# the reference's documented large-system example, verbatim (R/odeintr.R:396-401); `laplace4` is promised by the
+# documentation but missing from the reference's sources, here it is provided
+BISTABLE_DOC = """
+ laplace4(x, dxdt, D);  // parallel 4-point discrete laplacian
+ #pragma omp parallel for
+ for (int i = 0; i < N; ++i)
+   dxdt[i] += a * x[i] * (1 - x[i]) * (x[i] - b);
+"""

@@ -121,6 +121,9 @@ def test_cell_loop_parser():
     assert [o.replace(" ", "") for o in loops.offsets] == ["odeintr_c", "L+odeintr_c"]
     loops = codegen.parse_cell_loops(BISTABLE_2D)
     assert len(loops.bodies) == 2 and len(loops.offsets) == 1 and "odeintr_k[0] +=" in loops.bodies[1]
+    from systems import BISTABLE_DOC
+    loops = codegen.parse_cell_loops(BISTABLE_DOC)
+    assert len(loops.bodies) == 2 and "laplace2D(x, odeintr_i / M, odeintr_i % M)" in loops.bodies[0]
     with pytest.raises(OdeintrError, match="same range"):
         codegen.parse_cell_loops("for (int i = 0; i < N; ++i) dxdt[i] = 1; for (int i = 1; i < N; ++i) dxdt[i] += 1;")
     g = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i

@@ -6,7 +6,7 @@ import pytest
 
 import odeintr_b200
 from oracle import build_oracle as bo
-from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
+from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_DOC, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
 
 pytestmark = pytest.mark.gpu
 
@@ -207,3 +207,21 @@ def test_2d_lattice_strip_traversal_bit_exact():
     fin = env["b2s_no_record"](x0, 1.0, 0.1)
     ref = ora.integrate_adaptive(x0, 0.0, 1.0, 0.1)
     assert np.array_equal(bits(fin), bits(ref["x"]))
+
+
+def test_documented_bistable_example_with_laplace4():
+    # R/odeintr.R:393-413: compile_sys_openmp("bistable", bistable, sys_dim = M * M, pars = c(D = 0.1, a = 1.0, b = 1/2),
+    # const = TRUE); bistable_at(inic, 10 ^ (0:3)) -- default method rk5_i, M = 200 in the documentation
+    m = 64
+    env = {}
+    odeintr_b200.compile_sys_openmp("bistable", BISTABLE_DOC, sys_dim=m * m, pars={"D": 0.1, "a": 1.0, "b": 1 / 2},
+                                    const=True, env=env)
+    ora = bo.build(BISTABLE_DOC, {"D": 0.1, "a": 1.0, "b": 1 / 2}, True, "rk5_i", sys_dim=m * m)
+    rng = np.random.default_rng(81)
+    inic = rng.integers(0, 2, m * m).astype(np.float64)
+    at = 10.0 ** np.arange(0, 3)
+    df = env["bistable_at"](inic, at)
+    adv = ora.integrate_const(inic, 0.0, at[0], 1.0, record=False)
+    ref = ora.integrate_times(adv["x"], at, 1.0)
+    assert df.shape == (3, m * m + 1)
+    assert np.max(np.abs(cols(df) - ref["rec"])) <= 1e-5

@@ -75,6 +75,10 @@ ODEINTR_DEV bool flat_times_dense(St& st, Sys& sys, vec<N>& x, const double* tim
 }
 
 template <class St, class Sys, int N, class Obs>
+ODEINTR_DEV bool flat_adaptive_dense(St& st, Sys& sys, vec<N>& x, const double t0, const double t1, const double dt,
+                                     Obs& obs);
+
+template <class St, class Sys, int N, class Obs>
 ODEINTR_DEV bool flat_const_dense(St& st, Sys& sys, vec<N>& x, const double t0, const double t1, const double dt,
                                   Obs& obs) {
   double time = t0;
@@ -83,7 +87,7 @@ ODEINTR_DEV bool flat_const_dense(St& st, Sys& sys, vec<N>& x, const double t0, 
   time += dt;
   long long obs_step = 1;
   int mode = 0;  // 0: top of Boost's outer loop, 1: inside `while (st.t <= time) do_step`, 2: the single last step
-  bool in_step = false, ok = true, done = false;
+  bool in_step = false, ok = true, done = false, stepped = false;
   int idle = 0;
   while (!done) {
     if (!in_step) {
@@ -119,12 +123,19 @@ ODEINTR_DEV bool flat_const_dense(St& st, Sys& sys, vec<N>& x, const double t0, 
       idle = 0;
     }
     const int r = st.try_once(sys);
-    if (r > 0) { in_step = false; if (mode == 2) mode = 0; }
+    if (r > 0) { in_step = false; stepped = true; if (mode == 2) mode = 0; }
     else if (r < 0) { ok = false; done = true; }
   }
   if (ok && less_eq_with_sign(time, t1, dt)) {
-    st.calc_state(time, x);
-    obs(x, time);
+    if (!stepped) {
+      // no step was taken (dt <= t1 - t0 < 2 dt), so there is no interpolant: integrate to the sample time with
+      // real steps instead of Boost's read of unset stage vectors (see integrate_const_dense in integrate_loops.cuh)
+      null_observer quiet;
+      ok = flat_adaptive_dense(st, sys, x, t0, time, dt, quiet);
+    } else {
+      st.calc_state(time, x);
+    }
+    if (ok) obs(x, time);
   }
   return ok;
 }

@@ -84,6 +84,7 @@ ODEINTR_HD bool integrate_const_dense(St& st, Sys& sys, State& x, const double t
   obs(x, time);
   time += dt;
   long long obs_step = 1;
+  bool stepped = false;
   while (less_eq_with_sign(time + dt, t1, dt)) {
     bool progressed = false;
     while (less_eq_with_sign(time, st.t, dt)) {  // every sample the last real step already covers
@@ -96,12 +97,12 @@ ODEINTR_HD bool integrate_const_dense(St& st, Sys& sys, State& x, const double t
     if (less_with_sign(st.t + st.dt, t1, st.dt)) {
       while (less_eq_with_sign(st.t, time, dt)) {
         if (!st.do_step(sys)) return false;
-        progressed = true;
+        progressed = true; stepped = true;
       }
     } else if (less_with_sign(st.t, t1, st.dt)) {
       st.initialize(st.current_state(), st.t, t1 - st.t);
       if (!st.do_step(sys)) return false;
-      progressed = true;
+      progressed = true; stepped = true;
     }
     if (!progressed) {
       // st.t is NaN (or the step collapsed): Boost's loop would spin here forever; stop this instance
@@ -110,7 +111,16 @@ ODEINTR_HD bool integrate_const_dense(St& st, Sys& sys, State& x, const double t
     }
   }
   if (less_eq_with_sign(time, t1, dt)) {
-    st.calc_state(time, x);
+    if (!stepped) {
+      // dt <= t1 - t0 < 2 dt: the loop above never took a step, so there is no interpolant; Boost calls
+      // calc_state anyway and reads unset stage vectors (undefined behaviour - this is what name_at() runs into
+      // when times[0] - start equals step_size, e.g. the documented bistable_at(inic, 10^(0:3)) example).
+      // Conscious fix: integrate to the sample time with real steps instead.
+      null_observer quiet;
+      if (!integrate_adaptive_dense(st, sys, x, t0, time, dt, quiet)) return false;
+    } else {
+      st.calc_state(time, x);
+    }
     obs(x, time);
   }
   return true;

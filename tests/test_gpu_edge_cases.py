@@ -99,3 +99,26 @@ def test_wider_system_lorenz96_in_registers():
     e = ora.ensemble(0, x0.copy(), Fs[None, :], 0.0, 1.0, 0.01, out_rows=rec.rows, threads=2)
     assert np.array_equal(bits(rec.x), bits(e["out"]))
     assert code.system.kernel_attributes("odeintr_plain_ensemble")["local_bytes"] == 0
+
+
+@pytest.mark.parametrize("kind", ["rk5_i", "implicit"])
+def test_at_with_first_time_one_step_after_start(kind):
+    # name_at(init, times, step_size, start) with times[0] - start == step_size: Boost's dense integrate_const
+    # evaluates its interpolant before any step was taken (undefined behaviour in the reference: unset stage
+    # vectors).  Product and oracle make the same conscious fix: real steps to times[0].
+    env = {}
+    src = "dxdt[0] = -x[0] * x[0]"
+    if kind == "implicit":
+        odeintr_b200.compile_implicit("q", src, env=env)
+        ora = bo.build(src, method="rosenbrock4")
+    else:
+        odeintr_b200.compile_sys("q", src, env=env)
+        ora = bo.build(src, method="rk5_i")
+    times = np.array([1.0, 10.0, 100.0])
+    df = env["q_at"](2.0, times)  # default step_size = 1, start = 0
+    adv = ora.integrate_const([2.0], 0.0, 1.0, 1.0, record=False)
+    ref = ora.integrate_times(adv["x"], times, 1.0)
+    assert np.all(np.isfinite(df["X1"]))
+    close(df[["X1"]].to_numpy(), ref["rec"], 1e-6)
+    exact = 2.0 / (1.0 + 2.0 * times)
+    assert np.max(np.abs(df["X1"].to_numpy() - exact)) < 1e-4

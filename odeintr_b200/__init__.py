@@ -6,7 +6,7 @@ the R-closure ``integrate_sys`` path): ``compile_sys``, ``comp
 """
 from .codegen import JacobianCpp, OdeintrError, r_num  # noqa: F401
 from .api import compile_sys, compile_sys_openmp, compile_implicit, attached  # noqa: F401
-from .system import CompiledSystem, EnsembleRecord  # noqa: F401
+from .system import CompiledSystem, EnsembleRecord, proc_output  # noqa: F401
 
 __all__ = ["compile_sys", "compile_sys_openmp", "compile_implicit", "JacobianCpp", "OdeintrError",
            "CompiledSystem", "EnsembleRecord", "attached"]

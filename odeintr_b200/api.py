@@ -23,12 +23,12 @@ class GeneratedCode(str):
     env = None
 
 
-def _install(gen: codegen.Generated, compile: bool, env: Optional[dict], flags: int) -> GeneratedCode:
+def _install(gen: codegen.Generated, compile: bool, env: Optional[dict], flags: int, observer=None) -> GeneratedCode:
     code = GeneratedCode(gen.code)
     if compile:
         from .system import CompiledSystem
 
-        system = CompiledSystem(gen, flags=flags)
+        system = CompiledSystem(gen, flags=flags, observer=observer)
         if env is None:
             env = {}
         env.update(system.exports())
@@ -40,11 +40,13 @@ def _install(gen: codegen.Generated, compile: bool, env: Optional[dict], flags: 
 
 def compile_sys(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, atol=1e-6, rtol=1e-6, globals="",
                 headers="", footers="", compile=True, observer=None, env=None, flags=0):
-    """R/odeintr.R:293-357.  ``observer`` (an R closure in the reference, SURVEY.md §2 #7) is out of scope."""
-    if observer is not None:
-        raise OdeintrError("custom observer functions are not provided by odeintr_b200")
+    """R/odeintr.R:293-357.  ``observer`` is a callable ``f(x, t)`` (an R closure in the reference): it is replayed on
+    the host over the samples the GPU recorded, and NAME_get/set_observer and NAME_get/set_output_processor are
+    installed as the reference's observer template does (R/odeintr.R:343-347)."""
+    if observer is not None and not callable(observer):
+        raise OdeintrError("observer must be a function of (x, t)")
     gen = codegen.generate_sys(name, sys, pars, const, method, sys_dim, atol, rtol, globals, headers, footers)
-    return _install(gen, compile, env, flags)
+    return _install(gen, compile, env, flags, observer)
 
 
 def compile_sys_openmp(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, atol=1e-6, rtol=1e-6,

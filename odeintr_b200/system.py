@@ -49,10 +49,34 @@ def _frame(time: np.ndarray, cols: np.ndarray):
     return pd.DataFrame(data)
 
 
+def proc_output(res):
+    """Default output processor of the observer path, R/utils.R:242-262: ``res`` = [times, list of observer results]
+    -> data frame with Time + the results' names (X1..Xk when unnamed); the raw list when the results are ragged."""
+    import pandas as pd
+
+    times, xs = res[0], res[1]
+    if len(times) == 0:
+        return None
+    rows = [list(x.values()) if isinstance(x, dict) else list(np.atleast_1d(x)) for x in xs]
+    if len({len(r) for r in rows}) != 1:
+        return res
+    first = xs[0]
+    names = list(first.keys()) if isinstance(first, dict) else ["X%d" % (k + 1) for k in range(len(rows[0]))]
+    data = {"Time": np.asarray(times)}
+    for k, n in enumerate(names):
+        data[n] = [r[k] for r in rows]
+    return pd.DataFrame(data)
+
+
 class CompiledSystem:
     """One NVRTC-compiled system resident on one GPU."""
 
-    def __init__(self, gen: Generated, flags: int = 0):
+    def __init__(self, gen: Generated, flags: int = 0, observer=None):
+        # observer: the Python analogue of compile_sys(..., observer = f) (compile_sys_r_obs_template.cpp:44-53).
+        # The reference calls the closure from inside the stepper loop; here the states are recorded on the GPU and
+        # the closure is replayed over the stored samples on the host (SURVEY.md §8 f4): same (x, t) sequence.
+        self.observer = observer
+        self.output_processor = proc_output
         self.gen = gen
         self.name = gen.name
         self.N = gen.sys_dim
@@ -128,6 +152,29 @@ class CompiledSystem:
         self._check(self._lib.odeintr_reset_observer(self._h))
 
     def get_output(self):
+        if self.observer is not None:
+            return self._get_observed_output()
+        return self._get_state_output()
+
+    def _get_observed_output(self):
+        """NAME_get_output() of the observer template (compile_sys_r_obs_template.cpp:64-71): the observer sees every
+        recorded (x, t); results of length 0 are skipped; the output processor shapes the list."""
+        rec = self._get_state_output()
+        if isinstance(rec, EnsembleRecord):
+            raise OdeintrError("custom observers are replayed for single trajectories only")
+        times, xs = [], []
+        if rec is not None:
+            t = rec["Time"].to_numpy()
+            x = rec.iloc[:, 1:].to_numpy()
+            for k in range(len(t)):
+                r = self.observer(x[k].copy(), float(t[k]))
+                if r is None or (hasattr(r, "__len__") and len(r) == 0):
+                    continue
+                xs.append(r)
+                times.append(float(t[k]))
+        return self.output_processor([times, xs])
+
+    def _get_state_output(self):
         rows = int(self._lib.odeintr_output_rows(self._h))
         m = self.n_instances
         ragged = bool(self._lib.odeintr_output_is_ragged(self._h))
@@ -323,4 +370,9 @@ class CompiledSystem:
         if self.P:
             fns[n + "_set_params"] = self.set_params
             fns[n + "_get_params"] = self.get_params
+        if self.observer is not None:  # compile_sys_r_obs_template.cpp:171-197
+            fns[n + "_get_observer"] = lambda: self.observer
+            fns[n + "_set_observer"] = lambda f: setattr(self, "observer", f)
+            fns[n + "_get_output_processor"] = lambda: self.output_processor
+            fns[n + "_set_output_processor"] = lambda f: setattr(self, "output_processor", f)
         return fns

@@ -122,3 +122,25 @@ def test_at_with_first_time_one_step_after_start(kind):
     close(df[["X1"]].to_numpy(), ref["rec"], 1e-6)
     exact = 2.0 / (1.0 + 2.0 * times)
     assert np.max(np.abs(df["X1"].to_numpy() - exact)) < 1e-4
+
+
+def test_custom_observer_is_replayed_over_recorded_samples():
+    # README.md:66-90 style: compile_sys(..., observer = function(x, t) c(Prey = x[1], Predator = x[2], Ratio = x[1] / x[2]))
+    lv = "dxdt[0] = x[0] - x[0] * x[1]; dxdt[1] = x[0] * x[1] - x[1]"
+    env = {}
+    obs = lambda x, t: {"Prey": x[0], "Predator": x[1], "Ratio": x[0] / x[1]}
+    odeintr_b200.compile_sys("lv", lv, method="rk4", observer=obs, env=env)
+    plain = {}
+    odeintr_b200.compile_sys("lv0", lv, method="rk4", env=plain)
+    df = env["lv"](np.array([1.0, 0.5]), 5.0, 0.1)
+    ref = plain["lv0"](np.array([1.0, 0.5]), 5.0, 0.1)
+    assert list(df.columns) == ["Time", "Prey", "Predator", "Ratio"] and len(df) == len(ref)
+    assert np.array_equal(df["Prey"].to_numpy(), ref["X1"].to_numpy())
+    assert np.array_equal(df["Ratio"].to_numpy(), (ref["X1"] / ref["X2"]).to_numpy())
+    # unnamed results get X1..Xk (proc_output), samples for which the observer returns nothing are skipped
+    env["lv_set_observer"](lambda x, t: [x[0] + x[1]] if t >= 1.0 else [])
+    out = env["lv_get_output"]()
+    assert list(out.columns) == ["Time", "X1"] and out["Time"].iloc[0] >= 1.0 - 1e-12
+    assert env["lv_get_observer"]() is not None
+    env["lv_set_output_processor"](lambda res: len(res[0]))
+    assert env["lv_get_output"]() == len(out)

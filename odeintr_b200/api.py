@@ -50,10 +50,17 @@ def compile_sys(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, a
 
 
 def compile_sys_openmp(name, sys, pars=None, const=False, method="rk5_i", sys_dim=-1, atol=1e-6, rtol=1e-6,
-                       globals="", headers="", footers="", compile=True, env=None, flags=0):
-    """R/odeintr.R:418-470: the large-system variant (Boost openmp_range_algebra in the reference)."""
+                       globals="", headers="", footers="", compile=True, env=None, flags=0, halo=None):
+    """R/odeintr.R:418-470: the large-system variant (Boost openmp_range_algebra in the reference).
+
+    ``halo`` (extension, optional): the stencil radius of the loop body on a 1-D lattice -- how many cells to the
+    left / right of cell i the body reads.  Declaring it lets a fixed-step rk4 step run as one temporally blocked
+    kernel (8x less HBM traffic, same bits); accesses beyond it are detected at run time and reported."""
     gen = codegen.generate_sys_openmp(name, sys, pars, const, method, sys_dim, atol, rtol, globals, headers, footers)
-    return _install(gen, compile, env, flags)
+    code = _install(gen, compile, env, flags)
+    if halo is not None and compile:
+        code.system.set_halo(int(halo), gen.n_fields)
+    return code
 
 
 def compile_implicit(name, sys, pars=None, const=False, sys_dim=-1, jacobian=None, atol=1e-6, rtol=1e-6, globals="",

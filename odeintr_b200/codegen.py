@@ -300,6 +300,7 @@ class Generated:
     family: str          # "plain" | "adaptive" | "implicit" | "lattice"
     atol: float
     rtol: float
+    n_fields: int = 1    # large systems: distinct dxdt[i + offset] targets of the cell loop
 
 
 def _fill(template: str, subs: Dict[str, str]) -> str:
@@ -549,4 +550,4 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     mode = "dense" if method.endswith("_i") else ("controlled" if method.endswith("_a") else "plain")
     spec = StepperSpec(method, base, mode, boost_type, make_stepper_constr(method, atol, rtol), "lattice_rk.cuh",
                        "lattice_" + base)
-    return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol))
+    return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol), len(loops.offsets))

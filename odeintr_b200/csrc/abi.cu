@@ -180,7 +180,11 @@ struct odeintr_system_s {
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
-               k_combo = nullptr;
+               k_combo = nullptr, k_tiled = nullptr;
+  long long lattice_halo = 0;   // stencil radius declared for the tiled rk4 kernel (0 = use the staged kernels)
+  long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
+  size_t tiled_smem = 0;
+  dev_buf<int> lat_flag;
   int lattice_method = 0;  // 0 = fixed step (rk4 / euler), 1 = rk5_a, 2 = rk5_i
   dev_buf<double> lat_work;
   dev_buf<unsigned long long> lat_err;
@@ -537,6 +541,29 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   double* acc = h->lat_acc;
   const unsigned grid = (unsigned)h->sm_count * 8u, block = 256u;
   int rc;
+  if (h->lattice_stages == 4 && h->lattice_halo > 0 && h->k_tiled && !w.sharded) {
+    // declared stencil radius: the whole rk4 step in one temporally blocked launch, x -> A, then the buffers
+    // trade places (16 B per cell per step instead of 128)
+    odeintr_lattice_tiled_args ta;
+    std::memset(&ta, 0, sizeof(ta));
+    ta.x_in = x; ta.x_out = A;
+    ta.pars = a.pars;
+    ta.n = w.n; ta.n_total = h->lattice_cells ? h->lattice_cells : w.n_total;
+    ta.c0 = 0; ta.ghost = 0; ta.pitch = 0;
+    ta.lo = 0; ta.hi = ta.n_total;
+    ta.halo = h->lattice_halo;
+    ta.t = t; ta.dt = dt;
+    ta.sharded = 0;
+    ta.flag = h->lat_flag.p;
+    const long long tile = 256 * 4;
+    const unsigned tiles = (unsigned)((ta.hi - ta.lo + tile - 1) / tile);
+    void* params[1] = {&ta};
+    CU_TRY(cudaLaunchKernel((const void*)h->k_tiled, dim3(tiles), dim3(256), params, h->tiled_smem, h->stream));
+    h->last_launches += 1;
+    g_total_launches += 1;
+    std::swap(h->lat_x, h->lat_a);
+    return ODEINTR_OK;
+  }
   auto stage = [&](int s, int n_stages, const double* xs, double* xt, const double* acc_in, double* acc_out,
                    double ts, double a_dt, double b_dt) {
     a.xs = xs; a.x = x; a.xt = xt; a.acc_in = acc_in; a.acc_out = acc_out; a.t = ts; a.a_dt = a_dt; a.b_dt = b_dt;
@@ -583,6 +610,8 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   h->lat_x = h->x.p; h->lat_a = h->lat_buf_a.p; h->lat_b = h->lat_buf_b.p; h->lat_acc = h->lat_buf_acc.p;
   if (sc.record && (rc = reserve_out(h, sc.rec_t.size()))) return rc;
   lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0};
+  CU_TRY(h->lat_flag.reserve(1));
+  CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
   if ((rc = begin_timing(h))) return rc;
   size_t row = 0;
   auto observe = [&]() -> int {
@@ -617,6 +646,14 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
     h->rows = sc.rec_t.size();
     h->out_m = 1;
     h->ragged = false;
+  }
+  if (h->lattice_halo > 0) {
+    int flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (flag)
+      return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
+                                         std::to_string(h->lattice_halo) + " cells) from the cell it computes");
   }
   return ODEINTR_OK;
 }
@@ -905,6 +942,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_lattice_sharded, h->lib, "odeintr_lattice_stage_sharded") != cudaSuccess)
     h->k_lattice_sharded = nullptr;
   if (cudaLibraryGetKernel(&h->k_combo, h->lib, "odeintr_lattice_combo") != cudaSuccess) h->k_combo = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled, h->lib, "odeintr_lattice_rk4_tiled") != cudaSuccess) h->k_tiled = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);
@@ -934,7 +972,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release(); h->rows_min.release();
   h->work_counter.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
-  h->lat_work.release(); h->lat_err.release();
+  h->lat_work.release(); h->lat_err.release(); h->lat_flag.release();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
@@ -1202,6 +1240,24 @@ int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
   if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
   h->last_launches = 0;
   if ((rc = lattice_step_halo(h, w, t, dt, h->sh_halo))) return rc;
+  return ODEINTR_OK;
+}
+
+int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->k_lattice) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
+  if (halo < 0 || fields < 1 || (long long)h->N % fields != 0) return fail(ODEINTR_E_INVALID, "Invalid halo specification");
+  if (halo > 0 && !h->k_tiled) return fail(ODEINTR_E_STATE, "the generated translation unit has no tiled kernel");
+  if (halo > 0) {
+    const size_t width = 256 * 4 + 8 * (size_t)halo;
+    const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
+    if (bytes > 200 * 1024) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
+    CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h->tiled_smem = bytes;
+  }
+  h->lattice_halo = halo;
+  h->lattice_cells = (long long)h->N / fields;
   return ODEINTR_OK;
 }
 

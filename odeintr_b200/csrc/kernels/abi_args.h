@@ -126,3 +126,22 @@ struct odeintr_lattice_combo_args {
   long long n_total;
   double t;
 };
+
+// One rk4 step of a large 1-D system in one launch, temporally blocked in shared memory (lattice_tiled.cuh).
+struct odeintr_lattice_tiled_args {
+  const double* x_in;         // state at the start of the step (local cell 0 of field 0)
+  double* x_out;              // state after the step (must not alias x_in)
+  const double* pars;
+  long long n;                // cells per field owned by this rank
+  long long n_total;          // global cells per field
+  long long c0;               // global cell index of local cell 0
+  long long ghost;            // ghost cells on each side of the local slab (sharded)
+  long long pitch;            // doubles between field slabs (sharded)
+  long long lo;               // owned cells [lo, hi) in global cell numbering
+  long long hi;
+  long long halo;             // stencil radius declared by the user
+  double t;
+  double dt;
+  int sharded;
+  int* flag;                  // set to 1 when the snippet reaches beyond the declared halo
+};

@@ -1,0 +1,141 @@
+// odeintr_b200/csrc/kernels/lattice_tiled.cuh
+// K4t: a whole rk4 step of a large 1-D system in ONE kernel, temporally blocked in shared memory.
+//
+// The stage-per-launch schedule of lattice_rk.cuh moves 128 B per cell per step through HBM (every stage re-reads
+// and re-writes the state-sized work arrays).  When the stencil radius of the user's loop is known (`halo`, an
+// optional argument of compile_sys_openmp), a block can load its tile of T cells plus 4*halo cells on each side
+// ONCE, run all four stages in shared memory on windows that shrink by `halo` per stage (the same redundant-edge
+// scheme the multi-GPU path uses between ranks), and write only the new state: 16 B per cell per step, 8x less
+// traffic, so the step becomes bound by the FP64 pipe and shared memory instead of HBM.
+// Every cell goes through exactly the operations of the staged schedule (Boost's order, no FMA): bit-identical.
+//
+// The declared radius is verified at run time: the shared-memory view checks every access of the snippet
+// against the cell being computed and raises a flag if it reaches further than `halo`.
+#pragma once
+#include "odeintr_b200/lattice_view.cuh"
+
+#ifndef ODEINTR_TILE_CPT
+#define ODEINTR_TILE_CPT 4  // cells per thread and stage: tile = 256 * 4 cells
+#endif
+
+namespace odeintr_b200 {
+
+// view of one stage's input held in shared memory; indexed with the snippet's GLOBAL indices
+struct lattice_tile_view {
+  const double* s;        // [field][tile_cells + 2 * margin], cell `tile_lo - margin` of field 0 first
+  long long n_total;      // cells per field (L)
+  long long tile_lo;      // global cell of the first tile cell
+  long long centre;       // global cell currently being computed (for the radius check)
+  int width;              // tile_cells + 2 * margin
+  int margin;             // 4 * halo
+  int halo;
+  int* flag;              // global error word
+
+  ODEINTR_DEV double operator[](const long long g) const {
+#if defined(ODEINTR_NFIELDS) && ODEINTR_NFIELDS > 1
+    long long f = 0;
+#pragma unroll
+    for (int j = 1; j < ODEINTR_NFIELDS; ++j)
+      if (g >= j * n_total) f = j;
+    const long long c = g - f * n_total;
+#else
+    const long long f = 0;
+    const long long c = g;
+#endif
+    long long r = c - centre;  // periodic distance from the cell being computed
+    if (r > n_total / 2) r -= n_total; else if (r < -(n_total / 2)) r += n_total;
+    if (r > halo || r < -halo) { *flag = 1; return 0.0; }
+    long long d = centre - tile_lo;  // the computed cell is always inside the window
+    return s[f * width + (d + r) + margin];
+  }
+  ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
+};
+
+}  // namespace odeintr_b200
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) {
+  using namespace odeintr_b200;
+  typedef odeintr::system_type_t<lattice_tile_view> Sys;
+  constexpr int F = ODEINTR_NFIELDS;
+  constexpr int T = 256 * ODEINTR_TILE_CPT;
+  extern __shared__ double smem[];
+  const int margin = 4 * (int)a.halo;
+  const int W = T + 2 * margin;
+  double* sx = smem;               // state at the start of the step
+  double* sa = sx + F * W;         // stage states, ping
+  double* sb = sa + F * W;         // stage states, pong
+  double* sacc = sb + F * W;       // running weighted sum
+
+  Sys sys;
+  sys.load_params(a.pars, 1, 0);
+  long long off[F];
+  sys.field_offsets(off);
+  const long long start = sys.cell_start(), bound = sys.cell_bound();
+  const long long L = a.n_total;
+  // tiles cover the cells this launch owns: [lo, hi) (the user loop's range on one GPU, the rank's slab otherwise)
+  const long long lo = a.sharded ? a.lo : (start > a.lo ? start : a.lo);
+  const long long hi = a.sharded ? a.hi : (bound < a.hi ? bound : a.hi);
+  const long long tile_lo = lo + (long long)blockIdx.x * T;
+  if (tile_lo >= hi) return;
+  const long long tile_hi = tile_lo + T < hi ? tile_lo + T : hi;
+  const int tn = (int)(tile_hi - tile_lo);
+
+  // load x on [tile_lo - margin, tile_lo + T + margin) of every field, periodic in the cell index
+  lattice_view_t<LATTICE_WRAP> gw;
+  gw.p = a.x_in; gw.n_total = L; gw.n_local = a.n; gw.c0 = a.c0; gw.ghost = a.ghost; gw.pitch = a.pitch;
+  for (int f = 0; f < F; ++f) {
+    const long long fld = off[f] / L;  // field number of the f-th written entry
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      long long c = tile_lo - margin + j;
+      if (c < 0) c += L; else if (c >= L) c -= L;
+      const double v = a.sharded ? gw[fld * L + c] : __ldg(a.x_in + fld * L + c);
+      sx[fld * W + j] = v;
+      sa[fld * W + j] = v;   // cells outside the user loop keep their value in every stage
+      sb[fld * W + j] = v;
+      sacc[fld * W + j] = v;
+    }
+  }
+  __syncthreads();
+
+  lattice_tile_view view;
+  view.n_total = L; view.tile_lo = tile_lo; view.width = W; view.margin = margin; view.halo = (int)a.halo;
+  view.flag = a.flag;
+  const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
+  const double dt = a.dt;
+#pragma unroll 1
+  for (int stage = 1; stage <= 4; ++stage) {
+    // stage s works on the window [-(4-s)*halo, tn + (4-s)*halo) around the tile
+    const int m = (4 - stage) * (int)a.halo;
+    const double* src = stage == 1 ? sx : (stage == 2 ? sa : (stage == 3 ? sb : sa));
+    double* dst = stage == 1 ? sa : (stage == 2 ? sb : sa);  // stage 3 overwrites sa, which stage 2 has finished reading
+    const double a_dt = stage == 1 ? half * dt : (stage == 2 ? half * dt : 1.0 * dt);
+    const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
+    const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
+    view.s = src;
+    for (int j = threadIdx.x - m; j < tn + m; j += blockDim.x) {
+      long long cg = tile_lo + j;  // global cell, possibly a periodic image
+      if (cg < 0) cg += L; else if (cg >= L) cg -= L;
+      if (cg < start || cg >= bound) continue;  // not a cell of the user's loop: keeps its value
+      double k[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) k[f] = 0.0;
+      view.centre = cg;
+      view.tile_lo = tile_lo + (cg - (tile_lo + j));  // same window, expressed in the image the snippet indexes
+      sys.cell(view, k, cg, ts);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int q = (int)(off[f] / L) * W + j + margin;
+        if (stage < 4) {
+          dst[q] = sx[q] + a_dt * k[f];
+          sacc[q] = sacc[q] + b_dt * k[f];
+        } else {
+          // new state of an owned cell: the only global store of the step
+          const long long idx = a.sharded ? (off[f] / L) * a.pitch - a.c0 + (tile_lo + j) : off[f] + (tile_lo + j);
+          a.x_out[idx] = sacc[q] + b_dt * k[f];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}

@@ -331,6 +331,10 @@ class CompiledSystem:
                      [start + self.last_steps() * step_size])
         return EnsembleRecord(t, out), x_final
 
+    def set_halo(self, halo: int, fields: int = 1):
+        """Declare the stencil radius of a large system (odeintr_lattice_set_halo)."""
+        self._check(self._lib.odeintr_lattice_set_halo(self._h, halo, fields))
+
     # -- measurement ----------------------------------------------------------------------------------
     def last_kernel_ms(self) -> float:
         return float(self._lib.odeintr_last_kernel_ms(self._h))

@@ -10,7 +10,8 @@ lib = _abi.load()
 for name, src, pars, glob, logn in (("bistable", BISTABLE_1D, BISTABLE_PARS, "", 28), ("chain", CHAIN, CHAIN_PARS, CHAIN_GLOBALS, 28),
                                     ("bistable", BISTABLE_1D, BISTABLE_PARS, "", 24)):
     n = 1 << logn
-    code = odeintr_b200.compile_sys_openmp(name, src, pars, True, method="rk4", sys_dim=n, globals=glob)
+    code = odeintr_b200.compile_sys_openmp(name, src, pars, True, method="rk4", sys_dim=n, globals=glob,
+                                           halo=(1 if os.environ.get("TILED") else None))
     s = code.system
     print(name, n, s.kernel_attributes("odeintr_lattice_stage"), flush=True)
     if name == "chain":
@@ -24,6 +25,6 @@ for name, src, pars, glob, logn in (("bistable", BISTABLE_1D, BISTABLE_PARS, "",
         assert rc == 0, _abi.last_error()
         ms = s.last_kernel_ms()
         steps = s.last_steps()
-        print("%s n=2^%d steps=%d %.2f ms -> %.4g cell-steps/s, %.1f GB/s algorithmic (128 B/cell/step)" %
+        print("%s n=2^%d steps=%d %.2f ms -> %.4g cell-steps/s, %.1f GB/s at 128 B/cell/step" %
               (name, logn, steps, ms, n * steps / ms * 1e3, 128.0 * n * steps / ms * 1e3 / 1e9), flush=True)
     s.close()

@@ -225,3 +225,40 @@ def test_documented_bistable_example_with_laplace4():
     ref = ora.integrate_times(adv["x"], at, 1.0)
     assert df.shape == (3, m * m + 1)
     assert np.max(np.abs(cols(df) - ref["rec"])) <= 1e-5
+
+
+@pytest.mark.parametrize("case", ["bistable", "chain", "wide"])
+def test_tiled_rk4_with_declared_halo_bit_exact(case):
+    # halo declared -> one temporally blocked kernel per rk4 step (tile + 4*halo cells staged in shared memory);
+    # several tiles, a ragged last tile, the periodic seam inside the first / last tile
+    if case == "bistable":
+        n, src, pars, glob, halo = 5003, BISTABLE_1D, BISTABLE_PARS, "", 1
+        x0 = np.random.default_rng(91).integers(0, 2, n).astype(np.float64)
+    elif case == "chain":
+        n, src, pars, glob, halo = 2 * 3001, CHAIN, CHAIN_PARS, CHAIN_GLOBALS, 1
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n // 2) / (n // 2)), np.zeros(n // 2)])
+    else:  # radius-2 stencil (4th-order Laplacian)
+        n, pars, glob, halo = 4100, {"D": 0.05}, "", 2
+        src = """
+        for (int i = 0; i < N; ++i)
+          dxdt[i] = D * (-x[(i + N - 2) % N] + 16.0 * x[(i + N - 1) % N] - 30.0 * x[i] + 16.0 * x[(i + 1) % N] - x[(i + 2) % N]) / 12.0
+                    + x[i] * (1 - x[i]) * (x[i] - 0.5);
+        """
+        x0 = np.random.default_rng(92).uniform(0, 1, n)
+    env = {}
+    odeintr_b200.compile_sys_openmp("t", src, pars, True, method="rk4", sys_dim=n, globals=glob, env=env, halo=halo)
+    ora = bo.build(src, pars, True, "rk4", sys_dim=n, globals=glob)
+    df = env["t"](x0, 1.3, 0.1)  # 13 steps, every state observed
+    ref = ora.integrate_const(x0, 0, 1.3, 0.1)
+    assert df.shape == (ref["rows"], n + 1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["t_no_record"](x0, 2.05, 0.1)  # 20 steps + a remainder step
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 2.05, 0.1)["x"]))
+
+
+def test_tiled_rk4_detects_a_stencil_wider_than_declared():
+    src = "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + 2) % N] - x[i];"
+    env = {}
+    odeintr_b200.compile_sys_openmp("w", src, method="rk4", sys_dim=3000, env=env, halo=1)
+    with pytest.raises(odeintr_b200.OdeintrError, match="further than the declared halo"):
+        env["w"](np.ones(3000), 1.0, 0.1)

@@ -180,7 +180,8 @@ struct odeintr_system_s {
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
-               k_combo = nullptr, k_tiled = nullptr;
+               k_combo = nullptr, k_tiled = nullptr, k_tiled_fast = nullptr;
+  bool tiled_checked = false;   // the checked tiled kernel has run in the current integrate call
   long long lattice_halo = 0;   // stencil radius declared for the tiled rk4 kernel (0 = use the staged kernels)
   long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
   size_t tiled_smem = 0;
@@ -558,7 +559,10 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     const long long tile = 256 * 4;
     const unsigned tiles = (unsigned)((ta.hi - ta.lo + tile - 1) / tile);
     void* params[1] = {&ta};
-    CU_TRY(cudaLaunchKernel((const void*)h->k_tiled, dim3(tiles), dim3(256), params, h->tiled_smem, h->stream));
+    // the first step of an integrate call verifies the declared radius on every access, the rest trust it
+    cudaKernel_t kern = (h->tiled_checked && h->k_tiled_fast) ? h->k_tiled_fast : h->k_tiled;
+    h->tiled_checked = true;
+    CU_TRY(cudaLaunchKernel((const void*)kern, dim3(tiles), dim3(256), params, h->tiled_smem, h->stream));
     h->last_launches += 1;
     g_total_launches += 1;
     std::swap(h->lat_x, h->lat_a);
@@ -612,6 +616,7 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0};
   CU_TRY(h->lat_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  h->tiled_checked = false;
   if ((rc = begin_timing(h))) return rc;
   size_t row = 0;
   auto observe = [&]() -> int {
@@ -943,6 +948,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     h->k_lattice_sharded = nullptr;
   if (cudaLibraryGetKernel(&h->k_combo, h->lib, "odeintr_lattice_combo") != cudaSuccess) h->k_combo = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled, h->lib, "odeintr_lattice_rk4_tiled") != cudaSuccess) h->k_tiled = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled_fast, h->lib, "odeintr_lattice_rk4_tiled_fast") != cudaSuccess)
+    h->k_tiled_fast = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);
@@ -1254,6 +1261,8 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
     const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
     if (bytes > 200 * 1024) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
     CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (h->k_tiled_fast)
+      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     h->tiled_smem = bytes;
   }
   h->lattice_halo = halo;

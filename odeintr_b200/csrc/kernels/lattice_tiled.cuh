@@ -20,12 +20,15 @@
 
 namespace odeintr_b200 {
 
-// view of one stage's input held in shared memory; indexed with the snippet's GLOBAL indices
+// view of one stage's input held in shared memory; indexed with the snippet's GLOBAL indices.
+// CHECK = true verifies every access against the declared radius (used for the first step of every integrate
+// call); the unchecked variant trusts it (an index pattern that passed once does not change from step to step).
+template <bool CHECK>
 struct lattice_tile_view {
-  const double* s;        // [field][tile_cells + 2 * margin], cell `tile_lo - margin` of field 0 first
+  const double* s;        // [field][tile_cells + 2 * margin]
   long long n_total;      // cells per field (L)
-  long long tile_lo;      // global cell of the first tile cell
-  long long centre;       // global cell currently being computed (for the radius check)
+  long long centre;       // global cell currently being computed
+  int j;                  // window index of that cell (0 = first tile cell)
   int width;              // tile_cells + 2 * margin
   int margin;             // 4 * halo
   int halo;
@@ -33,30 +36,30 @@ struct lattice_tile_view {
 
   ODEINTR_DEV double operator[](const long long g) const {
 #if defined(ODEINTR_NFIELDS) && ODEINTR_NFIELDS > 1
-    long long f = 0;
+    int f = 0;
 #pragma unroll
-    for (int j = 1; j < ODEINTR_NFIELDS; ++j)
-      if (g >= j * n_total) f = j;
-    const long long c = g - f * n_total;
+    for (int q = 1; q < ODEINTR_NFIELDS; ++q)
+      if (g >= q * n_total) f = q;
+    long long r = (g - f * n_total) - centre;
 #else
-    const long long f = 0;
-    const long long c = g;
+    const int f = 0;
+    long long r = g - centre;
 #endif
-    long long r = c - centre;  // periodic distance from the cell being computed
-    if (r > n_total / 2) r -= n_total; else if (r < -(n_total / 2)) r += n_total;
-    if (r > halo || r < -halo) { *flag = 1; return 0.0; }
-    long long d = centre - tile_lo;  // the computed cell is always inside the window
-    return s[f * width + (d + r) + margin];
+    // a neighbour across the periodic seam is L - r cells away in index space
+    if (r > halo) r -= n_total; else if (r < -halo) r += n_total;
+    if (CHECK && (r > halo || r < -halo)) { *flag = 1; return 0.0; }
+    return s[f * width + j + static_cast<int>(r) + margin];
   }
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
 
 }  // namespace odeintr_b200
 
-extern "C" __global__ void __launch_bounds__(256)
-odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) {
-  using namespace odeintr_b200;
-  typedef odeintr::system_type_t<lattice_tile_view> Sys;
+namespace odeintr_b200 {
+
+template <bool CHECK>
+ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
+  typedef odeintr::system_type_t<lattice_tile_view<CHECK> > Sys;
   constexpr int F = ODEINTR_NFIELDS;
   constexpr int T = 256 * ODEINTR_TILE_CPT;
   extern __shared__ double smem[];
@@ -98,8 +101,8 @@ odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) {
   }
   __syncthreads();
 
-  lattice_tile_view view;
-  view.n_total = L; view.tile_lo = tile_lo; view.width = W; view.margin = margin; view.halo = (int)a.halo;
+  lattice_tile_view<CHECK> view;
+  view.n_total = L; view.width = W; view.margin = margin; view.halo = (int)a.halo;
   view.flag = a.flag;
   const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
   const double dt = a.dt;
@@ -121,7 +124,7 @@ odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) {
 #pragma unroll
       for (int f = 0; f < F; ++f) k[f] = 0.0;
       view.centre = cg;
-      view.tile_lo = tile_lo + (cg - (tile_lo + j));  // same window, expressed in the image the snippet indexes
+      view.j = j;
       sys.cell(view, k, cg, ts);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
@@ -139,3 +142,11 @@ odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) {
     __syncthreads();
   }
 }
+
+}  // namespace odeintr_b200
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body<true>(a); }
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_rk4_tiled_fast(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body<false>(a); }

@@ -560,11 +560,21 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     const unsigned tiles = (unsigned)((ta.hi - ta.lo + tile - 1) / tile);
     void* params[1] = {&ta};
     // the first step of an integrate call verifies the declared radius on every access, the rest trust it
-    cudaKernel_t kern = (h->tiled_checked && h->k_tiled_fast) ? h->k_tiled_fast : h->k_tiled;
-    h->tiled_checked = true;
+    const bool checked = !(h->tiled_checked && h->k_tiled_fast);
+    cudaKernel_t kern = checked ? h->k_tiled : h->k_tiled_fast;
     CU_TRY(cudaLaunchKernel((const void*)kern, dim3(tiles), dim3(256), params, h->tiled_smem, h->stream));
     h->last_launches += 1;
     g_total_launches += 1;
+    if (checked) {
+      // the unchecked kernel may only follow once the checked one has vouched for the declared radius
+      int flag = 0;
+      CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(cudaStreamSynchronize(h->stream));
+      if (flag)
+        return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
+                                           std::to_string(h->lattice_halo) + " cells) from the cell it computes");
+      h->tiled_checked = true;
+    }
     std::swap(h->lat_x, h->lat_a);
     return ODEINTR_OK;
   }

@@ -1266,6 +1266,8 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
   if (!h->k_lattice) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
   if (halo < 0 || fields < 1 || (long long)h->N % fields != 0) return fail(ODEINTR_E_INVALID, "Invalid halo specification");
   if (halo > 0 && !h->k_tiled) return fail(ODEINTR_E_STATE, "the generated translation unit has no tiled kernel");
+  if (halo > 0 && (long long)h->N / fields >= (1LL << 31))
+    return fail(ODEINTR_E_INVALID, "the tiled kernel indexes cells with 32 bits: at most 2^31 - 1 cells per field");
   if (halo > 0) {
     const size_t width = 256 * 4 + 8 * (size_t)halo;
     const size_t bytes = 4 * (size_t)fields * width * sizeof(double);

@@ -26,29 +26,32 @@ namespace odeintr_b200 {
 template <bool CHECK>
 struct lattice_tile_view {
   const double* s;        // [field][tile_cells + 2 * margin]
-  long long n_total;      // cells per field (L)
-  long long centre;       // global cell currently being computed
+  long long n_total;      // cells per field (L < 2^31: the host refuses wider lattices for this kernel)
+  int centre;             // global cell currently being computed (low 32 bits are all that matters below)
+  int cells;              // (int) n_total
   int j;                  // window index of that cell (0 = first tile cell)
   int width;              // tile_cells + 2 * margin
   int margin;             // 4 * halo
   int halo;
   int* flag;              // global error word
 
+  // Only the DISTANCE of the requested entry from the cell being computed matters, and it fits 32 bits, so the
+  // high halves of the snippet's 64-bit index expressions are dead code for the compiler.
   ODEINTR_DEV double operator[](const long long g) const {
 #if defined(ODEINTR_NFIELDS) && ODEINTR_NFIELDS > 1
     int f = 0;
 #pragma unroll
     for (int q = 1; q < ODEINTR_NFIELDS; ++q)
       if (g >= q * n_total) f = q;
-    long long r = (g - f * n_total) - centre;
+    int r = static_cast<int>(g - f * n_total) - centre;
 #else
     const int f = 0;
-    long long r = g - centre;
+    int r = static_cast<int>(g) - centre;
 #endif
     // a neighbour across the periodic seam is L - r cells away in index space
-    if (r > halo) r -= n_total; else if (r < -halo) r += n_total;
+    if (r > halo) r -= cells; else if (r < -halo) r += cells;
     if (CHECK && (r > halo || r < -halo)) { *flag = 1; return 0.0; }
-    return s[f * width + j + static_cast<int>(r) + margin];
+    return s[f * width + j + r + margin];
   }
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
@@ -102,8 +105,16 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   __syncthreads();
 
   lattice_tile_view<CHECK> view;
-  view.n_total = L; view.width = W; view.margin = margin; view.halo = (int)a.halo;
+  view.n_total = L; view.cells = static_cast<int>(L); view.width = W; view.margin = margin; view.halo = (int)a.halo;
   view.flag = a.flag;
+  int fld[F];
+  long long out_base[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    fld[f] = static_cast<int>(off[f] / L);
+    out_base[f] = a.sharded ? (off[f] / L) * a.pitch - a.c0 : off[f];
+  }
+  const bool interior = tile_lo - margin >= (start > 0 ? start : 0) && tile_lo + T + margin <= (bound < L ? bound : L);
   const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
   const double dt = a.dt;
 #pragma unroll 1
@@ -116,27 +127,34 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
     const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
     const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
     view.s = src;
-    for (int j = threadIdx.x - m; j < tn + m; j += blockDim.x) {
-      long long cg = tile_lo + j;  // global cell, possibly a periodic image
-      if (cg < 0) cg += L; else if (cg >= L) cg -= L;
-      if (cg < start || cg >= bound) continue;  // not a cell of the user's loop: keeps its value
+    auto cell = [&](const int j, const long long cg) {
       double k[F];
 #pragma unroll
       for (int f = 0; f < F; ++f) k[f] = 0.0;
-      view.centre = cg;
+      view.centre = static_cast<int>(cg);
       view.j = j;
       sys.cell(view, k, cg, ts);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
-        const int q = (int)(off[f] / L) * W + j + margin;
+        const int q = fld[f] * W + j + margin;
         if (stage < 4) {
           dst[q] = sx[q] + a_dt * k[f];
           sacc[q] = sacc[q] + b_dt * k[f];
         } else {
           // new state of an owned cell: the only global store of the step
-          const long long idx = a.sharded ? (off[f] / L) * a.pitch - a.c0 + (tile_lo + j) : off[f] + (tile_lo + j);
-          a.x_out[idx] = sacc[q] + b_dt * k[f];
+          a.x_out[out_base[f] + (tile_lo + j)] = sacc[q] + b_dt * k[f];
         }
+      }
+    };
+    if (interior) {
+      // the whole window lies inside the user loop's range and away from the periodic seam: no per-cell checks
+      for (int j = threadIdx.x - m; j < tn + m; j += blockDim.x) cell(j, tile_lo + j);
+    } else {
+      for (int j = threadIdx.x - m; j < tn + m; j += blockDim.x) {
+        long long cg = tile_lo + j;  // global cell, possibly a periodic image
+        if (cg < 0) cg += L; else if (cg >= L) cg -= L;
+        if (cg < start || cg >= bound) continue;  // not a cell of the user's loop: keeps its value
+        cell(j, cg);
       }
     }
     __syncthreads();

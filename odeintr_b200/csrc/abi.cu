@@ -127,6 +127,13 @@ struct dev_buf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// cells per thread and stage of the tiled rk4 kernel (ODEINTR_TILE_CPT in lattice_tiled.cuh; env knob for sweeps)
+int tile_cpt() {
+  const char* c = std::getenv("ODEINTR_TILE_CPT");
+  const int v = c ? std::atoi(c) : 4;
+  return v > 0 ? v : 4;
+}
+
 std::vector<std::string> nvrtc_options(unsigned flags) {
   std::vector<std::string> o;
   o.push_back("--gpu-architecture=sm_100a");
@@ -140,6 +147,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* b = std::getenv("ODEINTR_BLOCK")) o.push_back(std::string("-DODEINTR_BLOCK=") + b);
   if (const char* b = std::getenv("ODEINTR_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_MIN_BLOCKS=") + b);
   if (std::getenv("ODEINTR_NESTED_LOOPS")) o.push_back("-DODEINTR_NESTED_LOOPS=1");
+  if (const char* c = std::getenv("ODEINTR_TILE_CPT")) o.push_back(std::string("-DODEINTR_TILE_CPT=") + c);
   return o;
 }
 
@@ -556,7 +564,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     ta.t = t; ta.dt = dt;
     ta.sharded = 0;
     ta.flag = h->lat_flag.p;
-    const long long tile = 256 * 4;
+    const long long tile = 256 * (long long)tile_cpt();
     const unsigned tiles = (unsigned)((ta.hi - ta.lo + tile - 1) / tile);
     void* params[1] = {&ta};
     // the first step of an integrate call verifies the declared radius on every access, the rest trust it
@@ -1269,7 +1277,7 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
   if (halo > 0 && (long long)h->N / fields >= (1LL << 31))
     return fail(ODEINTR_E_INVALID, "the tiled kernel indexes cells with 32 bits: at most 2^31 - 1 cells per field");
   if (halo > 0) {
-    const size_t width = 256 * 4 + 8 * (size_t)halo;
+    const size_t width = 256 * (size_t)tile_cpt() + 8 * (size_t)halo;
     const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
     if (bytes > 200 * 1024) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
     CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

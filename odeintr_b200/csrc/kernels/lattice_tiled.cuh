@@ -87,19 +87,31 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   const long long tile_hi = tile_lo + T < hi ? tile_lo + T : hi;
   const int tn = (int)(tile_hi - tile_lo);
 
+  int fld[F];
+  long long out_base[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    fld[f] = static_cast<int>(off[f] / L);  // field number of the f-th written entry
+    out_base[f] = a.sharded ? (off[f] / L) * a.pitch - a.c0 : off[f];
+  }
+  // a tile whose whole window lies inside the user loop's range and away from the periodic seam needs no per-cell
+  // checks, and every stage overwrites all it later reads, so only x itself has to be staged
+  const bool interior = tile_lo - margin >= (start > 0 ? start : 0) && tile_lo + T + margin <= (bound < L ? bound : L);
+
   // load x on [tile_lo - margin, tile_lo + T + margin) of every field, periodic in the cell index
   lattice_view_t<LATTICE_WRAP> gw;
   gw.p = a.x_in; gw.n_total = L; gw.n_local = a.n; gw.c0 = a.c0; gw.ghost = a.ghost; gw.pitch = a.pitch;
   for (int f = 0; f < F; ++f) {
-    const long long fld = off[f] / L;  // field number of the f-th written entry
     for (int j = threadIdx.x; j < W; j += blockDim.x) {
       long long c = tile_lo - margin + j;
       if (c < 0) c += L; else if (c >= L) c -= L;
-      const double v = a.sharded ? gw[fld * L + c] : __ldg(a.x_in + fld * L + c);
-      sx[fld * W + j] = v;
-      sa[fld * W + j] = v;   // cells outside the user loop keep their value in every stage
-      sb[fld * W + j] = v;
-      sacc[fld * W + j] = v;
+      const double v = a.sharded ? gw[fld[f] * L + c] : __ldg(a.x_in + fld[f] * L + c);
+      sx[fld[f] * W + j] = v;
+      if (!interior) {  // cells outside the user loop keep their value in every stage
+        sa[fld[f] * W + j] = v;
+        sb[fld[f] * W + j] = v;
+        sacc[fld[f] * W + j] = v;
+      }
     }
   }
   __syncthreads();
@@ -107,14 +119,7 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   lattice_tile_view<CHECK> view;
   view.n_total = L; view.cells = static_cast<int>(L); view.width = W; view.margin = margin; view.halo = (int)a.halo;
   view.flag = a.flag;
-  int fld[F];
-  long long out_base[F];
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    fld[f] = static_cast<int>(off[f] / L);
-    out_base[f] = a.sharded ? (off[f] / L) * a.pitch - a.c0 : off[f];
-  }
-  const bool interior = tile_lo - margin >= (start > 0 ? start : 0) && tile_lo + T + margin <= (bound < L ? bound : L);
+
   const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
   const double dt = a.dt;
 #pragma unroll 1
@@ -137,7 +142,10 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         const int q = fld[f] * W + j + margin;
-        if (stage < 4) {
+        if (stage == 1) {
+          dst[q] = sx[q] + a_dt * k[f];
+          sacc[q] = sx[q] + b_dt * k[f];  // the running sum starts from x
+        } else if (stage < 4) {
           dst[q] = sx[q] + a_dt * k[f];
           sacc[q] = sacc[q] + b_dt * k[f];
         } else {

@@ -528,7 +528,7 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     loops = parse_cell_loops(sys)
     cell = []
     for var, body in zip(loops.var_names, loops.bodies):
-        cell.append("{ const %s %s = static_cast<%s>(odeintr_c); %s }" % (loops.var_type, var, loops.var_type, body))
+        cell.append("{ const auto %s = odeintr_b200::loop_index<%s>(odeintr_c); %s }" % (var, loops.var_type, body))
     offs = ", ".join("static_cast<long long>(%s)" % o for o in loops.offsets)
     code = _fill(read_template("compile_sys_openmp_template"), {
         "__FUNCNAME__": name,

@@ -188,11 +188,15 @@ struct odeintr_system_s {
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
-               k_combo = nullptr, k_tiled = nullptr, k_tiled_fast = nullptr;
+               k_combo = nullptr, k_tiled = nullptr, k_tiled_fast = nullptr, k_tiled_int = nullptr,
+               k_tiled_int_fast = nullptr, k_range = nullptr;
   bool tiled_checked = false;   // the checked tiled kernel has run in the current integrate call
   long long lattice_halo = 0;   // stencil radius declared for the tiled rk4 kernel (0 = use the staged kernels)
   long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
-  size_t tiled_smem = 0;
+  size_t tiled_smem = 0;        // dynamic shared memory of the general tiled kernel (4 arrays per field)
+  size_t tiled_int_smem = 0;    // ... of the interior kernel (2 arrays per field)
+  long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_range)
+  long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
   int lattice_method = 0;  // 0 = fixed step (rk4 / euler), 1 = rk5_a, 2 = rk5_i
   dev_buf<double> lat_work;
@@ -565,14 +569,36 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     ta.sharded = 0;
     ta.flag = h->lat_flag.p;
     const long long tile = 256 * (long long)tile_cpt();
-    const unsigned tiles = (unsigned)((ta.hi - ta.lo + tile - 1) / tile);
+    // the kernels tile the cells of the user's loop, [lo, hi)
+    const long long lo = h->lat_start > 0 ? h->lat_start : 0;
+    const long long hi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+    const long long tiles = hi > lo ? (hi - lo + tile - 1) / tile : 0;
+    // interior tiles: full, and the whole window of 4 * halo cells around them lies inside [lo, hi) -- no periodic
+    // images, no cells the loop leaves alone; they go to the register-blocked interior kernel
+    const long long margin = 4 * h->lattice_halo;
+    long long first = (margin + tile - 1) / tile, last = (hi - lo - margin) / tile;  // interior: [first, last)
+    if (!h->k_tiled_int || h->lat_cells_ct != ta.n_total || 8 * h->lattice_halo > 256 || last <= first || std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
+      first = last = 0;
+    ta.tile_first = (int)first;
+    ta.tile_skip = (int)(last - first);
     void* params[1] = {&ta};
     // the first step of an integrate call verifies the declared radius on every access, the rest trust it
-    const bool checked = !(h->tiled_checked && h->k_tiled_fast);
-    cudaKernel_t kern = checked ? h->k_tiled : h->k_tiled_fast;
-    CU_TRY(cudaLaunchKernel((const void*)kern, dim3(tiles), dim3(256), params, h->tiled_smem, h->stream));
-    h->last_launches += 1;
-    g_total_launches += 1;
+    const bool checked = !(h->tiled_checked && h->k_tiled_fast && (!h->k_tiled_int || h->k_tiled_int_fast));
+    if (tiles - ta.tile_skip > 0) {
+      cudaKernel_t kern = checked ? h->k_tiled : h->k_tiled_fast;
+      CU_TRY(cudaLaunchKernel((const void*)kern, dim3((unsigned)(tiles - ta.tile_skip)), dim3(256), params,
+                              h->tiled_smem, h->stream));
+      h->last_launches += 1;
+      g_total_launches += 1;
+    }
+    if (ta.tile_skip > 0) {
+      cudaKernel_t kern = checked ? h->k_tiled_int : h->k_tiled_int_fast;
+      ta.lo = lo;
+      CU_TRY(cudaLaunchKernel((const void*)kern, dim3((unsigned)ta.tile_skip), dim3(256), params, h->tiled_int_smem,
+                              h->stream));
+      h->last_launches += 1;
+      g_total_launches += 1;
+    }
     if (checked) {
       // the unchecked kernel may only follow once the checked one has vouched for the declared radius
       int flag = 0;
@@ -968,6 +994,11 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_tiled, h->lib, "odeintr_lattice_rk4_tiled") != cudaSuccess) h->k_tiled = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled_fast, h->lib, "odeintr_lattice_rk4_tiled_fast") != cudaSuccess)
     h->k_tiled_fast = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled_int, h->lib, "odeintr_lattice_rk4_tiled_interior") != cudaSuccess)
+    h->k_tiled_int = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled_int_fast, h->lib, "odeintr_lattice_rk4_tiled_interior_fast") != cudaSuccess)
+    h->k_tiled_int_fast = nullptr;
+  if (cudaLibraryGetKernel(&h->k_range, h->lib, "odeintr_lattice_range") != cudaSuccess) h->k_range = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);
@@ -1284,6 +1315,27 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
     if (h->k_tiled_fast)
       CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     h->tiled_smem = bytes;
+    h->tiled_int_smem = bytes / 2;
+    if (h->k_tiled_int)
+      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes / 2)));
+    if (h->k_tiled_int_fast)
+      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_int_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(bytes / 2)));
+    // the range of the user's loop decides which tiles are interior
+    h->lat_start = 0;
+    h->lat_bound = (long long)h->N / fields;
+    if (h->k_range) {
+      CU_TRY(h->lat_flag.reserve(6));  // 24 bytes: three long long
+      void* out = h->lat_flag.p;
+      void* params[1] = {&out};
+      CU_TRY(cudaLaunchKernel((const void*)h->k_range, dim3(1), dim3(1), params, 0, h->stream));
+      long long range[3] = {0, 0, 0};
+      CU_TRY(cudaMemcpyAsync(range, h->lat_flag.p, sizeof(range), cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(cudaStreamSynchronize(h->stream));
+      h->lat_start = range[0];
+      h->lat_bound = range[1];
+      h->lat_cells_ct = range[2];
+    }
   }
   h->lattice_halo = halo;
   h->lattice_cells = (long long)h->N / fields;

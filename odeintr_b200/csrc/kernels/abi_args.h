@@ -144,4 +144,6 @@ struct odeintr_lattice_tiled_args {
   double dt;
   int sharded;
   int* flag;                  // set to 1 when the snippet reaches beyond the declared halo
+  int tile_first;             // tiles [tile_first, tile_first + tile_skip) are interior: the general kernel skips
+  int tile_skip;              // them, the interior kernel's block b computes tile tile_first + b
 };

@@ -13,6 +13,7 @@
 // against the cell being computed and raises a flag if it reaches further than `halo`.
 #pragma once
 #include "odeintr_b200/lattice_view.cuh"
+#include "odeintr_b200/lattice_index.cuh"
 
 #ifndef ODEINTR_TILE_CPT
 #define ODEINTR_TILE_CPT 4  // cells per thread and stage: tile = 256 * 4 cells
@@ -82,7 +83,9 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   // tiles cover the cells this launch owns: [lo, hi) (the user loop's range on one GPU, the rank's slab otherwise)
   const long long lo = a.sharded ? a.lo : (start > a.lo ? start : a.lo);
   const long long hi = a.sharded ? a.hi : (bound < a.hi ? bound : a.hi);
-  const long long tile_lo = lo + (long long)blockIdx.x * T;
+  // the host hands the tiles [tile_first, tile_first + tile_skip) to the interior kernel below
+  const long long tile = (int)blockIdx.x < a.tile_first ? (long long)blockIdx.x : (long long)blockIdx.x + a.tile_skip;
+  const long long tile_lo = lo + tile * T;
   if (tile_lo >= hi) return;
   const long long tile_hi = tile_lo + T < hi ? tile_lo + T : hi;
   const int tn = (int)(tile_hi - tile_lo);
@@ -170,6 +173,167 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
 }
 
 }  // namespace odeintr_b200
+
+namespace odeintr_b200 {
+
+// View of one stage's input for a cell of an INTERIOR tile (full tile, whole window inside the user loop's range and
+// away from the periodic seam).  Indexed with a rel_index, the address is `p + constant`: p points at the entry
+// (field 0, cell being computed) of the stage's input, the displacement folds at compile time.
+template <bool CHECK>
+struct lattice_tile_rel_view {
+  const double* p;
+  long long n_total;  // cells per field
+  int width;          // doubles between fields in shared memory
+  int halo;
+  int centre;         // global number of the cell being computed (generic path only)
+  int* flag;
+
+  ODEINTR_DEV double at(const long long f, const long long d) const {
+    if (CHECK && (f < 0 || f >= ODEINTR_NFIELDS || d > halo || d < -halo)) { *flag = 1; return 0.0; }
+    return p[f * width + d];
+  }
+  ODEINTR_DEV double operator[](const rel_index& r) const {
+    if (!r.rel) return (*this)[r.off];
+    // off = f * L + d with |d| small: nearest multiple of L
+    const long long L = n_total;
+    const long long f = r.off >= 0 ? (r.off + L / 2) / L : -((-r.off + L / 2) / L);
+    return at(f, r.off - f * L);
+  }
+  // absolute index: no periodic image can be within reach of an interior cell, so the distance is taken as is
+  ODEINTR_DEV double operator[](const long long g) const {
+    const long long f = g / n_total;
+    return at(f, g - f * n_total - centre);
+  }
+  ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
+};
+
+// Interior tiles.  Every thread owns CPT cells of the tile (tid + k * 256) for the whole step: the state at the start
+// of the step and the running weighted sum of those cells never leave its registers; only the stage states, which the
+// neighbours read, go through shared memory (two buffers, ping-pong).  The cells of the shrinking margins (3, 2, 1
+// times halo on each side in stages 1, 2, 3) belong to the first 6 * halo threads, one each.
+// Per cell and step: 1 LDG + 1 STG, 4 * (stencil reads) LDS + 4 STS -- against 20 LDS + 8 STS of the general body.
+template <bool CHECK>
+ODEINTR_DEV void lattice_rk4_tiled_interior_body(const odeintr_lattice_tiled_args& a) {
+  typedef odeintr::system_type_t<lattice_tile_rel_view<CHECK> > Sys;
+  constexpr int F = ODEINTR_NFIELDS;
+  constexpr int C = ODEINTR_TILE_CPT;
+  constexpr int T = 256 * C;
+  extern __shared__ double smem[];
+  const int h = (int)a.halo;
+  const int margin = 4 * h;
+  const int W = T + 2 * margin;
+  double* s0 = smem;          // x, then the stage-2 state
+  double* s1 = smem + F * W;  // stage-1 state, then the stage-3 state
+  const int tid = threadIdx.x;
+
+  Sys sys;
+  sys.load_params(a.pars, 1, 0);
+  long long off[F];
+  sys.field_offsets(off);
+  // cells per field, a compile-time constant here (the host checks it against its own count): the snippet's index
+  // expressions can only fold against a constant lattice length
+  constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
+  const long long tile_lo = a.lo + ((long long)a.tile_first + blockIdx.x) * T;
+  int fld[F];
+  long long out_base[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    fld[f] = static_cast<int>(off[f] / L);
+    out_base[f] = off[f];
+  }
+
+  // stage the window of x; the thread's own cells stay in registers as well
+  double xs[C][F], acc[C][F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const double* g = a.x_in + fld[f] * L + tile_lo;
+    double* s = s0 + fld[f] * W + margin;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const double v = __ldg(g + tid + k * 256);
+      xs[k][f] = v;
+      s[tid + k * 256] = v;
+    }
+    if (tid < 2 * margin) {
+      const int j = tid < margin ? tid - margin : T + (tid - margin);
+      s[j] = __ldg(g + j);
+    }
+  }
+  __syncthreads();
+  // the margin cell of this thread: je, at distance de + 1 from the tile, takes part in stage s while de < (4-s)*halo
+  const bool has_edge = tid < 6 * h;
+  const int de = tid < 3 * h ? tid : tid - 3 * h;
+  const int je = tid < 3 * h ? -1 - tid : T + (tid - 3 * h);
+  double xe[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) xe[f] = has_edge ? s0[fld[f] * W + margin + je] : 0.0;
+
+  lattice_tile_rel_view<CHECK> view;
+  view.n_total = L; view.width = W; view.halo = h; view.flag = a.flag;
+  rel_index idx;
+  idx.off = 0; idx.cells = static_cast<int>(L); idx.rel = true;
+
+  const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
+  const double dt = a.dt;
+#pragma unroll
+  for (int stage = 1; stage <= 4; ++stage) {
+    const double* src = (stage & 1) ? s0 : s1;
+    double* dst = (stage & 1) ? s1 : s0;
+    const double a_dt = stage == 1 ? half * dt : (stage == 2 ? half * dt : 1.0 * dt);
+    const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
+    const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const int j = tid + k * 256;
+      double kk[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) kk[f] = 0.0;
+      view.p = src + margin + j;
+      view.centre = idx.centre = static_cast<int>(tile_lo) + j;
+      sys.cell(view, kk, idx, ts);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        if (stage < 4) dst[fld[f] * W + margin + j] = xs[k][f] + a_dt * kk[f];
+        acc[k][f] = (stage == 1 ? xs[k][f] : acc[k][f]) + b_dt * kk[f];  // the running sum starts from x
+        // new state of an owned cell: the only global store of the step
+        if (stage == 4) a.x_out[out_base[f] + tile_lo + j] = acc[k][f];
+      }
+    }
+    if (stage < 4) {
+      if (has_edge && de < (4 - stage) * h) {
+        double kk[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) kk[f] = 0.0;
+        view.p = src + margin + je;
+        view.centre = idx.centre = static_cast<int>(tile_lo) + je;
+        sys.cell(view, kk, idx, ts);
+#pragma unroll
+        for (int f = 0; f < F; ++f) dst[fld[f] * W + margin + je] = xe[f] + a_dt * kk[f];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace odeintr_b200
+
+// first cell and bound of the user's loop, for the host's split into general and interior tiles
+extern "C" __global__ void odeintr_lattice_range(long long* out) {
+  odeintr::system_type_t<odeintr_b200::lattice_tile_view<false> > sys;
+  out[0] = sys.cell_start();
+  out[1] = sys.cell_bound();
+  out[2] = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;  // cells per field the interior kernel assumes
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_rk4_tiled_interior(const odeintr_lattice_tiled_args a) {
+  odeintr_b200::lattice_rk4_tiled_interior_body<true>(a);
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+odeintr_lattice_rk4_tiled_interior_fast(const odeintr_lattice_tiled_args a) {
+  odeintr_b200::lattice_rk4_tiled_interior_body<false>(a);
+}
 
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body<true>(a); }

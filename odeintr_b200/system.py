@@ -342,6 +342,9 @@ class CompiledSystem:
     def last_steps(self) -> int:
         return int(self._lib.odeintr_last_steps(self._h))
 
+    def last_launches(self) -> int:
+        return int(self._lib.odeintr_last_launches(self._h))
+
     def kernel_attributes(self, kernel: str):
         r, l, s, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._check(self._lib.odeintr_kernel_attributes(self._h, kernel.encode(), C.byref(r), C.byref(l), C.byref(s),

@@ -256,6 +256,35 @@ def test_tiled_rk4_with_declared_halo_bit_exact(case):
     assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 2.05, 0.1)["x"]))
 
 
+@pytest.mark.parametrize("case", ["fixed_ends", "computed_index", "long_index"])
+def test_tiled_rk4_interior_tiles_other_index_forms(case):
+    # the interior kernel follows `i + c`, `i - c` and `% N` symbolically; everything else must fall back to the
+    # absolute index and still give the staged schedule's bits
+    n = 6 * 1024 + 77
+    if case == "fixed_ends":  # Dirichlet ends: cells 0 and N-1 are not cells of the loop and keep their value
+        src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + x[i] * (1 - x[i]) * (x[i] - 0.5);"
+    elif case == "computed_index":  # i * 1 is an ordinary integer again: generic path of the tile view
+        src = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[(i * 1 + N - 1) % N] + x[(i + 1) % N] - 2.0 * x[i * 1]);"
+    else:
+        src = "for (size_t i = 0; i < N; ++i) dxdt[i] = D * (x[(i + N - 1) % N] + x[(i + 1) % N] - 2.0 * x[i]) - 0.1 * x[i];"
+    pars = {"D": 0.2}
+    x0 = np.random.default_rng(93).uniform(0, 1, n)
+    env = {}
+    odeintr_b200.compile_sys_openmp("t", src, pars, True, method="rk4", sys_dim=n, env=env, halo=1)
+    ora = bo.build(src, pars, True, "rk4", sys_dim=n)
+    fin = env["t_no_record"](x0, 1.25, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.25, 0.1)["x"]))
+
+
+def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():
+    # only interior tiles see the far read: cells next to the ends stay within reach
+    src = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"
+    env = {}
+    odeintr_b200.compile_sys_openmp("w", src, method="rk4", sys_dim=5000, env=env, halo=1)
+    with pytest.raises(odeintr_b200.OdeintrError, match="further than the declared halo"):
+        env["w"](np.ones(5000), 1.0, 0.1)
+
+
 def test_tiled_rk4_detects_a_stencil_wider_than_declared():
     src = "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + 2) % N] - x[i];"
     env = {}

@@ -133,13 +133,19 @@ int odeintr_integrate_const_host(odeintr_system_t h, const double* x, size_t n_i
 /* rows integrate_const records for (t0, t1, dt, obs_stride) with a fixed-step stepper */
 size_t odeintr_const_rows(double t0, double t1, double dt, long long obs_stride);
 
-/* Declare the stencil radius of a compile_sys_openmp system (cells the loop body reads to the left / right of the
- * cell it computes, periodic distance) and its number of fields.  With halo > 0 a fixed-step rk4 step runs as ONE
- * temporally blocked kernel (tile + 4*halo cells per side staged in shared memory, all four stages on chip,
- * 16 B instead of 128 B of HBM traffic per cell and step; bit-identical results).  Every access is checked against
- * the declared radius; a violation makes the integrate call fail with ODEINTR_E_INVALID.  halo = 0 (default)
- * selects the stage-per-launch kernels, which need no such declaration. */
+/* Temporally blocked rk4 step for 1-D compile_sys_openmp systems.  When the loop body of a cell reads x at most
+ * `halo` cells to the left / right of the cell (periodic distance, in every field), a fixed-step rk4 step runs as
+ * ONE kernel pass: tile + 4*halo cells per side staged in shared memory, all four stages on chip, 16 B instead of
+ * 128 B of HBM traffic per cell and step; bit-identical results.
+ *   halo < 0   measure the radius (a probe kernel evaluates every cell's index expressions at the next integrate
+ *              call) and use the tiled kernels when it is at most 32 cells; `fields` is ignored.  Every access of
+ *              every step is still checked: if a read ever reaches further (indices that depend on the state or on
+ *              time), the integrate call is repeated with the stage-per-launch kernels.
+ *   halo > 0   declared radius; a violation makes the integrate call fail with ODEINTR_E_INVALID.
+ *   halo = 0   stage-per-launch kernels (the state a freshly compiled system is in).
+ * odeintr_lattice_get_halo returns the radius in use, or -1 when the stage-per-launch kernels are. */
 int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields);
+long long odeintr_lattice_get_halo(odeintr_system_t h);
 
 /* ---- large systems sharded over several GPUs (one process per GPU) ------------------------------------
  * The state of a compile_sys_openmp system is `fields` arrays of `cells_total` cells (sys_dim = fields *
@@ -156,6 +162,12 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields);
 int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long first_cell, long long n_local,
                           int fields, int halo, double* x_dev);
 long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo);
+/* rk4 slabs with a stencil radius of at most 32 cells step through the temporally blocked kernels (see
+ * odeintr_lattice_set_halo): one pass per step, 16 B per cell.  Their ghost zone can be made `steps` times wider
+ * (ghost = 4 * halo * steps), so that odeintr_lattice_shard_run exchanges halos only every `steps` steps: each step
+ * consumes 4 * halo ghost cells per side and recomputes the rest (communication-avoiding, bit-identical).  Call
+ * before odeintr_lattice_ghost_width / _pad_width / _pitch and odeintr_lattice_shard.  Default 1. */
+int odeintr_lattice_set_exchange_interval(odeintr_system_t h, int steps);
 long long odeintr_lattice_pad_width(odeintr_system_t h, int halo);
 long long odeintr_lattice_pitch(odeintr_system_t h, int halo, long long n_local);
 int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt);

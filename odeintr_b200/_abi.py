@@ -44,6 +44,8 @@ SIGNATURES = {
                                                C.c_size_t]),
     "odeintr_const_rows": (C.c_size_t, [C.c_double, C.c_double, C.c_double, C.c_longlong]),
     "odeintr_lattice_set_halo": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
+    "odeintr_lattice_get_halo": (C.c_longlong, [C.c_void_p]),
+    "odeintr_lattice_set_exchange_interval": (C.c_int, [C.c_void_p, C.c_int]),
     "odeintr_lattice_shard": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                         C.c_void_p]),
     "odeintr_lattice_ghost_width": (C.c_longlong, [C.c_void_p, C.c_int]),

@@ -54,12 +54,15 @@ def compile_sys_openmp(name, sys, pars=None, const=False, method="rk5_i", sys_di
     """R/odeintr.R:418-470: the large-system variant (Boost openmp_range_algebra in the reference).
 
     ``halo`` (extension, optional): the stencil radius of the loop body on a 1-D lattice -- how many cells to the
-    left / right of cell i the body reads.  Declaring it lets a fixed-step rk4 step run as one temporally blocked
-    kernel (8x less HBM traffic, same bits); accesses beyond it are detected at run time and reported."""
+    left / right of cell i the body reads.  When it is small, a fixed-step rk4 step runs as one temporally blocked
+    kernel (8x less HBM traffic, same bits).  ``None`` (default): measured from the snippet's index expressions at the
+    first integrate call (and verified on every access; a snippet that outgrows it is re-integrated by the
+    stage-per-launch kernels); a positive number: declared, accesses beyond it are reported as an error; ``0``:
+    always the stage-per-launch kernels."""
     gen = codegen.generate_sys_openmp(name, sys, pars, const, method, sys_dim, atol, rtol, globals, headers, footers)
     code = _install(gen, compile, env, flags)
-    if halo is not None and compile:
-        code.system.set_halo(int(halo), gen.n_fields)
+    if compile and method == "rk4":
+        code.system.set_halo(-1 if halo is None else int(halo), gen.n_fields)
     return code
 
 

@@ -188,14 +188,15 @@ struct odeintr_system_s {
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
-               k_combo = nullptr, k_tiled = nullptr, k_tiled_fast = nullptr, k_tiled_int = nullptr,
-               k_tiled_int_fast = nullptr, k_range = nullptr;
-  bool tiled_checked = false;   // the checked tiled kernel has run in the current integrate call
-  long long lattice_halo = 0;   // stencil radius declared for the tiled rk4 kernel (0 = use the staged kernels)
+               k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_info = nullptr, k_probe = nullptr;
+  bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
+  bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
+  bool tiled_pending = false;   // measure the radius at the next integrate call
+  long long lattice_halo = 0;   // stencil radius the tiled kernels stage (declared, or measured by the probe)
   long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
   size_t tiled_smem = 0;        // dynamic shared memory of the general tiled kernel (4 arrays per field)
   size_t tiled_int_smem = 0;    // ... of the interior kernel (2 arrays per field)
-  long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_range)
+  long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_info)
   long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
   int lattice_method = 0;  // 0 = fixed step (rk4 / euler), 1 = rk5_a, 2 = rk5_i
@@ -221,6 +222,9 @@ struct odeintr_system_s {
   bool sharded = false, sh_primed = false;
   long long sh_total = 0, sh_c0 = 0, sh_n = 0, sh_ghost = 0, sh_pitch = 0, sh_pad = 0;
   int sh_fields = 1, sh_halo = 1;
+  int sh_interval = 1;          // rk4 steps per halo exchange requested for the tiled kernels (ghost = 4 * halo * interval)
+  int sh_steps_per_exchange = 1;  // ... in effect for the current slab
+  bool sh_tiled = false;        // the slab steps through the tiled kernels
   double* sh_x = nullptr;
   long long max_tries = 20000000;  // per-instance step-attempt budget per call
   bool dense = false;    // the adaptive kernel wraps a dense-output stepper (rk5_i, rosenbrock4)
@@ -539,6 +543,7 @@ int run_plain_host(odeintr_system_t h, const plain_schedule& sc, const double* x
 struct lattice_window {      // which cells a launch computes and how local buffers map to global cells
   long long n, n_total, c0, ghost, pitch;
   int sharded;
+  long long lo, hi;          // sharded run through the tiled kernels: cells the step must produce
 };
 
 int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
@@ -554,62 +559,60 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   double* acc = h->lat_acc;
   const unsigned grid = (unsigned)h->sm_count * 8u, block = 256u;
   int rc;
-  if (h->lattice_stages == 4 && h->lattice_halo > 0 && h->k_tiled && !w.sharded) {
-    // declared stencil radius: the whole rk4 step in one temporally blocked launch, x -> A, then the buffers
-    // trade places (16 B per cell per step instead of 128)
+  if (h->lattice_stages == 4 && h->k_tiled && (w.sharded ? h->sh_tiled : h->tiled_on)) {
+    // known stencil radius: the whole rk4 step in one temporally blocked pass, x -> A, then the caller lets the
+    // buffers trade places (16 B per cell per step instead of 128)
     odeintr_lattice_tiled_args ta;
     std::memset(&ta, 0, sizeof(ta));
     ta.x_in = x; ta.x_out = A;
     ta.pars = a.pars;
-    ta.n = w.n; ta.n_total = h->lattice_cells ? h->lattice_cells : w.n_total;
-    ta.c0 = 0; ta.ghost = 0; ta.pitch = 0;
-    ta.lo = 0; ta.hi = ta.n_total;
     ta.halo = h->lattice_halo;
     ta.t = t; ta.dt = dt;
-    ta.sharded = 0;
     ta.flag = h->lat_flag.p;
     const long long tile = 256 * (long long)tile_cpt();
-    // the kernels tile the cells of the user's loop, [lo, hi)
-    const long long lo = h->lat_start > 0 ? h->lat_start : 0;
-    const long long hi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+    // cells of the user's loop, and the cells this launch produces: [lo, hi)
+    long long glo, ghi, lo, hi;
+    if (w.sharded) {
+      ta.n = w.n; ta.n_total = w.n_total; ta.c0 = w.c0; ta.ghost = w.ghost; ta.pitch = w.pitch;
+      ta.lo = w.lo; ta.hi = w.hi; ta.sharded = 1;
+      glo = h->lat_start > 0 ? h->lat_start : 0;
+      ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+      lo = w.lo; hi = w.hi;
+    } else {
+      ta.n = w.n; ta.n_total = h->lattice_cells ? h->lattice_cells : w.n_total;
+      ta.c0 = 0; ta.ghost = 0; ta.pitch = ta.n_total;
+      ta.lo = 0; ta.hi = ta.n_total;
+      lo = glo = h->lat_start > 0 ? h->lat_start : 0;
+      hi = ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+    }
     const long long tiles = hi > lo ? (hi - lo + tile - 1) / tile : 0;
-    // interior tiles: full, and the whole window of 4 * halo cells around them lies inside [lo, hi) -- no periodic
-    // images, no cells the loop leaves alone; they go to the register-blocked interior kernel
+    // interior tiles: full, and the whole window of 4 * halo cells around them lies inside the user loop's range
+    // [glo, ghi) -- no periodic images, no cells the loop leaves alone; they go to the register-blocked kernel
     const long long margin = 4 * h->lattice_halo;
-    long long first = (margin + tile - 1) / tile, last = (hi - lo - margin) / tile;  // interior: [first, last)
-    if (!h->k_tiled_int || h->lat_cells_ct != ta.n_total || 8 * h->lattice_halo > 256 || last <= first || std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
+    long long first = glo + margin > lo ? (glo + margin - lo + tile - 1) / tile : 0;  // interior: [first, last)
+    long long last = std::min((hi - lo) / tile, ghi - margin > lo ? (ghi - margin - lo) / tile : 0);
+    if (!h->k_tiled_int || h->lat_cells_ct != ta.n_total || 8 * h->lattice_halo > 256 || last <= first ||
+        std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
       first = last = 0;
     ta.tile_first = (int)first;
     ta.tile_skip = (int)(last - first);
     void* params[1] = {&ta};
-    // the first step of an integrate call verifies the declared radius on every access, the rest trust it
-    const bool checked = !(h->tiled_checked && h->k_tiled_fast && (!h->k_tiled_int || h->k_tiled_int_fast));
+    // every access of every step is checked against the radius; run_lattice reads the flag when the call is over
     if (tiles - ta.tile_skip > 0) {
-      cudaKernel_t kern = checked ? h->k_tiled : h->k_tiled_fast;
-      CU_TRY(cudaLaunchKernel((const void*)kern, dim3((unsigned)(tiles - ta.tile_skip)), dim3(256), params,
+      CU_TRY(cudaLaunchKernel((const void*)h->k_tiled, dim3((unsigned)(tiles - ta.tile_skip)), dim3(256), params,
                               h->tiled_smem, h->stream));
       h->last_launches += 1;
       g_total_launches += 1;
     }
     if (ta.tile_skip > 0) {
-      cudaKernel_t kern = checked ? h->k_tiled_int : h->k_tiled_int_fast;
       ta.lo = lo;
-      CU_TRY(cudaLaunchKernel((const void*)kern, dim3((unsigned)ta.tile_skip), dim3(256), params, h->tiled_int_smem,
-                              h->stream));
+      ta.sharded = 0;  // the interior kernel addresses both layouts through (pitch, c0)
+      CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_int, dim3((unsigned)ta.tile_skip), dim3(256), params,
+                              h->tiled_int_smem, h->stream));
       h->last_launches += 1;
       g_total_launches += 1;
     }
-    if (checked) {
-      // the unchecked kernel may only follow once the checked one has vouched for the declared radius
-      int flag = 0;
-      CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CU_TRY(cudaStreamSynchronize(h->stream));
-      if (flag)
-        return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
-                                           std::to_string(h->lattice_halo) + " cells) from the cell it computes");
-      h->tiled_checked = true;
-    }
-    std::swap(h->lat_x, h->lat_a);
+    if (!w.sharded) std::swap(h->lat_x, h->lat_a);
     return ODEINTR_OK;
   }
   auto stage = [&](int s, int n_stages, const double* xs, double* xt, const double* acc_in, double* acc_out,
@@ -649,7 +652,81 @@ int lattice_prepare(odeintr_system_t h, size_t total) {
   return ODEINTR_OK;
 }
 
-int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
+// shared-memory budgets of the two tiled kernels for a stencil radius; false when no tile can hold it
+bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
+  if (!h->k_tiled || halo < 0 || halo > 4096) return false;
+  const size_t width = 256 * (size_t)tile_cpt() + 8 * (size_t)halo;
+  const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
+  if (bytes > 200 * 1024) return false;
+  if (cudaFuncSetAttribute((const void*)h->k_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+      (h->k_tiled_int && cudaFuncSetAttribute((const void*)h->k_tiled_int, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(bytes / 2)) != cudaSuccess)) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  h->tiled_smem = bytes;
+  h->tiled_int_smem = bytes / 2;
+  h->lattice_halo = halo;
+  return true;
+}
+
+// a slab of a sharded run can step through the tiled kernels: rk4, radius a tile can hold
+bool slab_tiled_possible(odeintr_system_t h, int halo) {
+  return h->k_tiled && h->lattice_stages == 4 && halo >= 1 && halo <= 32 && h->lat_cells_ct > 0 &&
+         h->lat_cells_ct < (1LL << 31) && !std::getenv("ODEINTR_NO_TILED");
+}
+
+// odeintr_lattice_info: loop range, cells per field, layout of the dxdt targets
+int lattice_query_info(odeintr_system_t h) {
+  h->lat_start = 0;
+  h->lat_bound = h->lat_cells_ct = 0;
+  if (!h->k_info) return ODEINTR_OK;
+  CU_TRY(h->lat_flag.reserve(8));  // 32 bytes: four long long
+  void* out = h->lat_flag.p;
+  void* params[1] = {&out};
+  CU_TRY(cudaLaunchKernel((const void*)h->k_info, dim3(1), dim3(1), params, 0, h->stream));
+  long long info[4] = {0, 0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(info, h->lat_flag.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->lat_start = info[0];
+  h->lat_bound = info[1];
+  h->lat_cells_ct = info[2];
+  if (!info[3])
+    return fail(ODEINTR_E_INVALID, "large systems must write dxdt[loop variable + constant] "
+                                   "(one contiguous field per written entry)");
+  return ODEINTR_OK;
+}
+
+// Measure the reach of the loop body (odeintr_lattice_probe) and switch the tiled kernels on when a tile can hold it.
+int tiled_autodetect(odeintr_system_t h) {
+  h->tiled_pending = false;
+  h->tiled_on = false;
+  if (!h->k_probe || !h->k_tiled || h->lattice_stages != 4 || h->lat_cells_ct <= 0 ||
+      h->lat_cells_ct >= (1LL << 31) || std::getenv("ODEINTR_NO_TILED"))
+    return ODEINTR_OK;
+  const int fields = (int)((long long)h->N / h->lat_cells_ct);
+  CU_TRY(h->lat_flag.reserve(8));
+  CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  const double* pars = h->P ? h->pars.p : nullptr;
+  double t = 0.0;
+  int* out = h->lat_flag.p;
+  void* params[3] = {&pars, &t, &out};
+  CU_TRY(cudaLaunchKernel((const void*)h->k_probe, dim3((unsigned)h->sm_count * 8u), dim3(256), params, 0, h->stream));
+  int reach = 0;
+  CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  // beyond 32 cells the margins (4 * halo per side, recomputed by every tile) stop paying for themselves, and the
+  // interior kernel's one-margin-cell-per-thread layout ends
+  if (reach > 32 || !tiled_configure(h, reach, fields)) return ODEINTR_OK;
+  h->lattice_cells = h->lat_cells_ct;
+  h->tiled_on = true;
+  h->tiled_auto = true;
+  return ODEINTR_OK;
+}
+
+enum { LATTICE_REACH_EXCEEDED = -1000 };  // internal: a tiled step read further than the staged radius
+
+int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
   if (h->m != 1) return fail(ODEINTR_E_STATE, "Invalid initial state");
   const size_t N = (size_t)h->N;
   int rc;
@@ -657,10 +734,9 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   if ((rc = lattice_prepare(h, N))) return rc;
   h->lat_x = h->x.p; h->lat_a = h->lat_buf_a.p; h->lat_b = h->lat_buf_b.p; h->lat_acc = h->lat_buf_acc.p;
   if (sc.record && (rc = reserve_out(h, sc.rec_t.size()))) return rc;
-  lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0};
+  lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0, 0, 0};
   CU_TRY(h->lat_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
-  h->tiled_checked = false;
   if ((rc = begin_timing(h))) return rc;
   size_t row = 0;
   auto observe = [&]() -> int {
@@ -696,15 +772,29 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
     h->out_m = 1;
     h->ragged = false;
   }
-  if (h->lattice_halo > 0) {
+  if (h->tiled_on) {
     int flag = 0;
     CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
-    if (flag)
-      return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
-                                         std::to_string(h->lattice_halo) + " cells) from the cell it computes");
+    if (flag) return LATTICE_REACH_EXCEEDED;
   }
   return ODEINTR_OK;
+}
+
+int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
+  int rc;
+  if (h->tiled_pending && (rc = tiled_autodetect(h))) return rc;
+  rc = run_lattice_once(h, sc);
+  if (rc != LATTICE_REACH_EXCEEDED) return rc;
+  if (!h->tiled_auto)
+    return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
+                                       std::to_string(h->lattice_halo) + " cells) from the cell it computes");
+  // The probe saw a shorter reach than the run needed (the snippet's indices depend on the state or on time):
+  // the staged kernels have no such limit.  lattice_prepare left the initial state in the second stage buffer,
+  // which the tiled kernels never touch.
+  h->tiled_on = false;
+  CU_TRY(cudaMemcpyAsync(h->x.p, h->lat_buf_b.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return run_lattice_once(h, sc);
 }
 
 #include "lattice_adaptive.h"
@@ -992,13 +1082,10 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     h->k_lattice_sharded = nullptr;
   if (cudaLibraryGetKernel(&h->k_combo, h->lib, "odeintr_lattice_combo") != cudaSuccess) h->k_combo = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled, h->lib, "odeintr_lattice_rk4_tiled") != cudaSuccess) h->k_tiled = nullptr;
-  if (cudaLibraryGetKernel(&h->k_tiled_fast, h->lib, "odeintr_lattice_rk4_tiled_fast") != cudaSuccess)
-    h->k_tiled_fast = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled_int, h->lib, "odeintr_lattice_rk4_tiled_interior") != cudaSuccess)
     h->k_tiled_int = nullptr;
-  if (cudaLibraryGetKernel(&h->k_tiled_int_fast, h->lib, "odeintr_lattice_rk4_tiled_interior_fast") != cudaSuccess)
-    h->k_tiled_int_fast = nullptr;
-  if (cudaLibraryGetKernel(&h->k_range, h->lib, "odeintr_lattice_range") != cudaSuccess) h->k_range = nullptr;
+  if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
+  if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
     odeintr_destroy(h);
@@ -1015,6 +1102,13 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->own_stream = true;
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if (h->k_lattice) {
+    const int rc = lattice_query_info(h);
+    if (rc) {
+      odeintr_destroy(h);
+      return rc;
+    }
+  }
   *out = h;
   return ODEINTR_OK;
 }
@@ -1244,7 +1338,9 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
     return fail(ODEINTR_E_INVALID, "Invalid shard specification");
   if ((long long)fields * cells_total != (long long)h->N) return fail(ODEINTR_E_INVALID, "fields * cells_total must equal sys_dim");
   if (!x_dev) return fail(ODEINTR_E_INVALID, "null state pointer");
-  const long long ghost = (long long)halo * h->lattice_stages;
+  h->sh_tiled = slab_tiled_possible(h, halo) && cells_total == h->lat_cells_ct && tiled_configure(h, halo, fields);
+  h->sh_steps_per_exchange = h->sh_tiled ? h->sh_interval : 1;
+  const long long ghost = (long long)halo * h->lattice_stages * h->sh_steps_per_exchange;
   if (n_local + 2 * ghost > cells_total && n_local != cells_total)
     return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
   if (n_local < ghost) return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
@@ -1254,13 +1350,26 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
   h->sh_pitch = odeintr_lattice_pitch(h, halo, n_local);
   h->sh_x = x_dev;
   const size_t total = (size_t)fields * (size_t)h->sh_pitch;
-  CU_TRY(h->lat_buf_a.reserve(total)); CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total));
+  CU_TRY(h->lat_buf_a.reserve(total));
+  if (!h->sh_tiled) { CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total)); }
+  CU_TRY(h->lat_flag.reserve(8));
+  CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  h->sh_primed = false;
   h->sharded = true;
   return ODEINTR_OK;
 }
 
 long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo) {
-  return h ? (long long)halo * h->lattice_stages : 0;
+  if (!h) return 0;
+  return (long long)halo * h->lattice_stages * (slab_tiled_possible(h, halo) ? h->sh_interval : 1);
+}
+
+int odeintr_lattice_set_exchange_interval(odeintr_system_t h, int steps) {
+  if (!h) return fail(ODEINTR_E_INVALID, "null system handle");
+  if (steps < 1 || steps > 64) return fail(ODEINTR_E_INVALID, "steps per halo exchange must be in [1, 64]");
+  if (h->sharded) return fail(ODEINTR_E_STATE, "set the exchange interval before odeintr_lattice_shard");
+  h->sh_interval = steps;
+  return ODEINTR_OK;
 }
 
 // cells reserved in front of (and behind) the owned cells of every field: the ghost width rounded up to a
@@ -1276,25 +1385,61 @@ long long odeintr_lattice_pitch(odeintr_system_t h, int halo, long long n_local)
   return (pad + n_local + pad + 15) / 16 * 16;
 }
 
+namespace {
+// one rk4 step of the slab through the tiled kernels: `cur` -> `other` (both laid out like the caller's buffer), the
+// ghost cells of `cur` being valid out to ghost - phase * 4 * halo cells (phase = steps since the last exchange)
+int slab_tiled_step(odeintr_system_t h, double* cur, double* other, double t, double dt, int phase) {
+  const long long g = h->sh_ghost, pad = h->sh_pad, margin = 4 * (long long)h->sh_halo;
+  h->lat_x = cur + pad; h->lat_a = other + pad;
+  lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1, 0, 0};
+  w.lo = h->sh_c0 - g + margin * (phase + 1);
+  w.hi = h->sh_c0 + h->sh_n + g - margin * (phase + 1);
+  return lattice_step_halo(h, w, t, dt, h->sh_halo);
+}
+
+int slab_check_reach(odeintr_system_t h) {
+  int flag = 0;
+  CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (flag)
+    return fail(ODEINTR_E_INVALID, "the system definition reads x further than the declared halo (" +
+                                       std::to_string(h->sh_halo) + " cells) from the cell it computes");
+  return ODEINTR_OK;
+}
+
+int slab_prime(odeintr_system_t h) {
+  // work buffers start as copies of the state so that entries no loop writes keep their value
+  if (h->sh_primed) return ODEINTR_OK;
+  const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
+  CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (!h->sh_tiled) {
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->sh_primed = true;
+  return ODEINTR_OK;
+}
+}  // namespace
+
 int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
   int rc = activate(h);
   if (rc) return rc;
   if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
   if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
-  const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
-  // stage buffers start as copies of the state so that entries no loop writes keep their value
-  if (!h->sh_primed) {
-    CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    h->sh_primed = true;
+  if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
+  if ((rc = slab_prime(h))) return rc;
+  h->last_launches = 0;
+  if (h->sh_tiled) {
+    // single-step entry point: the caller has just exchanged the halos and finds the new state in its own buffer
+    const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
+    if ((rc = slab_tiled_step(h, h->sh_x, h->lat_buf_a.p, t, dt, 0))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->sh_x, h->lat_buf_a.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return slab_check_reach(h);
   }
   const long long g = h->sh_ghost, pad = h->sh_pad;
   h->lat_x = h->sh_x + pad; h->lat_a = h->lat_buf_a.p + pad; h->lat_b = h->lat_buf_b.p + pad;
   h->lat_acc = h->lat_buf_acc.p + pad;
-  lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1};
-  if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
-  h->last_launches = 0;
+  lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1, 0, 0};
   if ((rc = lattice_step_halo(h, w, t, dt, h->sh_halo))) return rc;
   return ODEINTR_OK;
 }
@@ -1303,43 +1448,30 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
   int rc = activate(h);
   if (rc) return rc;
   if (!h->k_lattice) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
-  if (halo < 0 || fields < 1 || (long long)h->N % fields != 0) return fail(ODEINTR_E_INVALID, "Invalid halo specification");
-  if (halo > 0 && !h->k_tiled) return fail(ODEINTR_E_STATE, "the generated translation unit has no tiled kernel");
-  if (halo > 0 && (long long)h->N / fields >= (1LL << 31))
-    return fail(ODEINTR_E_INVALID, "the tiled kernel indexes cells with 32 bits: at most 2^31 - 1 cells per field");
-  if (halo > 0) {
-    const size_t width = 256 * (size_t)tile_cpt() + 8 * (size_t)halo;
-    const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
-    if (bytes > 200 * 1024) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
-    CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    if (h->k_tiled_fast)
-      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    h->tiled_smem = bytes;
-    h->tiled_int_smem = bytes / 2;
-    if (h->k_tiled_int)
-      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes / 2)));
-    if (h->k_tiled_int_fast)
-      CU_TRY(cudaFuncSetAttribute((const void*)h->k_tiled_int_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(bytes / 2)));
-    // the range of the user's loop decides which tiles are interior
-    h->lat_start = 0;
-    h->lat_bound = (long long)h->N / fields;
-    if (h->k_range) {
-      CU_TRY(h->lat_flag.reserve(6));  // 24 bytes: three long long
-      void* out = h->lat_flag.p;
-      void* params[1] = {&out};
-      CU_TRY(cudaLaunchKernel((const void*)h->k_range, dim3(1), dim3(1), params, 0, h->stream));
-      long long range[3] = {0, 0, 0};
-      CU_TRY(cudaMemcpyAsync(range, h->lat_flag.p, sizeof(range), cudaMemcpyDeviceToHost, h->stream));
-      CU_TRY(cudaStreamSynchronize(h->stream));
-      h->lat_start = range[0];
-      h->lat_bound = range[1];
-      h->lat_cells_ct = range[2];
-    }
+  h->tiled_on = h->tiled_auto = h->tiled_pending = false;
+  if (halo < 0) {  // measured at the first integrate call, when the parameters are in place
+    h->tiled_pending = true;
+    return ODEINTR_OK;
   }
-  h->lattice_halo = halo;
+  if (fields < 1 || (long long)h->N % fields != 0) return fail(ODEINTR_E_INVALID, "Invalid halo specification");
+  if (h->lat_cells_ct > 0 && (long long)h->N / fields != h->lat_cells_ct)
+    return fail(ODEINTR_E_INVALID, "Invalid halo specification: the system writes " +
+                                       std::to_string((long long)h->N / h->lat_cells_ct) + " field(s)");
+  if (halo == 0) return ODEINTR_OK;  // staged kernels
+  if (!h->k_tiled) return fail(ODEINTR_E_STATE, "the generated translation unit has no tiled kernel");
+  if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "the tiled kernel is an rk4 step");
+  if ((long long)h->N / fields >= (1LL << 31))
+    return fail(ODEINTR_E_INVALID, "the tiled kernel indexes cells with 32 bits: at most 2^31 - 1 cells per field");
+  if (!tiled_configure(h, halo, fields)) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
   h->lattice_cells = (long long)h->N / fields;
+  h->tiled_on = true;
   return ODEINTR_OK;
+}
+
+long long odeintr_lattice_get_halo(odeintr_system_t h) {
+  if (!h || activate(h)) return -1;
+  if (h->tiled_pending && tiled_autodetect(h)) return -1;
+  return h->tiled_on ? h->lattice_halo : -1;
 }
 
 int odeintr_nccl_unique_id(void* id_out, size_t cap) {
@@ -1368,7 +1500,7 @@ int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const voi
 
 namespace {
 // ghost cells <- ring neighbours' boundary cells, every field, one NCCL group (or local copies for one rank)
-int lattice_exchange(odeintr_system_t h) {
+int lattice_exchange(odeintr_system_t h, double* buf) {
   const long long g = h->sh_ghost, n = h->sh_n, pitch = h->sh_pitch;
   if (g == 0) return ODEINTR_OK;
   const int world = h->comm_world, rank = h->comm_rank;
@@ -1376,7 +1508,7 @@ int lattice_exchange(odeintr_system_t h) {
   // per field: owned cells live at [pad, pad + n); ghost cells at [pad - g, pad) and [pad + n, pad + n + g)
   if (world == 1) {
     for (int f = 0; f < h->sh_fields; ++f) {
-      double* own = h->sh_x + (long long)f * pitch + pad;
+      double* own = buf + (long long)f * pitch + pad;
       CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
       CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
@@ -1386,7 +1518,7 @@ int lattice_exchange(odeintr_system_t h) {
   const int left = (rank + world - 1) % world, right = (rank + 1) % world;
   NCCL_TRY(g_nccl.GroupStart());
   for (int f = 0; f < h->sh_fields; ++f) {
-    double* own = h->sh_x + (long long)f * pitch + pad;
+    double* own = buf + (long long)f * pitch + pad;
     // order matters when left == right (two ranks): sends (to right, to left) pair with recvs (from left, from right)
     NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, h->stream));
     NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, h->stream));
@@ -1403,13 +1535,40 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
   if (rc) return rc;
   if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
   if (n_steps < 0) return fail(ODEINTR_E_INVALID, "negative step count");
+  if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "sharded stepping is provided for rk4");
+  if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+  if ((rc = slab_prime(h))) return rc;
   if ((rc = begin_timing(h))) return rc;
-  for (long long s = 0; s < n_steps; ++s) {
-    if ((rc = lattice_exchange(h))) return rc;
-    const long long keep = h->last_launches;
-    if ((rc = odeintr_lattice_shard_step(h, t0 + static_cast<double>(first_step + s) * dt, dt))) return rc;  // integrate_const time rule
-    h->last_launches += keep;
+  if (h->sh_tiled) {
+    // the state ping-pongs between the caller's buffer and ours; ghost cells are wide enough for
+    // sh_steps_per_exchange steps (each consumes 4 * halo of them), so the ring exchange runs once per round
+    double* cur = h->sh_x;
+    double* other = h->lat_buf_a.p;
+    long long launches = 0;
+    for (long long s = 0; s < n_steps; ++s) {
+      const int phase = (int)(s % h->sh_steps_per_exchange);
+      if (phase == 0 && (rc = lattice_exchange(h, cur))) return rc;
+      h->last_launches = 0;
+      if ((rc = slab_tiled_step(h, cur, other, t0 + static_cast<double>(first_step + s) * dt, dt, phase))) return rc;
+      launches += h->last_launches;
+      std::swap(cur, other);
+    }
+    h->last_launches = launches;
+    if (cur != h->sh_x) {
+      const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
+      CU_TRY(cudaMemcpyAsync(h->sh_x, cur, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if ((rc = end_timing(h))) return rc;
+    h->last_steps = n_steps;
+    return slab_check_reach(h);
   }
+  long long launches = 0;
+  for (long long s = 0; s < n_steps; ++s) {
+    if ((rc = lattice_exchange(h, h->sh_x))) return rc;
+    if ((rc = odeintr_lattice_shard_step(h, t0 + static_cast<double>(first_step + s) * dt, dt))) return rc;  // integrate_const time rule
+    launches += h->last_launches;
+  }
+  h->last_launches = launches;
   if ((rc = end_timing(h))) return rc;
   h->last_steps = n_steps;
   return ODEINTR_OK;

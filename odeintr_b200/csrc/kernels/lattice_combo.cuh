@@ -18,7 +18,7 @@ odeintr_lattice_combo(const odeintr_lattice_combo_args a) {
   Sys sys;
   sys.load_params(a.pars, 1, 0);
   long long off[F];
-  sys.field_offsets(off);
+  sys.field_offsets(off, 0);
   odeintr_b200::lattice_view_t<odeintr_b200::LATTICE_PLAIN> xs;
   xs.p = a.xs; xs.n_total = a.n_total; xs.n_local = a.n_total; xs.c0 = 0; xs.ghost = 0; xs.pitch = 0;
 

@@ -56,7 +56,7 @@ ODEINTR_DEV void lattice_stage_body(const odeintr_lattice_args& a) {
   long long off[F];
   {
     odeintr::system_type_t<lattice_view_t<LATTICE_PLAIN> > sys;
-    sys.field_offsets(off);
+    sys.field_offsets(off, 0);
   }
   // local position of entry (field f, cell c) is base[f] + c: fields are `pitch` apart, cell c sits at c - c0
   long long base[F];

@@ -70,9 +70,11 @@ class ShardedLattice:
     C-ABI on that memory.  Fixed-step rk4, periodic lattice, stencil radius `halo`."""
 
     def __init__(self, system, cells_total: int, fields: int = 1, halo: int = 1, rank: int = 0, world: int = 1,
-                 group=None, device=None, native: bool = True):
+                 group=None, device=None, native: bool = True, steps_per_exchange: int = 8):
         """native=True: the C-ABI owns an NCCL communicator and runs exchange + step loops itself
-        (odeintr_lattice_shard_run); torch.distributed only ships the 128-byte NCCL unique id.
+        (odeintr_lattice_shard_run); torch.distributed only ships the 128-byte NCCL unique id.  Slabs that step
+        through the temporally blocked rk4 kernels (radius <= 32) keep ghost zones `steps_per_exchange` steps wide
+        and exchange them only that often (odeintr_lattice_set_exchange_interval).
         native=False: halos are exchanged by torch.distributed P2P ops between the C-ABI's steps."""
         import torch
 
@@ -84,6 +86,8 @@ class ShardedLattice:
         self.begin, self.end = shard_range(cells_total, rank, world)
         self.n_local = self.end - self.begin
         self.lib = _abi.load()
+        if self.lib.odeintr_lattice_set_exchange_interval(system._h, steps_per_exchange if native else 1) != 0:
+            raise OdeintrError(_abi.last_error())
         self.ghost = int(self.lib.odeintr_lattice_ghost_width(system._h, halo))
         self.pad = int(self.lib.odeintr_lattice_pad_width(system._h, halo))
         self.pitch = int(self.lib.odeintr_lattice_pitch(system._h, halo, self.n_local))

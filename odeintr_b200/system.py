@@ -332,8 +332,13 @@ class CompiledSystem:
         return EnsembleRecord(t, out), x_final
 
     def set_halo(self, halo: int, fields: int = 1):
-        """Declare the stencil radius of a large system (odeintr_lattice_set_halo)."""
+        """Stencil radius of a large system for the tiled rk4 kernels: declared (> 0), measured (< 0) or
+        none (0 = stage-per-launch kernels) -- odeintr_lattice_set_halo."""
         self._check(self._lib.odeintr_lattice_set_halo(self._h, halo, fields))
+
+    def get_halo(self) -> int:
+        """Radius the tiled rk4 kernels run with, -1 when the stage-per-launch kernels are in use."""
+        return int(self._lib.odeintr_lattice_get_halo(self._h))
 
     # -- measurement ----------------------------------------------------------------------------------
     def last_kernel_ms(self) -> float:

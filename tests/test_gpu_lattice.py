@@ -19,11 +19,15 @@ def cols(df):
     return df.iloc[:, 1:].to_numpy()
 
 
-@pytest.mark.parametrize("method", ["rk4", "euler"])
-def test_bistable_chain_bit_exact(method):
-    n = 4099  # not a multiple of anything: ragged last block, `% N` wrap at both ends
+@pytest.mark.parametrize("method,halo", [("rk4", None), ("rk4", 0), ("euler", None)])
+def test_bistable_chain_bit_exact(method, halo):
+    # halo=None: the drop-in call; for rk4 the stencil radius is measured and the temporally blocked kernels run.
+    # halo=0: the stage-per-launch kernels.
+    n = 4099  # not a multiple of anything: ragged last block / tile, `% N` wrap at both ends
     env = {}
-    odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
+    code = odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n,
+                                           env=env, halo=halo)
+    assert code.system.get_halo() == (1 if (method, halo) == ("rk4", None) else -1)
     ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=n)
     rng = np.random.default_rng(11)
     x0 = rng.integers(0, 2, n).astype(np.float64)  # inic = rbinom(M * M, 1, 1/2) in the reference's example
@@ -55,16 +59,18 @@ def test_two_loops_and_laplace2d_helper():
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
 
 
-def test_oscillator_chain_two_fields_runtime_parameters():
+@pytest.mark.parametrize("halo", [None, 0])
+def test_oscillator_chain_two_fields_runtime_parameters(halo):
     n = 2 * 3001
     env = {}
-    odeintr_b200.compile_sys_openmp("chain", CHAIN, CHAIN_PARS, False, method="rk4", sys_dim=n, globals=CHAIN_GLOBALS,
-                                    env=env)
+    code = odeintr_b200.compile_sys_openmp("chain", CHAIN, CHAIN_PARS, False, method="rk4", sys_dim=n,
+                                           globals=CHAIN_GLOBALS, env=env, halo=halo)
     ora = bo.build(CHAIN, CHAIN_PARS, False, "rk4", sys_dim=n, globals=CHAIN_GLOBALS)
     L = n // 2
     x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(L) / L), np.zeros(L)])
     env["chain_set_params"](beta=0.7, K=0.45)
     df = env["chain"](x0, 2.0, 0.01)
+    assert code.system.get_halo() == (1 if halo is None else -1)
     ref = ora.integrate_const(x0, 0, 2.0, 0.01, pars=[0.7, 0.45])
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
     # the symplectic-ish energy drifts only slightly over 200 rk4 steps: a size-independent sanity property
@@ -274,6 +280,42 @@ def test_tiled_rk4_interior_tiles_other_index_forms(case):
     ora = bo.build(src, pars, True, "rk4", sys_dim=n)
     fin = env["t_no_record"](x0, 1.25, 0.1)
     assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.25, 0.1)["x"]))
+
+
+def test_tiled_rk4_measured_radius():
+    # the probe evaluates the index expressions of every cell: radius 2 for the 4th-order Laplacian, 3 where only a
+    # few cells reach that far, none (staged kernels) for an M x M lattice whose rows are M cells apart
+    wide = "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + N - 2) % N] + x[(i + 2) % N] - 2.0 * x[i];"
+    some = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"
+    for src, n, want in ((wide, 5000, 2), (some, 5000, 3), (BISTABLE_2D, 64 * 64, -1)):
+        env = {}
+        code = odeintr_b200.compile_sys_openmp("p", src, BISTABLE_PARS, True, method="rk4", sys_dim=n, env=env)
+        x0 = np.random.default_rng(94).uniform(0, 1, n)
+        fin = env["p_no_record"](x0, 0.5, 0.1)
+        assert code.system.get_halo() == want
+        ora = bo.build(src, BISTABLE_PARS, True, "rk4", sys_dim=n)
+        assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 0.5, 0.1)["x"]))
+
+
+def test_tiled_rk4_state_dependent_reach_falls_back_to_the_staged_kernels():
+    # the probe (which reads 1.0 everywhere) sees radius 1; the run reads 5 cells away wherever x > 1.5.  The
+    # per-access check catches it and the call is repeated with the stage-per-launch kernels: same bits as the oracle
+    src = "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + (x[i] > 1.5 ? 5 : 1)) % N] - x[i];"
+    n = 5000
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("f", src, method="rk4", sys_dim=n, env=env)
+    x0 = np.random.default_rng(95).uniform(0, 2, n)
+    df = env["f"](x0, 1.0, 0.1)
+    assert code.system.get_halo() == -1  # switched off for this system from now on
+    ora = bo.build(src, None, False, "rk4", sys_dim=n)
+    ref = ora.integrate_const(x0, 0, 1.0, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+
+
+def test_large_system_rejects_strided_targets():
+    with pytest.raises(odeintr_b200.OdeintrError, match="loop variable \\+ constant"):
+        odeintr_b200.compile_sys_openmp("s", "for (int i = 0; i < N / 2; ++i) { dxdt[2 * i] = x[2 * i + 1]; dxdt[2 * i + 1] = -x[2 * i]; }",
+                                        method="rk4", sys_dim=64)
 
 
 def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():

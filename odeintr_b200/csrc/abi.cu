@@ -148,6 +148,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* b = std::getenv("ODEINTR_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_MIN_BLOCKS=") + b);
   if (std::getenv("ODEINTR_NESTED_LOOPS")) o.push_back("-DODEINTR_NESTED_LOOPS=1");
   if (const char* c = std::getenv("ODEINTR_TILE_CPT")) o.push_back(std::string("-DODEINTR_TILE_CPT=") + c);
+  if (const char* c = std::getenv("ODEINTR_TILE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
   return o;
 }
 
@@ -188,7 +190,8 @@ struct odeintr_system_s {
   unsigned flags = 0;
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
-               k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_info = nullptr, k_probe = nullptr;
+               k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
+               k_info = nullptr, k_probe = nullptr;
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -196,6 +199,8 @@ struct odeintr_system_s {
   long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
   size_t tiled_smem = 0;        // dynamic shared memory of the general tiled kernel (4 arrays per field)
   size_t tiled_int_smem = 0;    // ... of the interior kernel (2 arrays per field)
+  size_t tiled_tma_smem = 0;    // ... of the persistent TMA kernel (4 arrays per field + 2 mbarriers)
+  int tiled_tma_blocks = 0;     // resident blocks per SM of the persistent TMA kernel (0 = not available)
   long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_info)
   long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
@@ -607,8 +612,18 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     if (ta.tile_skip > 0) {
       ta.lo = lo;
       ta.sharded = 0;  // the interior kernel addresses both layouts through (pitch, c0)
-      CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_int, dim3((unsigned)ta.tile_skip), dim3(256), params,
-                              h->tiled_int_smem, h->stream));
+      // 16-byte aligned windows (even start, even distance between fields) can be fetched by the TMA engine: the
+      // persistent kernel prefetches the next tile's window while it computes the current one
+      const bool aligned = (reinterpret_cast<uintptr_t>(ta.x_in) % 16 == 0) && ((lo - ta.c0) % 2 == 0) &&
+                           (ta.pitch % 2 == 0 || h->lat_cells_ct == (long long)h->N);
+      if (h->tiled_tma_blocks > 0 && aligned) {
+        const long long slots = (long long)h->sm_count * h->tiled_tma_blocks;
+        const unsigned grid = (unsigned)std::min<long long>(ta.tile_skip, slots);
+        CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_tma, dim3(grid), dim3(256), params, h->tiled_tma_smem, h->stream));
+      } else {
+        CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_int, dim3((unsigned)ta.tile_skip), dim3(256), params,
+                                h->tiled_int_smem, h->stream));
+      }
       h->last_launches += 1;
       g_total_launches += 1;
     }
@@ -667,6 +682,16 @@ bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
   h->tiled_smem = bytes;
   h->tiled_int_smem = bytes / 2;
   h->lattice_halo = halo;
+  h->tiled_tma_blocks = 0;
+  h->tiled_tma_smem = bytes + 16;
+  if (h->k_tiled_tma && h->k_tiled_int && !std::getenv("ODEINTR_NO_TMA") &&
+      cudaFuncSetAttribute((const void*)h->k_tiled_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)h->tiled_tma_smem) == cudaSuccess) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_tiled_tma, 256, h->tiled_tma_smem) == cudaSuccess)
+      h->tiled_tma_blocks = nb;
+  }
+  (void)cudaGetLastError();
   return true;
 }
 
@@ -1084,6 +1109,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_tiled, h->lib, "odeintr_lattice_rk4_tiled") != cudaSuccess) h->k_tiled = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled_int, h->lib, "odeintr_lattice_rk4_tiled_interior") != cudaSuccess)
     h->k_tiled_int = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled_tma, h->lib, "odeintr_lattice_rk4_tiled_tma") != cudaSuccess)
+    h->k_tiled_tma = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();

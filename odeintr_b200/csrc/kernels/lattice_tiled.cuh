@@ -170,8 +170,11 @@ struct lattice_tile_rel_view {
   int halo;
   int centre;         // global number of the cell being computed (generic path only)
   mutable int bad;    // a read reached beyond the halo or outside the state
+  const double* own;  // the stage's input at the cell being computed, per field: the thread wrote it itself
 
   ODEINTR_DEV double at(long long f, long long d) const {
+    // the cell's own entries come from registers (a compile-time test for ordinary stencils)
+    if (d == 0 && f >= 0 && f < ODEINTR_NFIELDS) return own[f];
     // out-of-reach reads are served from a clamped position (never outside the staged window) and reported once
     // per thread at the end of the kernel
     if (f < 0) { bad = 1; f = 0; }
@@ -196,74 +199,63 @@ struct lattice_tile_rel_view {
 };
 
 // Interior tiles.  Every thread owns CPT cells of the tile (tid + k * 256) for the whole step: the state at the start
-// of the step and the running weighted sum of those cells never leave its registers; only the stage states, which the
-// neighbours read, go through shared memory (two buffers, ping-pong).  The cells of the shrinking margins (3, 2, 1
+// of the step, the running weighted sum and the current stage state of those cells never leave its registers; the
+// stage states also go to shared memory, where the neighbours read them.  The cells of the shrinking margins (3, 2, 1
 // times halo on each side in stages 1, 2, 3) belong to the first 6 * halo threads, one each.
-// Per cell and step: 1 LDG + 1 STG, 4 * (stencil reads) LDS + 4 STS -- against 20 LDS + 8 STS of the general body.
+// Per cell and step: 8 bytes in + 8 bytes out of HBM, 4 * (stencil reads other than the cell itself) LDS + 3 STS --
+// against 20 LDS + 8 STS of the general body.
 // Entry (field f, global cell c) of x_in / x_out sits at f * pitch + (c - c0): one GPU has pitch = L, c0 = 0; a rank
 // of a sharded run its slab geometry (ghost cells at the negative offsets make every window contiguous).
-ODEINTR_DEV void lattice_rk4_tiled_interior_body(const odeintr_lattice_tiled_args& a) {
-  typedef odeintr::system_type_t<lattice_tile_rel_view> Sys;
+struct lattice_tile_ctx {
+  odeintr::system_type_t<lattice_tile_rel_view> sys;
+  int fld[ODEINTR_NFIELDS];  // field number of the f-th written entry
+  int h, margin, W;
+};
+
+// One tile whose window of x is already staged in `in` ([field][W]).  Stage states: 1 -> sa, 2 -> in, 3 -> sb
+// (sb may be sa), 4 -> x_out.  Ends without a barrier: the last stage only reads sb.
+template <bool TMA_INPUT>
+ODEINTR_DEV void lattice_rk4_tile(const odeintr_lattice_tiled_args& a, lattice_tile_ctx& cx, double* in, double* sa,
+                                  double* sb, const long long tile_lo, int& bad) {
   constexpr int F = ODEINTR_NFIELDS;
   constexpr int C = ODEINTR_TILE_CPT;
   constexpr int T = 256 * C;
-  extern __shared__ double smem[];
-  const int h = (int)a.halo;
-  const int margin = 4 * h;
-  const int W = T + 2 * margin;
-  double* s0 = smem;          // x, then the stage-2 state
-  double* s1 = smem + F * W;  // stage-1 state, then the stage-3 state
-  const int tid = threadIdx.x;
-
-  Sys sys;
-  sys.load_params(a.pars, 1, 0);
-  long long off[F];
-  sys.field_offsets(off, 0);
-  // cells per field, a compile-time constant here (the host checks it against its own count): the snippet's index
-  // expressions can only fold against a constant lattice length
   constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
-  const long long tile_lo = a.lo + ((long long)a.tile_first + blockIdx.x) * T;
-  int fld[F];
-#pragma unroll
-  for (int f = 0; f < F; ++f) fld[f] = static_cast<int>(off[f] / L);
+  const int tid = threadIdx.x, h = cx.h, margin = cx.margin, W = cx.W;
 
-  // stage the window of x; the thread's own cells stay in registers as well
-  double xs[C][F], acc[C][F];
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const double* g = a.x_in + fld[f] * a.pitch + (tile_lo - a.c0);
-    double* s = s0 + fld[f] * W + margin;
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      const double v = __ldg(g + tid + k * 256);
-      xs[k][f] = v;
-      s[tid + k * 256] = v;
-    }
-    if (tid < 2 * margin) {
-      const int j = tid < margin ? tid - margin : T + (tid - margin);
-      s[j] = __ldg(g + j);
-    }
-  }
-  __syncthreads();
-  // the margin cell of this thread: je, at distance de + 1 from the tile, takes part in stage s while de < (4-s)*halo
+  // the thread's own cells, and its margin cell je: at distance de + 1 from the tile, it takes part in stage s while
+  // de < (4 - s) * halo
+  double xs[C][F], acc[C][F], xe[F];
   const bool has_edge = tid < 6 * h;
   const int de = tid < 3 * h ? tid : tid - 3 * h;
   const int je = tid < 3 * h ? -1 - tid : T + (tid - 3 * h);
-  double xe[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) xe[f] = has_edge ? s0[fld[f] * W + margin + je] : 0.0;
+  for (int f = 0; f < F; ++f) {
+#pragma unroll
+    for (int k = 0; k < C; ++k) xs[k][f] = in[cx.fld[f] * W + margin + tid + k * 256];
+    xe[f] = has_edge ? in[cx.fld[f] * W + margin + je] : 0.0;
+  }
 
   lattice_tile_rel_view view;
   view.n_total = L; view.width = W; view.halo = h; view.bad = 0;
   rel_index idx;
   idx.off = 0; idx.cells = static_cast<int>(L); idx.rel = true;
 
+  // the stage's input at the thread's own cells, by field number (what the thread stored in the previous stage)
+  double own[C][F], own_e[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+#pragma unroll
+    for (int k = 0; k < C; ++k) own[k][cx.fld[f]] = xs[k][f];
+    own_e[cx.fld[f]] = xe[f];
+  }
+
   const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
   const double dt = a.dt;
 #pragma unroll
   for (int stage = 1; stage <= 4; ++stage) {
-    const double* src = (stage & 1) ? s0 : s1;
-    double* dst = (stage & 1) ? s1 : s0;
+    const double* src = stage == 1 ? in : (stage == 2 ? sa : (stage == 3 ? in : sb));
+    double* dst = stage == 1 ? sa : (stage == 2 ? in : sb);
     const double a_dt = stage == 1 ? half * dt : (stage == 2 ? half * dt : 1.0 * dt);
     const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
     const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
@@ -274,14 +266,19 @@ ODEINTR_DEV void lattice_rk4_tiled_interior_body(const odeintr_lattice_tiled_arg
 #pragma unroll
       for (int f = 0; f < F; ++f) kk[f] = 0.0;
       view.p = src + margin + j;
+      view.own = own[k];
       view.centre = idx.centre = static_cast<int>(tile_lo) + j;
-      sys.cell(view, kk, idx, ts);
+      cx.sys.cell(view, kk, idx, ts);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
-        if (stage < 4) dst[fld[f] * W + margin + j] = xs[k][f] + a_dt * kk[f];
+        if (stage < 4) {
+          const double v = xs[k][f] + a_dt * kk[f];
+          dst[cx.fld[f] * W + margin + j] = v;
+          own[k][cx.fld[f]] = v;
+        }
         acc[k][f] = (stage == 1 ? xs[k][f] : acc[k][f]) + b_dt * kk[f];  // the running sum starts from x
         // new state of an owned cell: the only global store of the step
-        if (stage == 4) a.x_out[fld[f] * a.pitch + (tile_lo - a.c0) + j] = acc[k][f];
+        if (stage == 4) a.x_out[cx.fld[f] * a.pitch + (tile_lo - a.c0) + j] = acc[k][f];
       }
     }
     if (stage < 4) {
@@ -290,15 +287,148 @@ ODEINTR_DEV void lattice_rk4_tiled_interior_body(const odeintr_lattice_tiled_arg
 #pragma unroll
         for (int f = 0; f < F; ++f) kk[f] = 0.0;
         view.p = src + margin + je;
+        view.own = own_e;
         view.centre = idx.centre = static_cast<int>(tile_lo) + je;
-        sys.cell(view, kk, idx, ts);
+        cx.sys.cell(view, kk, idx, ts);
 #pragma unroll
-        for (int f = 0; f < F; ++f) dst[fld[f] * W + margin + je] = xe[f] + a_dt * kk[f];
+        for (int f = 0; f < F; ++f) {
+          const double v = xe[f] + a_dt * kk[f];
+          dst[cx.fld[f] * W + margin + je] = v;
+          own_e[cx.fld[f]] = v;
+        }
       }
+      // stage 2 stores into the buffer the TMA engine refills later: make them visible to the async proxy
+      if (TMA_INPUT && stage == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
   }
-  if (view.bad) *a.flag = 1;
+  bad |= view.bad;
+}
+
+ODEINTR_DEV void lattice_tile_ctx_init(const odeintr_lattice_tiled_args& a, lattice_tile_ctx& cx) {
+  constexpr int F = ODEINTR_NFIELDS;
+  // cells per field, a compile-time constant here (the host checks it against its own count): the snippet's index
+  // expressions can only fold against a constant lattice length
+  constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
+  cx.sys.load_params(a.pars, 1, 0);
+  long long off[F];
+  cx.sys.field_offsets(off, 0);
+#pragma unroll
+  for (int f = 0; f < F; ++f) cx.fld[f] = static_cast<int>(off[f] / L);
+  cx.h = (int)a.halo;
+  cx.margin = 4 * cx.h;
+  cx.W = 256 * ODEINTR_TILE_CPT + 2 * cx.margin;
+}
+
+// one block per tile, window staged with ordinary loads (any alignment)
+ODEINTR_DEV void lattice_rk4_tiled_interior_body(const odeintr_lattice_tiled_args& a) {
+  constexpr int F = ODEINTR_NFIELDS;
+  constexpr int T = 256 * ODEINTR_TILE_CPT;
+  extern __shared__ double smem[];
+  lattice_tile_ctx cx;
+  lattice_tile_ctx_init(a, cx);
+  const int tid = threadIdx.x, margin = cx.margin, W = cx.W;
+  double* s0 = smem;          // x, then the stage-2 state
+  double* s1 = smem + F * W;  // stage-1 state, then the stage-3 state
+  const long long tile_lo = a.lo + ((long long)a.tile_first + blockIdx.x) * T;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const double* g = a.x_in + cx.fld[f] * a.pitch + (tile_lo - a.c0);
+    double* s = s0 + cx.fld[f] * W + margin;
+    double v[ODEINTR_TILE_CPT];  // all loads in flight before the first store
+#pragma unroll
+    for (int k = 0; k < ODEINTR_TILE_CPT; ++k) v[k] = __ldg(g + tid + k * 256);
+    if (tid < 2 * margin) {
+      const int j = tid < margin ? tid - margin : T + (tid - margin);
+      s[j] = __ldg(g + j);
+    }
+#pragma unroll
+    for (int k = 0; k < ODEINTR_TILE_CPT; ++k) s[tid + k * 256] = v[k];
+  }
+  __syncthreads();
+  int bad = 0;
+  lattice_rk4_tile<false>(a, cx, s0, s1, s1, tile_lo, bad);
+  if (bad) *a.flag = 1;
+}
+
+// ---- TMA-staged, persistent variant ----------------------------------------------------------------------------
+// One block per SM slot walks over the interior tiles b, b + gridDim.x, ...  The window of the NEXT tile is fetched
+// by the TMA engine (cp.async.bulk global -> shared, one bulk copy per field, completion counted in bytes on an
+// mbarrier) into the second input buffer while the block computes the current tile, so no warp ever waits for HBM.
+// Needs 16-byte aligned windows (the host checks: even window start, even pitch); otherwise the kernel above runs.
+ODEINTR_DEV unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+ODEINTR_DEV void mbar_init(unsigned long long* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+ODEINTR_DEV void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+ODEINTR_DEV void mbar_wait(unsigned long long* bar, const unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+ODEINTR_DEV void tma_load_1d(void* dst, const void* src, const unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+ODEINTR_DEV void lattice_rk4_tiled_tma_body(const odeintr_lattice_tiled_args& a) {
+  constexpr int F = ODEINTR_NFIELDS;
+  constexpr int T = 256 * ODEINTR_TILE_CPT;
+  extern __shared__ __align__(128) double smem_tma[];
+  double* smem = smem_tma;
+  lattice_tile_ctx cx;
+  lattice_tile_ctx_init(a, cx);
+  const int tid = threadIdx.x, margin = cx.margin, W = cx.W;
+  // input windows of the current and the next tile (then stage-2 states) at smem + b * F * W, b = 0, 1
+  double* s1 = smem + 2 * F * W;         // stage-1 states
+  double* s2 = smem + 3 * F * W;         // stage-3 states: a buffer of their own, so that a warp starting the next
+                                         // tile's stage 1 cannot overwrite what a slower warp still reads in stage 4
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + 4 * F * W);
+  const long long n_tiles = a.tile_skip;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned bytes = static_cast<unsigned>(W * sizeof(double));
+  int bad = 0;
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    if (tid == 0) {
+      // one thread asks the TMA engine for the window of a tile: -> input buffer nb, completion on bar[nb].
+      // First pass: this tile's own window as well.  Every thread has passed the barrier that ends stage 3 of the
+      // previous tile, the last use of the other buffer; the proxy fence orders those ordinary shared-memory
+      // accesses before the engine's writes.
+      for (int ahead = (it == 0 ? 0 : 1); ahead <= 1; ++ahead) {
+        const long long tl = tile + ahead * (long long)gridDim.x;
+        if (tl >= n_tiles) break;
+        const int nb = b ^ ahead;
+        const long long lo = a.lo + (a.tile_first + tl) * T - margin;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar + nb, bytes * F);
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+          tma_load_1d(smem + (nb * F + cx.fld[f]) * W, a.x_in + cx.fld[f] * a.pitch + (lo - a.c0), bytes, bar + nb);
+      }
+    }
+    mbar_wait(bar + b, (it >> 1) & 1);
+    lattice_rk4_tile<true>(a, cx, smem + b * F * W, s1, s2, a.lo + (a.tile_first + tile) * T, bad);
+  }
+  if (bad) *a.flag = 1;
 }
 
 // Reach probe: evaluates the loop body of every cell against a view that reads nothing and records how far from the
@@ -374,7 +504,18 @@ extern "C" __global__ void odeintr_lattice_info(long long* out) {
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body(a); }
 
-extern "C" __global__ void __launch_bounds__(256)
+#ifndef ODEINTR_TILE_MIN_BLOCKS  // resident blocks per SM the interior kernel is compiled for (register cap)
+#define ODEINTR_TILE_MIN_BLOCKS (ODEINTR_NFIELDS > 1 ? 3 : 4)
+#endif
+
+extern "C" __global__ void __launch_bounds__(256, ODEINTR_TILE_MIN_BLOCKS)
 odeintr_lattice_rk4_tiled_interior(const odeintr_lattice_tiled_args a) {
   odeintr_b200::lattice_rk4_tiled_interior_body(a);
 }
+
+#ifndef ODEINTR_TMA_MIN_BLOCKS  // the persistent kernel hides latency by prefetching, not by occupancy
+#define ODEINTR_TMA_MIN_BLOCKS (ODEINTR_NFIELDS > 1 ? 2 : 4)
+#endif
+
+extern "C" __global__ void __launch_bounds__(256, ODEINTR_TMA_MIN_BLOCKS)
+odeintr_lattice_rk4_tiled_tma(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_tma_body(a); }

@@ -14,7 +14,10 @@ lib = _abi.load()
 logn = int(os.environ.get("LOGN", "28"))
 steps = int(os.environ.get("STEPS", "100"))
 check = os.environ.get("CHECK", "1") == "1"
+cases = os.environ.get("CASES", "bistable,chain").split(",")
 for name, src, pars, glob in (("bistable", BISTABLE_1D, BISTABLE_PARS, ""), ("chain", CHAIN, CHAIN_PARS, CHAIN_GLOBALS)):
+    if name not in cases:
+        continue
     n = 1 << logn
     if name == "chain":
         L = n // 2

@@ -191,7 +191,7 @@ struct odeintr_system_s {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
-               k_info = nullptr, k_probe = nullptr;
+               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr;
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -806,8 +806,76 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
   return ODEINTR_OK;
 }
 
+// Ensemble of wider systems (m > 1 trajectories of a compile_sys_openmp system): one block per trajectory, the
+// whole integrate call in one launch of odeintr_lattice_ensemble (lattice_ensemble.cuh).
+int run_lattice_ensemble(odeintr_system_t h, const plain_schedule& sc) {
+  if (!h->k_lat_ens)
+    return fail(ODEINTR_E_STATE, "ensembles of large systems are provided for fixed-step rk4 and at most 8192 / fields "
+                                 "cells per field; run the trajectories one at a time");
+  if (h->lat_cells_ct <= 0) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
+  int rc;
+  // stencil radius: declared, or measured by the probe (parameters of instance 0; index expressions that depend on
+  // parameters or state are caught by the per-access check)
+  long long halo = h->lattice_halo;
+  if (!h->tiled_on) {
+    const bool pending = h->tiled_pending, was_auto = h->tiled_auto;
+    if ((rc = tiled_autodetect(h))) return rc;  // sets lattice_halo when a tile can hold the reach
+    if (!h->tiled_on) {
+      h->tiled_pending = pending; h->tiled_auto = was_auto;
+      return fail(ODEINTR_E_INVALID, "ensembles of large systems need a stencil radius of at most 32 cells");
+    }
+    halo = h->lattice_halo;
+  }
+  const long long L = h->lat_cells_ct;
+  const int fields = (int)((long long)h->N / L);
+  if (2 * halo + 1 > L) return fail(ODEINTR_E_INVALID, "stencil radius too wide for the lattice");
+  odeintr_lattice_ensemble_args a;
+  std::memset(&a, 0, sizeof(a));
+  if ((rc = param_view(h, a.p.pars, a.p.par_ld, a.p.par_inc))) return rc;
+  if (sc.record && (rc = reserve_out(h, sc.rec_t.size()))) return rc;
+  if ((rc = upload_schedule(h, sc, a.p))) return rc;
+  a.p.x = h->x.p;
+  a.p.out = sc.record ? h->out.p : nullptr;
+  a.p.m = (long long)h->m;
+  a.p.ld = (long long)h->m;
+  a.first = 0;
+  a.halo = halo;
+  CU_TRY(h->lat_flag.reserve(8));
+  CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  a.flag = h->lat_flag.p;
+  // threads per trajectory and trajectories per block, as lattice_ensemble.cuh derives them from the lattice length
+  const unsigned nt = (unsigned)(L > 2048 ? 512 : (L >= 256 ? 256 : (L + 31) / 32 * 32));
+  const unsigned group = nt == 32 ? 4 : 1;
+  const size_t smem = group * 2 * (size_t)fields * (size_t)(L + 2 * halo) * sizeof(double);
+  if (smem > 200 * 1024) return fail(ODEINTR_E_INVALID, "lattice too large for one block's shared memory");
+  CU_TRY(cudaFuncSetAttribute((const void*)h->k_lat_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned block = nt * group;
+  const unsigned grid = (unsigned)((h->m + group - 1) / group);
+  if ((rc = begin_timing(h))) return rc;
+  void* params[1] = {&a};
+  CU_TRY(cudaLaunchKernel((const void*)h->k_lat_ens, dim3(grid), dim3(block), params, smem, h->stream));
+  h->last_launches += 1;
+  g_total_launches += 1;
+  if ((rc = end_timing(h))) return rc;
+  h->last_steps = sc.total_steps;
+  if (sc.record) {
+    h->rec_t = sc.rec_t;
+    h->rows = sc.rec_t.size();
+    h->out_m = h->m;
+    h->ragged = false;
+  }
+  int flag = 0;
+  CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (flag)
+    return fail(ODEINTR_E_INVALID, "the system definition reads x further than the stencil radius (" +
+                                       std::to_string(halo) + " cells) from the cell it computes");
+  return ODEINTR_OK;
+}
+
 int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   int rc;
+  if (h->m > 1) return run_lattice_ensemble(h, sc);
   if (h->tiled_pending && (rc = tiled_autodetect(h))) return rc;
   rc = run_lattice_once(h, sc);
   if (rc != LATTICE_REACH_EXCEEDED) return rc;
@@ -1111,6 +1179,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     h->k_tiled_int = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled_tma, h->lib, "odeintr_lattice_rk4_tiled_tma") != cudaSuccess)
     h->k_tiled_tma = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();

@@ -127,6 +127,15 @@ struct odeintr_lattice_combo_args {
   double t;
 };
 
+// Ensemble of wider systems, one trajectory per block (lattice_ensemble.cuh): the fixed-step schedule of
+// odeintr_plain_args, block b integrating instance first + b.
+struct odeintr_lattice_ensemble_args {
+  odeintr_plain_args p;
+  long long first;
+  long long halo;             // stencil radius (ghost cells per side of the shared-memory rings)
+  int* flag;                  // set to 1 when the snippet reaches beyond the halo
+};
+
 // One rk4 step of a large 1-D system in one launch, temporally blocked in shared memory (lattice_tiled.cuh).
 struct odeintr_lattice_tiled_args {
   const double* x_in;         // state at the start of the step (local cell 0 of field 0)

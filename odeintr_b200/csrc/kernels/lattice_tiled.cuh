@@ -163,7 +163,8 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
 // away from the periodic seam).  Indexed with a rel_index, the address is `p + constant`: p points at the entry
 // (field 0, cell being computed) of the stage's input, the displacement folds at compile time -- and so does the
 // reach check against the (block-uniform) halo.
-struct lattice_tile_rel_view {
+template <bool RING>
+struct lattice_rel_view {
   const double* p;
   long long n_total;  // cells per field
   int width;          // doubles between fields in shared memory
@@ -190,13 +191,20 @@ struct lattice_tile_rel_view {
     const long long f = r.off >= 0 ? (r.off + L / 2) / L : -((-r.off + L / 2) / L);
     return at(f, r.off - f * L);
   }
-  // absolute index: no periodic image can be within reach of an interior cell, so the distance is taken as is
+  // absolute index.  Tile view: no periodic image can be within reach of an interior cell, so the distance is taken
+  // as is.  RING (the whole lattice is staged, ghost cells hold the periodic images): nearest image.
   ODEINTR_DEV double operator[](const long long g) const {
     const long long f = g >= 0 ? g / n_total : -1;
-    return at(f, g - f * n_total - centre);
+    long long d = g - f * n_total - centre;
+    if (RING) {
+      if (d > n_total / 2) d -= n_total;
+      else if (d < -(n_total / 2)) d += n_total;
+    }
+    return at(f, d);
   }
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
+typedef lattice_rel_view<false> lattice_tile_rel_view;
 
 // Interior tiles.  Every thread owns CPT cells of the tile (tid + k * 256) for the whole step: the state at the start
 // of the step, the running weighted sum and the current stage state of those cells never leave its registers; the

@@ -1,0 +1,98 @@
+"""GPU parity for ensembles of wider systems (K5, lattice_ensemble.cuh): M trajectories of a compile_sys_openmp
+system, one warp / block per trajectory, the whole integrate call on chip.  In the reference this is an R loop around
+NAME_set_params() + NAME() (README.md:157-163); every trajectory must carry the bits of that loop, i.e. of the oracle
+run one trajectory at a time."""
+import numpy as np
+import pytest
+
+import odeintr_b200
+from oracle import build_oracle as bo
+from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("cells", [32, 37, 300, 1024, 2500])
+def test_bistable_sweep_one_block_per_trajectory(cells):
+    # 32 cells: one warp per trajectory (four to a block; m = 42 leaves the last block half empty); 37: a ragged warp;
+    # 300: two cells per thread, ragged; 1024: four per thread; 2500: 512 threads, five cells per thread, ragged
+    m = 42 if cells < 1024 else 300
+    rng = np.random.default_rng(cells)
+    x0 = rng.integers(0, 2, (cells, m)).astype(np.float64)
+    D = rng.uniform(0.05, 0.3, m)
+    b = rng.uniform(0.3, 0.7, m)
+    env = {}
+    odeintr_b200.compile_sys_openmp("bis", BISTABLE_1D, BISTABLE_PARS, False, method="rk4", sys_dim=cells, env=env)
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, False, "rk4", sys_dim=cells)
+    env["bis_set_params"](D=D, a=1.0, b=b)
+    rec = env["bis"](x0, 2.0, 0.1)  # 20 steps, every state observed
+    assert rec.x.shape == (21, cells, m)
+    fin = env["bis_get_state"]()
+    for i in (list(range(m)) if cells < 1024 else [0, 1, 147, 148, 299]):
+        ref = ora.integrate_const(x0[:, i].copy(), 0, 2.0, 0.1, pars=[D[i], 1.0, b[i]])
+        assert np.array_equal(bits(rec.x[:, :, i]), bits(ref["rec"])), i
+        assert np.array_equal(bits(fin[:, i]), bits(ref["rec"][-1])), i
+    assert np.array_equal(rec.time, ref["t"])
+    # NAME_at and NAME_no_record take the same kernel (remainder steps, integrate_times time rule)
+    at = np.array([0.5, 1.0, 10.0 ** 0.25, 2.2])
+    rec = env["bis_at"](x0, at, 0.2)
+    i = m - 1
+    adv = ora.integrate_const(x0[:, i].copy(), 0.0, at[0], 0.2, record=False, pars=[D[i], 1.0, b[i]])
+    ref = ora.integrate_times(adv["x"], at, 0.2, pars=[D[i], 1.0, b[i]])
+    assert np.array_equal(bits(rec.x[:, :, i]), bits(ref["rec"]))
+    fin = env["bis_no_record"](x0, 1.05, 0.1)
+    ref = ora.integrate_adaptive(x0[:, 3].copy(), 0, 1.05, 0.1, pars=[D[3], 1.0, b[3]])
+    assert np.array_equal(bits(fin[:, 3]), bits(ref["x"]))
+
+
+def test_oscillator_chain_ensemble_two_fields():
+    n, m = 2 * 300, 25
+    L = n // 2
+    rng = np.random.default_rng(7)
+    amp = rng.uniform(0.5, 1.5, m)
+    x0 = np.concatenate([np.sin(2 * np.pi * 3 * np.arange(L) / L)[:, None] * amp[None, :], np.zeros((L, m))])
+    K = rng.uniform(0.2, 0.8, m)
+    env = {}
+    odeintr_b200.compile_sys_openmp("chain", CHAIN, CHAIN_PARS, False, method="rk4", sys_dim=n, globals=CHAIN_GLOBALS,
+                                    env=env)
+    ora = bo.build(CHAIN, CHAIN_PARS, False, "rk4", sys_dim=n, globals=CHAIN_GLOBALS)
+    env["chain_set_params"](beta=1.0, K=K)
+    rec = env["chain"](x0, 1.0, 0.01, 0.0, 10)  # observer every 10 steps
+    assert rec.x.shape == (11, n, m)
+    for i in range(m):
+        ref = ora.integrate_const(x0[:, i].copy(), 0, 1.0, 0.01, pars=[1.0, K[i]])
+        assert np.array_equal(bits(rec.x[:, :, i]), bits(ref["rec"][::10])), i
+
+
+def test_fixed_ends_ensemble_and_broadcast_parameters():
+    src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]);"
+    cells, m = 129, 12
+    x0 = np.random.default_rng(3).uniform(0, 1, (cells, m))
+    env = {}
+    odeintr_b200.compile_sys_openmp("heat", src, {"D": 0.2}, True, method="rk4", sys_dim=cells, env=env)
+    ora = bo.build(src, {"D": 0.2}, True, "rk4", sys_dim=cells)
+    fin = env["heat_no_record"](x0, 1.5, 0.1)
+    for i in range(m):
+        ref = ora.integrate_adaptive(x0[:, i].copy(), 0, 1.5, 0.1)
+        assert np.array_equal(bits(fin[:, i]), bits(ref["x"])), i
+    assert np.array_equal(fin[0], x0[0]) and np.array_equal(fin[-1], x0[-1])  # the ends are not cells of the loop
+
+
+def test_ensemble_limits_are_reported():
+    env = {}
+    odeintr_b200.compile_sys_openmp("b2d", BISTABLE_2D, BISTABLE_PARS, True, method="rk4", sys_dim=48 * 48, env=env)
+    with pytest.raises(odeintr_b200.OdeintrError, match="stencil radius of at most 32"):
+        env["b2d"](np.zeros((48 * 48, 3)), 1.0, 0.1)
+    env = {}
+    odeintr_b200.compile_sys_openmp("big", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=16384, env=env)
+    with pytest.raises(odeintr_b200.OdeintrError, match="one at a time"):
+        env["big"](np.zeros((16384, 3)), 1.0, 0.1)
+    env = {}
+    odeintr_b200.compile_sys_openmp("far", "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + (x[i] > 1.5 ? 7 : 1)) % N] - x[i];",
+                                    method="rk4", sys_dim=64, env=env)
+    with pytest.raises(odeintr_b200.OdeintrError, match="further than the stencil radius"):
+        env["far"](np.random.default_rng(1).uniform(0, 2, (64, 5)), 1.0, 0.1)

@@ -191,10 +191,13 @@ struct odeintr_system_s {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
-               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr;
+               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr;
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
+  bool tiled2d_on = false;      // M x M lattice: rk4 steps go through odeintr_lattice_rk4_tiled2d
+  long long lat_side = 0;       // M when the snippet addresses an M x M lattice (one field), else 0
+  size_t tiled2d_smem = 0;
   long long lattice_halo = 0;   // stencil radius the tiled kernels stage (declared, or measured by the probe)
   long long lattice_cells = 0;  // cells per field (sys_dim / fields) for the tiled kernel
   size_t tiled_smem = 0;        // dynamic shared memory of the general tiled kernel (4 arrays per field)
@@ -564,6 +567,25 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   double* acc = h->lat_acc;
   const unsigned grid = (unsigned)h->sm_count * 8u, block = 256u;
   int rc;
+  if (h->lattice_stages == 4 && h->tiled2d_on && h->k_tiled2d && !w.sharded) {
+    // M x M lattice with a short reach: the whole rk4 step in one temporally blocked pass over 32 x 64 tiles
+    odeintr_lattice_tiled_args ta;
+    std::memset(&ta, 0, sizeof(ta));
+    ta.x_in = x; ta.x_out = A;
+    ta.pars = a.pars;
+    ta.n = w.n; ta.n_total = w.n_total;
+    ta.halo = h->lattice_halo;
+    ta.t = t; ta.dt = dt;
+    ta.flag = h->lat_flag.p;
+    const long long side = h->lat_side;
+    const unsigned tiles = (unsigned)(((side + 63) / 64) * ((side + 31) / 32));
+    void* params[1] = {&ta};
+    CU_TRY(cudaLaunchKernel((const void*)h->k_tiled2d, dim3(tiles), dim3(256), params, h->tiled2d_smem, h->stream));
+    h->last_launches += 1;
+    g_total_launches += 1;
+    std::swap(h->lat_x, h->lat_a);
+    return ODEINTR_OK;
+  }
   if (h->lattice_stages == 4 && h->k_tiled && (w.sharded ? h->sh_tiled : h->tiled_on)) {
     // known stencil radius: the whole rk4 step in one temporally blocked pass, x -> A, then the caller lets the
     // buffers trade places (16 B per cell per step instead of 128)
@@ -695,6 +717,19 @@ bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
   return true;
 }
 
+// M x M lattices: shared-memory budget of odeintr_lattice_rk4_tiled2d (three windows of (32 + 8 halo) x (64 + 8 halo))
+bool tiled2d_configure(odeintr_system_t h, long long halo) {
+  if (!h->k_tiled2d || h->lat_side <= 0 || halo < 0 || halo > 2 || 2 * halo + 1 > h->lat_side) return false;
+  const size_t bytes = 3 * (size_t)(32 + 8 * halo) * (size_t)(64 + 8 * halo) * sizeof(double);
+  if (cudaFuncSetAttribute((const void*)h->k_tiled2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  h->tiled2d_smem = bytes;
+  h->lattice_halo = halo;
+  return true;
+}
+
 // a slab of a sharded run can step through the tiled kernels: rk4, radius a tile can hold
 bool slab_tiled_possible(odeintr_system_t h, int halo) {
   return h->k_tiled && h->lattice_stages == 4 && halo >= 1 && halo <= 32 && h->lat_cells_ct > 0 &&
@@ -706,16 +741,17 @@ int lattice_query_info(odeintr_system_t h) {
   h->lat_start = 0;
   h->lat_bound = h->lat_cells_ct = 0;
   if (!h->k_info) return ODEINTR_OK;
-  CU_TRY(h->lat_flag.reserve(8));  // 32 bytes: four long long
+  CU_TRY(h->lat_flag.reserve(10));  // 40 bytes: five long long
   void* out = h->lat_flag.p;
   void* params[1] = {&out};
   CU_TRY(cudaLaunchKernel((const void*)h->k_info, dim3(1), dim3(1), params, 0, h->stream));
-  long long info[4] = {0, 0, 0, 0};
+  long long info[5] = {0, 0, 0, 0, 0};
   CU_TRY(cudaMemcpyAsync(info, h->lat_flag.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   h->lat_start = info[0];
   h->lat_bound = info[1];
   h->lat_cells_ct = info[2];
+  h->lat_side = info[4];
   if (!info[3])
     return fail(ODEINTR_E_INVALID, "large systems must write dxdt[loop variable + constant] "
                                    "(one contiguous field per written entry)");
@@ -725,8 +761,8 @@ int lattice_query_info(odeintr_system_t h) {
 // Measure the reach of the loop body (odeintr_lattice_probe) and switch the tiled kernels on when a tile can hold it.
 int tiled_autodetect(odeintr_system_t h) {
   h->tiled_pending = false;
-  h->tiled_on = false;
-  if (!h->k_probe || !h->k_tiled || h->lattice_stages != 4 || h->lat_cells_ct <= 0 ||
+  h->tiled_on = h->tiled2d_on = false;
+  if (!h->k_probe || !(h->k_tiled || h->k_tiled2d) || h->lattice_stages != 4 || h->lat_cells_ct <= 0 ||
       h->lat_cells_ct >= (1LL << 31) || std::getenv("ODEINTR_NO_TILED"))
     return ODEINTR_OK;
   const int fields = (int)((long long)h->N / h->lat_cells_ct);
@@ -742,6 +778,12 @@ int tiled_autodetect(odeintr_system_t h) {
   CU_TRY(cudaStreamSynchronize(h->stream));
   // beyond 32 cells the margins (4 * halo per side, recomputed by every tile) stop paying for themselves, and the
   // interior kernel's one-margin-cell-per-thread layout ends
+  if (h->lat_side > 0) {  // M x M lattice: the probe reports the larger of the row and column reach
+    if (!tiled2d_configure(h, reach)) return ODEINTR_OK;
+    h->tiled2d_on = true;
+    h->tiled_auto = true;
+    return ODEINTR_OK;
+  }
   if (reach > 32 || !tiled_configure(h, reach, fields)) return ODEINTR_OK;
   h->lattice_cells = h->lat_cells_ct;
   h->tiled_on = true;
@@ -797,7 +839,7 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
     h->out_m = 1;
     h->ragged = false;
   }
-  if (h->tiled_on) {
+  if (h->tiled_on || h->tiled2d_on) {
     int flag = 0;
     CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
@@ -885,7 +927,7 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   // The probe saw a shorter reach than the run needed (the snippet's indices depend on the state or on time):
   // the staged kernels have no such limit.  lattice_prepare left the initial state in the second stage buffer,
   // which the tiled kernels never touch.
-  h->tiled_on = false;
+  h->tiled_on = h->tiled2d_on = false;
   CU_TRY(cudaMemcpyAsync(h->x.p, h->lat_buf_b.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   return run_lattice_once(h, sc);
 }
@@ -1180,6 +1222,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_tiled_tma, h->lib, "odeintr_lattice_rk4_tiled_tma") != cudaSuccess)
     h->k_tiled_tma = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled2d, h->lib, "odeintr_lattice_rk4_tiled2d") != cudaSuccess) h->k_tiled2d = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();
@@ -1544,7 +1587,7 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
   int rc = activate(h);
   if (rc) return rc;
   if (!h->k_lattice) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
-  h->tiled_on = h->tiled_auto = h->tiled_pending = false;
+  h->tiled_on = h->tiled2d_on = h->tiled_auto = h->tiled_pending = false;
   if (halo < 0) {  // measured at the first integrate call, when the parameters are in place
     h->tiled_pending = true;
     return ODEINTR_OK;
@@ -1554,6 +1597,12 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
     return fail(ODEINTR_E_INVALID, "Invalid halo specification: the system writes " +
                                        std::to_string((long long)h->N / h->lat_cells_ct) + " field(s)");
   if (halo == 0) return ODEINTR_OK;  // staged kernels
+  if (h->lat_side > 0) {  // M x M lattice
+    if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "the tiled kernel is an rk4 step");
+    if (!tiled2d_configure(h, halo)) return fail(ODEINTR_E_INVALID, "halo too wide for the shared-memory tile");
+    h->tiled2d_on = true;
+    return ODEINTR_OK;
+  }
   if (!h->k_tiled) return fail(ODEINTR_E_STATE, "the generated translation unit has no tiled kernel");
   if (h->lattice_stages != 4) return fail(ODEINTR_E_STATE, "the tiled kernel is an rk4 step");
   if ((long long)h->N / fields >= (1LL << 31))
@@ -1567,7 +1616,7 @@ int odeintr_lattice_set_halo(odeintr_system_t h, long long halo, int fields) {
 long long odeintr_lattice_get_halo(odeintr_system_t h) {
   if (!h || activate(h)) return -1;
   if (h->tiled_pending && tiled_autodetect(h)) return -1;
-  return h->tiled_on ? h->lattice_halo : -1;
+  return (h->tiled_on || h->tiled2d_on) ? h->lattice_halo : -1;
 }
 
 int odeintr_nccl_unique_id(void* id_out, size_t cap) {

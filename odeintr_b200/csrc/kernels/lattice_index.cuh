@@ -12,6 +12,7 @@
 // the implicit conversion and takes the view's generic path: slower, same result.
 #pragma once
 #include "odeintr_b200/prelude.cuh"
+#define ODEINTR_HAVE_REL_INDEX 1  // lattice_helpers.cuh adds the overloads for symbolic coordinates
 
 namespace odeintr_b200 {
 
@@ -75,5 +76,116 @@ ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator%
 
 template <class V> ODEINTR_DEV V loop_index(const long long c) { return static_cast<V>(c); }
 template <class V> ODEINTR_DEV rel_index loop_index(const rel_index& c) { return c; }
+
+}  // namespace odeintr_b200
+
+// ---- M x M lattices (laplace2D & friends, inst/include/utils.h:6-31) ------------------------------------------------
+// The reference's large-system example walks a flat index i over an M x M row-major lattice and recovers the
+// coordinates as `i / M`, `i % M`; its helpers wrap neighbours with bound() and index x[row * M + col].  The same
+// symbolic treatment as above, per coordinate: rel_coord is "the cell's own row (column) + displacement", bound()
+// keeps the displacement (the nearest periodic image), `row * M + col` assembles a rel_cell2 that the 2-D tile view
+// serves as one shared-memory load at a fixed (d_row, d_col) offset.  Everything else degrades to absolute values.
+namespace odeintr_b200 {
+
+struct rel_coord {
+  long long off;   // rel: displacement from the cell's own coordinate; otherwise the absolute value
+  int centre;      // the cell's own coordinate
+  int side;        // M
+  bool rel;
+  bool row;        // a row number (true) or a column number (false)
+  bool wrapped;    // went through bound(): the absolute value is taken modulo M
+  ODEINTR_DEV long long value() const {
+    if (!rel) return off;
+    long long v = static_cast<long long>(centre) + off;
+    if (wrapped) {
+      v %= side;
+      if (v < 0) v += side;
+    }
+    return v;
+  }
+  ODEINTR_DEV operator long long() const { return value(); }
+};
+
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator+(rel_coord a, const I b) {
+  if (a.rel && a.wrapped) { a.off = a.value(); a.rel = false; }  // arithmetic after bound(): plain numbers again
+  a.off += static_cast<long long>(b);
+  return a;
+}
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator+(const I b, const rel_coord a) {
+  return a + b;
+}
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator-(const rel_coord a, const I b) {
+  return a + (-static_cast<long long>(b));
+}
+
+// flat index (row * M + col) being assembled from symbolic coordinates
+struct rel_cell2 {
+  long long dr, dc;        // displacements (rel)
+  long long abs;           // absolute flat value of the parts seen so far
+  bool rel, has_row, has_col;
+  ODEINTR_DEV operator long long() const { return abs; }
+};
+
+// row * M
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_cell2>::type operator*(const rel_coord a, const I m) {
+  rel_cell2 c;
+  c.abs = a.value() * static_cast<long long>(m);
+  c.rel = a.rel && a.row && static_cast<long long>(m) == a.side;
+  c.dr = a.off; c.dc = 0;
+  c.has_row = true; c.has_col = false;
+  return c;
+}
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_cell2>::type operator*(const I m, const rel_coord a) {
+  return a * m;
+}
+// row * M + col
+ODEINTR_DEV rel_cell2 operator+(rel_cell2 c, const rel_coord b) {
+  c.abs += b.value();
+  c.rel = c.rel && b.rel && !b.row && c.has_row && !c.has_col;
+  c.dc = b.off;
+  c.has_col = true;
+  return c;
+}
+ODEINTR_DEV rel_cell2 operator+(const rel_coord b, const rel_cell2 c) { return c + b; }
+// anything else added to a flat index: a plain number
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_cell2>::type operator+(rel_cell2 c, const I b) {
+  c.abs += static_cast<long long>(b);
+  c.rel = false;
+  return c;
+}
+
+// The loop variable on an M x M lattice: the flat cell number with its coordinates.  `i / M` and `i % M` give the
+// symbolic row and column; any other arithmetic sees the plain flat number.
+struct rel_index2 {
+  int centre;  // flat number of the cell being computed (row * M + col)
+  int row, col;
+  int side;    // M
+  ODEINTR_DEV operator long long() const { return centre; }
+};
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator/(const rel_index2& i, const I m) {
+  rel_coord r;
+  r.side = i.side; r.row = true; r.wrapped = false;
+  r.rel = static_cast<long long>(m) == i.side;
+  r.centre = i.row;
+  r.off = r.rel ? 0 : static_cast<long long>(i.centre) / static_cast<long long>(m);
+  return r;
+}
+template <class I>
+ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator%(const rel_index2& i, const I m) {
+  rel_coord r;
+  r.side = i.side; r.row = false; r.wrapped = false;
+  r.rel = static_cast<long long>(m) == i.side;
+  r.centre = i.col;
+  r.off = r.rel ? 0 : static_cast<long long>(i.centre) % static_cast<long long>(m);
+  return r;
+}
+template <class V> ODEINTR_DEV rel_index2 loop_index(const rel_index2& c) { return c; }
 
 }  // namespace odeintr_b200

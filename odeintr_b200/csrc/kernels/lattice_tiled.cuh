@@ -60,6 +60,8 @@ struct lattice_tile_view {
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
 
+#ifndef ODEINTR_LATTICE_2D  // M x M lattices have their own tiled kernel (lattice_tiled2d.cuh)
+
 ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   typedef odeintr::system_type_t<lattice_tile_view> Sys;
   constexpr int F = ODEINTR_NFIELDS;
@@ -467,8 +469,11 @@ struct lattice_probe_view {
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
 
+#endif  // !ODEINTR_LATTICE_2D
+
 }  // namespace odeintr_b200
 
+#ifndef ODEINTR_LATTICE_2D
 // out[0] = largest distance (in cells) between a cell and an entry its loop body reads
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_probe(const double* pars, const double t, int* out) {
@@ -491,9 +496,12 @@ odeintr_lattice_probe(const double* pars, const double t, int* out) {
   if (view.reach) atomicMax(out, view.reach);
 }
 
+#endif  // !ODEINTR_LATTICE_2D
+
 // what the host needs to know about the generated loop nest:
 // out[0], out[1] = first cell and bound of the user's loop; out[2] = cells per field the interior kernel assumes;
-// out[3] = 1 when every dxdt[...] target is `loop variable + constant` (the layout all lattice kernels write)
+// out[3] = 1 when every dxdt[...] target is `loop variable + constant` (the layout all lattice kernels write);
+// out[4] = M when the snippet addresses an M x M lattice (one field), else 0
 extern "C" __global__ void odeintr_lattice_info(long long* out) {
   odeintr::system_type_t<odeintr_b200::lattice_tile_view> sys;
   out[0] = sys.cell_start();
@@ -507,8 +515,14 @@ extern "C" __global__ void odeintr_lattice_info(long long* out) {
   for (int f = 0; f < ODEINTR_NFIELDS; ++f)
     if (o1[f] - o0[f] != 1 || o7[f] - o0[f] != 7) unit = 0;
   out[3] = unit;
+#if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1
+  out[4] = odeintr_b200::isqrt(ODEINTR_SYS_SIZE);
+#else
+  out[4] = 0;
+#endif
 }
 
+#ifndef ODEINTR_LATTICE_2D
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body(a); }
 
@@ -527,3 +541,4 @@ odeintr_lattice_rk4_tiled_interior(const odeintr_lattice_tiled_args a) {
 
 extern "C" __global__ void __launch_bounds__(256, ODEINTR_TMA_MIN_BLOCKS)
 odeintr_lattice_rk4_tiled_tma(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_tma_body(a); }
+#endif  // !ODEINTR_LATTICE_2D

@@ -206,13 +206,63 @@ def test_2d_lattice_strip_traversal_bit_exact():
     # above / below); the visiting order must not change a single bit
     m = 512
     env = {}
-    odeintr_b200.compile_sys_openmp("b2s", BISTABLE_2D, BISTABLE_PARS, True, method="rk4", sys_dim=m * m, env=env)
+    odeintr_b200.compile_sys_openmp("b2s", BISTABLE_2D, BISTABLE_PARS, True, method="rk4", sys_dim=m * m, env=env,
+                                    halo=0)
     ora = bo.build(BISTABLE_2D, BISTABLE_PARS, True, "rk4", sys_dim=m * m)
     rng = np.random.default_rng(71)
     x0 = rng.integers(0, 2, m * m).astype(np.float64)
     fin = env["b2s_no_record"](x0, 1.0, 0.1)
     ref = ora.integrate_adaptive(x0, 0.0, 1.0, 0.1)
     assert np.array_equal(bits(fin), bits(ref["x"]))
+
+
+# a hand-written 9-point stencil in the reference's idiom: coordinates from the flat index, neighbours through bound()
+NINE_POINT = """
+for (int i = 0; i < N; ++i) {
+  const int r = i / M, c = i % M;
+  dxdt[i] = D * (x[bound(r - 1) * M + c] + x[bound(r + 1) * M + c] + x[r * M + bound(c - 1)] + x[r * M + bound(c + 1)]
+                 + 0.5 * (x[bound(r - 1) * M + bound(c - 1)] + x[bound(r + 1) * M + bound(c + 1)]) - 5.0 * x[i]);
+}
+"""
+NINE_POINT_AUTO = NINE_POINT.replace("const int r = i / M, c = i % M;", "const auto r = i / M; const auto c = i % M;")
+
+
+@pytest.mark.parametrize("case", ["laplace2D_48", "laplace2D_200", "laplace4_doc_96", "nine_point_int", "nine_point_auto",
+                                  "inner_cells_only", "reach_3"])
+def test_2d_lattice_tiled_rk4_bit_exact(case):
+    # M x M lattices step through odeintr_lattice_rk4_tiled2d when the loop body reaches at most 2 rows / columns:
+    # ragged tiles (48, 200, 96 are no multiples of the 32 x 64 tile), lattices narrower than a tile, the reference's
+    # helpers, hand-written index arithmetic (`int` coordinates take the absolute path, `auto` ones stay symbolic),
+    # loops that leave the border alone, and a reach the tile cannot hold (-> stage-per-launch kernels)
+    want = 1
+    pars = BISTABLE_PARS
+    if case == "laplace2D_48":
+        m, src = 48, BISTABLE_2D
+    elif case == "laplace2D_200":
+        m, src = 200, BISTABLE_2D
+    elif case == "laplace4_doc_96":
+        m, src = 96, BISTABLE_DOC
+    elif case == "nine_point_int":
+        m, src = 80, NINE_POINT
+    elif case == "nine_point_auto":
+        m, src = 80, NINE_POINT_AUTO
+    elif case == "inner_cells_only":
+        m = 72
+        src = "for (int i = M + 1; i < N - M - 1; ++i) dxdt[i] = D * (x[i - M] + x[i + M] + x[i - 1] + x[i + 1] - 4.0 * x[i]);"
+    else:
+        m, want = 64, -1
+        src = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[bound(i / M + 3) * M + i % M] - x[i]);"
+    n = m * m
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("t2", src, pars, True, method="rk4", sys_dim=n, env=env)
+    ora = bo.build(src, pars, True, "rk4", sys_dim=n)
+    x0 = np.random.default_rng(m).uniform(0, 1, n)
+    df = env["t2"](x0, 0.6, 0.1)  # 6 steps, every state observed
+    assert code.system.get_halo() == want
+    ref = ora.integrate_const(x0, 0, 0.6, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["t2_no_record"](x0, 1.05, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.05, 0.1)["x"]))
 
 
 def test_documented_bistable_example_with_laplace4():
@@ -284,10 +334,10 @@ def test_tiled_rk4_interior_tiles_other_index_forms(case):
 
 def test_tiled_rk4_measured_radius():
     # the probe evaluates the index expressions of every cell: radius 2 for the 4th-order Laplacian, 3 where only a
-    # few cells reach that far, none (staged kernels) for an M x M lattice whose rows are M cells apart
+    # few cells reach that far
     wide = "for (int i = 0; i < N; ++i) dxdt[i] = x[(i + N - 2) % N] + x[(i + 2) % N] - 2.0 * x[i];"
     some = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"
-    for src, n, want in ((wide, 5000, 2), (some, 5000, 3), (BISTABLE_2D, 64 * 64, -1)):
+    for src, n, want in ((wide, 5000, 2), (some, 5000, 3)):
         env = {}
         code = odeintr_b200.compile_sys_openmp("p", src, BISTABLE_PARS, True, method="rk4", sys_dim=n, env=env)
         x0 = np.random.default_rng(94).uniform(0, 1, n)

@@ -134,6 +134,13 @@ int tile_cpt() {
   return v > 0 ? v : 4;
 }
 
+// rows of a tile of the 2-D tiled rk4 kernel (ODEINTR_TILE2_ROWS in lattice_tiled2d.cuh; env knob for sweeps)
+int tile2_rows() {
+  const char* c = std::getenv("ODEINTR_TILE2_ROWS");
+  const int v = c ? std::atoi(c) : 32;
+  return (v > 0 && v % 4 == 0) ? v : 32;
+}
+
 std::vector<std::string> nvrtc_options(unsigned flags) {
   std::vector<std::string> o;
   o.push_back("--gpu-architecture=sm_100a");
@@ -150,6 +157,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TILE_CPT")) o.push_back(std::string("-DODEINTR_TILE_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_TILE2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE2_MIN_BLOCKS=") + c);
+  if (std::getenv("ODEINTR_TILE2_ROWS")) o.push_back("-DODEINTR_TILE2_ROWS=" + std::to_string(tile2_rows()));
   return o;
 }
 
@@ -191,7 +200,7 @@ struct odeintr_system_s {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
-               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr;
+               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr, k_tiled2d_h[3] = {nullptr, nullptr, nullptr};
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -578,7 +587,8 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     ta.t = t; ta.dt = dt;
     ta.flag = h->lat_flag.p;
     const long long side = h->lat_side;
-    const unsigned tiles = (unsigned)(((side + 63) / 64) * ((side + 31) / 32));
+    const long long th = tile2_rows();
+    const unsigned tiles = (unsigned)(((side + 63) / 64) * ((side + th - 1) / th));
     void* params[1] = {&ta};
     CU_TRY(cudaLaunchKernel((const void*)h->k_tiled2d, dim3(tiles), dim3(256), params, h->tiled2d_smem, h->stream));
     h->last_launches += 1;
@@ -717,10 +727,13 @@ bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
   return true;
 }
 
-// M x M lattices: shared-memory budget of odeintr_lattice_rk4_tiled2d (three windows of (32 + 8 halo) x (64 + 8 halo))
+// M x M lattices: shared-memory budget of odeintr_lattice_rk4_tiled2d (two windows of (32 + 8 halo) x (64 + 8 halo))
 bool tiled2d_configure(odeintr_system_t h, long long halo) {
-  if (!h->k_tiled2d || h->lat_side <= 0 || halo < 0 || halo > 2 || 2 * halo + 1 > h->lat_side) return false;
-  const size_t bytes = 3 * (size_t)(32 + 8 * halo) * (size_t)(64 + 8 * halo) * sizeof(double);
+  if (h->lat_side <= 0 || halo < 0 || halo > 2 || 2 * halo + 1 > h->lat_side) return false;
+  if (halo == 0) halo = 1;  // no coupling at all: the radius-1 kernel does
+  if (!h->k_tiled2d_h[halo]) return false;
+  h->k_tiled2d = h->k_tiled2d_h[halo];
+  const size_t bytes = 2 * (size_t)(tile2_rows() + 8 * halo) * (size_t)(64 + 8 * halo) * sizeof(double);
   if (cudaFuncSetAttribute((const void*)h->k_tiled2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
     (void)cudaGetLastError();
     return false;
@@ -1222,7 +1235,9 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_tiled_tma, h->lib, "odeintr_lattice_rk4_tiled_tma") != cudaSuccess)
     h->k_tiled_tma = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
-  if (cudaLibraryGetKernel(&h->k_tiled2d, h->lib, "odeintr_lattice_rk4_tiled2d") != cudaSuccess) h->k_tiled2d = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled2d_h[1], h->lib, "odeintr_lattice_rk4_tiled2d_h1") != cudaSuccess) h->k_tiled2d_h[1] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_tiled2d_h[2], h->lib, "odeintr_lattice_rk4_tiled2d_h2") != cudaSuccess) h->k_tiled2d_h[2] = nullptr;
+  h->k_tiled2d = h->k_tiled2d_h[1];
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();

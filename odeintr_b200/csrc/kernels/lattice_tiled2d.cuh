@@ -7,8 +7,10 @@
 // wrapped periodically while loading, so the window in shared memory is plain and every tile is treated alike), runs
 // the four stages on windows that shrink by `halo` per stage and writes the new state of its tile: 8 bytes read
 // (x 1.4 for the margins) and 8 written per cell and step instead of the 128 of the stage-per-launch schedule.
-// Every thread owns TH/4 cells of one tile column: their x, running sum and stage state stay in registers.  The
-// margin ("frame") cells of stages 1-3 are dealt round-robin; their x comes from the staged copy of the window.
+// Every thread owns TH/4 consecutive cells of one tile column: their x, running sum and stage state stay in registers
+// (so the rows above / below are register reads too).  The
+// margin ("frame") cells of stages 1-3 are dealt round-robin, their x is kept in registers too; two shared-memory
+// windows (x / stage 2, stage 1 / stage 3) carry what the neighbours read.
 // The snippet's coordinates are symbolic (lattice_index.cuh): `laplace2D(x, i / M, i % M)` compiles to four
 // shared-memory loads at fixed (row, column) offsets from the thread's cell.
 // Bit-identical to the staged schedule; every access is checked against the radius (see lattice_tiled.cuh).
@@ -36,12 +38,16 @@ ODEINTR_DEV long long min_image(long long d, const long long m) {
 struct lattice_tile2_view {
   const double* p;  // the cell being computed
   double own;       // its value
+  const double* mine;  // the stage's input at the thread's own cells (consecutive rows of one column), or null
+  int k, n_mine;       // which of them is being computed
   int pitch, halo;
   int row, col, side;
   mutable int bad;
 
   ODEINTR_DEV double at2(long long dr, long long dc) const {
     if (dr == 0 && dc == 0) return own;
+    // the rows above / below in the thread's own column strip: registers (compile-time test after unrolling)
+    if (dc == 0 && mine && k + dr >= 0 && k + dr < n_mine) return mine[k + dr];
     if (dr > halo) { bad = 1; dr = halo; }
     if (dr < -halo) { bad = 1; dr = -halo; }
     if (dc > halo) { bad = 1; dc = halo; }
@@ -111,23 +117,24 @@ odeintr_lattice_probe(const double* pars, const double t, int* out) {
 }
 
 #ifndef ODEINTR_TILE2_MIN_BLOCKS
-#define ODEINTR_TILE2_MIN_BLOCKS 2
+#define ODEINTR_TILE2_MIN_BLOCKS 3
 #endif
 
-extern "C" __global__ void __launch_bounds__(256, ODEINTR_TILE2_MIN_BLOCKS)
-odeintr_lattice_rk4_tiled2d(const odeintr_lattice_tiled_args a) {
-  using namespace odeintr_b200;
+namespace odeintr_b200 {
+
+// H = stencil radius, a compile-time constant: window pitch, frame geometry and every shared-memory offset fold
+template <int H>
+ODEINTR_DEV void lattice_rk4_tiled2d_body(const odeintr_lattice_tiled_args& a) {
   typedef odeintr::system_type_t<lattice_tile2_view> Sys;
   constexpr int MM = isqrt(ODEINTR_SYS_SIZE);
   constexpr int TH = ODEINTR_TILE2_ROWS, TW = ODEINTR_TILE2_COLS;
-  constexpr int C = TH / 4;  // cells per thread: rows ty, ty + 4, ... of column tx
+  constexpr int C = TH / 4;  // cells per thread: rows ty * C ... ty * C + C - 1 of column tx
+  constexpr int mg = 4 * H;
+  constexpr int PW = TW + 2 * mg, PH = TH + 2 * mg;
   extern __shared__ double smem[];
   const int tid = threadIdx.x, tx = tid & (TW - 1), ty = tid / TW;
-  const int h = (int)a.halo, mg = 4 * h;
-  const int PW = TW + 2 * mg, PH = TH + 2 * mg;
-  double* const X = smem;             // x on the window (kept: the margin cells' x)
-  double* const A = X + PH * PW;      // stage-1 states, then stage-3 states
-  double* const B = A + PH * PW;      // stage-2 states
+  double* const P = smem;             // x on the window, then the stage-2 states
+  double* const A = P + PH * PW;      // stage-1 states, then stage-3 states
 
   Sys sys;
   sys.load_params(a.pars, 1, 0);
@@ -141,31 +148,29 @@ odeintr_lattice_rk4_tiled2d(const odeintr_lattice_tiled_args a) {
     while (v >= MM) v -= MM;
     return v;
   };
-  // stage the window, rows and columns wrapped periodically
-  for (int q = tid; q < PH * PW; q += 256) {
-    const int y = q / PW, x = q - y * PW;
-    const double v = __ldg(a.x_in + (long long)wrap(r0 - mg + y) * MM + wrap(c0 - mg + x));
-    X[q] = v;
-    if (!all_live) {  // cells the loop does not write keep their value in every stage
-      A[q] = v;
-      B[q] = v;
+  // stage the window, rows and columns wrapped periodically; all loads in flight before the first store
+  {
+    constexpr int NL = (PH * PW + 255) / 256;
+    double v[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int q = tid + k * 256;
+      const int y = q / PW, x = q - y * PW;
+      v[k] = q < PH * PW ? __ldg(a.x_in + (long long)wrap(r0 - mg + y) * MM + wrap(c0 - mg + x)) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int q = tid + k * 256;
+      if (q < PH * PW) {
+        P[q] = v[k];
+        if (!all_live) A[q] = v[k];  // cells the loop does not write keep their value in every stage
+      }
     }
   }
   __syncthreads();
 
-  double xs[C], acc[C], own[C];
-  bool live[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    const int y = ty + 4 * k;
-    xs[k] = own[k] = X[(mg + y) * PW + mg + tx];
-    acc[k] = xs[k];
-    const long long flat = (long long)wrap(r0 + y) * MM + wrap(c0 + tx);
-    live[k] = all_live || (flat >= start && flat < bound);
-  }
-
   lattice_tile2_view view;
-  view.pitch = PW; view.halo = h; view.side = MM; view.bad = 0;
+  view.pitch = PW; view.halo = H; view.side = MM; view.bad = 0;
   rel_index2 idx;
   idx.side = MM;
   auto at_cell = [&](const int y, const int x) {  // window-relative cell (y, x), tile origin at (0, 0)
@@ -174,68 +179,112 @@ odeintr_lattice_rk4_tiled2d(const odeintr_lattice_tiled_args a) {
     idx.centre = idx.row * MM + idx.col;
   };
 
+  // the thread's own cells of the tile ...
+  double xs[C], acc[C], own[2][C];  // own[s & 1]: the input of stage s at the thread's cells
+  bool live[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    const int y = ty * C + k;
+    xs[k] = own[1][k] = P[(mg + y) * PW + mg + tx];
+    acc[k] = xs[k];
+    const long long flat = (long long)wrap(r0 + y) * MM + wrap(c0 + tx);
+    live[k] = all_live || (flat >= start && flat < bound);
+  }
+  // ... and its cells of the frame of width 3 H around the tile (stage 1 computes all of it, stages 2 and 3 the
+  // inner 2 H and H): top and bottom bands of full width first, then the left and right bands
+  constexpr int FM = 3 * H, FW = TW + 2 * FM;
+  constexpr int N_BAND = FM * FW, N_SIDE = TH * FM, N_FRAME = 2 * N_BAND + 2 * N_SIDE;
+  constexpr int NF = (N_FRAME + 255) / 256;
+  double fx[NF];
+  int fw[NF], fd[NF];  // window offset, distance from the tile (0 = not a frame cell of this thread)
+#pragma unroll
+  for (int e = 0; e < NF; ++e) {
+    const int q = tid + e * 256;
+    int y, x;
+    if (q < 2 * N_BAND) {
+      const int b = q < N_BAND ? q : q - N_BAND;
+      const int yy = b / FW;
+      y = q < N_BAND ? yy - FM : TH + yy;
+      x = b - yy * FW - FM;
+    } else {
+      const int sq = q - 2 * N_BAND;
+      const int b = sq < N_SIDE ? sq : sq - N_SIDE;
+      y = b / FM;
+      const int xx = b - y * FM;
+      x = sq < N_SIDE ? xx - FM : TW + xx;
+    }
+    const int dy = y < 0 ? -y : (y >= TH ? y - (TH - 1) : 0), dx = x < 0 ? -x : (x >= TW ? x - (TW - 1) : 0);
+    fw[e] = (mg + y) * PW + mg + x;
+    fd[e] = q < N_FRAME ? (dy > dx ? dy : dx) : 0;
+    fx[e] = 0.0;
+    if (fd[e]) {
+      fx[e] = P[fw[e]];
+      if (!all_live) {
+        at_cell(y, x);
+        if (!(idx.centre >= start && idx.centre < bound)) fd[e] = 0;  // keeps its value
+      }
+    }
+  }
+
   const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
   const double dt = a.dt;
 #pragma unroll
   for (int stage = 1; stage <= 4; ++stage) {
-    const double* src = stage == 1 ? X : (stage == 2 ? A : (stage == 3 ? B : A));
-    double* dst = stage == 1 ? A : (stage == 2 ? B : A);
+    const double* src = (stage & 1) ? P : A;
+    double* dst = (stage & 1) ? A : P;
     const double a_dt = stage == 1 ? half * dt : (stage == 2 ? half * dt : 1.0 * dt);
     const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
     const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
-    // the thread's own cells
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-      if (!live[k]) continue;
-      const int y = ty + 4 * k;
+      if (!live[k]) {
+        own[(stage + 1) & 1][k] = xs[k];  // keeps its value in every stage
+        continue;
+      }
+      const int y = ty * C + k;
       const int q = (mg + y) * PW + mg + tx;
       double kk[1] = {0.0};
       view.p = src + q;
-      view.own = own[k];
+      view.own = own[stage & 1][k];
+      view.mine = own[stage & 1]; view.k = k; view.n_mine = C;
       at_cell(y, tx);
       sys.cell(view, kk, idx, ts);
       acc[k] = (stage == 1 ? xs[k] : acc[k]) + b_dt * kk[0];  // the running sum starts from x
       if (stage < 4) {
         const double v = xs[k] + a_dt * kk[0];
         dst[q] = v;
-        own[k] = v;
+        own[(stage + 1) & 1][k] = v;
       } else if (r0 + y < MM && c0 + tx < MM) {
         // new state of a real cell of the tile (cells of a ragged tile beyond the lattice are periodic images)
         a.x_out[(long long)(r0 + y) * MM + (c0 + tx)] = acc[k];
       }
     }
     if (stage < 4) {
-      // the frame of width m around the tile: top and bottom bands of full width, then the left and right bands
-      const int m = (4 - stage) * h;
-      const int fw = TW + 2 * m;
-      const int n_band = m * fw, n_side = TH * m;
-      for (int q = tid; q < 2 * n_band + 2 * n_side; q += 256) {
-        int y, x;
-        if (q < 2 * n_band) {
-          const int b = q < n_band ? q : q - n_band;
-          const int yy = b / fw;
-          y = q < n_band ? yy - m : TH + yy;
-          x = b - yy * fw - m;
-        } else {
-          const int s = q - 2 * n_band;
-          const int b = s < n_side ? s : s - n_side;
-          y = b / m;
-          const int xx = b - y * m;
-          x = s < n_side ? xx - m : TW + xx;
-        }
-        const int w = (mg + y) * PW + mg + x;
+#pragma unroll
+      for (int e = 0; e < NF; ++e) {
+        if (fd[e] == 0 || fd[e] > (4 - stage) * H) continue;
+        const int w = fw[e];
+        const int y = w / PW - mg, x = w - (y + mg) * PW - mg;
         at_cell(y, x);
-        if (!all_live && !(idx.centre >= start && idx.centre < bound)) continue;
         double kk[1] = {0.0};
         view.p = src + w;
         view.own = src[w];
+        view.mine = nullptr;
         sys.cell(view, kk, idx, ts);
-        dst[w] = X[w] + a_dt * kk[0];
+        dst[w] = fx[e] + a_dt * kk[0];
       }
       __syncthreads();
     }
   }
   if (view.bad) *a.flag = 1;
 }
+
+}  // namespace odeintr_b200
+
+extern "C" __global__ void __launch_bounds__(256, ODEINTR_TILE2_MIN_BLOCKS)
+odeintr_lattice_rk4_tiled2d_h1(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled2d_body<1>(a); }
+
+extern "C" __global__ void __launch_bounds__(256, 2)
+odeintr_lattice_rk4_tiled2d_h2(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled2d_body<2>(a); }
 
 #endif  // ODEINTR_LATTICE_2D

@@ -355,10 +355,13 @@ def main():
     # ---- secondary: BASELINE.json configs[4] on one GPU (reported beside the headline, never instead of it) ----------
     secondary = None
     if world == 1 and not args.no_secondary:
-        try:
-            secondary = {"lattice_rk4": lattice_secondary(lib, dp_peak.value)}
-        except Exception as exc:  # the headline line must survive whatever happens here
-            secondary = {"lattice_rk4": {"error": str(exc)[:300]}}
+        secondary = {}
+        for key, fn in (("lattice_rk4", lattice_secondary), ("lattice2d_rk4", lattice2d_secondary),
+                        ("lattice_ensemble_rk4", lattice_ensemble_secondary)):
+            try:
+                secondary[key] = fn(lib, dp_peak.value)
+            except Exception as exc:  # the headline line must survive whatever happens here
+                secondary[key] = {"error": str(exc)[:300]}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------
     cpu = None
@@ -462,6 +465,82 @@ def lattice_secondary(lib, dp_peak):
                                  "and is HBM-bound at 0.90 of the peak = 4.6e10 cell-steps/s; temporal blocking "
                                  "leaves 16 B and an FP64-bound step"},
         }
+    finally:
+        s.close()
+
+
+BISTABLE_2D = """
+for (int i = 0; i < N; ++i)
+  dxdt[i] = D * laplace2D(x, i / M, i % M);
+for (int i = 0; i < N; ++i)
+  dxdt[i] += a * x[i] * (1 - x[i]) * (x[i] - b);
+"""
+
+
+def lattice2d_secondary(lib, dp_peak):
+    """The reference's documented large-system example (R/odeintr.R:393-413): periodic M x M bistable lattice through
+    laplace2D, M = 8192, rk4, plain compile_sys_openmp call (2-D temporally blocked kernel).  66 DP instructions per
+    cell and step (4 x 13 RHS + 14)."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    m, steps, dt = 8192, 40, 0.01
+    n = m * m
+    s = odeintr_b200.compile_sys_openmp("bistable2d", BISTABLE_2D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, method="rk4",
+                                        sys_dim=n).system
+    try:
+        s.set_state((np.arange(n) % 7 < 3).astype(np.float64))
+        ms = []
+        for rep in range(4):
+            if lib.odeintr_integrate_const(s._h, 0.0, steps * dt, dt, 1, 0) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        t = statistics.mean(ms) * 1e-3
+        rate = n * steps / t
+        return {"workload": "periodic 8192 x 8192 bistable lattice through laplace2D (the reference's compile_sys_openmp "
+                            "example), rk4 fixed step, %d steps per pass, 512 MiB per array > L2" % steps,
+                "metric": "lattice_rk4_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
+                "ms_per_step": 1e3 * t / steps, "halo": s.get_halo(), "gpu_launches": s.last_launches(),
+                "roofline": {"bound": "fp64", "achieved": rate * 66.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 66.0 / dp_peak, "kernel": "odeintr_lattice_rk4_tiled2d_h1"}}
+    finally:
+        s.close()
+
+
+def lattice_ensemble_secondary(lib, dp_peak):
+    """Ensemble of wider systems: 2^14 trajectories of a 1024-cell bistable lattice with per-trajectory parameters, rk4,
+    1000 steps, observer every 100 steps; one block per trajectory, the whole call on chip (odeintr_lattice_ensemble).
+    54 DP instructions per cell and step (run-time parameters: 4 x 10 RHS + 14)."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    cells, m, steps = 1024, 1 << 14, 1000
+    s = odeintr_b200.compile_sys_openmp("bis", BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, False, method="rk4",
+                                        sys_dim=cells).system
+    try:
+        rng = np.random.default_rng(1)
+        x0 = rng.integers(0, 2, (cells, m)).astype(np.float64)
+        s.set_params(D=rng.uniform(0.05, 0.3, m), a=1.0, b=rng.uniform(0.3, 0.7, m))
+        ms = []
+        for rep in range(4):
+            s.set_state(x0)
+            if lib.odeintr_integrate_const(s._h, 0.0, steps * 0.01, 0.01, 100, 1) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        t = statistics.mean(ms) * 1e-3
+        rate = cells * m * steps / t
+        return {"workload": "%d trajectories x %d-cell bistable lattice, per-trajectory parameters, rk4, %d steps, "
+                            "observer every 100 steps" % (m, cells, steps),
+                "metric": "lattice_ensemble_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
+                "ms_per_pass": 1e3 * t, "gpu_launches": s.last_launches(),
+                "roofline": {"bound": "fp64", "achieved": rate * 54.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 54.0 / dp_peak, "kernel": "odeintr_lattice_ensemble"}}
     finally:
         s.close()
 

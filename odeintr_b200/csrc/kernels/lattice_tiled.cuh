@@ -522,7 +522,7 @@ extern "C" __global__ void odeintr_lattice_info(long long* out) {
 #endif
 }
 
-#ifndef ODEINTR_LATTICE_2D
+#if !defined(ODEINTR_LATTICE_2D) && ODEINTR_LATTICE_STAGES == 4
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body(a); }
 
@@ -541,4 +541,4 @@ odeintr_lattice_rk4_tiled_interior(const odeintr_lattice_tiled_args a) {
 
 extern "C" __global__ void __launch_bounds__(256, ODEINTR_TMA_MIN_BLOCKS)
 odeintr_lattice_rk4_tiled_tma(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_tma_body(a); }
-#endif  // !ODEINTR_LATTICE_2D
+#endif  // rk4 on a 1-D lattice

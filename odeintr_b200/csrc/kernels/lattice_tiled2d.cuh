@@ -281,10 +281,12 @@ ODEINTR_DEV void lattice_rk4_tiled2d_body(const odeintr_lattice_tiled_args& a) {
 
 }  // namespace odeintr_b200
 
+#if ODEINTR_LATTICE_STAGES == 4
 extern "C" __global__ void __launch_bounds__(256, ODEINTR_TILE2_MIN_BLOCKS)
 odeintr_lattice_rk4_tiled2d_h1(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled2d_body<1>(a); }
 
 extern "C" __global__ void __launch_bounds__(256, 2)
 odeintr_lattice_rk4_tiled2d_h2(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled2d_body<2>(a); }
+#endif
 
 #endif  // ODEINTR_LATTICE_2D

@@ -158,6 +158,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TILE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE2_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_TILE5_CPT")) o.push_back(std::string("-DODEINTR_TILE5_CPT=") + c);
+  if (const char* c = std::getenv("ODEINTR_TILE5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE5_MIN_BLOCKS=") + c);
   if (std::getenv("ODEINTR_TILE2_ROWS")) o.push_back("-DODEINTR_TILE2_ROWS=" + std::to_string(tile2_rows()));
   return o;
 }
@@ -200,11 +202,15 @@ struct odeintr_system_s {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
-               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr, k_tiled2d_h[3] = {nullptr, nullptr, nullptr};
+               k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr, k_tiled2d_h[3] = {nullptr, nullptr, nullptr},
+               k_dopri5_tiled = nullptr;
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
   bool tiled2d_on = false;      // M x M lattice: rk4 steps go through odeintr_lattice_rk4_tiled2d
+  int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
+  long long tiled5_halo = 0;
+  size_t tiled5_smem = 0;
   long long lat_side = 0;       // M when the snippet addresses an M x M lattice (one field), else 0
   size_t tiled2d_smem = 0;
   long long lattice_halo = 0;   // stencil radius the tiled kernels stage (declared, or measured by the probe)
@@ -945,6 +951,45 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
   return run_lattice_once(h, sc);
 }
 
+// cells per thread of the tiled dopri5 kernel (ODEINTR_TILE5_CPT in lattice_dopri5_tiled.cuh)
+int tile5_cpt(int fields) {
+  const char* c = std::getenv("ODEINTR_TILE5_CPT");
+  const int v = c ? std::atoi(c) : (fields > 1 ? 1 : 2);
+  return v > 0 ? v : 1;
+}
+
+// Decide once per system whether dopri5 attempts run through the temporally blocked kernel: measure the reach of
+// the loop body (odeintr_lattice_probe) and check that a tile with 6 * halo margin cells per side fits.
+int tiled5_decide(odeintr_system_t h) {
+  if (h->tiled5 >= 0) return ODEINTR_OK;
+  h->tiled5 = 0;
+  if (!h->k_dopri5_tiled || !h->k_probe || h->lat_cells_ct <= 0 || h->lat_cells_ct >= (1LL << 31) ||
+      std::getenv("ODEINTR_NO_TILED"))
+    return ODEINTR_OK;
+  CU_TRY(h->lat_flag.reserve(10));
+  CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  const double* pars = h->P ? h->pars.p : nullptr;
+  double t = 0.0;
+  int* out = h->lat_flag.p;
+  void* params[3] = {&pars, &t, &out};
+  CU_TRY(cudaLaunchKernel((const void*)h->k_probe, dim3((unsigned)h->sm_count * 8u), dim3(256), params, 0, h->stream));
+  int reach = 0;
+  CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  const int fields = (int)((long long)h->N / h->lat_cells_ct);
+  if (reach > 16 || 12 * reach > 256 || 2 * reach + 1 > h->lat_cells_ct) return ODEINTR_OK;
+  const size_t smem = 2 * (size_t)fields * (256 * (size_t)tile5_cpt(fields) + 12 * (size_t)reach) * sizeof(double);
+  if (smem > 200 * 1024 ||
+      cudaFuncSetAttribute((const void*)h->k_dopri5_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ODEINTR_OK;
+  }
+  h->tiled5_halo = reach;
+  h->tiled5_smem = smem;
+  h->tiled5 = 1;
+  return ODEINTR_OK;
+}
+
 #include "lattice_adaptive.h"
 
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
@@ -955,7 +1000,11 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
   const size_t N = (size_t)h->N;
   CU_TRY(h->lat_work.reserve(13 * N));
-  CU_TRY(h->lat_err.reserve(1));
+  CU_TRY(h->lat_err.reserve(2));  // max-norm error bits, reach flag
+  {
+    const int rc5 = tiled5_decide(h);
+    if (rc5) return rc5;
+  }
   double* w = h->lat_work.p;
   // state-like vectors start as copies of x, derivative-like ones as zeros: entries no user loop writes keep
   // their value / a zero derivative through every stage
@@ -1238,6 +1287,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[1], h->lib, "odeintr_lattice_rk4_tiled2d_h1") != cudaSuccess) h->k_tiled2d_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[2], h->lib, "odeintr_lattice_rk4_tiled2d_h2") != cudaSuccess) h->k_tiled2d_h[2] = nullptr;
   h->k_tiled2d = h->k_tiled2d_h[1];
+  if (cudaLibraryGetKernel(&h->k_dopri5_tiled, h->lib, "odeintr_lattice_dopri5_tiled") != cudaSuccess)
+    h->k_dopri5_tiled = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();

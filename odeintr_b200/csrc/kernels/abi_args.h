@@ -127,6 +127,24 @@ struct odeintr_lattice_combo_args {
   double t;
 };
 
+// One attempted dopri5 step of a large 1-D system in one launch (lattice_dopri5_tiled.cuh).
+struct odeintr_lattice_dopri5_args {
+  const double* x_in;         // state at the start of the step
+  const double* d_in;         // its derivative k1 = f(x_in, t)
+  double* x_out;              // 5th-order solution (must not alias x_in)
+  double* d_out;              // k7 = f(x_out, t + dt)
+  double* k3;                 // stage derivatives for the dense output, or all four null
+  double* k4;
+  double* k5;
+  double* k6;
+  const double* pars;
+  long long halo;             // stencil radius
+  double t, dt;
+  double eps_abs, eps_rel, adt;
+  unsigned long long* err_max;  // bit pattern of the max-norm error (atomicMax)
+  int* flag;                  // set to 1 when the snippet reaches beyond the halo
+};
+
 // Ensemble of wider systems, one trajectory per block (lattice_ensemble.cuh): the fixed-step schedule of
 // odeintr_plain_args, block b integrating instance first + b.
 struct odeintr_lattice_ensemble_args {

@@ -1,0 +1,197 @@
+// odeintr_b200/csrc/kernels/lattice_dopri5_tiled.cuh
+// K4d: one ATTEMPTED Dormand-Prince 5(4) step of a large 1-D system in ONE kernel pass -- the temporally blocked
+// counterpart of the seven odeintr_lattice_combo launches behind compile_sys_openmp's default method rk5_i (and
+// rk5_a): runge_kutta_dopri5::do_step_impl + default_error_checker::error, i.e.
+//     (x, k1 = f(x)) -> x_new, k7 = f(x_new), max-norm of the embedded error estimate   [+ k3..k6 for dense output]
+// A block owns a tile of T cells.  Stage states are formed on windows that shrink by `halo` per stage from
+// T + 12 halo cells (six right-hand sides depend on neighbours: k2 .. k7), so the attempt reads x and k1 once and
+// writes x_new and k7 once: 32 B per cell instead of the ~260 B the stage-per-launch schedule moves.
+// Every thread owns CPT cells of the tile and one margin cell; their x and k1 .. k6 live in registers, only the
+// stage states y_s travel through two shared-memory windows.  The window is loaded with the cell index wrapped
+// periodically, so every tile (seam, ragged end) is treated alike: cells beyond the lattice end are periodic images
+// that are computed but not stored.  Operation order and coefficients are those of lattice_adaptive.h (Boost's
+// scale_sumN, left to right, coefficient * dt first): bit-identical to the staged path, controller on the host.
+#pragma once
+#include "odeintr_b200/lattice_tiled.cuh"
+
+#if !defined(ODEINTR_LATTICE_2D) && ODEINTR_LATTICE_STAGES == 7
+
+#ifndef ODEINTR_TILE5_CPT
+#define ODEINTR_TILE5_CPT (ODEINTR_NFIELDS > 1 ? 1 : 2)
+#endif
+#ifndef ODEINTR_TILE5_MIN_BLOCKS
+#define ODEINTR_TILE5_MIN_BLOCKS 3
+#endif
+
+extern "C" __global__ void __launch_bounds__(256, ODEINTR_TILE5_MIN_BLOCKS)
+odeintr_lattice_dopri5_tiled(const odeintr_lattice_dopri5_args a) {
+  using namespace odeintr_b200;
+  typedef lattice_rel_view<true> View;
+  typedef odeintr::system_type_t<View> Sys;
+  constexpr int F = ODEINTR_NFIELDS;
+  constexpr int C = ODEINTR_TILE5_CPT;
+  constexpr int T = 256 * C;
+  constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
+  constexpr int NC = C + 1;  // the thread's cells: C of the tile, then its margin cell
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int h = (int)a.halo, margin = 6 * h, W = T + 2 * margin;
+  double* const SA = smem;
+  double* const SB = smem + F * W;
+
+  Sys sys;
+  sys.load_params(a.pars, 1, 0);
+  long long off[F];
+  sys.field_offsets(off, 0);
+  int fld[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) fld[f] = static_cast<int>(off[f] / L);
+  const long long start = sys.cell_start(), bound = sys.cell_bound();
+  const long long tile_lo = (long long)blockIdx.x * T;
+
+  // window position, distance from the tile (0 inside), global cell (wrapped) and role of each of the thread's cells
+  int jj[NC], dist[NC];
+  long long cg[NC];
+  bool live[NC], store[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    if (k < C) { jj[k] = tid + k * 256; dist[k] = 0; }
+    else if (tid < margin) { jj[k] = -1 - tid; dist[k] = tid + 1; }
+    else if (tid < 2 * margin) { jj[k] = T + (tid - margin); dist[k] = tid - margin + 1; }
+    else { jj[k] = 0; dist[k] = 1 << 20; }  // no margin cell
+    long long c = tile_lo + jj[k];
+    c %= L;
+    if (c < 0) c += L;
+    cg[k] = c;
+    live[k] = dist[k] <= margin && c >= start && c < bound;
+    store[k] = k < C && tile_lo + jj[k] < L && live[k];
+  }
+
+  double x[NC][F], k1[NC][F], k2[NC][F], k3[NC][F], k4[NC][F], k5[NC][F], k6[NC][F], y[NC][F];
+#pragma unroll
+  for (int k = 0; k < NC; ++k)
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      x[k][f] = k1[k][f] = 0.0;
+      if (dist[k] <= margin) {
+        x[k][f] = __ldg(a.x_in + fld[f] * L + cg[k]);
+        k1[k][f] = __ldg(a.d_in + fld[f] * L + cg[k]);
+      }
+    }
+
+  const double dt = a.dt, t = a.t;
+  const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+  const double b21 = 1.0 / 5.0;
+  const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+  const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+  const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+  const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
+               b65 = -5103.0 / 18656.0;
+  const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+  const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
+               dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+
+  // y2 = x + dt*b21*k1 on the whole window; cells the loop does not write show x in every stage
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    if (dist[k] > margin) continue;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      y[k][fld[f]] = live[k] ? x[k][f] + (dt * b21) * k1[k][f] : x[k][f];
+      SA[fld[f] * W + margin + jj[k]] = y[k][fld[f]];
+      if (!live[k]) SB[fld[f] * W + margin + jj[k]] = x[k][f];
+    }
+  }
+  __syncthreads();
+
+  View view;
+  view.n_total = L; view.width = W; view.halo = h; view.bad = 0;
+  rel_index idx;
+  idx.off = 0; idx.cells = static_cast<int>(L); idx.rel = true;
+  double emax = 0.0;
+
+#pragma unroll
+  for (int stage = 2; stage <= 7; ++stage) {
+    const double* src = (stage & 1) ? SB : SA;
+    double* dst = (stage & 1) ? SA : SB;
+    const double ts = stage == 2 ? t + dt * a2 : (stage == 3 ? t + dt * a3 : (stage == 4 ? t + dt * a4 :
+                      (stage == 5 ? t + dt * a5 : t + dt)));
+    const int reach = (7 - stage) * h;  // this stage's window: the tile and `reach` cells on each side
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if (!live[k] || dist[k] > reach) continue;
+      double kk[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) kk[f] = 0.0;
+      view.p = src + margin + jj[k];
+      view.own = y[k];
+      view.centre = idx.centre = static_cast<int>(cg[k]);
+      sys.cell(view, kk, idx, ts);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int q = fld[f] * W + margin + jj[k];
+        const long long g = fld[f] * L + cg[k];
+        double v;
+        if (stage == 2) {
+          k2[k][f] = kk[f];
+          v = x[k][f] + (dt * b31) * k1[k][f];
+          v = v + (dt * b32) * kk[f];
+        } else if (stage == 3) {
+          k3[k][f] = kk[f];
+          v = x[k][f] + (dt * b41) * k1[k][f];
+          v = v + (dt * b42) * k2[k][f];
+          v = v + (dt * b43) * kk[f];
+          if (a.k3 && store[k]) a.k3[g] = kk[f];
+        } else if (stage == 4) {
+          k4[k][f] = kk[f];
+          v = x[k][f] + (dt * b51) * k1[k][f];
+          v = v + (dt * b52) * k2[k][f];
+          v = v + (dt * b53) * k3[k][f];
+          v = v + (dt * b54) * kk[f];
+          if (a.k3 && store[k]) a.k4[g] = kk[f];
+        } else if (stage == 5) {
+          k5[k][f] = kk[f];
+          v = x[k][f] + (dt * b61) * k1[k][f];
+          v = v + (dt * b62) * k2[k][f];
+          v = v + (dt * b63) * k3[k][f];
+          v = v + (dt * b64) * k4[k][f];
+          v = v + (dt * b65) * kk[f];
+          if (a.k3 && store[k]) a.k5[g] = kk[f];
+        } else if (stage == 6) {
+          k6[k][f] = kk[f];
+          v = x[k][f] + (dt * c1) * k1[k][f];
+          v = v + (dt * c3) * k3[k][f];
+          v = v + (dt * c4) * k4[k][f];
+          v = v + (dt * c5) * k5[k][f];
+          v = v + (dt * c6) * kk[f];
+          if (store[k]) a.x_out[g] = v;  // x_new
+          if (a.k3 && store[k]) a.k6[g] = kk[f];
+        } else {
+          // k7 = f(x_new): the derivative handed to the next step, and the last term of the error estimate
+          if (store[k]) a.d_out[g] = kk[f];
+          v = (dt * dc1) * k1[k][f];
+          v = v + (dt * dc3) * k3[k][f];
+          v = v + (dt * dc4) * k4[k][f];
+          v = v + (dt * dc5) * k5[k][f];
+          v = v + (dt * dc6) * k6[k][f];
+          v = v + (dt * dc7) * kk[f];
+          if (store[k]) {
+            const double e = fabs(v) / (a.eps_abs + a.eps_rel * (1.0 * fabs(x[k][f]) + a.adt * fabs(k1[k][f])));
+            emax = fmax(emax, e);
+          }
+        }
+        if (stage < 7) {
+          dst[q] = v;
+          y[k][fld[f]] = v;
+        }
+      }
+    }
+    if (stage < 7) __syncthreads();
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, s));
+  if ((tid & 31) == 0 && emax > 0.0) atomicMax(a.err_max, (unsigned long long)__double_as_longlong(emax));
+  if (view.bad) *a.flag = 1;
+}
+
+#endif

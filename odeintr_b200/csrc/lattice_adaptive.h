@@ -59,9 +59,64 @@ struct lattice_dopri5 {
     return r;
   }
 
+  // --- temporally blocked attempt (kernels/lattice_dopri5_tiled.cuh) ---------------------------------------------
+  // The stage derivatives k3..k6 are only needed by the dense output.  They are written when the previous step was
+  // interpolated (observations come every step or so); otherwise calc_state() repeats the last accepted attempt
+  // once with the stores switched on -- the same arithmetic, so the same bits.
+  bool k_valid = true, store_k = false, interpolated = false, sticky = false;
+  const double *last_in = nullptr, *last_din = nullptr;
+  double last_t = 0.0, last_dt = 0.0;
+
+  // returns the max-norm error, or a negative number when the kernel could not be used
+  double tiled_attempt(const double* in, const double* d_in, double t, double* out, double* d_out, double dt,
+                       bool with_k) {
+    odeintr_lattice_dopri5_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.x_in = in; a.d_in = d_in; a.x_out = out; a.d_out = d_out;
+    if (with_k) { a.k3 = k3; a.k4 = k4; a.k5 = k5; a.k6 = k6; }
+    a.pars = h->P ? h->pars.p : nullptr;
+    a.halo = h->tiled5_halo;
+    a.t = t; a.dt = dt;
+    a.eps_abs = h->atol; a.eps_rel = h->rtol; a.adt = 1.0 * std::fabs(dt);
+    a.err_max = h->lat_err.p;
+    a.flag = reinterpret_cast<int*>(h->lat_err.p + 1);
+    cudaMemsetAsync(h->lat_err.p, 0, 2 * sizeof(unsigned long long), h->stream);
+    const long long L = h->lat_cells_ct;
+    const long long tile = 256LL * tile5_cpt((int)((long long)h->N / L));
+    void* params[1] = {&a};
+    if (cudaLaunchKernel((const void*)h->k_dopri5_tiled, dim3((unsigned)((L + tile - 1) / tile)), dim3(256), params,
+                         h->tiled5_smem, h->stream) != cudaSuccess) {
+      if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_tiled failed");
+      return -1.0;
+    }
+    h->last_launches += 1;
+    g_total_launches += 1;
+    unsigned long long words[2] = {0, 0};
+    cudaMemcpyAsync(words, h->lat_err.p, sizeof(words), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (words[1] & 0xffffffffull) return -1.0;  // a read beyond the measured radius: not this kernel's system
+    double err;
+    std::memcpy(&err, &words[0], sizeof(err));
+    return err;
+  }
+
   // runge_kutta_dopri5::do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt, xerr) + default_error_checker::error
   // returns the max-norm error (A.2); out / dxdt_out must not alias in / dxdt_in
   double step_with_error(const double* in, const double* d_in, double t, double* out, double* d_out, double dt) {
+    if (h->tiled5 == 1) {
+      store_k = interpolated || sticky;  // stays on for one more attempt: a rejected try does not switch it off
+      sticky = interpolated;
+      interpolated = false;
+      const double e = tiled_attempt(in, d_in, t, out, d_out, dt, store_k);
+      if (e >= 0.0) {
+        k_valid = store_k;
+        last_in = in; last_din = d_in; last_t = t; last_dt = dt;
+        return e;
+      }
+      if (rc) return 0.0;
+      h->tiled5 = 0;  // the stage-per-launch path below has no reach limit
+    }
+    k_valid = true;
     const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
     const double b21 = 1.0 / 5.0;
     const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
@@ -119,6 +174,12 @@ struct lattice_dopri5 {
   // dense output (A.2) between (t_old, x_old, d_old) and (t_new, ., d_new) with the k3..k6 of the last step
   void calc_state(double t, double* x, const double* x_old, const double* d_old, double t_old, const double* d_new,
                   double t_new) {
+    interpolated = true;
+    if (!k_valid && last_in) {
+      // k3..k6 of the last accepted attempt were not written: repeat it (outputs to the scratch vectors)
+      tiled_attempt(last_in, last_din, last_t, xtA, xtB, last_dt, true);
+      k_valid = true;
+    }
     const double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
     const double dt = (t_new - t_old);
     const double theta = (t - t_old) / dt;

@@ -203,7 +203,7 @@ struct odeintr_system_s {
   cudaKernel_t k_plain = nullptr, k_adaptive = nullptr, k_lattice = nullptr, k_lattice_sharded = nullptr,
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
                k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr, k_tiled2d_h[3] = {nullptr, nullptr, nullptr},
-               k_dopri5_tiled = nullptr;
+               k_dopri5_tiled = nullptr, k_dopri5_tiled_h[3] = {nullptr, nullptr, nullptr};
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -954,7 +954,7 @@ int run_lattice(odeintr_system_t h, const plain_schedule& sc) {
 // cells per thread of the tiled dopri5 kernel (ODEINTR_TILE5_CPT in lattice_dopri5_tiled.cuh)
 int tile5_cpt(int fields) {
   const char* c = std::getenv("ODEINTR_TILE5_CPT");
-  const int v = c ? std::atoi(c) : (fields > 1 ? 1 : 2);
+  const int v = c ? std::atoi(c) : (fields > 1 ? 2 : 4);
   return v > 0 ? v : 1;
 }
 
@@ -979,6 +979,9 @@ int tiled5_decide(odeintr_system_t h) {
   const int fields = (int)((long long)h->N / h->lat_cells_ct);
   if (reach > 16 || 12 * reach > 256 || 2 * reach + 1 > h->lat_cells_ct) return ODEINTR_OK;
   const size_t smem = 2 * (size_t)fields * (256 * (size_t)tile5_cpt(fields) + 12 * (size_t)reach) * sizeof(double);
+  // radius 1 and 2 have kernels with the radius folded in (they hand seam / ragged tiles to the general form)
+  if ((reach == 1 || reach == 2) && h->k_dopri5_tiled_h[reach] && !std::getenv("ODEINTR_TILE5_GENERAL_ONLY"))
+    h->k_dopri5_tiled = h->k_dopri5_tiled_h[reach];
   if (smem > 200 * 1024 ||
       cudaFuncSetAttribute((const void*)h->k_dopri5_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -1289,6 +1292,10 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->k_tiled2d = h->k_tiled2d_h[1];
   if (cudaLibraryGetKernel(&h->k_dopri5_tiled, h->lib, "odeintr_lattice_dopri5_tiled") != cudaSuccess)
     h->k_dopri5_tiled = nullptr;
+  if (cudaLibraryGetKernel(&h->k_dopri5_tiled_h[1], h->lib, "odeintr_lattice_dopri5_tiled_h1") != cudaSuccess)
+    h->k_dopri5_tiled_h[1] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_dopri5_tiled_h[2], h->lib, "odeintr_lattice_dopri5_tiled_h2") != cudaSuccess)
+    h->k_dopri5_tiled_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();

@@ -133,10 +133,8 @@ struct odeintr_lattice_dopri5_args {
   const double* d_in;         // its derivative k1 = f(x_in, t)
   double* x_out;              // 5th-order solution (must not alias x_in)
   double* d_out;              // k7 = f(x_out, t + dt)
-  double* k3;                 // stage derivatives for the dense output, or all four null
-  double* k4;
-  double* k5;
-  double* k6;
+  double* dense_out;          // null, or: evaluate the dense output of this step instead (x_out, d_out and err_max
+  double dcoef[6];            //   stay untouched): dense_out = x_in + dcoef . (k1, k3, k4, k5, k6, k7), left to right
   const double* pars;
   long long halo;             // stencil radius
   double t, dt;

@@ -60,20 +60,20 @@ struct lattice_dopri5 {
   }
 
   // --- temporally blocked attempt (kernels/lattice_dopri5_tiled.cuh) ---------------------------------------------
-  // The stage derivatives k3..k6 are only needed by the dense output.  They are written when the previous step was
-  // interpolated (observations come every step or so); otherwise calc_state() repeats the last accepted attempt
-  // once with the stores switched on -- the same arithmetic, so the same bits.
-  bool k_valid = true, store_k = false, interpolated = false, sticky = false;
+  // The stage derivatives k3..k6 never reach HBM on this path: the dense output of a step is evaluated by repeating
+  // the accepted attempt with the interpolation folded into its last stage (same arithmetic, same bits).
+  bool k_valid = true;  // k3..k6 hold the last step's stage derivatives (stage-per-launch path)
   const double *last_in = nullptr, *last_din = nullptr;
   double last_t = 0.0, last_dt = 0.0;
 
   // returns the max-norm error, or a negative number when the kernel could not be used
   double tiled_attempt(const double* in, const double* d_in, double t, double* out, double* d_out, double dt,
-                       bool with_k) {
+                       double* dense_out = nullptr, const double* dcoef = nullptr) {
     odeintr_lattice_dopri5_args a;
     std::memset(&a, 0, sizeof(a));
     a.x_in = in; a.d_in = d_in; a.x_out = out; a.d_out = d_out;
-    if (with_k) { a.k3 = k3; a.k4 = k4; a.k5 = k5; a.k6 = k6; }
+    a.dense_out = dense_out;
+    if (dense_out) for (int j = 0; j < 6; ++j) a.dcoef[j] = dcoef[j];
     a.pars = h->P ? h->pars.p : nullptr;
     a.halo = h->tiled5_halo;
     a.t = t; a.dt = dt;
@@ -91,6 +91,7 @@ struct lattice_dopri5 {
     }
     h->last_launches += 1;
     g_total_launches += 1;
+    if (dense_out) return 0.0;  // nothing to read back: the attempt it repeats has already been vetted
     unsigned long long words[2] = {0, 0};
     cudaMemcpyAsync(words, h->lat_err.p, sizeof(words), cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -104,12 +105,9 @@ struct lattice_dopri5 {
   // returns the max-norm error (A.2); out / dxdt_out must not alias in / dxdt_in
   double step_with_error(const double* in, const double* d_in, double t, double* out, double* d_out, double dt) {
     if (h->tiled5 == 1) {
-      store_k = interpolated || sticky;  // stays on for one more attempt: a rejected try does not switch it off
-      sticky = interpolated;
-      interpolated = false;
-      const double e = tiled_attempt(in, d_in, t, out, d_out, dt, store_k);
+      const double e = tiled_attempt(in, d_in, t, out, d_out, dt);
       if (e >= 0.0) {
-        k_valid = store_k;
+        k_valid = false;
         last_in = in; last_din = d_in; last_t = t; last_dt = dt;
         return e;
       }
@@ -174,12 +172,6 @@ struct lattice_dopri5 {
   // dense output (A.2) between (t_old, x_old, d_old) and (t_new, ., d_new) with the k3..k6 of the last step
   void calc_state(double t, double* x, const double* x_old, const double* d_old, double t_old, const double* d_new,
                   double t_new) {
-    interpolated = true;
-    if (!k_valid && last_in) {
-      // k3..k6 of the last accepted attempt were not written: repeat it (outputs to the scratch vectors)
-      tiled_attempt(last_in, last_din, last_t, xtA, xtB, last_dt, true);
-      k_valid = true;
-    }
     const double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
     const double dt = (t_new - t_old);
     const double theta = (t - t_old) / dt;
@@ -203,6 +195,11 @@ struct lattice_dopri5 {
     const double b7_theta = B + C * X7;
     const double* v[] = {d_old, k3, k4, k5, k6, d_new};
     const double c[] = {dt * b1_theta, dt * b3_theta, dt * b4_theta, dt * b5_theta, dt * b6_theta, dt * b7_theta};
+    if (!k_valid && last_in) {
+      // tiled path: repeat the accepted attempt (x_old, d_old, its t and dt) with the interpolation in its last stage
+      tiled_attempt(last_in, last_din, last_t, nullptr, nullptr, last_dt, x, c);
+      return;
+    }
     combo(nullptr, x_old, 6, v, c, 0.0, x, nullptr, t);
   }
 

@@ -201,6 +201,57 @@ def test_large_system_adaptive_dopri5(method):
     assert np.max(np.abs(cols(df) - ref["rec"])) <= 1e-5
 
 
+@pytest.mark.parametrize("case", ["bistable_5003", "chain_two_fields", "fixed_ends", "radius_2", "radius_3",
+                                  "bistable_staged"])
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a"])
+def test_tiled_dopri5_attempt_bit_exact(case, method, monkeypatch):
+    # adaptive dopri5 on 1-D lattices runs one temporally blocked kernel per attempt (odeintr_lattice_dopri5_tiled*):
+    # several tiles with a ragged last one, two fields, cells the loop leaves alone, the radius-2 kernel and the
+    # general-radius one; "staged" forces the seven-launch path.  All of them must give the oracle's bits: same
+    # operation order on the device, the controller's pow() in glibc on both sides.
+    pars, glob = BISTABLE_PARS, ""
+    if case in ("bistable_5003", "bistable_staged"):
+        n, src = 5003, BISTABLE_1D
+        x0 = np.random.default_rng(61).uniform(0, 1, n)
+        if case == "bistable_staged":
+            monkeypatch.setenv("ODEINTR_NO_TILED", "1")
+    elif case == "chain_two_fields":
+        n, src, pars, glob = 2 * 3001, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n // 2) / (n // 2)), np.zeros(n // 2)])
+    elif case == "fixed_ends":
+        n = 4100
+        src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + x[i] * (1 - x[i]) * (x[i] - 0.5);"
+        x0 = np.random.default_rng(62).uniform(0, 1, n)
+    else:
+        k = 2 if case == "radius_2" else 3
+        n = 4100
+        src = ("for (int i = 0; i < N; ++i) dxdt[i] = D * (x[(i + N - %d) %% N] + x[(i + %d) %% N] + x[(i + N - 1) %% N] "
+               "+ x[(i + 1) %% N] - 4.0 * x[i]) - 0.2 * x[i];" % (k, k))
+        x0 = np.random.default_rng(63).uniform(0, 1, n)
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("d5", src, pars, True, method=method, sys_dim=n, globals=glob, env=env,
+                                           atol=1e-7, rtol=1e-7)
+    ora = bo.build(src, pars, True, method, sys_dim=n, globals=glob, atol=1e-7, rtol=1e-7)
+    # observations every 0.25: several steps between most of them, more than one inside some steps
+    df = env["d5"](x0, 3.0, 0.25)
+    ref = ora.integrate_const(x0, 0, 3.0, 0.25)
+    assert df.shape == (ref["rows"], n + 1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    st = code.system.stats()
+    assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
+    launches = code.system.last_launches()
+    tries = int(st["accepted"][0] + st["rejected"][0])
+    if case == "bistable_staged":
+        assert launches > 6 * tries        # seven stage launches per attempt
+    else:
+        assert launches < 3 * tries + 20   # one launch per attempt (+ one per interpolated observation)
+    at = np.array([0.5, 1.0, 1.0 + 1e-3, 2.75])
+    df = env["d5_at"](x0, at, 0.1)
+    adv = ora.integrate_const(x0, 0.0, at[0], 0.1, record=False)
+    ref = ora.integrate_times(adv["x"], at, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+
+
 def test_2d_lattice_strip_traversal_bit_exact():
     # M a multiple of the block width: the stage kernel walks the lattice in column strips (L1 reuse of the rows
     # above / below); the visiting order must not change a single bit

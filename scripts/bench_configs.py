@@ -2,7 +2,7 @@
 """Secondary measurements for BASELINE.json configs[2..4] (the headline, configs[1], is bench.py):
   config 3  Van der Pol mu-sweep, 10 M instances, adaptive dopri5 (rk5_i, atol = rtol = 1e-8), name_at dense output
   config 4  Robertson, 10 M instances (alpha sweep), compile_implicit rosenbrock4, log-spaced name_at
-  config 5  1-D lattice of 2^28 states, rk4 (fused stage kernels), single GPU
+  config 5  1-D lattice of 2^28 states, rk4 (temporally blocked step; the stage-per-launch schedule beside it), single GPU
 Each prints one JSON line: device-timed value, a parity spot check against the oracle, and the oracle's CPU
 throughput on a bounded sample (all host cores).  Usage: python scripts/bench_configs.py [3] [4] [5]"""
 import ctypes as C, json, os, sys, time
@@ -104,15 +104,20 @@ if 4 in which:
 
 if 5 in which:
     n, steps = 1 << 28, 100
-    code = odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n)
-    s = code.system
     x0 = (np.arange(n) % 7 < 3).astype(np.float64)
-    s.set_state(x0)
-    best = None
-    for rep in range(3):
-        assert lib.odeintr_integrate_const(s._h, 0.0, steps * 0.01, 0.01, 1, 0) == 0, _abi.last_error()
-        best = s.last_kernel_ms() if best is None else min(best, s.last_kernel_ms())
-    nsteps = s.last_steps()
+    res = {}
+    for label, halo in (("tiled", None), ("staged", 0)):
+        code = odeintr_b200.compile_sys_openmp("bistable", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=n, halo=halo)
+        s = code.system
+        best = None
+        for rep in range(3):
+            s.set_state(x0)
+            assert lib.odeintr_integrate_const(s._h, 0.0, steps * 0.01, 0.01, 1, 0) == 0, _abi.last_error()
+            best = s.last_kernel_ms() if best is None else min(best, s.last_kernel_ms())
+        res[label] = (best, s.last_steps(), s.get_state().copy(), s.last_launches())
+        s.close()
+    best, nsteps, fin, launches = res["tiled"]
+    same = bool(np.array_equal(fin.view(np.uint64), res["staged"][2].view(np.uint64)))
     # parity at 2^20 cells (the oracle finishes in seconds), same system and initial pattern
     ns = 1 << 20
     code_s = odeintr_b200.compile_sys_openmp("bistable_s", BISTABLE_1D, BISTABLE_PARS, True, method="rk4", sys_dim=ns)
@@ -123,14 +128,21 @@ if 5 in which:
     exact = bool(np.array_equal(got.view(np.uint64), ref["x"].view(np.uint64)))
     # size-independent property at full size: the initial pattern has period 7, and 2^28 = 7 * 38347922 + 2, so the
     # state is not periodic at the wrap; away from it every cell must equal the cell 7 places on (translation symmetry)
-    fin = s.get_state()
     sym = bool(np.array_equal(fin[1000:100000], fin[1007:100007]))
-    gbs = 128.0 * n * nsteps / best / 1e6
-    print(json.dumps({"config": 5, "metric": "lattice_rk4_cell_steps_per_s", "value": n * nsteps / best * 1e3, "unit": "cell-steps/s",
-        "cells": n, "steps": nsteps, "ms_per_step": best / nsteps,
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "algorithmic_bytes_per_cell_step": 128},
-        "parity": {"bit_exact_vs_oracle_2^20_cells_20_steps": exact, "translation_symmetry_full_size": sym},
+    rate = n * nsteps / best * 1e3
+    sbest = res["staged"][0]
+    sgbs = 128.0 * n * nsteps / sbest / 1e6
+    print(json.dumps({"config": 5, "metric": "lattice_rk4_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
+        "cells": n, "steps": nsteps, "ms_per_step": best / nsteps, "gpu_launches": launches,
+        "kernel": "odeintr_lattice_rk4_tiled_tma (temporally blocked step, radius measured by the probe)",
+        "roofline": {"bound": "fp64", "achieved": rate * 50.0 / 1e12, "peak": dp_peak.value / 1e12, "unit": "TFLOP/s",
+                     "frac": rate * 50.0 / dp_peak.value, "dp_instr_per_cell_step": 50,
+                     "hbm": {"bytes_per_cell_step": 16, "achieved_GBps": rate * 16.0 / 1e9, "peak_GBps": hbm_peak,
+                             "frac": rate * 16.0 / 1e9 / hbm_peak}},
+        "staged_schedule": {"value": n * nsteps / sbest * 1e3, "ms_per_step": sbest / nsteps,
+                            "roofline": {"bound": "hbm", "achieved": sgbs, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": sgbs / hbm_peak, "algorithmic_bytes_per_cell_step": 128}},
+        "parity": {"bit_exact_vs_oracle_2^20_cells_20_steps": exact, "tiled_equals_staged_bit_for_bit_2^28_cells": same,
+                   "translation_symmetry_full_size": sym},
         "cpu_baseline": {"value": ns * 20 / tc, "unit": "cell-steps/s", "cores": threads, "kind": "port",
                          "sample": "2^20 cells x 20 rk4 steps, user loop under #pragma omp parallel for"}}), flush=True)
-    s.close()

@@ -46,6 +46,7 @@ enum {
 
 /* compile flags */
 #define ODEINTR_FLAG_FMAD 1u            /* allow FMA contraction (fast mode; NOT bit-compatible with the reference) */
+#define ODEINTR_FLAG_RECIPROCAL 32u      /* rosenbrock4: divide by the step size and the LU pivots through reciprocals computed once per attempt (fast mode; agrees with the reference to rounding, NOT bit for bit) */
 #define ODEINTR_FLAG_KEEP_ZERO_TERMS 2u /* also add Boost's zero tableau entries (x + 0*dt*k) */
 #define ODEINTR_FLAG_LATTICE_EULER 8u   /* large-system TU stepped with euler (1 stage) instead of rk4 (4 stages): set by the generator */
 #define ODEINTR_FLAG_LATTICE_ADAPTIVE 16u /* large-system TU stepped with adaptive dopri5 (rk5_a; rk5_i with DENSE_OUTPUT): set by the generator */

@@ -149,6 +149,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   o.push_back("-lineinfo");
   o.push_back((flags & ODEINTR_FLAG_FMAD) ? "--fmad=true" : "--fmad=false");
   if (flags & ODEINTR_FLAG_KEEP_ZERO_TERMS) o.push_back("-DODEINTR_KEEP_ZERO_TERMS=1");
+  if (flags & ODEINTR_FLAG_RECIPROCAL) o.push_back("-DODEINTR_RECIPROCAL=1");
   // tuning knobs for experiments (scripts/explore_*.py): register cap and block size of the ensemble kernels
   if (const char* r = std::getenv("ODEINTR_MAXRREGCOUNT")) o.push_back(std::string("--maxrregcount=") + r);
   if (const char* b = std::getenv("ODEINTR_BLOCK")) o.push_back(std::string("-DODEINTR_BLOCK=") + b);

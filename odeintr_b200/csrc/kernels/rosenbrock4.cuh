@@ -52,6 +52,17 @@ struct lu_factors {
     }
   }
 
+#ifdef ODEINTR_RECIPROCAL
+  // fast mode (ODEINTR_FLAG_RECIPROCAL): the six solves of an attempt multiply by the reciprocals of U's diagonal
+  double inv_diag[N];
+  ODEINTR_DEV void prepare() {
+#pragma unroll
+    for (int n = 0; n < N; ++n) inv_diag[n] = 1.0 / m(n, n);
+  }
+#else
+  ODEINTR_DEV void prepare() {}
+#endif
+
   // uBLAS lu_substitute: row swaps, unit-lower forward solve, upper backward solve (column oriented)
   ODEINTR_DEV void substitute(vec<N>& v) const {
 #pragma unroll
@@ -72,7 +83,11 @@ struct lu_factors {
     }
 #pragma unroll
     for (int n = N - 1; n >= 0; --n) {
+#ifdef ODEINTR_RECIPROCAL
+      const double t = v[n] *= inv_diag[n];
+#else
       const double t = v[n] /= m(n, n);
+#endif
 #pragma unroll
       for (int r = 0; r < n; ++r) v[r] -= t * m(r, n);
     }
@@ -137,6 +152,13 @@ struct rosenbrock4_dense {
         if (r == c) lu.m(r, c) += diag * 1.0;
       }
     lu.factorize();
+    lu.prepare();
+#ifdef ODEINTR_RECIPROCAL
+    const double rh = 1.0 / h;
+#define ODEINTR_OVER_H(e) ((e) * rh)
+#else
+#define ODEINTR_OVER_H(e) ((e) / h)
+#endif
 #pragma unroll
     for (int i = 0; i < N; ++i) g1[i] = dxdt[i] + h * K::d1 * dfdt[i];
     lu.substitute(g1);
@@ -144,36 +166,37 @@ struct rosenbrock4_dense {
     for (int i = 0; i < N; ++i) xt[i] = x[i] + K::a21 * g1[i];
     sys.sys(xt, dn, tt + K::c2 * h);
 #pragma unroll
-    for (int i = 0; i < N; ++i) g2[i] = dn[i] + h * K::d2 * dfdt[i] + K::c21 * g1[i] / h;
+    for (int i = 0; i < N; ++i) g2[i] = dn[i] + h * K::d2 * dfdt[i] + ODEINTR_OVER_H(K::c21 * g1[i]);
     lu.substitute(g2);
 #pragma unroll
     for (int i = 0; i < N; ++i) xt[i] = x[i] + K::a31 * g1[i] + K::a32 * g2[i];
     sys.sys(xt, dn, tt + K::c3 * h);
 #pragma unroll
-    for (int i = 0; i < N; ++i) g3[i] = dn[i] + h * K::d3 * dfdt[i] + (K::c31 * g1[i] + K::c32 * g2[i]) / h;
+    for (int i = 0; i < N; ++i) g3[i] = dn[i] + h * K::d3 * dfdt[i] + ODEINTR_OVER_H(K::c31 * g1[i] + K::c32 * g2[i]);
     lu.substitute(g3);
 #pragma unroll
     for (int i = 0; i < N; ++i) xt[i] = x[i] + K::a41 * g1[i] + K::a42 * g2[i] + K::a43 * g3[i];
     sys.sys(xt, dn, tt + K::c4 * h);
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      g4[i] = dn[i] + h * K::d4 * dfdt[i] + (K::c41 * g1[i] + K::c42 * g2[i] + K::c43 * g3[i]) / h;
+      g4[i] = dn[i] + h * K::d4 * dfdt[i] + ODEINTR_OVER_H(K::c41 * g1[i] + K::c42 * g2[i] + K::c43 * g3[i]);
     lu.substitute(g4);
 #pragma unroll
     for (int i = 0; i < N; ++i) xt[i] = x[i] + K::a51 * g1[i] + K::a52 * g2[i] + K::a53 * g3[i] + K::a54 * g4[i];
     sys.sys(xt, dn, tt + h);
 #pragma unroll
-    for (int i = 0; i < N; ++i) g5[i] = dn[i] + (K::c51 * g1[i] + K::c52 * g2[i] + K::c53 * g3[i] + K::c54 * g4[i]) / h;
+    for (int i = 0; i < N; ++i) g5[i] = dn[i] + ODEINTR_OVER_H(K::c51 * g1[i] + K::c52 * g2[i] + K::c53 * g3[i] + K::c54 * g4[i]);
     lu.substitute(g5);
 #pragma unroll
     for (int i = 0; i < N; ++i) xt[i] += g5[i];
     sys.sys(xt, dn, tt + h);
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      xerr[i] = dn[i] + (K::c61 * g1[i] + K::c62 * g2[i] + K::c63 * g3[i] + K::c64 * g4[i] + K::c65 * g5[i]) / h;
+      xerr[i] = dn[i] + ODEINTR_OVER_H(K::c61 * g1[i] + K::c62 * g2[i] + K::c63 * g3[i] + K::c64 * g4[i] + K::c65 * g5[i]);
     lu.substitute(xerr);
 #pragma unroll
     for (int i = 0; i < N; ++i) xout[i] = xt[i] + xerr[i];
+#undef ODEINTR_OVER_H
   }
 
   // rosenbrock4_controller::try_step(sys, x, t, xout, dt)
@@ -185,7 +208,12 @@ struct rosenbrock4_dense {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double sk = atol + rtol * fmax(fabs(x[i]), fabs(xout[i]));
+#ifdef ODEINTR_RECIPROCAL
+      const double e = xerr[i] * (1.0 / sk);
+      err += e * e;
+#else
       err += xerr[i] * xerr[i] / sk / sk;
+#endif
     }
     err = sqrt(err / static_cast<double>(N));
     double fac = fmax(fac2, fmin(fac1, pow(err, 0.25) / safe));

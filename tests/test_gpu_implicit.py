@@ -80,3 +80,28 @@ def test_config4_robertson_ensemble_at_log_times():
     adv = ora_c.integrate_const([1.0, 0.0, 0.0], 0.0, float(times[0]), 1.0, record=False)
     r = ora_c.integrate_times(adv["x"], times, 1.0)
     close(df[["X1", "X2", "X3"]].to_numpy(), r["rec"], 1e-6)
+
+
+def test_reciprocal_fast_mode_stays_within_the_stated_tolerance():
+    # ODEINTR_FLAG_RECIPROCAL: the divisions by the step size and by the LU pivots become multiplications by
+    # reciprocals computed once per attempt.  Not bit-compatible; north_star's bar for implicit steppers is final-state
+    # agreement within 10 x rtol with the step counts reported.
+    from odeintr_b200 import _abi
+
+    env = {}
+    code = odeintr_b200.compile_implicit("robertson", ROBERTSON, ROBERTSON_PARS, env=env, flags=_abi.FLAG_RECIPROCAL)
+    ora = bo.build(ROBERTSON, ROBERTSON_PARS, False, "rosenbrock4")
+    m = 97
+    alphas = np.linspace(0.02, 0.08, m)
+    env["robertson_set_params"](alpha=alphas)
+    times = 10 ** np.linspace(-5, 5, 41)
+    rec = env["robertson_at"](np.array([1.0, 0.0, 0.0]), times)
+    P = np.stack([alphas, np.full(m, 1e4), np.full(m, 3e7)])
+    X0 = np.repeat(np.array([[1.0], [0.0], [0.0]]), m, axis=1)
+    adv = ora.ensemble(0, X0.copy(), P, 0.0, float(times[0]), 1.0, threads=ora.max_threads())
+    e = ora.ensemble(1, adv["x"].copy(), P, times=times, dt=1.0, out_rows=41, threads=ora.max_threads())
+    close(rec.x, e["out"], 10 * 1e-6)  # 10 x rtol (rtol = atol = 1e-6, the reference's defaults)
+    st = code.system.stats()
+    assert np.all(st["status"] == 0)
+    print("accepted steps, fast mode vs oracle:", int(st["accepted"].sum()), int(e["accepted"].sum()))
+    assert abs(int(st["accepted"].sum()) - int(e["accepted"].sum())) <= 0.01 * e["accepted"].sum()

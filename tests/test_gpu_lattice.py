@@ -419,6 +419,56 @@ def test_large_system_rejects_strided_targets():
                                         method="rk4", sys_dim=64)
 
 
+def test_tiled_rk4_wide_radius_and_declared_radius_variants():
+    # radius 8 (margins of 32 cells, the TMA windows shift by a multiple of 16 bytes), a declared radius larger than
+    # the stencil needs, and a 2-D stencil declared with radius 2 (the _h2 kernel on a radius-1 Laplacian)
+    src8 = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[(i + N - 8) % N] + x[(i + 8) % N] + x[(i + 1) % N] - 3.0 * x[i]);"
+    for src, n, halo, want in ((src8, 9001, None, 8), (BISTABLE_1D, 7000, 3, 3), (BISTABLE_2D, 96 * 96, 2, 2),
+                               (BISTABLE_2D, 96 * 96, 1, 1)):
+        env = {}
+        code = odeintr_b200.compile_sys_openmp("v", src, BISTABLE_PARS, True, method="rk4", sys_dim=n, env=env, halo=halo)
+        x0 = np.random.default_rng(n).uniform(0, 1, n)
+        fin = env["v_no_record"](x0, 0.7, 0.1)
+        assert code.system.get_halo() == want
+        ora = bo.build(src, BISTABLE_PARS, True, "rk4", sys_dim=n)
+        assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 0.7, 0.1)["x"]))
+
+
+def test_sharded_tiled_slabs_with_fixed_ends_emulated_ranks():
+    # non-periodic loop (cells 0 and N-1 keep their value) split into three slabs: the slabs at the lattice ends hold
+    # cells the loop does not write, so their first / last tiles take the general tiled kernel
+    import torch
+
+    from odeintr_b200.distributed import ShardedLattice
+
+    n_cells, world = 7001, 3
+    src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + x[i] * (1 - x[i]) * (x[i] - 0.5);"
+    x0 = np.random.default_rng(97).uniform(0, 1, n_cells)
+    build = lambda name: odeintr_b200.compile_sys_openmp(name, src, {"D": 0.2}, True, method="rk4", sys_dim=n_cells).system
+    ora = bo.build(src, {"D": 0.2}, True, "rk4", sys_dim=n_cells)
+    ref = ora.integrate_adaptive(x0, 0, 1.2, 0.1)["x"]  # 12 steps
+    lats = []
+    for r in range(world):
+        lat = ShardedLattice(build("r%d" % r), n_cells, fields=1, rank=r, world=world, native=False)
+        lat.set_state_from(lambda f, cells: x0[cells])
+        lats.append(lat)
+    g, pad = lats[0].ghost, lats[0].pad
+    for step in range(12):
+        for lat in lats:
+            lat.stream.synchronize()
+        for r, lat in enumerate(lats):
+            left, right = lats[(r - 1) % world], lats[(r + 1) % world]
+            lat.x[:, pad - g:pad] = left.x[:, pad + left.n_local - g:pad + left.n_local]
+            lat.x[:, pad + lat.n_local:pad + lat.n_local + g] = right.x[:, pad:pad + g]
+        torch.cuda.synchronize()
+        for lat in lats:
+            lat.step(1, 0.1, t0=0.0 if step == 0 else None, exchange=False)
+    for lat in lats:
+        lat.stream.synchronize()
+    got = torch.cat([lat.local_state() for lat in lats], dim=1).cpu().numpy().reshape(-1)
+    assert np.array_equal(bits(got), bits(ref))
+
+
 def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():
     # only interior tiles see the far read: cells next to the ends stay within reach
     src = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"

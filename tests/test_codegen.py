@@ -114,6 +114,45 @@ def test_implicit_and_large_system_code_compiles_without_a_device():
     assert "odeintr_k[1]" in g.code and _cubin(g.code) > 1000
 
 
+def _kernels(code: str):
+    """Names of the __global__ functions in the sm_100a cubin NVRTC builds from `code` (no device needed)."""
+    import subprocess
+    import tempfile
+
+    lib = _abi.load()
+    size = C.c_size_t(0)
+    assert lib.odeintr_compile_cubin(code.encode(), 0, None, 0, C.byref(size)) == 0, _abi.last_error()
+    buf = C.create_string_buffer(size.value)
+    assert lib.odeintr_compile_cubin(code.encode(), 0, buf, size.value, C.byref(size)) == 0
+    with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+        f.write(buf.raw[:size.value]); f.flush()
+        out = subprocess.run(["cuobjdump", "-elf", f.name], capture_output=True, text=True).stdout
+    return {w[len(".text."):] for line in out.splitlines() for w in line.split() if w.startswith(".text.odeintr_")}
+
+
+def test_large_system_translation_units_carry_the_kernels_their_method_can_use():
+    # which hand-written kernels a generated large-system TU instantiates (the host picks among them at run time)
+    from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_DOC, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
+    staged = {"odeintr_lattice_stage", "odeintr_lattice_stage_sharded", "odeintr_lattice_combo", "odeintr_lattice_info",
+              "odeintr_lattice_probe"}
+    tiled = {"odeintr_lattice_rk4_tiled", "odeintr_lattice_rk4_tiled_interior", "odeintr_lattice_rk4_tiled_tma"}
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "rk4", sys_dim=1 << 20).code)
+    assert k == staged | tiled  # a 2^20-cell lattice is too long for one block: no ensemble kernel
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk4", sys_dim=1024).code)
+    assert k == staged | tiled | {"odeintr_lattice_ensemble"}
+    k = _kernels(codegen.generate_sys_openmp("c", CHAIN, CHAIN_PARS, True, "rk4", sys_dim=2 * 300, globals=CHAIN_GLOBALS).code)
+    assert k == staged | tiled | {"odeintr_lattice_ensemble"}
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "rk5_i", sys_dim=1 << 20).code)
+    assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2"}
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "euler", sys_dim=1 << 20).code)
+    assert k == staged
+    for src in (BISTABLE_2D, BISTABLE_DOC):
+        k = _kernels(codegen.generate_sys_openmp("b2", src, BISTABLE_PARS, True, "rk4", sys_dim=96 * 96).code)
+        assert k == staged | {"odeintr_lattice_rk4_tiled2d_h1", "odeintr_lattice_rk4_tiled2d_h2"}
+    k = _kernels(codegen.generate_sys_openmp("b2", BISTABLE_2D, BISTABLE_PARS, True, "rk5_i", sys_dim=96 * 96).code)
+    assert k == staged
+
+
 def test_cell_loop_parser():
     from systems import BISTABLE_2D, CHAIN
     loops = codegen.parse_cell_loops(CHAIN)

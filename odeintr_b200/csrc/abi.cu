@@ -709,6 +709,8 @@ int lattice_prepare(odeintr_system_t h, size_t total) {
 // shared-memory budgets of the two tiled kernels for a stencil radius; false when no tile can hold it
 bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
   if (!h->k_tiled || halo < 0 || halo > 4096) return false;
+  // the window of a tile wraps around the lattice at most once: tiny lattices stay on the staged kernels
+  if ((long long)h->N / fields < 8 * halo + 2) return false;
   const size_t width = 256 * (size_t)tile_cpt() + 8 * (size_t)halo;
   const size_t bytes = 4 * (size_t)fields * width * sizeof(double);
   if (bytes > 200 * 1024) return false;
@@ -736,7 +738,7 @@ bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
 
 // M x M lattices: shared-memory budget of odeintr_lattice_rk4_tiled2d (two windows of (32 + 8 halo) x (64 + 8 halo))
 bool tiled2d_configure(odeintr_system_t h, long long halo) {
-  if (h->lat_side <= 0 || halo < 0 || halo > 2 || 2 * halo + 1 > h->lat_side) return false;
+  if (h->lat_side <= 0 || halo < 0 || halo > 2 || h->lat_side < 8) return false;
   if (halo == 0) halo = 1;  // no coupling at all: the radius-1 kernel does
   if (!h->k_tiled2d_h[halo]) return false;
   h->k_tiled2d = h->k_tiled2d_h[halo];

@@ -143,8 +143,8 @@ ODEINTR_DEV void lattice_rk4_tiled2d_body(const odeintr_lattice_tiled_args& a) {
   constexpr int tiles_x = (MM + TW - 1) / TW;
   const int r0 = (int)(blockIdx.x / tiles_x) * TH, c0 = (int)(blockIdx.x % tiles_x) * TW;
 
-  auto wrap = [&](int v) {  // coordinates reach at most one tile beyond the lattice
-    if (v < 0) v += MM;
+  auto wrap = [&](int v) {  // usually one step: coordinates reach at most one tile beyond the lattice
+    while (v < 0) v += MM;
     while (v >= MM) v -= MM;
     return v;
   };

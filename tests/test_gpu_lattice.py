@@ -472,6 +472,20 @@ def test_sharded_tiled_slabs_with_fixed_ends_emulated_ranks():
     assert bad.size == 0, (bad.size, bad[:12], bad[-12:])
 
 
+@pytest.mark.parametrize("method", ["rk4", "rk5_i"])
+def test_tiny_lattices(method):
+    # lattices shorter than a tile's margins: 1-D with 5 and 9 cells, 2-D with M = 3 and M = 8
+    for src, n in ((BISTABLE_1D, 5), (BISTABLE_1D, 9), (BISTABLE_1D, 40), (BISTABLE_2D, 9), (BISTABLE_2D, 64)):
+        env = {}
+        odeintr_b200.compile_sys_openmp("tiny", src, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
+        ora = bo.build(src, BISTABLE_PARS, True, method, sys_dim=n)
+        x0 = np.random.default_rng(n).uniform(0, 1, n)
+        df = env["tiny"](x0, 2.0, 0.25)
+        ref = ora.integrate_const(x0, 0, 2.0, 0.25)
+        assert df.shape == (ref["rows"], n + 1)
+        assert np.array_equal(bits(cols(df)), bits(ref["rec"])), (method, n)
+
+
 def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():
     # only interior tiles see the far read: cells next to the ends stay within reach
     src = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"

@@ -50,6 +50,7 @@ enum {
 #define ODEINTR_FLAG_KEEP_ZERO_TERMS 2u /* also add Boost's zero tableau entries (x + 0*dt*k) */
 #define ODEINTR_FLAG_LATTICE_EULER 8u   /* large-system TU stepped with euler (1 stage) instead of rk4 (4 stages): set by the generator */
 #define ODEINTR_FLAG_LATTICE_ADAPTIVE 16u /* large-system TU stepped with adaptive dopri5 (rk5_a; rk5_i with DENSE_OUTPUT): set by the generator */
+#define ODEINTR_FLAG_LATTICE_CK54 64u   /* large-system TU stepped with Cash-Karp 5(4) (rk54; rk54_a with LATTICE_ADAPTIVE): set by the generator */
 #define ODEINTR_FLAG_DENSE_OUTPUT 4u    /* the TU instantiates a dense-output stepper (rk5_i, rosenbrock4): set by the generator */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

@@ -86,6 +86,7 @@ FLAG_KEEP_ZERO_TERMS = 2
 FLAG_DENSE_OUTPUT = 4
 FLAG_LATTICE_EULER = 8
 FLAG_LATTICE_ADAPTIVE = 16
+FLAG_LATTICE_CK54 = 64  # large-system TU stepped with Cash-Karp (rk54 / rk54_a): set by the generator
 FLAG_RECIPROCAL = 32  # rosenbrock4 fast mode: reciprocals instead of repeated divisions (not bit-compatible)
 
 _lib = None

@@ -223,8 +223,9 @@ struct odeintr_system_s {
   long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_info)
   long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
-  int lattice_method = 0;  // 0 = fixed step (rk4 / euler), 1 = rk5_a, 2 = rk5_i
+  int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a
   dev_buf<double> lat_work;
+  bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 path hold copies of x / zeros
   dev_buf<unsigned long long> lat_err;
   int block_plain = 128, block_adaptive = 128;
   cudaStream_t stream = nullptr;
@@ -570,6 +571,8 @@ struct lattice_window {      // which cells a launch computes and how local buff
   long long lo, hi;          // sharded run through the tiled kernels: cells the step must produce
 };
 
+int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt);  // after lattice_adaptive.h
+
 int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
   // sharded runs compute a window that shrinks by the stencil radius `halo` with every stage, so one halo
   // exchange of width halo * stages per step is enough (redundant work on 2 * halo * stages * (stages-1)/2 cells)
@@ -678,6 +681,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     a.halo = halo;
     return launch(h, w.sharded ? h->k_lattice_sharded : h->k_lattice, h->stream, grid, block, &a);
   };
+  if (h->lattice_stages == 6) return lattice_ck54_fixed_step(h, t, dt);
   if (h->lattice_stages == 4) {
     // runge_kutta4 = explicit_generic_rk<4,4>: a = {1/2}, {0,1/2}, {0,0,1}; b = {1/6,1/3,1/3,1/6}
     const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
@@ -826,6 +830,7 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
   lattice_window w = {(long long)N, (long long)N, 0, 0, 0, 0, 0, 0};
   CU_TRY(h->lat_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+  h->lat_work_primed = false;
   if ((rc = begin_timing(h))) return rc;
   size_t row = 0;
   auto observe = [&]() -> int {
@@ -998,6 +1003,29 @@ int tiled5_decide(odeintr_system_t h) {
 
 #include "lattice_adaptive.h"
 
+// Fixed-step Cash-Karp (method "rk54") on a large system: six combo launches, the result replaces the state.
+int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt) {
+  const size_t N = (size_t)h->N;
+  CU_TRY(h->lat_work.reserve(9 * N));
+  double* w = h->lat_work.p;
+  if (!h->lat_work_primed) {
+    // state-like vectors start as copies of x, derivative-like ones as zeros (entries no loop writes)
+    for (int j = 0; j < 3; ++j)
+      CU_TRY(cudaMemcpyAsync(w + (size_t)j * N, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemsetAsync(w + 3 * N, 0, 6 * N * sizeof(double), h->stream));
+    h->lat_work_primed = true;
+  }
+  lattice_ck54 ck;
+  ck.core.h = h;
+  ck.core.xtA = w; ck.core.xtB = w + N;
+  ck.k1 = w + 3 * N;
+  ck.core.k2 = w + 4 * N; ck.core.k3 = w + 5 * N; ck.core.k4 = w + 6 * N; ck.core.k5 = w + 7 * N; ck.core.k6 = w + 8 * N;
+  ck.stages(h->lat_x, t, dt, w + 2 * N, false);
+  if (ck.core.rc) return ck.core.rc;
+  CU_TRY(cudaMemcpyAsync(h->lat_x, w + 2 * N, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return ODEINTR_OK;
+}
+
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
@@ -1063,6 +1091,23 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
                   : odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, nobs);
     cnt = st.ctl.cnt;
     if (st.ctl.core.rc) return st.ctl.core.rc;
+  } else if (h->lattice_method == 3) {
+    lattice_ck54_controlled st;
+    st.core = core;
+    st.cnt.budget = h->max_tries;
+    st.k1 = deriv_like[5]; st.xnew = state_like[2];
+    double dtc = dt, tc = t0;
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, obs)
+                  : odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, obs)
+                  : odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, obs)
+                  : odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, nobs);
+    cnt = st.cnt;
+    if (st.core.rc) return st.core.rc;
   } else {
     lattice_dopri5_controlled st;
     st.core = core;
@@ -1257,8 +1302,9 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->name = name ? name : "sys";
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
   h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
-  h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : 4;
+  h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : ((flags & ODEINTR_FLAG_LATTICE_CK54) ? 6 : 4);
   h->lattice_method = (flags & ODEINTR_FLAG_LATTICE_ADAPTIVE) ? ((flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 2 : 1) : 0;
+  if ((flags & ODEINTR_FLAG_LATTICE_CK54) && h->lattice_method) h->lattice_method = 3;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }

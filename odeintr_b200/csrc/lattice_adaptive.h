@@ -220,6 +220,99 @@ inline double lat_increase_step(double dt, double error, int stepper_order) {
   return dt;
 }
 
+// runge_kutta_cash_karp54 over device vectors: the six stages as combo launches, in the operation order of the
+// per-trajectory stepper (kernels/steppers_plain.cuh rk54_stepper, adaptive_steppers.cuh rk54_controlled)
+struct lattice_ck54 {
+  lattice_dopri5 core;  // combo() and the work vectors k2..k6, xtA, xtB
+  double* k1 = nullptr;
+  // x -> xnew (5th-order solution); with_error: returns default_error_checker's max norm of the embedded estimate
+  double stages(const double* x, double t, double dt, double* xnew, bool with_error) {
+    const double a21 = 1.0 / 5.0;
+    const double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+    const double a41 = 3.0 / 10.0, a42 = -9.0 / 10.0, a43 = 6.0 / 5.0;
+    const double a51 = -11.0 / 54.0, a52 = 5.0 / 2.0, a53 = -70.0 / 27.0, a54 = 35.0 / 27.0;
+    const double a61 = 1631.0 / 55296.0, a62 = 175.0 / 512.0, a63 = 575.0 / 13824.0,
+                 a64 = 44275.0 / 110592.0, a65 = 253.0 / 4096.0;
+    const double b1 = 37.0 / 378.0, b3 = 250.0 / 621.0, b4 = 125.0 / 594.0, b6 = 512.0 / 1771.0;
+    const double db1 = b1 - 2825.0 / 27648.0, db3 = b3 - 18575.0 / 48384.0, db4 = b4 - 13525.0 / 55296.0,
+                 db5 = -277.0 / 14336.0, db6 = b6 - 1.0 / 4.0;
+    const double c2 = 1.0 / 5.0, c3 = 3.0 / 10.0, c4 = 3.0 / 5.0, c5 = 1.0, c6 = 7.0 / 8.0;
+    double *k2 = core.k2, *k3 = core.k3, *k4 = core.k4, *k5 = core.k5, *k6 = core.k6, *xtA = core.xtA, *xtB = core.xtB;
+    core.rhs(x, k1, t);
+    {
+      const double* v[] = {k1};
+      const double c[] = {a21 * dt};
+      core.combo(nullptr, x, 1, v, c, 0.0, xtA, nullptr, t);
+    }
+    {  // k2; x + a31 k1 + a32 k2
+      const double* v[] = {k1};
+      const double c[] = {a31 * dt};
+      core.combo(xtA, x, 1, v, c, a32 * dt, xtB, k2, t + c2 * dt);
+    }
+    {  // k3
+      const double* v[] = {k1, k2};
+      const double c[] = {a41 * dt, a42 * dt};
+      core.combo(xtB, x, 2, v, c, a43 * dt, xtA, k3, t + c3 * dt);
+    }
+    {  // k4
+      const double* v[] = {k1, k2, k3};
+      const double c[] = {a51 * dt, a52 * dt, a53 * dt};
+      core.combo(xtA, x, 3, v, c, a54 * dt, xtB, k4, t + c4 * dt);
+    }
+    {  // k5
+      const double* v[] = {k1, k2, k3, k4};
+      const double c[] = {a61 * dt, a62 * dt, a63 * dt, a64 * dt};
+      core.combo(xtB, x, 4, v, c, a65 * dt, xtA, k5, t + c5 * dt);
+    }
+    {  // k6; xnew = x + b1 k1 + b3 k3 + b4 k4 + b6 k6
+      const double* v[] = {k1, k3, k4};
+      const double c[] = {b1 * dt, b3 * dt, b4 * dt};
+      core.combo(xtA, x, 3, v, c, b6 * dt, xnew, k6, t + c6 * dt);
+    }
+    if (!with_error) return 0.0;
+    cudaMemsetAsync(core.h->lat_err.p, 0, sizeof(unsigned long long), core.h->stream);
+    {  // xerr = db1 k1 + db3 k3 + db4 k4 + db5 k5 + db6 k6 and its norm against (x, k1)
+      const double* v[] = {k1, k3, k4, k5, k6};
+      const double c[] = {db1 * dt, db3 * dt, db4 * dt, db5 * dt, db6 * dt};
+      core.combo(nullptr, nullptr, 5, v, c, 0.0, nullptr, nullptr, t, x, k1, 1.0 * std::fabs(dt));
+    }
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(&bits, core.h->lat_err.p, sizeof(bits), cudaMemcpyDeviceToHost, core.h->stream);
+    cudaStreamSynchronize(core.h->stream);
+    double err;
+    std::memcpy(&err, &bits, sizeof(err));
+    return err;
+  }
+};
+
+// controlled_runge_kutta< runge_kutta_cash_karp54 > over device vectors (method "rk54_a"); not FSAL: f(x) is
+// evaluated at the start of every attempt
+struct lattice_ck54_controlled {
+  static constexpr bool is_dense = false;
+  lattice_dopri5 core;
+  double *k1 = nullptr, *xnew = nullptr;
+  lat_counters cnt;
+  lat_counters& counters() { return cnt; }
+  void restart() {}
+  bool try_step(lat_sys&, lat_state& x, double& t, double& dt) {
+    lattice_ck54 ck;
+    ck.core = core;
+    ck.k1 = k1;
+    const double err = ck.stages(x.p, t, dt, xnew, true);
+    if (ck.core.rc && !core.rc) core.rc = ck.core.rc;
+    if (err > 1.0) {
+      dt = lat_decrease_step(dt, err, 4);
+      cnt.rejected++;
+      return false;
+    }
+    t += dt;
+    dt = lat_increase_step(dt, err, 5);
+    cnt.accepted++;
+    cudaMemcpyAsync(x.p, xnew, (size_t)core.h->N * sizeof(double), cudaMemcpyDeviceToDevice, core.h->stream);
+    return true;
+  }
+};
+
 // controlled_runge_kutta< runge_kutta_dopri5 > over device vectors (method "rk5_a")
 struct lattice_dopri5_controlled {
   static constexpr bool is_dense = false;

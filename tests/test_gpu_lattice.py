@@ -252,6 +252,30 @@ def test_tiled_dopri5_attempt_bit_exact(case, method, monkeypatch):
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
 
 
+@pytest.mark.parametrize("method", ["rk54", "rk54_a"])
+def test_large_system_cash_karp(method):
+    # Cash-Karp 5(4) on a large system: six odeintr_lattice_combo launches per step / attempt, controller on the host
+    n = 3001
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("ck", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=n)
+    x0 = np.random.default_rng(52).uniform(0, 1, n)
+    df = env["ck"](x0, 3.0, 0.25)
+    ref = ora.integrate_const(x0, 0, 3.0, 0.25)
+    assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    if method == "rk54_a":
+        st = code.system.stats()
+        assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
+    at = np.array([0.5, 1.0, 2.2])
+    df = env["ck_at"](x0, at, 0.1)
+    adv = ora.integrate_const(x0, 0.0, at[0], 0.1, record=False)
+    ref = ora.integrate_times(adv["x"], at, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["ck_no_record"](x0, 1.05, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.05, 0.1)["x"]))
+
+
 def test_2d_lattice_strip_traversal_bit_exact():
     # M a multiple of the block width: the stage kernel walks the lattice in column strips (L1 reuse of the rows
     # above / below); the visiting order must not change a single bit

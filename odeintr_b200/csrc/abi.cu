@@ -223,7 +223,7 @@ struct odeintr_system_s {
   long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_info)
   long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
-  int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a
+  int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a, 4 = rk78_a
   dev_buf<double> lat_work;
   bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 path hold copies of x / zeros
   dev_buf<unsigned long long> lat_err;
@@ -572,6 +572,7 @@ struct lattice_window {      // which cells a launch computes and how local buff
 };
 
 int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt);  // after lattice_adaptive.h
+int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt);
 
 int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
   // sharded runs compute a window that shrinks by the stencil radius `halo` with every stage, so one halo
@@ -682,6 +683,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     return launch(h, w.sharded ? h->k_lattice_sharded : h->k_lattice, h->stream, grid, block, &a);
   };
   if (h->lattice_stages == 6) return lattice_ck54_fixed_step(h, t, dt);
+  if (h->lattice_stages == 13) return lattice_rkf78_fixed_step(h, t, dt);
   if (h->lattice_stages == 4) {
     // runge_kutta4 = explicit_generic_rk<4,4>: a = {1/2}, {0,1/2}, {0,0,1}; b = {1/6,1/3,1/3,1/6}
     const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
@@ -1026,6 +1028,27 @@ int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt) {
   return ODEINTR_OK;
 }
 
+// Fixed-step Fehlberg 7(8) (method "rk78") on a large system: thirteen combo launches, the result replaces the state.
+int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt) {
+  const size_t N = (size_t)h->N;
+  CU_TRY(h->lat_work.reserve(16 * N));
+  double* w = h->lat_work.p;
+  if (!h->lat_work_primed) {
+    for (int j = 0; j < 3; ++j)
+      CU_TRY(cudaMemcpyAsync(w + (size_t)j * N, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemsetAsync(w + 3 * N, 0, 13 * N * sizeof(double), h->stream));
+    h->lat_work_primed = true;
+  }
+  lattice_rkf78 rk;
+  rk.core.h = h;
+  rk.xt[0] = w; rk.xt[1] = w + N;
+  for (int j = 0; j < 13; ++j) rk.k[j] = w + (size_t)(3 + j) * N;
+  rk.stages(h->lat_x, t, dt, w + 2 * N, false);
+  if (rk.core.rc) return rk.core.rc;
+  CU_TRY(cudaMemcpyAsync(h->lat_x, w + 2 * N, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return ODEINTR_OK;
+}
+
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
@@ -1033,7 +1056,7 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   if (h->m != 1) return fail(ODEINTR_E_STATE, "Invalid initial state");
   if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
   const size_t N = (size_t)h->N;
-  CU_TRY(h->lat_work.reserve(13 * N));
+  CU_TRY(h->lat_work.reserve((h->lattice_method == 4 ? 18 : 13) * N));
   CU_TRY(h->lat_err.reserve(2));  // max-norm error bits, reach flag
   {
     const int rc5 = tiled5_decide(h);
@@ -1091,6 +1114,27 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
                   : odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, nobs);
     cnt = st.ctl.cnt;
     if (st.ctl.core.rc) return st.ctl.core.rc;
+  } else if (h->lattice_method == 4) {
+    lattice_rkf78_controlled st;
+    st.rk.core = core;
+    st.cnt.budget = h->max_tries;
+    st.rk.xt[0] = state_like[0]; st.rk.xt[1] = state_like[1];
+    st.xnew = state_like[2];
+    for (int j = 0; j < 8; ++j) st.rk.k[j] = deriv_like[j];
+    CU_TRY(cudaMemsetAsync(w + 13 * N, 0, 5 * N * sizeof(double), h->stream));
+    for (int j = 8; j < 13; ++j) st.rk.k[j] = w + (size_t)(5 + j) * N;
+    double dtc = dt, tc = t0;
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, obs)
+                  : odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, obs)
+                  : odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, obs)
+                  : odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, nobs);
+    cnt = st.cnt;
+    if (st.rk.core.rc) return st.rk.core.rc;
   } else if (h->lattice_method == 3) {
     lattice_ck54_controlled st;
     st.core = core;
@@ -1302,9 +1346,11 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->name = name ? name : "sys";
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
   h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
-  h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : ((flags & ODEINTR_FLAG_LATTICE_CK54) ? 6 : 4);
+  h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : ((flags & ODEINTR_FLAG_LATTICE_CK54) ? 6 :
+                      ((flags & ODEINTR_FLAG_LATTICE_RKF78) ? 13 : 4));
   h->lattice_method = (flags & ODEINTR_FLAG_LATTICE_ADAPTIVE) ? ((flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 2 : 1) : 0;
   if ((flags & ODEINTR_FLAG_LATTICE_CK54) && h->lattice_method) h->lattice_method = 3;
+  if ((flags & ODEINTR_FLAG_LATTICE_RKF78) && h->lattice_method) h->lattice_method = 4;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }

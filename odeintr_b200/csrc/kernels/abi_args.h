@@ -112,8 +112,8 @@ struct odeintr_lattice_args {
 struct odeintr_lattice_combo_args {
   const double* xs;
   const double* base;
-  const double* in[7];
-  double c[7];
+  const double* in[12];
+  double c[12];
   int nin;
   double ck;
   double* out;

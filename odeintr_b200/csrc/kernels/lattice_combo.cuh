@@ -45,7 +45,7 @@ odeintr_lattice_combo(const odeintr_lattice_combo_args a) {
         else v = 0.0;
         for (; j < a.nin; ++j) v = v + a.c[j] * a.in[j][idx];
         if (a.xs) {
-          v = v + a.ck * k[f];
+          if (a.ck != 0.0) v = v + a.ck * k[f];  // a zero weight is a skipped tableau entry, not a term
           if (a.k_out) a.k_out[idx] = k[f];
         }
         if (a.out) a.out[idx] = v;

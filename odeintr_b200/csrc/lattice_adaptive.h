@@ -313,6 +313,96 @@ struct lattice_ck54_controlled {
   }
 };
 
+// runge_kutta_fehlberg78 over device vectors, tableau driven like kernels/rk78.cuh: zero entries are skipped, what
+// remains is Boost's left-to-right scale_sum with coefficient * dt formed first.  Launch s computes k_s = f(xt_s) and
+// forms the next stage state from the stored k's and (when its weight is non-zero) the fresh one.
+struct lattice_rkf78 {
+  lattice_dopri5 core;  // combo()
+  double* k[13] = {nullptr};
+  double* xt[2] = {nullptr, nullptr};
+  double stages(const double* x, double t, double dt, double* xnew, bool with_error) {
+    static const double a[13][12] = {
+        {0},
+        {2.0 / 27.0},
+        {1.0 / 36.0, 1.0 / 12.0},
+        {1.0 / 24.0, 0.0, 1.0 / 8.0},
+        {5.0 / 12.0, 0.0, -25.0 / 16.0, 25.0 / 16.0},
+        {1.0 / 20.0, 0.0, 0.0, 1.0 / 4.0, 1.0 / 5.0},
+        {-25.0 / 108.0, 0.0, 0.0, 125.0 / 108.0, -65.0 / 27.0, 125.0 / 54.0},
+        {31.0 / 300.0, 0.0, 0.0, 0.0, 61.0 / 225.0, -2.0 / 9.0, 13.0 / 900.0},
+        {2.0, 0.0, 0.0, -53.0 / 6.0, 704.0 / 45.0, -107.0 / 9.0, 67.0 / 90.0, 3.0},
+        {-91.0 / 108.0, 0.0, 0.0, 23.0 / 108.0, -976.0 / 135.0, 311.0 / 54.0, -19.0 / 60.0, 17.0 / 6.0, -1.0 / 12.0},
+        {2383.0 / 4100.0, 0.0, 0.0, -341.0 / 164.0, 4496.0 / 1025.0, -301.0 / 82.0, 2133.0 / 4100.0, 45.0 / 82.0,
+         45.0 / 164.0, 18.0 / 41.0},
+        {3.0 / 205.0, 0.0, 0.0, 0.0, 0.0, -6.0 / 41.0, -3.0 / 205.0, -3.0 / 41.0, 3.0 / 41.0, 6.0 / 41.0, 0.0},
+        {-1777.0 / 4100.0, 0.0, 0.0, -341.0 / 164.0, 4496.0 / 1025.0, -289.0 / 82.0, 2193.0 / 4100.0, 51.0 / 82.0,
+         33.0 / 164.0, 12.0 / 41.0, 0.0, 1.0}};
+    static const double c[13] = {0.0, 2.0 / 27.0, 1.0 / 9.0, 1.0 / 6.0, 5.0 / 12.0, 1.0 / 2.0, 5.0 / 6.0,
+                                 1.0 / 6.0, 2.0 / 3.0, 1.0 / 3.0, 1.0, 0.0, 1.0};
+    static const double b[13] = {0.0, 0.0, 0.0, 0.0, 0.0, 34.0 / 105.0, 9.0 / 35.0, 9.0 / 35.0, 9.0 / 280.0,
+                                 9.0 / 280.0, 0.0, 41.0 / 840.0, 41.0 / 840.0};
+    static const double db[13] = {0.0 - 41.0 / 840.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                                  0.0 - 41.0 / 840.0, 41.0 / 840.0, 41.0 / 840.0};
+    // weights of the state formed after k_s is known: row s + 1 of a, or b after the last stage
+    auto next_state = [&](int s, const double* xs, double* out) {
+      const double* w = s + 1 < 13 ? a[s + 1] : b;
+      const double* v[12];
+      double cc[12];
+      int n = 0;
+      for (int j = 0; j < s; ++j)
+        if (w[j] != 0.0) { v[n] = k[j]; cc[n] = w[j] * dt; ++n; }
+      const double ck = w[s] != 0.0 ? w[s] * dt : 0.0;
+      core.combo(xs, x, n, v, cc, ck, out, k[s], t + c[s] * dt);
+    };
+    core.rhs(x, k[0], t);
+    {  // xt_1 = x + a[1][0] * dt * k_0
+      const double* v[] = {k[0]};
+      const double cc[] = {a[1][0] * dt};
+      core.combo(nullptr, x, 1, v, cc, 0.0, xt[1], nullptr, t);
+    }
+    for (int s = 1; s < 13; ++s) next_state(s, xt[s & 1], s + 1 < 13 ? xt[(s + 1) & 1] : xnew);
+    if (!with_error) return 0.0;
+    cudaMemsetAsync(core.h->lat_err.p, 0, sizeof(unsigned long long), core.h->stream);
+    {
+      const double* v[12];
+      double cc[12];
+      int n = 0;
+      for (int j = 0; j < 13; ++j)
+        if (db[j] != 0.0) { v[n] = k[j]; cc[n] = db[j] * dt; ++n; }
+      core.combo(nullptr, nullptr, n, v, cc, 0.0, nullptr, nullptr, t, x, k[0], 1.0 * std::fabs(dt));
+    }
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(&bits, core.h->lat_err.p, sizeof(bits), cudaMemcpyDeviceToHost, core.h->stream);
+    cudaStreamSynchronize(core.h->stream);
+    double err;
+    std::memcpy(&err, &bits, sizeof(err));
+    return err;
+  }
+};
+
+// controlled_runge_kutta< runge_kutta_fehlberg78 > (method "rk78_a"): error order 7, stepper order 8
+struct lattice_rkf78_controlled {
+  static constexpr bool is_dense = false;
+  lattice_rkf78 rk;
+  double* xnew = nullptr;
+  lat_counters cnt;
+  lat_counters& counters() { return cnt; }
+  void restart() {}
+  bool try_step(lat_sys&, lat_state& x, double& t, double& dt) {
+    const double err = rk.stages(x.p, t, dt, xnew, true);
+    if (err > 1.0) {
+      dt = lat_decrease_step(dt, err, 7);
+      cnt.rejected++;
+      return false;
+    }
+    t += dt;
+    dt = lat_increase_step(dt, err, 8);
+    cnt.accepted++;
+    cudaMemcpyAsync(x.p, xnew, (size_t)rk.core.h->N * sizeof(double), cudaMemcpyDeviceToDevice, rk.core.h->stream);
+    return true;
+  }
+};
+
 // controlled_runge_kutta< runge_kutta_dopri5 > over device vectors (method "rk5_a")
 struct lattice_dopri5_controlled {
   static constexpr bool is_dense = false;

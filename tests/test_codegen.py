@@ -144,7 +144,7 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "rk5_i", sys_dim=1 << 20).code)
     assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2"}
-    for method in ("euler", "rk54", "rk54_a"):
+    for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged
     for src in (BISTABLE_2D, BISTABLE_DOC):
@@ -169,4 +169,4 @@ def test_cell_loop_parser():
     g = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i
     assert g.stepper.method == "rk5_i" and g.stepper.mode == "dense" and _cubin(g.code) > 1000
     with pytest.raises(OdeintrError, match="not yet provided for large systems"):
-        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method="rk78_a")
+        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method="bs")

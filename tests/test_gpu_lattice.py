@@ -252,9 +252,10 @@ def test_tiled_dopri5_attempt_bit_exact(case, method, monkeypatch):
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
 
 
-@pytest.mark.parametrize("method", ["rk54", "rk54_a"])
-def test_large_system_cash_karp(method):
-    # Cash-Karp 5(4) on a large system: six odeintr_lattice_combo launches per step / attempt, controller on the host
+@pytest.mark.parametrize("method", ["rk54", "rk54_a", "rk78", "rk78_a"])
+def test_large_system_cash_karp_and_fehlberg(method):
+    # Cash-Karp 5(4) / Fehlberg 7(8) on a large system: six / thirteen odeintr_lattice_combo launches per step or
+    # attempt, tableau-driven on the host (zero entries skipped, Boost's left-to-right sums), controller on the host
     n = 3001
     env = {}
     code = odeintr_b200.compile_sys_openmp("ck", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
@@ -264,7 +265,7 @@ def test_large_system_cash_karp(method):
     ref = ora.integrate_const(x0, 0, 3.0, 0.25)
     assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
-    if method == "rk54_a":
+    if method.endswith("_a"):
         st = code.system.stats()
         assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
     at = np.array([0.5, 1.0, 2.2])

@@ -225,7 +225,8 @@ struct odeintr_system_s {
   dev_buf<int> lat_flag;
   int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a, 4 = rk78_a
   dev_buf<double> lat_work;
-  bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 path hold copies of x / zeros
+  bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 / rk78 / rk5 paths hold copies of x / zeros
+  int lat_rk5_parity = 0;        // which of the two derivative vectors holds k1 of the next rk5 step
   dev_buf<unsigned long long> lat_err;
   int block_plain = 128, block_adaptive = 128;
   cudaStream_t stream = nullptr;
@@ -573,6 +574,7 @@ struct lattice_window {      // which cells a launch computes and how local buff
 
 int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt);  // after lattice_adaptive.h
 int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt);
+int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt);
 
 int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
   // sharded runs compute a window that shrinks by the stencil radius `halo` with every stage, so one halo
@@ -684,6 +686,7 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   };
   if (h->lattice_stages == 6) return lattice_ck54_fixed_step(h, t, dt);
   if (h->lattice_stages == 13) return lattice_rkf78_fixed_step(h, t, dt);
+  if (h->lattice_stages == 7) return lattice_rk5_fixed_step(h, t, dt);
   if (h->lattice_stages == 4) {
     // runge_kutta4 = explicit_generic_rk<4,4>: a = {1/2}, {0,1/2}, {0,0,1}; b = {1/6,1/3,1/3,1/6}
     const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
@@ -1049,6 +1052,37 @@ int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt) {
   return ODEINTR_OK;
 }
 
+// dopri5 as a plain fixed-step stepper (method "rk5") on a large system.  explicit_error_stepper_fsal_base::do_step
+// evaluates f(x) on the first call only and hands k7 of every step to the next one as k1; a step is one launch of
+// the temporally blocked attempt kernel (or the seven combo launches), the error estimate is ignored.
+int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt) {
+  const size_t N = (size_t)h->N;
+  int rc;
+  CU_TRY(h->lat_work.reserve(11 * N));
+  CU_TRY(h->lat_err.reserve(2));
+  if ((rc = tiled5_decide(h))) return rc;
+  double* w = h->lat_work.p;
+  lattice_dopri5 core;
+  core.h = h;
+  core.xtA = w; core.xtB = w + N;
+  double* xnew = w + 2 * N;
+  core.k2 = w + 3 * N; core.k3 = w + 4 * N; core.k4 = w + 5 * N; core.k5 = w + 6 * N; core.k6 = w + 7 * N;
+  double* k1 = w + (size_t)(8 + (h->lat_rk5_parity & 1)) * N;
+  double* k7 = w + (size_t)(8 + ((h->lat_rk5_parity + 1) & 1)) * N;
+  if (!h->lat_work_primed) {
+    for (int j = 0; j < 3; ++j)
+      CU_TRY(cudaMemcpyAsync(w + (size_t)j * N, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemsetAsync(w + 3 * N, 0, 8 * N * sizeof(double), h->stream));
+    h->lat_work_primed = true;
+    core.rhs(h->lat_x, k1, t);  // first call of this integrate_* invocation
+  }
+  core.step_with_error(h->lat_x, k1, t, xnew, k7, dt);
+  if (core.rc) return core.rc;
+  CU_TRY(cudaMemcpyAsync(h->lat_x, xnew, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->lat_rk5_parity ^= 1;
+  return ODEINTR_OK;
+}
+
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
@@ -1347,7 +1381,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->N = sys_dim; h->P = n_pars; h->atol = atol; h->rtol = rtol; h->flags = flags;
   h->dense = (flags & ODEINTR_FLAG_DENSE_OUTPUT) != 0;
   h->lattice_stages = (flags & ODEINTR_FLAG_LATTICE_EULER) ? 1 : ((flags & ODEINTR_FLAG_LATTICE_CK54) ? 6 :
-                      ((flags & ODEINTR_FLAG_LATTICE_RKF78) ? 13 : 4));
+                      ((flags & ODEINTR_FLAG_LATTICE_RKF78) ? 13 : ((flags & ODEINTR_FLAG_LATTICE_RK5) ? 7 : 4)));
   h->lattice_method = (flags & ODEINTR_FLAG_LATTICE_ADAPTIVE) ? ((flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 2 : 1) : 0;
   if ((flags & ODEINTR_FLAG_LATTICE_CK54) && h->lattice_method) h->lattice_method = 3;
   if ((flags & ODEINTR_FLAG_LATTICE_RKF78) && h->lattice_method) h->lattice_method = 4;

@@ -88,6 +88,8 @@ class CompiledSystem:
             flags |= _abi.FLAG_DENSE_OUTPUT
         if gen.family == "lattice" and gen.stepper.base == "euler":
             flags |= _abi.FLAG_LATTICE_EULER
+        if gen.family == "lattice" and gen.stepper.method == "rk5":
+            flags |= _abi.FLAG_LATTICE_RK5
         if gen.family == "lattice" and gen.stepper.base == "rk54":
             flags |= _abi.FLAG_LATTICE_CK54
         if gen.family == "lattice" and gen.stepper.base == "rk78":

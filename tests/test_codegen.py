@@ -142,8 +142,9 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
     k = _kernels(codegen.generate_sys_openmp("c", CHAIN, CHAIN_PARS, True, "rk4", sys_dim=2 * 300, globals=CHAIN_GLOBALS).code)
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
-    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "rk5_i", sys_dim=1 << 20).code)
-    assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2"}
+    for method in ("rk5_i", "rk5_a", "rk5"):
+        k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
+        assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2"}
     for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged

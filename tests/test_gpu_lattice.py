@@ -252,10 +252,11 @@ def test_tiled_dopri5_attempt_bit_exact(case, method, monkeypatch):
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
 
 
-@pytest.mark.parametrize("method", ["rk54", "rk54_a", "rk78", "rk78_a"])
+@pytest.mark.parametrize("method", ["rk54", "rk54_a", "rk78", "rk78_a", "rk5"])
 def test_large_system_cash_karp_and_fehlberg(method):
     # Cash-Karp 5(4) / Fehlberg 7(8) on a large system: six / thirteen odeintr_lattice_combo launches per step or
-    # attempt, tableau-driven on the host (zero entries skipped, Boost's left-to-right sums), controller on the host
+    # attempt, tableau-driven on the host (zero entries skipped, Boost's left-to-right sums), controller on the host;
+    # rk5 = dopri5 as a plain fixed-step stepper: one temporally blocked attempt per step, k7 handed on as k1
     n = 3001
     env = {}
     code = odeintr_b200.compile_sys_openmp("ck", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)

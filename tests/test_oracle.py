@@ -158,3 +158,69 @@ def test_bulirsch_stoer_dense_output_is_exact_for_polynomial_solutions():
     o = bo.build(VDP, "mu", False, "bsd")
     r = o.integrate_const([1e-4, 1e-4], 0, 100, 0.01, pars=[1.0])
     assert r["rows"] == 10001
+
+
+def test_dopri5_and_rk4_single_steps_against_independent_implementations():
+    # an implementation the restatement does not share a line with: SciPy's Dormand-Prince tableau (RK45.A/B/C) driven
+    # by scipy.integrate._ivp.rk.rk_step, and the textbook RK4 formula in numpy.  Different summation orders, so the
+    # comparison is to a few ulps, over several steps of a nonlinear system
+    from scipy.integrate._ivp import rk as sp_rk
+
+    def f(t, y):
+        return np.array([y[1], 1.5 * (1 - y[0] * y[0]) * y[1] - y[0] + 0.1 * t])
+
+    src = "dxdt[0] = x[1]; dxdt[1] = 1.5 * (1 - x[0] * x[0]) * x[1] - x[0] + 0.1 * t;"
+    h = 0.05
+    o5 = bo.build(src, method="rk5")
+    o4 = bo.build(src, method="rk4")
+    y5 = y4 = np.array([1.2, -0.4])
+    t = 0.0
+    for step in range(8):
+        K = np.empty((7, 2))
+        y5_new, _ = sp_rk.rk_step(f, t, y5, f(t, y5), h, sp_rk.RK45.A, sp_rk.RK45.B, sp_rk.RK45.C, K)
+        k1 = f(t, y4); k2 = f(t + h / 2, y4 + h / 2 * k1); k3 = f(t + h / 2, y4 + h / 2 * k2); k4 = f(t + h, y4 + h * k3)
+        y4_new = y4 + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        r5 = o5.integrate_const(y5, t, t + 1.5 * h, h, record=False)  # exactly one step of h
+        r4 = o4.integrate_const(y4, t, t + 1.5 * h, h, record=False)
+        assert np.max(np.abs(r5["x"] - y5_new)) < 4e-15, (step, r5["x"], y5_new)
+        assert np.max(np.abs(r4["x"] - y4_new)) < 4e-15, (step, r4["x"], y4_new)
+        y5, y4, t = r5["x"], r4["x"], t + h
+
+
+def test_dopri5_error_estimate_and_controller_against_scipy_tableau():
+    # integrate_adaptive with rk5_a: the accepted time grid depends on the embedded error estimate and on Boost's
+    # default_error_checker / default_step_adjuster.  Rebuilt here from SciPy's RK45 tableau and error weights (RK45.E)
+    # plus the controller formulas of SURVEY.md A.2; the restated oracle must walk the same grid
+    from scipy.integrate._ivp import rk as sp_rk
+
+    def f(t, y):
+        return np.array([y[1], 2.0 * (1 - y[0] * y[0]) * y[1] - y[0]])
+
+    src = "dxdt[0] = x[1]; dxdt[1] = 2.0 * (1 - x[0] * x[0]) * x[1] - x[0];"
+    atol = rtol = 1e-6
+    o = bo.build(src, method="rk5_a", atol=atol, rtol=rtol)
+    t1, dt = 6.0, 0.1
+    ref = o.integrate_adaptive([2.0, 0.0], 0.0, t1, dt, record=True)
+    t, y, grid, rejected = 0.0, np.array([2.0, 0.0]), [0.0], 0
+    while t < t1 - 1e-15 * max(abs(t), abs(t1)):
+        if t + dt > t1:
+            dt = t1 - t
+        while True:
+            K = np.empty((7, 2))
+            d = f(t, y)
+            y_new, _ = sp_rk.rk_step(f, t, y, d, dt, sp_rk.RK45.A, sp_rk.RK45.B, sp_rk.RK45.C, K)
+            xerr = dt * (K.T @ sp_rk.RK45.E)
+            err = np.max(np.abs(xerr) / (atol + rtol * (np.abs(y) + abs(dt) * np.abs(d))))
+            if err > 1.0:
+                dt *= max(0.9 * err ** (-1.0 / 3.0), 0.2)
+                rejected += 1
+                continue
+            t += dt
+            if err < 0.5:
+                dt *= 0.9 * max(5.0 ** -5, err) ** (-1.0 / 5.0)
+            y = y_new
+            break
+        grid.append(t)
+    assert len(grid) == ref["rows"] and rejected == ref["rejected"], (len(grid), ref["rows"], rejected, ref["rejected"])
+    assert np.max(np.abs(np.array(grid) - ref["t"])) < 1e-9
+    assert np.max(np.abs(y - ref["rec"][-1])) < 1e-9

@@ -791,6 +791,9 @@ int lattice_query_info(odeintr_system_t h) {
 
 // Measure the reach of the loop body (odeintr_lattice_probe) and switch the tiled kernels on when a tile can hold it.
 int tiled_autodetect(odeintr_system_t h) {
+  // the probe evaluates the snippet with the system's parameters: wait until they are in place (the integrate call
+  // that follows reports "Invalid parameter vector" if they never arrive)
+  if (h->P && !h->pars.p) return ODEINTR_OK;
   h->tiled_pending = false;
   h->tiled_on = h->tiled2d_on = false;
   if (!h->k_probe || !(h->k_tiled || h->k_tiled2d) || h->lattice_stages != 4 || h->lat_cells_ct <= 0 ||
@@ -887,6 +890,7 @@ int run_lattice_ensemble(odeintr_system_t h, const plain_schedule& sc) {
     return fail(ODEINTR_E_STATE, "ensembles of large systems are provided for fixed-step rk4 and at most 8192 / fields "
                                  "cells per field; run the trajectories one at a time");
   if (h->lat_cells_ct <= 0) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
+  if (h->P && !h->pars.p) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
   int rc;
   // stencil radius: declared, or measured by the probe (parameters of instance 0; index expressions that depend on
   // parameters or state are caught by the per-access check)
@@ -975,6 +979,7 @@ int tile5_cpt(int fields) {
 // the loop body (odeintr_lattice_probe) and check that a tile with 6 * halo margin cells per side fits.
 int tiled5_decide(odeintr_system_t h) {
   if (h->tiled5 >= 0) return ODEINTR_OK;
+  if (h->P && !h->pars.p) return ODEINTR_OK;  // no parameters yet: the probe would have nothing to read
   h->tiled5 = 0;
   if (!h->k_dopri5_tiled || !h->k_probe || h->lat_cells_ct <= 0 || h->lat_cells_ct >= (1LL << 31) ||
       std::getenv("ODEINTR_NO_TILED"))

@@ -74,6 +74,60 @@ def _worker(rank, world, port, n_total, steps, dt, x0, q):
     dist.destroy_process_group()
 
 
+def _worker_interval(rank, world, port, n_total, steps, dt, x0, interval, q):
+    """The scheme of odeintr_lattice_shard_run with the tiled kernels: ghost zone `interval` x 4 cells wide, one ring
+    exchange per `interval` steps; every step consumes 4 ghost cells per side and recomputes the rest."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ghost = 4 * interval
+    b, e = shard_range(n_total, rank, world)
+    slab = torch.zeros((1, (e - b) + 2 * ghost), dtype=torch.float64)
+    slab[0, ghost:ghost + (e - b)] = torch.from_numpy(x0[b:e])
+    for s in range(steps):
+        phase = s % interval
+        if phase == 0:
+            exchange_halos(slab, ghost, rank, world)
+        # valid cells before the step: owned +- (ghost - 4 * phase); the step leaves owned +- (ghost - 4 * (phase + 1))
+        lo = 4 * phase
+        window = slab[0, lo:slab.shape[1] - lo].numpy().copy()
+        slab[0, lo:slab.shape[1] - lo] = torch.from_numpy(_sharded_rk4_step(window, 4, dt))
+    q.put((rank, True, slab[0, ghost:ghost + (e - b)].numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("interval", [3, 8])
+def test_two_rank_exchange_every_k_steps_matches_oracle(interval):
+    # communication-avoiding variant: bit-identical to the oracle whatever the exchange interval (13 steps: the last
+    # round is incomplete)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import build_oracle as bo
+    from systems import BISTABLE_1D, BISTABLE_PARS
+
+    n_total, steps, dt = 211, 13, 0.1
+    x0 = np.random.default_rng(23).uniform(0, 1, n_total)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_interval, args=(r, 2, port, n_total, steps, dt, x0, interval, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = dict()
+    for _ in range(2):
+        rank, _, part = q.get(timeout=240)
+        parts[rank] = part
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.concatenate([parts[0], parts[1]])
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, "rk4", sys_dim=n_total)
+    rec = ora.integrate_const(x0, 0.0, steps * dt + dt / 2, dt)
+    assert rec["rows"] == steps + 1
+    assert np.array_equal(got.view(np.uint64), rec["rec"][-1].view(np.uint64))
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_wide_halo_rk4_matches_oracle():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

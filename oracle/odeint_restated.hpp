@@ -21,7 +21,9 @@
 // PARITY STATUS: "parity unpinned".  The reference's tests pin only row counts and first
 // rows (tests/testthat/test_odeintr.R:25-54) and real Boost output cannot be produced here.
 // The restatement is pinned instead against SURVEY.md Appendix B golden bit patterns
-// (tests/golden/lorenz_rk4_golden.json), analytic solutions and the 41-row / 4-row facts.
+// (tests/golden/lorenz_rk4_golden.json), analytic solutions, the 41-row / 4-row facts and, for dopri5, SciPy's
+// independent Dormand-Prince tableau and error weights (single steps to 4e-15; identical accepted / rejected step
+// grid under Boost's controller formulas) -- tests/test_oracle.py.
 #pragma once
 #include <algorithm>
 #include <array>

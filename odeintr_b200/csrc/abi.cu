@@ -165,11 +165,30 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   return o;
 }
 
+int nvrtc_to_cubin_once(const char* src, unsigned flags, bool staged_only, std::vector<char>& cubin, std::string& log);
+
+// Large-system translation units are first built with every kernel family; if the snippet does not compile with
+// the symbolic loop index the tiled kernels hand it (lattice_index.cuh), the unit is rebuilt with the
+// stage-per-launch kernels alone, where the loop variable is the plain integer the reference's code sees.
 int nvrtc_to_cubin(const char* src, unsigned flags, std::vector<char>& cubin, std::string& log) {
+  int rc = nvrtc_to_cubin_once(src, flags, false, cubin, log);
+  if (rc == ODEINTR_OK || !std::strstr(src, "ODEINTR_LATTICE_STAGES")) return rc;
+  const std::string first_error = odeintr_last_error();
+  std::string log2;
+  if (nvrtc_to_cubin_once(src, flags, true, cubin, log2) == ODEINTR_OK) {
+    log = "note: built with the stage-per-launch kernels only (the snippet does not compile with the symbolic loop "
+          "index of the tiled kernels)\n" + log2;
+    return ODEINTR_OK;
+  }
+  return fail(ODEINTR_E_COMPILE, first_error);  // the snippet itself is at fault: report the first diagnosis
+}
+
+int nvrtc_to_cubin_once(const char* src, unsigned flags, bool staged_only, std::vector<char>& cubin, std::string& log) {
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, src, "odeintr_system.cu", k_num_headers, k_header_srcs, k_header_names);
   if (r != NVRTC_SUCCESS) return fail(ODEINTR_E_COMPILE, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
   std::vector<std::string> opts = nvrtc_options(flags);
+  if (staged_only) opts.push_back("-DODEINTR_NO_SYMBOLIC=1");
   std::vector<const char*> copts;
   for (auto& s : opts) copts.push_back(s.c_str());
   r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());

@@ -16,7 +16,7 @@
 #pragma once
 #include "odeintr_b200/lattice_tiled.cuh"
 
-#if !defined(ODEINTR_LATTICE_2D) && ODEINTR_LATTICE_STAGES == 7
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 7
 
 #ifndef ODEINTR_TILE5_CPT
 #define ODEINTR_TILE5_CPT (ODEINTR_NFIELDS > 1 ? 2 : 4)

@@ -37,7 +37,7 @@
 #endif
 
 // registers: 3 doubles per owned state (x, running sum, stage state)
-#if !defined(ODEINTR_LATTICE_2D) && ODEINTR_LATTICE_STAGES == 4 && ODEINTR_ENS_CPT * ODEINTR_NFIELDS <= 16 && \
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4 && ODEINTR_ENS_CPT * ODEINTR_NFIELDS <= 16 && \
     ODEINTR_ENS_CELLS >= 3
 
 extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)

@@ -189,3 +189,26 @@ ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_coord>::type operator%
 template <class V> ODEINTR_DEV rel_index2 loop_index(const rel_index2& c) { return c; }
 
 }  // namespace odeintr_b200
+
+// std::min / std::max of a symbolic index and a plain integer (clamped boundaries such as x[std::max(i - 1, 0)]):
+// the function templates of <algorithm> need both arguments of one type, which held while the loop variable was an
+// int.  The result is an ordinary number; the access takes the views' absolute-index path.
+namespace std {
+#define ODEINTR_MIXED_MINMAX_(TYPE)                                                                              \
+  template <class I>                                                                                             \
+  ODEINTR_DEV typename odeintr_b200::enable_if_<odeintr_b200::is_integer<I>::value, long long>::type min(        \
+      const TYPE& a, const I b) { const long long v = a; return static_cast<long long>(b) < v ? static_cast<long long>(b) : v; } \
+  template <class I>                                                                                             \
+  ODEINTR_DEV typename odeintr_b200::enable_if_<odeintr_b200::is_integer<I>::value, long long>::type min(        \
+      const I b, const TYPE& a) { const long long v = a; return v < static_cast<long long>(b) ? v : static_cast<long long>(b); } \
+  template <class I>                                                                                             \
+  ODEINTR_DEV typename odeintr_b200::enable_if_<odeintr_b200::is_integer<I>::value, long long>::type max(        \
+      const TYPE& a, const I b) { const long long v = a; return v < static_cast<long long>(b) ? static_cast<long long>(b) : v; } \
+  template <class I>                                                                                             \
+  ODEINTR_DEV typename odeintr_b200::enable_if_<odeintr_b200::is_integer<I>::value, long long>::type max(        \
+      const I b, const TYPE& a) { const long long v = a; return static_cast<long long>(b) < v ? v : static_cast<long long>(b); }
+ODEINTR_MIXED_MINMAX_(odeintr_b200::rel_index)
+ODEINTR_MIXED_MINMAX_(odeintr_b200::rel_index2)
+ODEINTR_MIXED_MINMAX_(odeintr_b200::rel_coord)
+#undef ODEINTR_MIXED_MINMAX_
+}  // namespace std

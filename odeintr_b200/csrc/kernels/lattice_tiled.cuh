@@ -13,6 +13,9 @@
 // raises a flag (and is served from a clamped position), and the host then repeats the integration with the staged
 // kernels, so a snippet whose reach depends on the state or on time is still integrated correctly.
 //
+// ODEINTR_NO_SYMBOLIC (set by the host when the translation unit does not compile with the symbolic loop index, e.g.
+// a snippet that passes the loop variable to a template expecting an int) leaves only the stage-per-launch kernels.
+//
 // Two kernels share the work of one step:
 //   odeintr_lattice_rk4_tiled           general tiles: ragged last tile, tiles at the periodic seam, tiles that
 //                                       contain cells the user's loop does not write, slabs of a sharded run
@@ -60,7 +63,7 @@ struct lattice_tile_view {
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(n_total); }
 };
 
-#ifndef ODEINTR_LATTICE_2D  // M x M lattices have their own tiled kernel (lattice_tiled2d.cuh)
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC)  // M x M lattices: lattice_tiled2d.cuh
 
 ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   typedef odeintr::system_type_t<lattice_tile_view> Sys;
@@ -473,7 +476,7 @@ struct lattice_probe_view {
 
 }  // namespace odeintr_b200
 
-#ifndef ODEINTR_LATTICE_2D
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC)
 // out[0] = largest distance (in cells) between a cell and an entry its loop body reads
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_probe(const double* pars, const double t, int* out) {
@@ -522,7 +525,7 @@ extern "C" __global__ void odeintr_lattice_info(long long* out) {
 #endif
 }
 
-#if !defined(ODEINTR_LATTICE_2D) && ODEINTR_LATTICE_STAGES == 4
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
 extern "C" __global__ void __launch_bounds__(256)
 odeintr_lattice_rk4_tiled(const odeintr_lattice_tiled_args a) { odeintr_b200::lattice_rk4_tiled_body(a); }
 

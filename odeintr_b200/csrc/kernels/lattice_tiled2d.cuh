@@ -18,7 +18,7 @@
 #include "odeintr_b200/lattice_view.cuh"
 #include "odeintr_b200/lattice_index.cuh"
 
-#if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1
+#if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1 && !defined(ODEINTR_NO_SYMBOLIC)
 
 #ifndef ODEINTR_TILE2_ROWS
 #define ODEINTR_TILE2_ROWS 32

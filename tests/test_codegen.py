@@ -155,6 +155,28 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     assert k == staged
 
 
+def test_snippets_that_treat_the_loop_variable_as_an_int_still_build():
+    # the tiled kernels hand the snippet a symbolic loop index (lattice_index.cuh).  Clamped boundaries written with
+    # std::min / std::max keep compiling (mixed-type overloads); a snippet the symbolic index cannot serve at all (a
+    # user template that needs both arguments of one type) is rebuilt with the stage-per-launch kernels alone
+    clamp = "for (int i = 0; i < N; ++i) dxdt[i] = x[std::min(i + 1, (int)N - 1)] + x[std::max(i - 1, 0)] - 2.0 * x[i];"
+    k = _kernels(codegen.generate_sys_openmp("c", clamp, None, False, "rk4", sys_dim=5000).code)
+    assert "odeintr_lattice_rk4_tiled_tma" in k and "odeintr_lattice_probe" in k
+    k = _kernels(codegen.generate_sys_openmp("c", clamp, None, False, "rk5_i", sys_dim=5000).code)
+    assert "odeintr_lattice_dopri5_tiled_h1" in k
+    pick = "template <class T> __device__ T pick(T a, T b) { return a < b ? a : b; }"
+    odd = "for (int i = 0; i < N; ++i) dxdt[i] = x[pick(i + 1, (int)N - 1)] - x[i];"
+    for method in ("rk4", "rk5_i"):
+        k = _kernels(codegen.generate_sys_openmp("o", odd, None, False, method, sys_dim=5000, globals=pick).code)
+        assert k == {"odeintr_lattice_stage", "odeintr_lattice_stage_sharded", "odeintr_lattice_combo", "odeintr_lattice_info"}
+    # a snippet that is wrong either way reports the first diagnosis
+    lib = _abi.load()
+    size = C.c_size_t(0)
+    bad = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = undefined_name * x[i];", sys_dim=64)
+    assert lib.odeintr_compile_cubin(bad.code.encode(), 0, None, 0, C.byref(size)) != 0
+    assert "undefined_name" in _abi.last_error()
+
+
 def test_cell_loop_parser():
     from systems import BISTABLE_2D, CHAIN
     loops = codegen.parse_cell_loops(CHAIN)

@@ -512,6 +512,30 @@ def test_tiny_lattices(method):
         assert np.array_equal(bits(cols(df)), bits(ref["rec"])), (method, n)
 
 
+@pytest.mark.parametrize("method", ["rk4", "rk5_i"])
+@pytest.mark.parametrize("case", ["clamped_ends", "user_template"])
+def test_snippets_that_use_the_loop_variable_as_a_plain_int(case, method):
+    # clamped (zero-flux) ends through std::min / std::max keep the tiled kernels (mixed-type overloads, absolute-index
+    # path of the views); a snippet whose helper template cannot take the symbolic index is built with the
+    # stage-per-launch kernels only.  Same bits as the oracle either way.
+    n = 4500
+    if case == "clamped_ends":
+        src, glob = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[std::min(i + 1, (int)N - 1)] + x[std::max(i - 1, 0)] - 2.0 * x[i]) - 0.1 * x[i];", ""
+    else:
+        glob = "template <class T> T pick(T a, T b) { return a < b ? a : b; }"
+        src = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[pick(i + 1, (int)N - 1)] - x[i]) - 0.1 * x[i];"
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("s", src, {"D": 0.3}, True, method=method, sys_dim=n, globals=glob, env=env)
+    ora = bo.build(src, {"D": 0.3}, True, method, sys_dim=n, globals=glob)
+    x0 = np.random.default_rng(98).uniform(0, 1, n)
+    df = env["s"](x0, 1.5, 0.25)
+    ref = ora.integrate_const(x0, 0, 1.5, 0.25)
+    assert df.shape == (ref["rows"], n + 1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    if method == "rk4":
+        assert code.system.get_halo() == (1 if case == "clamped_ends" else -1)
+
+
 def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():
     # only interior tiles see the far read: cells next to the ends stay within reach
     src = "for (int i = 0; i < N; ++i) dxdt[i] = (i > 2000 && i < 2100 ? x[i + 3] : x[(i + 1) % N]) - x[i];"

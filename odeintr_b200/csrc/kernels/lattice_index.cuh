@@ -30,13 +30,23 @@ struct rel_index {
   int centre;     // global number of the cell being computed
   int cells;      // cells per field: the modulus of the periodic wrap
   bool rel;
+  bool wrapped = false;  // came out of `% cells`: as a NUMBER it is (centre + off) mod cells
 
-  ODEINTR_DEV long long value() const { return rel ? static_cast<long long>(centre) + off : off; }
+  ODEINTR_DEV long long value() const {
+    if (!rel) return off;
+    long long v = static_cast<long long>(centre) + off;
+    if (wrapped) {
+      v %= cells;
+      if (v < 0) v += cells;
+    }
+    return v;
+  }
   ODEINTR_DEV operator long long() const { return value(); }
   ODEINTR_DEV rel_index absolute(const long long v) const {
     rel_index r = *this;
     r.off = v;
     r.rel = false;
+    r.wrapped = false;
     return r;
   }
 };
@@ -45,16 +55,17 @@ struct rel_index {
 // reached through the conversion to long long
 template <class I>
 ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator+(rel_index a, const I b) {
+  if (a.rel && a.wrapped) a = a.absolute(a.value());  // arithmetic after the wrap: a plain number again
   a.off += static_cast<long long>(b);
   return a;
 }
 template <class I>
 ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator+(const I b, rel_index a) {
-  a.off += static_cast<long long>(b);
-  return a;
+  return a + b;
 }
 template <class I>
 ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator-(rel_index a, const I b) {
+  if (a.rel && a.wrapped) a = a.absolute(a.value());
   a.off -= static_cast<long long>(b);
   return a;
 }
@@ -63,12 +74,13 @@ ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator-
 template <class I>
 ODEINTR_DEV typename enable_if_<is_integer<I>::value, rel_index>::type operator%(const rel_index a, const I m) {
   const long long mm = static_cast<long long>(m);
-  if (a.rel && mm == static_cast<long long>(a.cells)) {
+  if (a.rel && !a.wrapped && mm == static_cast<long long>(a.cells)) {
     rel_index r = a;
     long long o = a.off % mm;
     if (o > mm / 2) o -= mm;
     else if (o < -(mm / 2)) o += mm;
     r.off = o;
+    r.wrapped = true;
     return r;
   }
   return a.absolute(a.value() % mm);

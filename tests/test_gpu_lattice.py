@@ -513,7 +513,7 @@ def test_tiny_lattices(method):
 
 
 @pytest.mark.parametrize("method", ["rk4", "rk5_i"])
-@pytest.mark.parametrize("case", ["clamped_ends", "user_template"])
+@pytest.mark.parametrize("case", ["clamped_ends", "user_template", "index_as_number"])
 def test_snippets_that_use_the_loop_variable_as_a_plain_int(case, method):
     # clamped (zero-flux) ends through std::min / std::max keep the tiled kernels (mixed-type overloads, absolute-index
     # path of the views); a snippet whose helper template cannot take the symbolic index is built with the
@@ -521,6 +521,10 @@ def test_snippets_that_use_the_loop_variable_as_a_plain_int(case, method):
     n = 4500
     if case == "clamped_ends":
         src, glob = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[std::min(i + 1, (int)N - 1)] + x[std::max(i - 1, 0)] - 2.0 * x[i]) - 0.1 * x[i];", ""
+    elif case == "index_as_number":
+        # the wrapped neighbour index also enters the arithmetic as a number, and is shifted after the wrap
+        src, glob = ("for (int i = 0; i < N; ++i) dxdt[i] = D * (x[(i + 1) % N] - x[i]) + 1e-4 * ((i + 3) % N) "
+                     "- 0.1 * x[((i + N - 1) % N + 1) % N] + (i > 100 ? 1e-3 : 0.0);"), ""
     else:
         glob = "template <class T> T pick(T a, T b) { return a < b ? a : b; }"
         src = "for (int i = 0; i < N; ++i) dxdt[i] = D * (x[pick(i + 1, (int)N - 1)] - x[i]) - 0.1 * x[i];"
@@ -533,7 +537,7 @@ def test_snippets_that_use_the_loop_variable_as_a_plain_int(case, method):
     assert df.shape == (ref["rows"], n + 1)
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
     if method == "rk4":
-        assert code.system.get_halo() == (1 if case == "clamped_ends" else -1)
+        assert code.system.get_halo() == (-1 if case == "user_template" else 1)
 
 
 def test_tiled_rk4_interior_kernel_flags_a_wide_stencil_too():

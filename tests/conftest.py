@@ -11,6 +11,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    # a fresh checkout has no built library (it is git-ignored): build it once instead of failing every test that
+    # loads the C-ABI.  nvcc cross-compiles sm_100a without a device.
+    lib = ROOT / "odeintr_b200" / "libodeintr_b200.so"
+    if not lib.exists():
+        import subprocess
+
+        subprocess.run(["make", "-C", str(ROOT / "odeintr_b200" / "csrc")], check=True, capture_output=True)
+
+
 def has_gpu() -> bool:
     try:
         import torch

@@ -47,3 +47,15 @@ def test_product_never_touches_the_oracle():
             text = p.read_text()
             assert "build_oracle" not in text and "odeint_restated" not in text, p
             assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), p
+
+
+def test_python_flag_constants_match_the_header():
+    import re
+
+    header = (ROOT / "include" / "odeintr_b200.h").read_text()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+ODEINTR_FLAG_(\w+)\s+(\d+)u", header)}
+    assert len(flags) >= 9
+    for name, value in flags.items():
+        assert getattr(_abi, "FLAG_" + name) == value, name
+    assert len(set(flags.values())) == len(flags)  # one bit each
+    assert all(v & (v - 1) == 0 for v in flags.values())

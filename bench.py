@@ -42,6 +42,9 @@ LO = (-20.0, -25.0, 5.0)
 HI = (20.0, 25.0, 45.0)
 T_END, DT, STRIDE = 1.0, 0.001, 100
 DP_INSTR_PER_STEP = 78.0      # exact mode: 4 RHS x 9 + 3 components x 14 (mul and add issue separately)
+# DP instructions per step ATTEMPT of the adaptive kernels (counted by ncu, profiles/r02_adaptive.md)
+DP_INSTR_PER_TRY_VDP = 250.0
+DP_INSTR_PER_TRY_ROBERTSON = 330.0
 METRIC = "lorenz_rk4_ensemble_trajectory_steps_per_s"
 UNIT = "trajectory-steps/s"
 
@@ -212,7 +215,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[4] lattice measurement (N = 1 only)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the measurements of the other BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -352,16 +355,34 @@ def main():
         }
         lib.odeintr_host_free(px); lib.odeintr_host_free(po)
 
-    # ---- secondary: BASELINE.json configs[4] on one GPU (reported beside the headline, never instead of it) ----------
+    # ---- secondary: the other BASELINE.json configs, reported beside the headline, never instead of it -------------
+    # N = 1: configs[2] (VdP dopri5), configs[3] (Robertson rosenbrock4), configs[4] on one GPU (bistable lattice and
+    # the two-field oscillator chain), the M x M lattice and the ensemble of wider systems.
+    # N > 1: configs[4] proper -- the 2^28-cell lattice slab-sharded over the N GPUs with the NCCL ring halo exchange
+    # (the only path with a collective), parity-asserted against the unsharded run first.
     secondary = None
-    if world == 1 and not args.no_secondary:
+    if not args.no_secondary:
+        if lib.odeintr_release_record(h) != 0:
+            raise RuntimeError(_abi.last_error())
+        system.close()
         secondary = {}
-        for key, fn in (("lattice_rk4", lattice_secondary), ("lattice2d_rk4", lattice2d_secondary),
-                        ("lattice_ensemble_rk4", lattice_ensemble_secondary)):
+        if world == 1:
+            os.sched_setaffinity(0, _ALL_CPUS)  # the CPU samples inside the secondaries get every host core
+            table = (("vdp_dopri5", vdp_secondary), ("robertson_rosenbrock4", robertson_secondary),
+                     ("lattice_rk4", lattice_secondary), ("lattice_chain_rk4", chain_secondary),
+                     ("lattice2d_rk4", lattice2d_secondary), ("lattice_ensemble_rk4", lattice_ensemble_secondary))
+            for key, fn in table:
+                t_sec = time.perf_counter()
+                try:
+                    secondary[key] = fn(lib, dp_peak.value)
+                except Exception as exc:  # the headline line must survive whatever happens here
+                    secondary[key] = {"error": str(exc)[:300]}
+                secondary[key]["bench_seconds"] = round(time.perf_counter() - t_sec, 1)
+        else:
             try:
-                secondary[key] = fn(lib, dp_peak.value)
-            except Exception as exc:  # the headline line must survive whatever happens here
-                secondary[key] = {"error": str(exc)[:300]}
+                secondary["lattice_sharded"] = lattice_sharded_secondary(lib, dp_peak.value, rank, world, local_rank, dist)
+            except Exception as exc:
+                secondary["lattice_sharded"] = {"error": str(exc)[:300]}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------
     cpu = None
@@ -451,7 +472,17 @@ def lattice_secondary(lib, dp_peak):
         t = statistics.mean(ms) * 1e-3
         rate = n * steps / t
         hbm = _measured_hbm()
+        # parity + CPU sample at 2^22 cells, 10 steps: same snippet through the oracle
+        ns = 1 << 22
+        ss = odeintr_b200.compile_sys_openmp("bistable_s", BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, method="rk4",
+                                             sys_dim=ns).system
+        xs = (np.arange(ns) % 7 < 3).astype(np.float64)
+        got = ss.no_record(xs, 10 * dt, dt)
+        ss.close()
+        ref, cpu = _cpu_lattice_sample(BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, ns, 10, dt, xs)
         return {
+            "parity": {"bit_exact_vs_oracle_2^22_cells_10_steps": bool(np.array_equal(got.view(np.uint64), ref.view(np.uint64)))},
+            "cpu_baseline": cpu,
             "workload": "BASELINE.json configs[4] on one GPU: 1-D periodic bistable lattice, 2^28 cells, rk4 fixed step, "
                         "%d steps per pass, state resident in HBM (2 GiB per array > L2)" % steps,
             "metric": "lattice_rk4_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
@@ -460,13 +491,301 @@ def lattice_secondary(lib, dp_peak):
                          "frac": rate * 50.0 / dp_peak,
                          "hbm": {"bytes_per_cell_step": 16, "achieved_GBps": rate * 16.0 / 1e9, "peak_GBps": hbm,
                                  "frac": rate * 16.0 / 1e9 / hbm},
-                         "kernel": "odeintr_lattice_rk4_tiled_tma",
+                         "kernel": s.lattice_kernel_name() if hasattr(s, "lattice_kernel_name") else "odeintr_lattice_rk4_tiled_tma",
                          "note": "the stage-per-launch schedule (odeintr_lattice_stage) moves 128 B per cell and step "
                                  "and is HBM-bound at 0.90 of the peak = 4.6e10 cell-steps/s; temporal blocking "
                                  "leaves 16 B and an FP64-bound step"},
         }
     finally:
         s.close()
+
+
+CHAIN = """
+for (int i = 0; i < L; ++i) {
+  const double q = x[i];
+  dxdt[i] = x[L + i];
+  dxdt[L + i] = -q - beta * q * q * q + K * (x[(i + L - 1) % L] - 2.0 * q + x[(i + 1) % L]);
+}
+"""
+
+
+def _cpu_lattice_sample(src, pars, n, steps, dt, x0, globals=""):
+    """Oracle port on a bounded sample of a lattice workload: n cells x steps rk4 steps, the user's loop and the
+    stepper's algebra under OpenMP on all host cores (what openmp_range_algebra does in the reference)."""
+    from oracle import build_oracle
+
+    ora = build_oracle.build(src, pars, True, "rk4", sys_dim=n, globals=globals)
+    t0 = time.perf_counter()
+    ref = ora.integrate_adaptive(x0, 0.0, steps * dt, dt)
+    secs = time.perf_counter() - t0
+    return ref["x"], {"value": n * steps / secs, "unit": "cell-steps/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                      "sample": "%d cells x %d rk4 steps (%.1f s), user loop and stepper algebra under OpenMP" % (n, steps, secs)}
+
+
+def chain_secondary(lib, dp_peak):
+    """SURVEY.md section 8(d) config 5 as written there: periodic chain of L = 2^27 anharmonic oscillators, SoA state
+    [q, p] of 2^28 doubles, rk4, dt = 0.01, q_i(0) = sin(2 pi 8 i / L), p = 0.  Two fields; 64 DP instructions per
+    site and step (4 x 9 RHS + 2 x 14 stage algebra) = 32 per state, 16 bytes per state and step through HBM."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    n, steps, dt = 1 << 28, 50, 0.01
+    L = n // 2
+    pars = {"beta": 1.0, "K": 0.5}
+    glob = "static const int L = N / 2;"
+    s = odeintr_b200.compile_sys_openmp("chain", CHAIN, pars, True, method="rk4", sys_dim=n, globals=glob).system
+    try:
+        x0 = np.zeros(n)
+        x0[:L] = np.sin(2 * np.pi * 8 * np.arange(L) / L)
+        s.set_state(x0)
+        del x0
+        ms = []
+        for rep in range(4):
+            if lib.odeintr_integrate_const(s._h, 0.0, steps * dt, dt, 1, 0) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        t = statistics.mean(ms) * 1e-3
+        rate = n * steps / t  # state-steps/s (two states per site)
+        hbm = _measured_hbm()
+        # parity + CPU sample at 2^21 sites, 10 steps: same snippet through the oracle
+        ns = 1 << 22
+        ss = odeintr_b200.compile_sys_openmp("chain_s", CHAIN, pars, True, method="rk4", sys_dim=ns, globals=glob).system
+        xs = np.zeros(ns)
+        xs[:ns // 2] = np.sin(2 * np.pi * 8 * np.arange(ns // 2) / (ns // 2))
+        got = ss.no_record(xs, 10 * dt, dt)
+        ss.close()
+        ref, cpu = _cpu_lattice_sample(CHAIN, pars, ns, 10, dt, xs, glob)
+        cpu["unit"] = "state-steps/s"
+        return {"workload": "SURVEY 8(d) config 5: periodic chain of 2^27 anharmonic oscillators (2^28 states, fields q and "
+                            "p), rk4 fixed step, %d steps per pass, state resident in HBM" % steps,
+                "metric": "lattice_rk4_state_steps_per_s", "value": rate, "unit": "state-steps/s",
+                "ms_per_step": 1e3 * t / steps, "halo": s.get_halo(), "gpu_launches": s.last_launches(),
+                "parity": {"bit_exact_vs_oracle_2^22_states_10_steps": bool(np.array_equal(got.view(np.uint64), ref.view(np.uint64)))},
+                "roofline": {"bound": "fp64", "achieved": rate * 32.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 32.0 / dp_peak, "dp_instr_per_state_step": 32,
+                             "hbm": {"bytes_per_state_step": 16, "achieved_GBps": rate * 16.0 / 1e9, "peak_GBps": hbm,
+                                     "frac": rate * 16.0 / 1e9 / hbm}},
+                "cpu_baseline": cpu}
+    finally:
+        s.close()
+
+
+VDP = "dxdt[0] = x[1]; dxdt[1] = mu * (1 - x[0] * x[0]) * x[1] - x[0];"
+ROBERTSON = """
+dxdt[0] = -alpha * x[0] + beta * x[1] * x[2];
+dxdt[1] = alpha * x[0] - beta * x[1] * x[2] - gamma * x[1] * x[1];
+dxdt[2] = gamma * x[1] * x[1];
+"""
+
+
+def _adaptive_secondary(lib, dp_peak, name, build_system, build_oracle_fn, par_lo, par_hi, x_init, times, dt, rtol,
+                        dp_instr_per_try, workload, metric):
+    """Shared driver of configs[2] and configs[3]: 10 M instances with a linear parameter sweep, name_at() at the given
+    times (dense output), accepted / rejected step counts, a 2 048-instance parity sample against the oracle and the
+    oracle's own throughput on a bounded sample."""
+    import numpy as np
+
+    from odeintr_b200 import _abi
+
+    m = 10_000_000
+    s = build_system()
+    try:
+        P = len(par_lo)
+        lo = (C.c_double * P)(*par_lo)
+        hi = (C.c_double * P)(*par_hi)
+        if lib.odeintr_fill_params_linspace(s._h, m, 0, m, lo, hi) != 0:
+            raise RuntimeError(_abi.last_error())
+        X = np.repeat(np.asarray(x_init, dtype=np.float64)[:, None], m, axis=1)
+        tt = np.ascontiguousarray(times, dtype=np.float64)
+        ms = []
+        for rep in range(3):
+            s.set_state(X)
+            if lib.odeintr_integrate_times(s._h, tt.ctypes.data_as(_abi.c_dbl_p), tt.size, dt) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        del X
+        t = statistics.mean(ms) * 1e-3
+        st = s.stats()
+        acc, rej = int(st["accepted"].sum()), int(st["rejected"].sum())
+        # parity sample: 2 048 instances spread over the sweep
+        N = len(x_init)
+        idx = np.linspace(0, m - 1, 2048).astype(np.int64)
+        sub = np.empty((1, N, tt.size))
+        got = np.empty((tt.size, N, idx.size))
+        for j, i in enumerate(idx):
+            if lib.odeintr_get_output(s._h, sub.ctypes.data_as(_abi.c_dbl_p), sub.size, int(i), 1) != 0:
+                raise RuntimeError(_abi.last_error())
+            got[:, :, j] = sub[0].T
+        ora = build_oracle_fn()
+        threads = len(os.sched_getaffinity(0))
+        frac = idx / (m - 1)
+        Ps = np.stack([par_lo[k] + (par_hi[k] - par_lo[k]) * frac for k in range(P)])
+        e = ora.ensemble(1, np.repeat(np.asarray(x_init, dtype=np.float64)[:, None], idx.size, axis=1), Ps, times=tt, dt=dt,
+                         out_rows=tt.size, threads=threads)
+        err = float(np.max(np.abs(got - e["out"]) / (1.0 + np.abs(e["out"]))))
+        # CPU sample
+        mc = 100_000
+        fc = np.arange(mc) / (mc - 1)
+        Pc = np.stack([par_lo[k] + (par_hi[k] - par_lo[k]) * fc for k in range(P)])
+        t0 = time.perf_counter()
+        ec = ora.ensemble(1, np.repeat(np.asarray(x_init, dtype=np.float64)[:, None], mc, axis=1), Pc, times=tt, dt=dt,
+                          out_rows=tt.size, threads=threads)
+        tc = time.perf_counter() - t0
+        tries = acc + rej
+        attrs = s.kernel_attributes("odeintr_adaptive_ensemble")
+        return {"workload": workload, "metric": metric, "value": acc / t, "unit": "accepted steps/s", "instances": m,
+                "kernel_ms": 1e3 * t, "accepted": acc, "rejected": rej, "tries_per_s": tries / t,
+                "samples_per_instance": int(tt.size), "record_bytes": int(tt.size * N * m * 8),
+                "gpu_launches": s.last_launches(),
+                "parity": {"instances_checked": int(idx.size), "max_err_over_1_plus_abs": err, "tolerance_10_rtol": 10 * rtol,
+                           "ok": bool(err <= 10 * rtol),
+                           "accepted_count_equal_fraction": float(np.mean(st["accepted"][idx] == e["accepted"])),
+                           "rejected_count_equal_fraction": float(np.mean(st["rejected"][idx] == e["rejected"]))},
+                "roofline": {"bound": "fp64", "achieved": tries / t * dp_instr_per_try / 1e12, "peak": dp_peak / 1e12,
+                             "unit": "TFLOP/s", "frac": tries / t * dp_instr_per_try / dp_peak,
+                             "dp_instr_per_attempt": dp_instr_per_try, "kernel": "odeintr_adaptive_ensemble (%s)" % name,
+                             "registers": attrs["registers"], "local_bytes": attrs["local_bytes"],
+                             "note": "DP instructions per step attempt counted by ncu (smsp__inst_executed_pipe_fp64 x 32 / "
+                                     "attempts, profiles/r02_adaptive.md); unit is DP instructions, not flops"},
+                "cpu_baseline": {"value": float(ec["accepted"].sum()) / tc, "unit": "accepted steps/s", "cores": threads,
+                                 "kind": "port", "sample": "%d instances of the sweep (%.1f s), OpenMP over instances" % (mc, tc)}}
+    finally:
+        s.close()
+
+
+def vdp_secondary(lib, dp_peak):
+    """BASELINE.json configs[2]: Van der Pol mu-sweep, 10 M instances, mu in [0.5, 2], adaptive dopri5 with dense output
+    (rk5_i, atol = rtol = 1e-8), name_at(seq(0, 20, by = 0.2)), step_size 0.01, x0 = (2, 0)."""
+    import numpy as np
+
+    import odeintr_b200
+    from oracle import build_oracle
+
+    rtol = 1e-8
+    return _adaptive_secondary(
+        lib, dp_peak, "dopri5_dense",
+        lambda: odeintr_b200.compile_sys("vpol", VDP, "mu", method="rk5_i", atol=rtol, rtol=rtol).system,
+        lambda: build_oracle.build(VDP, "mu", False, "rk5_i", atol=rtol, rtol=rtol),
+        [0.5], [2.0], [2.0, 0.0], np.arange(0, 20.0001, 0.2), 0.01, rtol, DP_INSTR_PER_TRY_VDP,
+        "BASELINE.json configs[2]: Van der Pol mu-sweep, 10 M instances, adaptive dopri5 (rk5_i, atol = rtol = 1e-8), "
+        "dense-output name_at at 101 times, record 16 GB resident in HBM", "vdp_dopri5_dense_accepted_steps_per_s")
+
+
+def robertson_secondary(lib, dp_peak):
+    """BASELINE.json configs[3]: Robertson, 10 M instances (alpha in [0.02, 0.08]), compile_implicit rosenbrock4 with
+    the symbolic Jacobian, name_at(10^seq(-5, 5, len = 41)), atol = rtol = 1e-6 (the reference's defaults)."""
+    import numpy as np
+
+    import odeintr_b200
+    from oracle import build_oracle
+
+    pars = {"alpha": 0.04, "beta": 1e4, "gamma": 3e7}
+    return _adaptive_secondary(
+        lib, dp_peak, "rosenbrock4_dense",
+        lambda: odeintr_b200.compile_implicit("rob", ROBERTSON, pars).system,
+        lambda: build_oracle.build(ROBERTSON, pars, False, "rosenbrock4"),
+        [0.02, 1e4, 3e7], [0.08, 1e4, 3e7], [1.0, 0.0, 0.0], 10 ** np.linspace(-5, 5, 41), 1e-6, 1e-6,
+        DP_INSTR_PER_TRY_ROBERTSON,
+        "BASELINE.json configs[3]: Robertson alpha-sweep, 10 M instances, compile_implicit rosenbrock4 (exact mode: Boost's "
+        "divisions), symbolic Jacobian, name_at at 41 log-spaced times", "robertson_rosenbrock4_accepted_steps_per_s")
+
+
+def lattice_sharded_secondary(lib, dp_peak, rank, world, local_rank, dist):
+    """BASELINE.json configs[4] proper: the 1-D bistable lattice slab-sharded over the N GPUs, temporally blocked rk4
+    kernels on every slab, NCCL ring halo exchange inside the C-ABI (odeintr_lattice_shard_run) every 8 steps.
+    1) parity: a 1 000 003-cell lattice, 10 steps, gathered state bit-compared with rank 0's unsharded run;
+    2) strong scaling: 2^28 cells over N GPUs; 3) weak scaling: 2^27 cells per GPU.  Device-timed, max over ranks."""
+    import numpy as np
+    import torch
+
+    import odeintr_b200
+    from odeintr_b200.distributed import ShardedLattice
+
+    pars = {"D": 0.1, "a": 1.0, "b": 0.5}
+    spe = 8
+
+    def init(f, cells):
+        return ((cells % 7) < 3).astype(np.float64)
+
+    n_small = 1_000_003
+    code = odeintr_b200.compile_sys_openmp("bs", BISTABLE_1D, pars, True, method="rk4", sys_dim=n_small)
+    lat = ShardedLattice(code.system, n_small, rank=rank, world=world, steps_per_exchange=spe)
+    lat.set_state_from(init)
+    lat.step(10, 0.1, t0=0.0)
+    full = lat.gather_state().cpu().numpy().reshape(-1)
+    ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if rank == 0:
+        code1 = odeintr_b200.compile_sys_openmp("bs1", BISTABLE_1D, pars, True, method="rk4", sys_dim=n_small)
+        ref = code1.system.no_record(init(0, np.arange(n_small)), 1.0, 0.1)
+        ok[0] = int(np.array_equal(full.view(np.uint64), ref.view(np.uint64)))
+        code1.system.close()
+    dist.broadcast(ok, src=0)
+    parity_ok = bool(int(ok.item()))
+    del lat
+    code.system.close()
+    out = {"workload": "BASELINE.json configs[4]: 1-D periodic bistable lattice, rk4 fixed step, slab-sharded over %d GPUs, "
+                       "NCCL ring halo exchange (ncclSend/ncclRecv, ghost zone %d steps wide)" % (world, spe),
+           "metric": "lattice_rk4_cell_steps_per_s", "unit": "cell-steps/s", "n_gpus": world, "steps_per_exchange": spe,
+           "parity_ok": parity_ok,
+           "parity": "%d cells x 10 steps sharded over %d ranks vs the unsharded single-GPU run, bit for bit" % (n_small, world)}
+    if not parity_ok:
+        out["error"] = "sharded result differs from the unsharded run"
+        return out
+
+    def timed(n_total, steps):
+        code = odeintr_b200.compile_sys_openmp("bsl", BISTABLE_1D, pars, True, method="rk4", sys_dim=n_total)
+        lat = ShardedLattice(code.system, n_total, rank=rank, world=world, steps_per_exchange=spe)
+        lat.set_state_from(init)
+        lat.step(2 * spe, 0.01, t0=0.0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms_all = []
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(lat.stream)
+            lat.step(steps, 0.01)
+            e1.record(lat.stream)
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ms_all.append(float(ms.item()))
+            dist.barrier()
+        # the ring exchange alone, back to back (its un-overlapped cost; the run above hides part of it)
+        ex = None
+        if hasattr(lib, "odeintr_lattice_exchange"):
+            reps = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                lib.odeintr_lattice_exchange(code.system._h)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record(lat.stream)
+            for _ in range(reps):
+                lib.odeintr_lattice_exchange(code.system._h)
+            e1.record(lat.stream)
+            torch.cuda.synchronize()
+            exm = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(exm, op=dist.ReduceOp.MAX)
+            ex = float(exm.item())
+        ghost, launches = lat.ghost, int(lib.odeintr_last_launches(code.system._h))
+        del lat
+        code.system.close()
+        best = min(ms_all)
+        return {"cells_total": n_total, "cells_per_gpu": n_total // world, "steps": steps, "value": n_total * steps / best * 1e3,
+                "ms_per_step": best / steps, "exchange_ms": ex, "exchange_ms_per_step": None if ex is None else ex / spe,
+                "ghost_cells_per_side": ghost, "gpu_launches_per_pass": launches,
+                "roofline": {"bound": "fp64", "frac": (n_total / world) * steps / best * 1e3 * 50.0 / dp_peak,
+                             "note": "per GPU: 50 DP instructions per cell and step against the measured issue peak"}}
+
+    strong = timed(1 << 28, 200)
+    weak = timed((1 << 27) * world, 100)
+    out.update({"value": strong["value"], "ms_per_step": strong["ms_per_step"],
+                "exchange_ms_per_step": strong["exchange_ms_per_step"], "scaling": "strong", "strong": strong, "weak": weak})
+    return out
 
 
 BISTABLE_2D = """

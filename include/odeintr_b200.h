@@ -184,6 +184,10 @@ int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt);
 int odeintr_nccl_unique_id(void* id_out, size_t cap);
 int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const void* id_bytes, size_t id_size);
 int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long long n_steps, double t0, double dt);
+/* One ring halo exchange of the slab registered with odeintr_lattice_shard, on the system's stream: the ghost cells
+ * of x_dev receive the ring neighbours' boundary cells (what odeintr_lattice_shard_run does between rounds).  For
+ * callers that step with odeintr_lattice_shard_step, and for timing the exchange alone.  Collective over the ranks. */
+int odeintr_lattice_exchange(odeintr_system_t h);
 
 /* ---- observer record ------------------------------------------------------------------------ */
 

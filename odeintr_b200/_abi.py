@@ -55,6 +55,7 @@ SIGNATURES = {
     "odeintr_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "odeintr_lattice_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "odeintr_lattice_shard_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_double, C.c_double]),
+    "odeintr_lattice_exchange": (C.c_int, [C.c_void_p]),
     "odeintr_reset_observer": (C.c_int, [C.c_void_p]),
     "odeintr_release_record": (C.c_int, [C.c_void_p]),
     "odeintr_output_rows": (C.c_size_t, [C.c_void_p]),

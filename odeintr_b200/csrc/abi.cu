@@ -287,6 +287,7 @@ struct odeintr_system_s {
   cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
   dev_buf<double> pipe_x[3], pipe_out[3], pipe_pars[3];
+  dev_buf<double> pipe_bcast;  // one broadcast parameter set of a host-buffer run (the resident sweep stays untouched)
 };
 
 namespace {
@@ -533,8 +534,8 @@ int run_plain_host(odeintr_system_t h, const plain_schedule& sc, const double* x
   int rc = upload_schedule(h, sc, base);
   if (rc) return rc;
   if (P && par_sets == 1) {
-    CU_TRY(h->pars.reserve(P));
-    if ((rc = upload(h, h->pars.p, pars_host, P * sizeof(double)))) return rc;
+    CU_TRY(h->pipe_bcast.reserve(P));
+    if ((rc = upload(h, h->pipe_bcast.p, pars_host, P * sizeof(double)))) return rc;
   }
   if ((rc = begin_timing(h))) return rc;
   // the chunk streams start after the schedule / broadcast-parameter uploads on the main stream
@@ -542,33 +543,45 @@ int run_plain_host(odeintr_system_t h, const plain_schedule& sc, const double* x
   CU_TRY(cudaEventRecord(start_ev, h->stream));
   for (int s = 0; s < kSlots; ++s) CU_TRY(cudaStreamWaitEvent(h->pipe_stream[s], start_ev, 0));
   const unsigned block = (unsigned)h->block_plain;
-  size_t j = 0;
-  for (size_t i0 = 0; i0 < n_inst; i0 += chunk, ++j) {
-    const int s = (int)(j % kSlots);
-    cudaStream_t st = h->pipe_stream[s];
-    const size_t c = std::min(chunk, n_inst - i0);
-    CU_TRY(cudaMemcpy2DAsync(h->pipe_x[s].p, c * sizeof(double), x_host + i0, n_inst * sizeof(double), c * sizeof(double),
-                             N, cudaMemcpyHostToDevice, st));
-    odeintr_plain_args a = base;
-    if (P) {
-      if (par_sets == 1) { a.pars = h->pars.p; a.par_ld = 1; a.par_inc = 0; }
-      else {
-        CU_TRY(cudaMemcpy2DAsync(h->pipe_pars[s].p, c * sizeof(double), pars_host + i0, n_inst * sizeof(double),
-                                 c * sizeof(double), P, cudaMemcpyHostToDevice, st));
-        a.pars = h->pipe_pars[s].p; a.par_ld = (long long)c; a.par_inc = 1;
+  // Copies of earlier chunks may still be reading / writing the caller's buffers when a later enqueue fails: drain
+  // every pipeline stream before reporting the failure, so the caller may free its arrays.
+  auto enqueue_chunks = [&]() -> int {
+    size_t j = 0;
+    for (size_t i0 = 0; i0 < n_inst; i0 += chunk, ++j) {
+      const int s = (int)(j % kSlots);
+      cudaStream_t st = h->pipe_stream[s];
+      const size_t c = std::min(chunk, n_inst - i0);
+      CU_TRY(cudaMemcpy2DAsync(h->pipe_x[s].p, c * sizeof(double), x_host + i0, n_inst * sizeof(double), c * sizeof(double),
+                               N, cudaMemcpyHostToDevice, st));
+      odeintr_plain_args a = base;
+      if (P) {
+        if (par_sets == 1) { a.pars = h->pipe_bcast.p; a.par_ld = 1; a.par_inc = 0; }
+        else {
+          CU_TRY(cudaMemcpy2DAsync(h->pipe_pars[s].p, c * sizeof(double), pars_host + i0, n_inst * sizeof(double),
+                                   c * sizeof(double), P, cudaMemcpyHostToDevice, st));
+          a.pars = h->pipe_pars[s].p; a.par_ld = (long long)c; a.par_inc = 1;
+        }
       }
+      a.x = h->pipe_x[s].p;
+      a.out = rows ? h->pipe_out[s].p : nullptr;
+      a.m = (long long)c;
+      a.ld = (long long)c;
+      if ((rc = launch(h, h->k_plain, st, (unsigned)((c + block - 1) / block), block, &a))) return rc;
+      if (rows)
+        CU_TRY(cudaMemcpy2DAsync(out_host + i0, n_inst * sizeof(double), h->pipe_out[s].p, c * sizeof(double),
+                                 c * sizeof(double), rows * N, cudaMemcpyDeviceToHost, st));
+      if (x_final_host)
+        CU_TRY(cudaMemcpy2DAsync(x_final_host + i0, n_inst * sizeof(double), h->pipe_x[s].p, c * sizeof(double),
+                                 c * sizeof(double), N, cudaMemcpyDeviceToHost, st));
     }
-    a.x = h->pipe_x[s].p;
-    a.out = rows ? h->pipe_out[s].p : nullptr;
-    a.m = (long long)c;
-    a.ld = (long long)c;
-    if ((rc = launch(h, h->k_plain, st, (unsigned)((c + block - 1) / block), block, &a))) return rc;
-    if (rows)
-      CU_TRY(cudaMemcpy2DAsync(out_host + i0, n_inst * sizeof(double), h->pipe_out[s].p, c * sizeof(double),
-                               c * sizeof(double), rows * N, cudaMemcpyDeviceToHost, st));
-    if (x_final_host)
-      CU_TRY(cudaMemcpy2DAsync(x_final_host + i0, n_inst * sizeof(double), h->pipe_x[s].p, c * sizeof(double),
-                               c * sizeof(double), N, cudaMemcpyDeviceToHost, st));
+    return ODEINTR_OK;
+  };
+  if ((rc = enqueue_chunks())) {
+    const std::string why = g_err;
+    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->pipe_stream[s]);
+    cudaStreamSynchronize(h->stream);
+    (void)cudaGetLastError();
+    return fail(rc, why);
   }
   for (int s = 0; s < kSlots; ++s) {
     CU_TRY(cudaEventRecord(h->pipe_done[s], h->pipe_stream[s]));
@@ -1487,7 +1500,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release(); h->rows_min.release();
   h->work_counter.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
-  h->lat_work.release(); h->lat_err.release(); h->lat_flag.release();
+  h->lat_work.release(); h->lat_err.release(); h->lat_flag.release(); h->pipe_bcast.release();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
@@ -1943,6 +1956,13 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
   if ((rc = end_timing(h))) return rc;
   h->last_steps = n_steps;
   return ODEINTR_OK;
+}
+
+int odeintr_lattice_exchange(odeintr_system_t h) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
+  return lattice_exchange(h, h->sh_x);
 }
 
 // ---- observer record -------------------------------------------------------------------------------

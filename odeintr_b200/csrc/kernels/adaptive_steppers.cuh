@@ -151,7 +151,7 @@ struct dopri5_dense {
     int fails = 0;
     if (ctl.cnt.exhausted()) return false;
     while (!ctl.try_step_full(sys, x_cur, d_cur, t, xn, dn, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails >= ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
     }
     x_old = x_cur; d_old = d_cur;
     x_cur = xn; d_cur = dn;
@@ -179,7 +179,7 @@ struct dopri5_dense {
       x_cur = xn; d_cur = dn;
       return 1;
     }
-    if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
+    if (++fails >= ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
     return 0;
   }
 };

@@ -284,7 +284,7 @@ struct bsd_dense {
       x_old = xs; d_old = ds;
       return 1;
     }
-    if (++fails > ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
+    if (++fails >= ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
     return 0;
   }
   ODEINTR_DEV bool do_step(Sys& sys) {

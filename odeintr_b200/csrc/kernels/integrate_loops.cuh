@@ -13,6 +13,9 @@ namespace odeintr_b200 {
 #ifndef ODEINTR_MAX_FAILED_STEPS
 #define ODEINTR_MAX_FAILED_STEPS 500  // Boost failed_step_checker
 #endif
+// Boost's do { try_step; fail_checker(); } while (fail) loops call the checker after EVERY attempt, so the 501st
+// attempt of a step throws whatever its outcome: a step may use at most 500 attempts (`++fails >= 500` after a
+// rejection).  integrate_times' controlled loop calls the checker on rejections only: 501 of them (`++fails > 500`).
 
 struct null_observer {
   template <class State> ODEINTR_HD void operator()(const State&, double) const {}
@@ -29,7 +32,7 @@ ODEINTR_HD bool integrate_adaptive_controlled(St& st, Sys& sys, State& x, double
     if (less_with_sign(t1, t + dt, dt)) dt = t1 - t;
     if (st.counters().exhausted()) return false;
     while (!st.try_step(sys, x, t, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { st.counters().status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails >= ODEINTR_MAX_FAILED_STEPS) { st.counters().status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
     }
     fails = 0;
   }

@@ -249,7 +249,7 @@ struct rosenbrock4_dense {
     int fails = 0;
     if (cnt.exhausted()) return false;
     while (!try_step(sys, x_cur, t, xn, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails >= ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {  // prepare_dense_output
@@ -276,7 +276,7 @@ struct rosenbrock4_dense {
       x_cur = xn;
       return 1;
     }
-    if (++fails > ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
+    if (++fails >= ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return -1; }
     return 0;
   }
 

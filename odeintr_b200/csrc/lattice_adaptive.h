@@ -457,7 +457,7 @@ struct lattice_dopri5_dense {
     int fails = 0;
     if (ctl.cnt.exhausted()) return false;
     while (!ctl.try_step_full(x_cur.p, d_cur, t, x_old.p, d_old, dt)) {
-      if (++fails > ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (++fails >= ODEINTR_MAX_FAILED_STEPS) { ctl.cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
       if (ctl.core.rc) return false;
     }
     std::swap(x_cur.p, x_old.p);  // toggle current / old like Boost's m_current_state_x1 flag

@@ -298,7 +298,17 @@ class CompiledSystem:
             # the reference reads rec_t.back() of an empty vector here (undefined behaviour)
             raise OdeintrError("no previous record to continue from")
         t = np.empty(rows, dtype=np.float64)
-        self._check(self._lib.odeintr_get_output_times(self._h, _dptr(t), rows))
+        if self._lib.odeintr_output_is_ragged(self._h):
+            # NAME_adap() with a controlled / dense stepper left one row per accepted step: the reference reads
+            # rec_t.back() (compile_sys_template.cpp:130), the time of the trajectory's last row.  Every instance of an
+            # ensemble ends at the same time, start + duration, so instance 0 answers for all.
+            m = self.n_instances
+            counts = np.empty(m, dtype=np.int32)
+            self._check(self._lib.odeintr_get_output_rows_per_instance(self._h, counts.ctypes.data_as(_abi.c_int_p), m))
+            self._check(self._lib.odeintr_get_output_times_per_instance(self._h, _dptr(t), rows, 0))
+            t = t[:int(counts[0])]
+        else:
+            self._check(self._lib.odeintr_get_output_times(self._h, _dptr(t), rows))
         start = float(t[-1])
         self.reset_observer()
         return self._at(times, step_size, start)

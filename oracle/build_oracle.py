@@ -93,6 +93,9 @@ class Oracle:
         lib.oracle_ensemble.argtypes = [C.c_int, c_dbl_p, c_dbl_p, C.c_size_t, C.c_int, C.c_double, C.c_double,
                                         C.c_double, c_dbl_p, C.c_size_t, C.c_long, c_dbl_p, C.c_size_t, c_long_p,
                                         c_long_p, C.c_int]
+        lib.oracle_rosenbrock4_step.restype = C.c_int
+        lib.oracle_rosenbrock4_step.argtypes = [c_dbl_p, c_dbl_p, C.c_double, C.c_double, C.c_double, c_dbl_p, c_dbl_p,
+                                                c_dbl_p]
         self.N = lib.oracle_sys_dim()
         self.P = lib.oracle_n_pars()
 
@@ -117,6 +120,15 @@ class Oracle:
             out["t"] = rec_t[:rows].copy()
             out["rec"] = rec_x[:rows].copy()
         return out
+
+    def rosenbrock4_step(self, x, t, dt, theta=0.5, pars=None):
+        """One raw rosenbrock4 step with a fixed step size: (x_new, x_err, dense(t + theta dt))."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(self.N))
+        p = None if pars is None else np.ascontiguousarray(np.asarray(pars, dtype=np.float64).reshape(-1))
+        xo, xe, xd = (np.empty(self.N) for _ in range(3))
+        if self.lib.oracle_rosenbrock4_step(_dp(x), _dp(p), t, dt, theta, _dp(xo), _dp(xe), _dp(xd)) != 0:
+            raise RuntimeError("oracle was not built with rosenbrock4")
+        return xo, xe, xd
 
     # single trajectory -- name(), name_at(), name_adap()/name_no_record() of the reference
     def integrate_const(self, x0, t0, t1, dt, pars=None, record=True):

@@ -34,6 +34,15 @@
 #include <utility>
 #include <vector>
 
+// Elementwise vector algebra of the large-system tests (2^28 states): the loop iterations are independent, so an
+// OpenMP split changes no bit.  This is what openmp_range_algebra does in the reference's compile_sys_openmp
+// (inst/templates/compile_sys_openmp_template.cpp:14, R/utils.R:34-38).  Small states (ensembles) stay serial.
+#ifdef _OPENMP
+#define ODEINT_RESTATED_OMP_FOR _Pragma("omp parallel for if (n > 65536)")
+#else
+#define ODEINT_RESTATED_OMP_FOR
+#endif
+
 namespace restated {
 
 typedef std::vector<double> state_type;
@@ -98,21 +107,25 @@ struct runge_kutta4 {
     sys(x, dxdt, t);
     {
       const double a0 = half * dt;
+      ODEINT_RESTATED_OMP_FOR
       for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i];
     }
     sys(xt, k2, t + half * dt);
     {
       const double a0 = zero * dt, a1 = half * dt;
+      ODEINT_RESTATED_OMP_FOR
       for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i] + a1 * k2[i];
     }
     sys(xt, k3, t + half * dt);
     {
       const double a0 = zero * dt, a1 = zero * dt, a2 = one * dt;
+      ODEINT_RESTATED_OMP_FOR
       for (std::size_t i = 0; i < n; ++i) xt[i] = one * x[i] + a0 * dxdt[i] + a1 * k2[i] + a2 * k3[i];
     }
     sys(xt, k4, t + one * dt);
     {
       const double c0 = b1 * dt, c1 = b2 * dt, c2 = b2 * dt, c3 = b1 * dt;
+      ODEINT_RESTATED_OMP_FOR
       for (std::size_t i = 0; i < n; ++i)
         x[i] = one * x[i] + c0 * dxdt[i] + c1 * k2[i] + c2 * k3[i] + c3 * k4[i];
     }

@@ -232,6 +232,29 @@ long oracle_run(int kind, double* x, const double* pars, double t0, double t1, d
   return (long)rec.rows;
 }
 
+// One raw rosenbrock4::do_step with a FIXED step size (no controller): xout = 4th-order result, xerr = the embedded
+// error estimate (xout - xerr is the 3rd-order companion), dense = interpolant at t + theta * dt.  Lets the tests
+// measure the orders of the Ross coefficients through the very arithmetic every implicit parity test relies on.
+// Returns -1 for explicit methods.
+int oracle_rosenbrock4_step(const double* x, const double* pars, double t, double dt, double theta, double* xout,
+                            double* xerr, double* dense) {
+#ifdef ORACLE_IMPLICIT
+  using namespace odeintr;
+  if (pars) set_pars(pars, 1, 0);
+  restated::rosenbrock4 st;
+  system_t sys = make_system(nullptr);
+  state_type xi(x, x + N), xo, xe, xd;
+  st.do_step(sys, xi, t, xo, dt, xe);
+  st.prepare_dense_output();
+  st.calc_state(t + theta * dt, xd, xi, t, xo, t + dt);
+  for (std::size_t i = 0; i < N; ++i) { xout[i] = xo[i]; xerr[i] = xe[i]; dense[i] = xd[i]; }
+  return 0;
+#else
+  (void)x; (void)pars; (void)t; (void)dt; (void)theta; (void)xout; (void)xerr; (void)dense;
+  return -1;
+#endif
+}
+
 // Ensemble: what a user of the reference does with an R loop over instances (README.md:157-163), here
 // as a C loop, optionally `#pragma omp parallel for` over instances ("all host cores" baseline).
 // X: N x m SoA in/out; P: NPARS x m SoA (par_inc 1) or NPARS values (par_inc 0) or null.

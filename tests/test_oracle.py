@@ -224,3 +224,105 @@ def test_dopri5_error_estimate_and_controller_against_scipy_tableau():
     assert len(grid) == ref["rows"] and rejected == ref["rejected"], (len(grid), ref["rows"], rejected, ref["rejected"])
     assert np.max(np.abs(np.array(grid) - ref["t"])) < 1e-9
     assert np.max(np.abs(y - ref["rec"][-1])) < 1e-9
+
+
+# ---- Rosenbrock4: pins for the ~45 Ross constants shared by the oracle and the K3 kernel ----------
+def _ross_constants(path, begin, end):
+    """name -> value for every `name = number` between two markers of a source file."""
+    import re
+
+    text = pathlib.Path(path).read_text()
+    block = text[text.index(begin):]
+    block = block[:block.index(end)]
+    return {k: float(v) for k, v in re.findall(r"\b([acd]\d{1,2}|gamma)\s*=\s*(-?[0-9.]+(?:e[+-]?[0-9]+)?)", block)}
+
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROSS_SOURCES = {
+    "oracle": (ROOT / "oracle" / "odeint_restated.hpp", "struct rosenbrock4 {", "state_type dxdt, dfdt"),
+    "kernel": (ROOT / "odeintr_b200" / "csrc" / "kernels" / "rosenbrock4.cuh", "struct ross_coef {", "};"),
+}
+
+
+@pytest.mark.parametrize("which", ["oracle", "kernel"])
+def test_rosenbrock4_constants_satisfy_the_order_conditions(which):
+    # Boost's rosenbrock4 works with the transformed increments g_i = sum_j gamma_ij k_j (no matrix-vector products):
+    # A = alpha Gamma^-1, C = diag(1/gamma) - Gamma^-1, m = b Gamma^-1.  Undo the transformation and check the classical
+    # order conditions of Rosenbrock methods (Hairer & Wanner, Solving ODEs II, IV.7, Table 7.1): order 4 for the
+    # solution weights, order 3 for the embedded ones, and the consistency of the non-autonomous terms.  A typo in any
+    # of the a / c constants breaks at least one of them by far more than the 1e-12 the published digits allow.
+    k = _ross_constants(*ROSS_SOURCES[which])
+    g = k["gamma"]
+    s = 6
+    A = np.zeros((s, s))
+    Cm = np.zeros((s, s))
+    for i in range(2, 6):
+        for j in range(1, i):
+            A[i - 1, j - 1] = k["a%d%d" % (i, j)]
+    A[5, :] = [k["a51"], k["a52"], k["a53"], k["a54"], 1.0, 0.0]  # stage 6 is evaluated at xtmp + g5
+    for i in range(2, 7):
+        for j in range(1, i):
+            Cm[i - 1, j - 1] = k["c%d%d" % (i, j)]
+    m = np.array([k["a51"], k["a52"], k["a53"], k["a54"], 1.0, 1.0])   # x_new = x + sum m_i g_i
+    mh = np.array([k["a51"], k["a52"], k["a53"], k["a54"], 1.0, 0.0])  # embedded: without g6 (= the error estimate)
+    Gamma = np.linalg.inv(np.eye(s) / g - Cm)
+    alpha = A @ Gamma
+    b, bh = m @ Gamma, mh @ Gamma
+    assert np.allclose(np.diag(Gamma), g, atol=1e-14) and np.allclose(np.triu(alpha), 0, atol=1e-13)
+    beta = alpha + Gamma - g * np.eye(s)  # beta_ij = alpha_ij + gamma_ij, j < i
+    ai, bi = alpha.sum(axis=1), beta.sum(axis=1)
+    tol = 2e-12
+    for w, order in ((b, 4), (bh, 3)):
+        assert abs(w.sum() - 1) < tol
+        assert abs(w @ bi - (0.5 - g)) < tol
+        assert abs(w @ ai ** 2 - 1 / 3) < tol
+        assert abs(w @ (beta @ bi) - (1 / 6 - g + g * g)) < tol
+        if order == 4:
+            assert abs(w @ ai ** 3 - 0.25) < tol
+            assert abs(w @ (ai * (alpha @ bi)) - (1 / 8 - g / 3)) < tol
+            assert abs(w @ (beta @ ai ** 2) - (1 / 12 - g / 3)) < tol
+            assert abs(w @ (beta @ (beta @ bi)) - (1 / 24 - g / 2 + 1.5 * g * g - g ** 3)) < tol
+    # the embedded weights are NOT of order 4 (otherwise the error estimate would be useless)
+    assert abs(bh @ ai ** 3 - 0.25) > 1e-3 or abs(bh @ (beta @ (beta @ bi)) - (1 / 24 - g / 2 + 1.5 * g * g - g ** 3)) > 1e-3
+    # non-autonomous terms: c_i = sum_j alpha_ij, d_i = gamma + sum_j gamma_ij (rows 5 and 6 have c = 1, d = 0)
+    assert np.allclose(ai[1:4], [k["c2"], k["c3"], k["c4"]], atol=1e-12) and np.allclose(ai[4:], 1.0, atol=1e-12)
+    assert np.allclose(Gamma.sum(axis=1)[:4], [k["d1"], k["d2"], k["d3"], k["d4"]], atol=1e-12)
+    assert np.allclose(Gamma.sum(axis=1)[4:], 0.0, atol=1e-12)
+
+
+def test_rosenbrock4_constants_identical_in_oracle_and_kernel():
+    a, b = (_ross_constants(*ROSS_SOURCES[w]) for w in ("oracle", "kernel"))
+    assert len(a) == 43 and a == b  # gamma, d1-d4, c2-c4, 15 c_ij, 10 a_ij, 10 dense-output d_ij
+
+
+def test_rosenbrock4_fixed_step_orders_through_the_oracle_arithmetic():
+    # one raw do_step of the oracle at h and h/2 on a nonlinear stiff-ish system with a known solution:
+    # local error of the 4th-order result ~ h^5 (ratio 32), of the embedded 3rd-order result ~ h^4 (ratio 16),
+    # of the dense output at mid-step ~ h^4; global error over a fixed-step integration ~ h^4
+    src = "dxdt[0] = -2.0 * x[0] + x[1] * x[1]; dxdt[1] = -x[1];"   # x1 = e^-t, x0 = (1 + t) e^-2t for x(0) = (1, 1)
+    o = bo.build(src, method="rosenbrock4")
+
+    def exact(t):
+        return np.array([(1 + t) * math.exp(-2 * t), math.exp(-t)])
+
+    e4, e3, ed = [], [], []
+    for h in (0.1, 0.05):
+        xn, xe, xd = o.rosenbrock4_step(exact(0.3), 0.3, h, 0.5)
+        e4.append(np.linalg.norm(xn - exact(0.3 + h)))
+        e3.append(np.linalg.norm((xn - xe) - exact(0.3 + h)))
+        ed.append(np.linalg.norm(xd - exact(0.3 + 0.5 * h)))
+    assert abs(math.log2(e4[0] / e4[1]) - 5) < 0.4, e4
+    assert abs(math.log2(e3[0] / e3[1]) - 4) < 0.4, e3
+    assert abs(math.log2(ed[0] / ed[1]) - 4) < 0.5, ed
+    # dense output is continuous: theta = 0 / 1 give the step's end points
+    x0 = exact(0.3)
+    xn, _, d0 = o.rosenbrock4_step(x0, 0.3, 0.1, 0.0)
+    _, _, d1 = o.rosenbrock4_step(x0, 0.3, 0.1, 1.0)
+    assert np.allclose(d0, x0, atol=1e-15) and np.allclose(d1, xn, atol=1e-15)
+    errs = []
+    for n in (20, 40):
+        x = exact(0.0)
+        for s in range(n):
+            x, _, _ = o.rosenbrock4_step(x, s / n, 1.0 / n)
+        errs.append(np.linalg.norm(x - exact(1.0)))
+    assert abs(math.log2(errs[0] / errs[1]) - 4) < 0.35, errs

@@ -224,6 +224,13 @@ struct odeintr_system_s {
                k_combo = nullptr, k_tiled = nullptr, k_tiled_int = nullptr, k_tiled_tma = nullptr,
                k_info = nullptr, k_probe = nullptr, k_lat_ens = nullptr, k_tiled2d = nullptr, k_tiled2d_h[3] = {nullptr, nullptr, nullptr},
                k_dopri5_tiled = nullptr, k_dopri5_tiled_h[3] = {nullptr, nullptr, nullptr};
+  cudaKernel_t k_warp_h[3] = {nullptr, nullptr, nullptr}, k_warp = nullptr, k_warp_info = nullptr;
+  int warp_cpt = 0;             // cells per lane the warp kernels were compiled with (ODEINTR_WARP_CPT)
+  int warp_halo = 0;            // radius of the selected warp kernel (1 or 2)
+  size_t warp_smem = 0;         // dynamic shared memory of the warp kernel
+  int warp_blocks = 0;          // its resident blocks per SM (0 = not available for the current radius)
+  cudaStream_t stream2 = nullptr;        // sharded runs: the halo exchange travels here, beside the interior kernels
+  cudaEvent_t ev_edges = nullptr, ev_xchg = nullptr;
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -608,6 +615,101 @@ int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt);  // after 
 int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt);
 int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt);
 
+// launch descriptor of the tiled rk4 kernels for one step x_in -> x_out of the window w
+void tiled_args_init(odeintr_system_t h, const lattice_window& w, const double* x_in, double* x_out, double t, double dt,
+                     odeintr_lattice_tiled_args& ta) {
+  std::memset(&ta, 0, sizeof(ta));
+  ta.x_in = x_in; ta.x_out = x_out;
+  ta.pars = h->P ? h->pars.p : nullptr;
+  ta.halo = h->lattice_halo;
+  ta.t = t; ta.dt = dt;
+  ta.flag = h->lat_flag.p;
+  ta.n = w.n;
+  if (w.sharded) {
+    ta.n_total = w.n_total; ta.c0 = w.c0; ta.ghost = w.ghost; ta.pitch = w.pitch; ta.sharded = 1;
+  } else {
+    ta.n_total = h->lattice_cells ? h->lattice_cells : w.n_total;
+    ta.c0 = 0; ta.ghost = 0; ta.pitch = ta.n_total;
+  }
+}
+
+int tiled_launch(odeintr_system_t h, cudaKernel_t k, unsigned grid, size_t smem, odeintr_lattice_tiled_args& ta) {
+  void* params[1] = {&ta};
+  CU_TRY(cudaLaunchKernel((const void*)k, dim3(grid), dim3(256), params, smem, h->stream));
+  h->last_launches += 1;
+  g_total_launches += 1;
+  return ODEINTR_OK;
+}
+
+// general tiles (odeintr_lattice_rk4_tiled) over the cells [lo, hi) and [lo2, hi2): seam, loop ends, slab ends, ragged ends
+int tiled_general(odeintr_system_t h, odeintr_lattice_tiled_args ta, long long lo, long long hi, long long lo2, long long hi2) {
+  const long long tile = 256 * (long long)tile_cpt();
+  const long long tiles = (hi > lo ? (hi - lo + tile - 1) / tile : 0) + (hi2 > lo2 ? (hi2 - lo2 + tile - 1) / tile : 0);
+  if (tiles <= 0) return ODEINTR_OK;
+  ta.lo = lo; ta.hi = hi > lo ? hi : lo; ta.lo2 = lo2; ta.hi2 = hi2;
+  return tiled_launch(h, h->k_tiled, (unsigned)tiles, h->tiled_smem, ta);
+}
+
+// One rk4 step of the cells [lo, hi).  Interior cells -- the whole window of 4 * halo cells around them lies inside the
+// user loop's range [glo, ghi): no periodic images, no cells the loop leaves alone -- go to the warp-autonomous
+// register kernel (radius <= 2) or to the block-tiled interior kernels (wider stencils); what is left at either end
+// goes to the general kernel.  Every access of every step is checked against the radius; the caller reads the flag
+// when the call is over.
+int tiled_produce(odeintr_system_t h, odeintr_lattice_tiled_args ta, long long lo, long long hi, long long glo,
+                  long long ghi, bool allow_interior) {
+  if (hi <= lo) return ODEINTR_OK;
+  int rc;
+  const long long tile = 256 * (long long)tile_cpt();
+  const long long margin = 4 * h->lattice_halo;
+  const int fields = (int)((long long)h->N / (h->lat_cells_ct > 0 ? h->lat_cells_ct : (long long)h->N));
+  long long ilo = std::max(lo, glo + margin), ihi = std::min(hi, ghi - margin);
+  const bool interior = allow_interior && h->lat_cells_ct == ta.n_total && ihi > ilo &&
+                        !std::getenv("ODEINTR_TILED_GENERAL_ONLY");
+  // 16-byte aligned windows can be moved by the TMA engine: even cell offsets, even distance between the fields
+  const bool even_fields = (reinterpret_cast<uintptr_t>(ta.x_in) % 16 == 0) && (reinterpret_cast<uintptr_t>(ta.x_out) % 16 == 0) &&
+                           (fields == 1 || ta.pitch % 2 == 0);
+  int mode = 0;  // 1 = warp kernel, 2 = block-tiled interior kernels
+  if (interior && h->k_warp && h->warp_blocks > 0 && !std::getenv("ODEINTR_NO_WARP")) {
+    const long long P = 32LL * h->warp_cpt - 8LL * h->warp_halo;
+    long long wlo = ilo, whi = ihi;
+    const bool tma = even_fields && !std::getenv("ODEINTR_NO_TMA");
+    if (tma) {
+      if ((wlo - ta.c0) & 1) ++wlo;
+      if ((whi - ta.c0) & 1) --whi;
+    }
+    if (whi - wlo >= P) {
+      mode = 1; ilo = wlo; ihi = whi; ta.tma = tma ? 1 : 0;
+    }
+  }
+  long long n_full = 0;
+  if (!mode && interior && h->k_tiled_int && 8 * h->lattice_halo <= 256) {
+    n_full = (ihi - ilo) / tile;
+    if (n_full > 0) { mode = 2; ihi = ilo + n_full * tile; }
+  }
+  if (!mode) ilo = ihi = hi;
+  if ((rc = tiled_general(h, ta, lo, ilo, ihi, hi))) return rc;
+  if (mode == 1) {
+    const long long P = 32LL * h->warp_cpt - 8LL * h->warp_halo;
+    const long long warp_tiles = (ihi - ilo + P - 1) / P;
+    ta.lo = ilo; ta.hi = ihi; ta.sharded = 0;  // the kernel addresses both layouts through (pitch, c0)
+    const long long slots = (long long)h->sm_count * h->warp_blocks;
+    const unsigned grid = (unsigned)std::min<long long>((warp_tiles + 7) / 8, slots);
+    return tiled_launch(h, h->k_warp, grid, h->warp_smem, ta);
+  }
+  if (mode == 2) {
+    ta.lo = ilo; ta.hi = ihi; ta.sharded = 0;
+    ta.tile_first = 0; ta.tile_skip = (int)n_full;
+    // the persistent kernel prefetches the next tile's window with the TMA engine while it computes the current one
+    const bool aligned = even_fields && ((ilo - ta.c0) % 2 == 0);
+    if (h->tiled_tma_blocks > 0 && aligned) {
+      const long long slots = (long long)h->sm_count * h->tiled_tma_blocks;
+      return tiled_launch(h, h->k_tiled_tma, (unsigned)std::min<long long>(n_full, slots), h->tiled_tma_smem, ta);
+    }
+    return tiled_launch(h, h->k_tiled_int, (unsigned)n_full, h->tiled_int_smem, ta);
+  }
+  return ODEINTR_OK;
+}
+
 int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, double dt, int halo) {
   // sharded runs compute a window that shrinks by the stencil radius `halo` with every stage, so one halo
   // exchange of width halo * stages per step is enough (redundant work on 2 * halo * stages * (stages-1)/2 cells)
@@ -645,65 +747,11 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     // known stencil radius: the whole rk4 step in one temporally blocked pass, x -> A, then the caller lets the
     // buffers trade places (16 B per cell per step instead of 128)
     odeintr_lattice_tiled_args ta;
-    std::memset(&ta, 0, sizeof(ta));
-    ta.x_in = x; ta.x_out = A;
-    ta.pars = a.pars;
-    ta.halo = h->lattice_halo;
-    ta.t = t; ta.dt = dt;
-    ta.flag = h->lat_flag.p;
-    const long long tile = 256 * (long long)tile_cpt();
-    // cells of the user's loop, and the cells this launch produces: [lo, hi)
-    long long glo, ghi, lo, hi;
-    if (w.sharded) {
-      ta.n = w.n; ta.n_total = w.n_total; ta.c0 = w.c0; ta.ghost = w.ghost; ta.pitch = w.pitch;
-      ta.lo = w.lo; ta.hi = w.hi; ta.sharded = 1;
-      glo = h->lat_start > 0 ? h->lat_start : 0;
-      ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
-      lo = w.lo; hi = w.hi;
-    } else {
-      ta.n = w.n; ta.n_total = h->lattice_cells ? h->lattice_cells : w.n_total;
-      ta.c0 = 0; ta.ghost = 0; ta.pitch = ta.n_total;
-      ta.lo = 0; ta.hi = ta.n_total;
-      lo = glo = h->lat_start > 0 ? h->lat_start : 0;
-      hi = ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
-    }
-    const long long tiles = hi > lo ? (hi - lo + tile - 1) / tile : 0;
-    // interior tiles: full, and the whole window of 4 * halo cells around them lies inside the user loop's range
-    // [glo, ghi) -- no periodic images, no cells the loop leaves alone; they go to the register-blocked kernel
-    const long long margin = 4 * h->lattice_halo;
-    long long first = glo + margin > lo ? (glo + margin - lo + tile - 1) / tile : 0;  // interior: [first, last)
-    long long last = std::min((hi - lo) / tile, ghi - margin > lo ? (ghi - margin - lo) / tile : 0);
-    if (!h->k_tiled_int || h->lat_cells_ct != ta.n_total || 8 * h->lattice_halo > 256 || last <= first ||
-        std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
-      first = last = 0;
-    ta.tile_first = (int)first;
-    ta.tile_skip = (int)(last - first);
-    void* params[1] = {&ta};
-    // every access of every step is checked against the radius; run_lattice reads the flag when the call is over
-    if (tiles - ta.tile_skip > 0) {
-      CU_TRY(cudaLaunchKernel((const void*)h->k_tiled, dim3((unsigned)(tiles - ta.tile_skip)), dim3(256), params,
-                              h->tiled_smem, h->stream));
-      h->last_launches += 1;
-      g_total_launches += 1;
-    }
-    if (ta.tile_skip > 0) {
-      ta.lo = lo;
-      ta.sharded = 0;  // the interior kernel addresses both layouts through (pitch, c0)
-      // 16-byte aligned windows (even start, even distance between fields) can be fetched by the TMA engine: the
-      // persistent kernel prefetches the next tile's window while it computes the current one
-      const bool aligned = (reinterpret_cast<uintptr_t>(ta.x_in) % 16 == 0) && ((lo - ta.c0) % 2 == 0) &&
-                           (ta.pitch % 2 == 0 || h->lat_cells_ct == (long long)h->N);
-      if (h->tiled_tma_blocks > 0 && aligned) {
-        const long long slots = (long long)h->sm_count * h->tiled_tma_blocks;
-        const unsigned grid = (unsigned)std::min<long long>(ta.tile_skip, slots);
-        CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_tma, dim3(grid), dim3(256), params, h->tiled_tma_smem, h->stream));
-      } else {
-        CU_TRY(cudaLaunchKernel((const void*)h->k_tiled_int, dim3((unsigned)ta.tile_skip), dim3(256), params,
-                                h->tiled_int_smem, h->stream));
-      }
-      h->last_launches += 1;
-      g_total_launches += 1;
-    }
+    tiled_args_init(h, w, x, A, t, dt, ta);
+    // cells of the user's loop [glo, ghi), and the cells this launch produces [lo, hi)
+    const long long glo = h->lat_start > 0 ? h->lat_start : 0;
+    const long long ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+    if ((rc = tiled_produce(h, ta, w.sharded ? w.lo : glo, w.sharded ? w.hi : ghi, glo, ghi, true))) return rc;
     if (!w.sharded) std::swap(h->lat_x, h->lat_a);
     return ODEINTR_OK;
   }
@@ -739,11 +787,27 @@ int lattice_step(odeintr_system_t h, const lattice_window& w, double t, double d
 }
 
 int lattice_prepare(odeintr_system_t h, size_t total) {
-  // work buffers; A and B start as copies of x so cells no loop writes keep their value in every stage
-  CU_TRY(h->lat_buf_a.reserve(total)); CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total));
-  CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // Work buffers of a fixed-step run, only what the selected path uses.  Stage-per-launch rk4: two stage states and
+  // the running sum, all starting as copies of x so that cells no loop writes keep their value in every stage.
+  // Tiled rk4 (and euler): ONE array the state trades places with; it needs the copy only when the user's loop leaves
+  // cells alone.  A radius measured by the probe may turn out too short during the run (indices that depend on the
+  // state): the second array then keeps the initial state for the repeat on the staged kernels.
+  const bool tiled = h->lattice_stages == 4 && ((h->tiled_on && h->k_tiled) || (h->tiled2d_on && h->k_tiled2d));
+  const bool euler = h->lattice_stages == 1;
+  const bool covers_all = h->lat_cells_ct > 0 && h->lat_start <= 0 && h->lat_bound >= h->lat_cells_ct;
+  const bool need_b = tiled ? h->tiled_auto : !euler;
+  const bool need_acc = !tiled && !euler;
+  CU_TRY(h->lat_buf_a.reserve(total));
+  if (!(tiled && covers_all))
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (need_b) {
+    CU_TRY(h->lat_buf_b.reserve(total));
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (need_acc) {
+    CU_TRY(h->lat_buf_acc.reserve(total));
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->x.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
   return ODEINTR_OK;
 }
 
@@ -774,6 +838,22 @@ bool tiled_configure(odeintr_system_t h, long long halo, int fields) {
       h->tiled_tma_blocks = nb;
   }
   (void)cudaGetLastError();
+  // radius <= 2: the warp-autonomous register kernel takes the interior cells (lattice_warp.cuh)
+  h->k_warp = nullptr; h->warp_blocks = 0;
+  const int wh = halo < 1 ? 1 : (int)halo;
+  if (wh <= 2 && h->k_warp_h[wh] && h->warp_cpt >= wh && (h->warp_cpt & 1)) {
+    const size_t wsmem = 8 * (4 * (size_t)fields * 32 * (size_t)h->warp_cpt * sizeof(double) + 2 * sizeof(unsigned long long));
+    int nb = 0;
+    if (wsmem <= 220 * 1024 &&
+        cudaFuncSetAttribute((const void*)h->k_warp_h[wh], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_warp_h[wh], 256, wsmem) == cudaSuccess && nb > 0) {
+      h->k_warp = h->k_warp_h[wh];
+      h->warp_halo = wh;
+      h->warp_smem = wsmem;
+      h->warp_blocks = nb;
+    }
+    (void)cudaGetLastError();
+  }
   return true;
 }
 
@@ -811,6 +891,15 @@ int lattice_query_info(odeintr_system_t h) {
   long long info[5] = {0, 0, 0, 0, 0};
   CU_TRY(cudaMemcpyAsync(info, h->lat_flag.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  if (h->k_warp_info) {  // cells per lane of the warp kernels
+    void* wout = h->lat_flag.p;
+    void* wparams[1] = {&wout};
+    int cpt = 0;
+    CU_TRY(cudaLaunchKernel((const void*)h->k_warp_info, dim3(1), dim3(1), wparams, 0, h->stream));
+    CU_TRY(cudaMemcpyAsync(&cpt, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->warp_cpt = cpt;
+  }
   h->lat_start = info[0];
   h->lat_bound = info[1];
   h->lat_cells_ct = info[2];
@@ -1452,6 +1541,9 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     h->k_tiled_int = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled_tma, h->lib, "odeintr_lattice_rk4_tiled_tma") != cudaSuccess)
     h->k_tiled_tma = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp_h[1], h->lib, "odeintr_lattice_rk4_warp_h1") != cudaSuccess) h->k_warp_h[1] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp_h[2], h->lib, "odeintr_lattice_rk4_warp_h2") != cudaSuccess) h->k_warp_h[2] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp_info, h->lib, "odeintr_lattice_warp_info") != cudaSuccess) h->k_warp_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[1], h->lib, "odeintr_lattice_rk4_tiled2d_h1") != cudaSuccess) h->k_tiled2d_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[2], h->lib, "odeintr_lattice_rk4_tiled2d_h2") != cudaSuccess) h->k_tiled2d_h[2] = nullptr;
@@ -1506,6 +1598,9 @@ int odeintr_destroy(odeintr_system_t h) {
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
     if (h->pipe_stream[s]) cudaStreamDestroy(h->pipe_stream[s]);
   }
+  if (h->ev_edges) cudaEventDestroy(h->ev_edges);
+  if (h->ev_xchg) cudaEventDestroy(h->ev_xchg);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1765,14 +1860,29 @@ long long odeintr_lattice_pitch(odeintr_system_t h, int halo, long long n_local)
 
 namespace {
 // one rk4 step of the slab through the tiled kernels: `cur` -> `other` (both laid out like the caller's buffer), the
-// ghost cells of `cur` being valid out to ghost - phase * 4 * halo cells (phase = steps since the last exchange)
-int slab_tiled_step(odeintr_system_t h, double* cur, double* other, double t, double dt, int phase) {
+// ghost cells of `cur` being valid out to ghost - phase * 4 * halo cells (phase = steps since the last exchange).
+// The cells of a step split into the MIDDLE [c0 + g, c0 + n - g), which in the first step after an exchange depends on
+// owned cells only, and the EDGES on either side of it, which need the ghost cells and, in the last step of a round,
+// are what the next exchange sends: odeintr_lattice_shard_run orders the two parts around the exchange so that the
+// ring transfer travels while the middle is being computed.
+enum { SLAB_ALL = 0, SLAB_EDGES = 1, SLAB_MIDDLE = 2 };
+int slab_tiled_step(odeintr_system_t h, double* cur, double* other, double t, double dt, int phase, int part) {
   const long long g = h->sh_ghost, pad = h->sh_pad, margin = 4 * (long long)h->sh_halo;
   h->lat_x = cur + pad; h->lat_a = other + pad;
   lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1, 0, 0};
   w.lo = h->sh_c0 - g + margin * (phase + 1);
   w.hi = h->sh_c0 + h->sh_n + g - margin * (phase + 1);
-  return lattice_step_halo(h, w, t, dt, h->sh_halo);
+  const long long e_lo = h->sh_c0 + g, e_hi = h->sh_c0 + h->sh_n - g;
+  if (part == SLAB_ALL || e_hi - e_lo < 1024) {  // (slabs too small to split: everything counts as edge)
+    if (part == SLAB_MIDDLE) return ODEINTR_OK;
+    return lattice_step_halo(h, w, t, dt, h->sh_halo);
+  }
+  odeintr_lattice_tiled_args ta;
+  tiled_args_init(h, w, h->lat_x, h->lat_a, t, dt, ta);
+  const long long glo = h->lat_start > 0 ? h->lat_start : 0;
+  const long long ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+  if (part == SLAB_EDGES) return tiled_general(h, ta, w.lo, e_lo, e_hi, w.hi);
+  return tiled_produce(h, ta, e_lo, e_hi, glo, ghi, true);
 }
 
 int slab_check_reach(odeintr_system_t h) {
@@ -1810,7 +1920,7 @@ int odeintr_lattice_shard_step(odeintr_system_t h, double t, double dt) {
   if (h->sh_tiled) {
     // single-step entry point: the caller has just exchanged the halos and finds the new state in its own buffer
     const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
-    if ((rc = slab_tiled_step(h, h->sh_x, h->lat_buf_a.p, t, dt, 0))) return rc;
+    if ((rc = slab_tiled_step(h, h->sh_x, h->lat_buf_a.p, t, dt, 0, SLAB_ALL))) return rc;
     CU_TRY(cudaMemcpyAsync(h->sh_x, h->lat_buf_a.p, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return slab_check_reach(h);
   }
@@ -1884,7 +1994,7 @@ int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const voi
 
 namespace {
 // ghost cells <- ring neighbours' boundary cells, every field, one NCCL group (or local copies for one rank)
-int lattice_exchange(odeintr_system_t h, double* buf) {
+int lattice_exchange(odeintr_system_t h, double* buf, cudaStream_t stream) {
   const long long g = h->sh_ghost, n = h->sh_n, pitch = h->sh_pitch;
   if (g == 0) return ODEINTR_OK;
   const int world = h->comm_world, rank = h->comm_rank;
@@ -1893,8 +2003,8 @@ int lattice_exchange(odeintr_system_t h, double* buf) {
   if (world == 1) {
     for (int f = 0; f < h->sh_fields; ++f) {
       double* own = buf + (long long)f * pitch + pad;
-      CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-      CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     }
     return ODEINTR_OK;
   }
@@ -1904,10 +2014,10 @@ int lattice_exchange(odeintr_system_t h, double* buf) {
   for (int f = 0; f < h->sh_fields; ++f) {
     double* own = buf + (long long)f * pitch + pad;
     // order matters when left == right (two ranks): sends (to right, to left) pair with recvs (from left, from right)
-    NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, h->stream));
-    NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, h->stream));
-    NCCL_TRY(g_nccl.Send(own, (size_t)g, ncclDouble, left, h->comm, h->stream));
-    NCCL_TRY(g_nccl.Recv(own + n, (size_t)g, ncclDouble, right, h->comm, h->stream));
+    NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, stream));
+    NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, stream));
+    NCCL_TRY(g_nccl.Send(own, (size_t)g, ncclDouble, left, h->comm, stream));
+    NCCL_TRY(g_nccl.Recv(own + n, (size_t)g, ncclDouble, right, h->comm, stream));
   }
   NCCL_TRY(g_nccl.GroupEnd());
   return ODEINTR_OK;
@@ -1925,15 +2035,55 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
   if ((rc = begin_timing(h))) return rc;
   if (h->sh_tiled) {
     // the state ping-pongs between the caller's buffer and ours; ghost cells are wide enough for
-    // sh_steps_per_exchange steps (each consumes 4 * halo of them), so the ring exchange runs once per round
+    // sh_steps_per_exchange steps (each consumes 4 * halo of them), so the ring exchange runs once per round.
+    // The exchange travels on a second stream: the last step of a round computes its edges first (the cells the
+    // exchange sends), hands them over and goes on with the middle of the slab; the first step of the next round
+    // starts with its middle and waits for the ghost cells only before its edges.
+    const bool overlap = !std::getenv("ODEINTR_NO_OVERLAP");
+    if (overlap && !h->stream2) {
+      int lo_prio = 0, hi_prio = 0;
+      CU_TRY(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+      CU_TRY(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi_prio));
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_xchg, cudaEventDisableTiming));
+    }
     double* cur = h->sh_x;
     double* other = h->lat_buf_a.p;
+    const int spe = h->sh_steps_per_exchange;
     long long launches = 0;
+    auto exchange_async = [&](double* buf) -> int {  // after everything queued on the main stream so far
+      CU_TRY(cudaEventRecord(h->ev_edges, h->stream));
+      CU_TRY(cudaStreamWaitEvent(h->stream2, h->ev_edges, 0));
+      int erc = lattice_exchange(h, buf, h->stream2);
+      if (erc) return erc;
+      CU_TRY(cudaEventRecord(h->ev_xchg, h->stream2));
+      return ODEINTR_OK;
+    };
     for (long long s = 0; s < n_steps; ++s) {
-      const int phase = (int)(s % h->sh_steps_per_exchange);
-      if (phase == 0 && (rc = lattice_exchange(h, cur))) return rc;
+      const int phase = (int)(s % spe);
+      const double t = t0 + static_cast<double>(first_step + s) * dt;
       h->last_launches = 0;
-      if ((rc = slab_tiled_step(h, cur, other, t0 + static_cast<double>(first_step + s) * dt, dt, phase))) return rc;
+      if (!overlap) {
+        if (phase == 0 && (rc = lattice_exchange(h, cur, h->stream))) return rc;
+        if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_ALL))) return rc;
+      } else {
+        const bool first_of_round = phase == 0;
+        const bool feeds_exchange = phase == spe - 1 && s + 1 < n_steps;  // the next step starts a round
+        if (s == 0 && (rc = exchange_async(cur))) return rc;
+        if (first_of_round) {
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_MIDDLE))) return rc;
+          CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_xchg, 0));
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_EDGES))) return rc;
+          if (feeds_exchange && (rc = exchange_async(other))) return rc;  // one step per round
+        } else if (feeds_exchange) {
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_EDGES))) return rc;
+          if ((rc = exchange_async(other))) return rc;
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_MIDDLE))) return rc;
+        } else {
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_EDGES))) return rc;
+          if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_MIDDLE))) return rc;
+        }
+      }
       launches += h->last_launches;
       std::swap(cur, other);
     }
@@ -1948,7 +2098,7 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
   }
   long long launches = 0;
   for (long long s = 0; s < n_steps; ++s) {
-    if ((rc = lattice_exchange(h, h->sh_x))) return rc;
+    if ((rc = lattice_exchange(h, h->sh_x, h->stream))) return rc;
     if ((rc = odeintr_lattice_shard_step(h, t0 + static_cast<double>(first_step + s) * dt, dt))) return rc;  // integrate_const time rule
     launches += h->last_launches;
   }
@@ -1962,7 +2112,7 @@ int odeintr_lattice_exchange(odeintr_system_t h) {
   int rc = activate(h);
   if (rc) return rc;
   if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
-  return lattice_exchange(h, h->sh_x);
+  return lattice_exchange(h, h->sh_x, h->stream);
 }
 
 // ---- observer record -------------------------------------------------------------------------------

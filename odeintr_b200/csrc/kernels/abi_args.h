@@ -169,6 +169,9 @@ struct odeintr_lattice_tiled_args {
   double dt;
   int sharded;
   int* flag;                  // set to 1 when the snippet reaches beyond the declared halo
-  int tile_first;             // tiles [tile_first, tile_first + tile_skip) are interior: the general kernel skips
-  int tile_skip;              // them, the interior kernel's block b computes tile tile_first + b
+  int tile_first;             // K4t interior kernels: block b computes the tile [lo + (tile_first + b) * T, ... + T),
+  int tile_skip;              // tile_skip tiles in all (the persistent TMA kernel walks over them)
+  long long lo2;              // general kernel: a second range of cells [lo2, hi2) after [lo, hi) -- what is left on
+  long long hi2;              // either side of the cells the interior / warp kernel produces
+  int tma;                    // warp kernel: windows are 16-byte aligned, move them with the TMA engine
 };

@@ -17,9 +17,12 @@
 // a snippet that passes the loop variable to a template expecting an int) leaves only the stage-per-launch kernels.
 //
 // Two kernels share the work of one step:
-//   odeintr_lattice_rk4_tiled           general tiles: ragged last tile, tiles at the periodic seam, tiles that
-//                                       contain cells the user's loop does not write, slabs of a sharded run
-//   odeintr_lattice_rk4_tiled_interior  all other tiles (all but two or three of them): register-blocked
+//   odeintr_lattice_rk4_tiled           general tiles: the cells at the periodic seam, at the ends of the user loop's
+//                                       range (and cells the loop does not write), at the ends of a slab of a sharded
+//                                       run, ragged ends
+//   the interior cells (all but a few hundred)
+//     radius 1 and 2:                   odeintr_lattice_rk4_warp_h1 / _h2 (lattice_warp.cuh): warp-autonomous, registers
+//     wider stencils:                   odeintr_lattice_rk4_tiled_tma / _tiled_interior below: block tiles
 #pragma once
 #include "odeintr_b200/lattice_view.cuh"
 #include "odeintr_b200/lattice_index.cuh"
@@ -83,11 +86,12 @@ ODEINTR_DEV void lattice_rk4_tiled_body(const odeintr_lattice_tiled_args& a) {
   sys.field_offsets(off, 0);
   const long long start = sys.cell_start(), bound = sys.cell_bound();
   const long long L = a.n_total;
-  // tiles cover the cells this launch owns: [lo, hi) (the user loop's range on one GPU, the rank's slab otherwise)
-  const long long lo = a.sharded ? a.lo : (start > a.lo ? start : a.lo);
-  const long long hi = a.sharded ? a.hi : (bound < a.hi ? bound : a.hi);
-  // the host hands the tiles [tile_first, tile_first + tile_skip) to the interior kernel below
-  const long long tile = (int)blockIdx.x < a.tile_first ? (long long)blockIdx.x : (long long)blockIdx.x + a.tile_skip;
+  // tiles cover the two ranges of cells this launch owns, [lo, hi) and [lo2, hi2): what the host did not hand to the
+  // interior / warp kernels (the ends of the user loop's range on one GPU, of the rank's slab otherwise)
+  const long long tiles_a = a.hi > a.lo ? (a.hi - a.lo + T - 1) / T : 0;
+  const bool second = static_cast<long long>(blockIdx.x) >= tiles_a;
+  const long long lo = second ? a.lo2 : a.lo, hi = second ? a.hi2 : a.hi;
+  const long long tile = second ? static_cast<long long>(blockIdx.x) - tiles_a : static_cast<long long>(blockIdx.x);
   const long long tile_lo = lo + tile * T;
   if (tile_lo >= hi) return;
   const long long tile_hi = tile_lo + T < hi ? tile_lo + T : hi;

@@ -135,7 +135,8 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     from systems import BISTABLE_1D, BISTABLE_2D, BISTABLE_DOC, BISTABLE_PARS, CHAIN, CHAIN_GLOBALS, CHAIN_PARS
     staged = {"odeintr_lattice_stage", "odeintr_lattice_stage_sharded", "odeintr_lattice_combo", "odeintr_lattice_info",
               "odeintr_lattice_probe"}
-    tiled = {"odeintr_lattice_rk4_tiled", "odeintr_lattice_rk4_tiled_interior", "odeintr_lattice_rk4_tiled_tma"}
+    tiled = {"odeintr_lattice_rk4_tiled", "odeintr_lattice_rk4_tiled_interior", "odeintr_lattice_rk4_tiled_tma",
+             "odeintr_lattice_rk4_warp_h1", "odeintr_lattice_rk4_warp_h2", "odeintr_lattice_warp_info"}
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, "rk4", sys_dim=1 << 20).code)
     assert k == staged | tiled  # a 2^20-cell lattice is too long for one block: no ensemble kernel
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk4", sys_dim=1024).code)

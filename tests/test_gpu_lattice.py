@@ -555,3 +555,39 @@ def test_tiled_rk4_detects_a_stencil_wider_than_declared():
     odeintr_b200.compile_sys_openmp("w", src, method="rk4", sys_dim=3000, env=env, halo=1)
     with pytest.raises(odeintr_b200.OdeintrError, match="further than the declared halo"):
         env["w"](np.ones(3000), 1.0, 0.1)
+
+
+@pytest.mark.parametrize("case,spe,steps", [("bistable", 8, (19, 6)), ("bistable", 1, (5, 3)), ("bistable", 3, (7, 3)),
+                                            ("chain", 8, (16, 9)), ("chain", 2, (5, 4)), ("fixed_ends", 4, (9, 4))])
+def test_native_shard_run_overlapped_exchange_matches_unsharded(case, spe, steps, monkeypatch):
+    # odeintr_lattice_shard_run sends the halo exchange down a second stream: the last step of a round computes its
+    # edge cells first, the exchange takes them while the middle of the slab is computed, the first step of the next
+    # round waits for the ghost cells only before its own edges.  Whatever the round length, the number of steps per
+    # call and where a call ends within a round, the slab must carry the bits of the unsharded run; the serial
+    # schedule (ODEINTR_NO_OVERLAP) is checked beside it.
+    import torch
+
+    from odeintr_b200.distributed import ShardedLattice
+
+    if case == "chain":
+        n_cells, fields, src, pars, glob = 2 * 5003, 2, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n_cells) / n_cells), 0.2 * np.cos(2 * np.pi * 5 * np.arange(n_cells) / n_cells)])
+    else:
+        n_cells, fields, pars, glob = 20011, 1, BISTABLE_PARS, ""
+        src = BISTABLE_1D if case == "bistable" else \
+            "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + a * x[i] * (1 - x[i]) * (x[i] - b);"
+        x0 = np.random.default_rng(43).uniform(0, 1, n_cells)
+    build = lambda name: odeintr_b200.compile_sys_openmp(name, src, pars, True, method="rk4", sys_dim=fields * n_cells,
+                                                         globals=glob).system
+    total = sum(steps)
+    ref = build("ref").no_record(x0, total * 0.1, 0.1)
+    for overlap in (True, False):
+        if not overlap:
+            monkeypatch.setenv("ODEINTR_NO_OVERLAP", "1")
+        lat = ShardedLattice(build("sh"), n_cells, fields=fields, halo=1, rank=0, world=1, native=True, steps_per_exchange=spe)
+        lat.set_state_from(lambda f, cells: x0[f * n_cells + cells])
+        lat.step(steps[0], 0.1, t0=0.0)
+        lat.step(steps[1], 0.1)
+        torch.cuda.synchronize()
+        got = lat.gather_state().cpu().numpy().reshape(-1)
+        assert np.array_equal(bits(got), bits(ref)), (case, spe, overlap)

@@ -87,6 +87,25 @@ int odeintr_synchronize(odeintr_system_t h);
  * ODEINTR_STATUS_STEP_BUDGET and the call returns ODEINTR_E_STEP. */
 int odeintr_set_max_tries(odeintr_system_t h, long long max_tries);
 
+/* Order in which the instances of an ensemble are dealt to the GPU's lanes by the adaptive steppers (controlled and
+ * dense-output: rk5_a, rk5_i, rk54_a, rk78_a, bs, bsd, rosenbrock4).  Results never depend on it: every trajectory is
+ * integrated by its own lane with its own step sizes and lands at its own index.  What changes is which trajectories
+ * share a warp: 32 lanes execute one instruction stream, so a lane whose neighbours reject, accept and cross their
+ * sample times at other moments pays for their branches too.  In the reference this loop is serial
+ * (README.md:157-163: one NAME_set_params() + NAME() per instance), so the question does not arise there.
+ *   ODEINTR_ORDER_INDEX        lane j integrates instance j (default; right for sorted parameter sweeps)
+ *   ODEINTR_ORDER_COST_PROXY   every integrate call first runs a pilot -- the first 12 step attempts of every instance
+ *                              on a scratch copy -- and sorts the instances by the step size the controller settled on
+ *                              (stable radix sort; index map perm[lane] = instance).  Shuffled or random ensembles
+ *                              regain the coherence of a sorted sweep.
+ *   ODEINTR_ORDER_PERMUTATION  the caller's own order: perm[0..n) (a permutation of 0..n-1, host memory, copied)
+ * perm / n are ignored for the first two modes.  odeintr_get_instance_order returns the map used by the last call. */
+#define ODEINTR_ORDER_INDEX 0
+#define ODEINTR_ORDER_COST_PROXY 1
+#define ODEINTR_ORDER_PERMUTATION 2
+int odeintr_set_instance_order(odeintr_system_t h, int mode, const int* perm, size_t n);
+int odeintr_get_instance_order(odeintr_system_t h, int* perm, size_t n);
+
 /* ---- state and parameters ------------------------------------------------------------------- */
 
 /* name_set_state(new_state), compile_sys_template.cpp:75-83.  x holds sys_dim x n_inst doubles (SoA).

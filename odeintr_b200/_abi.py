@@ -26,6 +26,8 @@ SIGNATURES = {
     "odeintr_set_device": (C.c_int, [C.c_int]),
     "odeintr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "odeintr_set_max_tries": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "odeintr_set_instance_order": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_size_t]),
+    "odeintr_get_instance_order": (C.c_int, [C.c_void_p, c_int_p, C.c_size_t]),
     "odeintr_synchronize": (C.c_int, [C.c_void_p]),
     "odeintr_set_state": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t, C.c_size_t]),
     "odeintr_get_state": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t]),
@@ -81,6 +83,8 @@ SIGNATURES = {
     "odeintr_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, c_int_p, c_int_p, c_int_p,
                                       C.POINTER(C.c_size_t)]),
 }
+
+ORDER_INDEX, ORDER_COST_PROXY, ORDER_PERMUTATION = 0, 1, 2
 
 FLAG_FMAD = 1
 FLAG_KEEP_ZERO_TERMS = 2

@@ -231,6 +231,13 @@ struct odeintr_system_s {
   int warp_blocks = 0;          // its resident blocks per SM (0 = not available for the current radius)
   cudaStream_t stream2 = nullptr;        // sharded runs: the halo exchange travels here, beside the interior kernels
   cudaEvent_t ev_edges = nullptr, ev_xchg = nullptr;
+  cudaKernel_t k_pilot = nullptr;
+  int order_mode = 0;           // K6: 0 = instances in index order, 1 = sorted by the pilot's cost proxy, 2 = caller's permutation
+  int pilot_attempts = 12;
+  dev_buf<int> perm, perm_iota;
+  dev_buf<unsigned> order_keys, order_keys_sorted;
+  dev_buf<unsigned char> sort_temp;
+  size_t perm_m = 0;            // instances the resident permutation was made for (mode 2)
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -1425,6 +1432,26 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   const unsigned grid = (unsigned)((m + block - 1) / block);
   CU_TRY(cudaMemsetAsync(h->fail_flags.p, 0, sizeof(int), h->stream));
   if ((rc = begin_timing(h))) return rc;
+  // K6: instance order.  The pilot and the sort are part of the call (and of its device time).
+  if (h->order_mode == 1 && h->k_pilot && m >= 64 && m < (1ull << 31)) {
+    CU_TRY(h->order_keys.reserve(m)); CU_TRY(h->order_keys_sorted.reserve(m));
+    CU_TRY(h->perm.reserve(m)); CU_TRY(h->perm_iota.reserve(m));
+    const size_t tb = odeintr_b200::sort_pairs_temp_bytes((long long)m);
+    CU_TRY(h->sort_temp.reserve(tb));
+    unsigned* keys = h->order_keys.p;
+    int attempts = h->pilot_attempts;
+    void* pparams[3] = {&a, &keys, &attempts};
+    CU_TRY(cudaLaunchKernel((const void*)h->k_pilot, dim3(grid), dim3(block), pparams, 0, h->stream));
+    h->last_launches += 1;
+    g_total_launches += 1;
+    if (odeintr_b200::launch_sort_by_key(h->sort_temp.p, tb, h->order_keys.p, h->order_keys_sorted.p, h->perm_iota.p,
+                                         h->perm.p, (long long)m, h->stream) != 0)
+      return fail(ODEINTR_E_CUDA, "instance-order sort failed");
+    g_total_launches += 2;
+    a.perm = h->perm.p;
+  } else if (h->order_mode == 2 && h->perm_m == m) {
+    a.perm = h->perm.p;
+  }
   bool ragged = false;
   int max_rows = 0;
   if (mode == ODEINTR_MODE_ADAPTIVE && record) {
@@ -1532,6 +1559,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   // whichever stepper kernels the generated TU instantiated
   if (cudaLibraryGetKernel(&h->k_plain, h->lib, "odeintr_plain_ensemble") != cudaSuccess) h->k_plain = nullptr;
   if (cudaLibraryGetKernel(&h->k_adaptive, h->lib, "odeintr_adaptive_ensemble") != cudaSuccess) h->k_adaptive = nullptr;
+  if (cudaLibraryGetKernel(&h->k_pilot, h->lib, "odeintr_adaptive_pilot") != cudaSuccess) h->k_pilot = nullptr;
   if (cudaLibraryGetKernel(&h->k_lattice, h->lib, "odeintr_lattice_stage") != cudaSuccess) h->k_lattice = nullptr;
   if (cudaLibraryGetKernel(&h->k_lattice_sharded, h->lib, "odeintr_lattice_stage_sharded") != cudaSuccess)
     h->k_lattice_sharded = nullptr;
@@ -1591,6 +1619,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->seg_nfull.release(); h->seg_hrem.release(); h->seg_t.release(); h->seg_obs.release(); h->times_dev.release();
   h->accepted.release(); h->rejected.release(); h->status.release(); h->rows_inst.release(); h->fail_flags.release(); h->rows_min.release();
   h->work_counter.release();
+  h->perm.release(); h->perm_iota.release(); h->order_keys.release(); h->order_keys_sorted.release(); h->sort_temp.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
   h->lat_work.release(); h->lat_err.release(); h->lat_flag.release(); h->pipe_bcast.release();
   for (int s = 0; s < 3; ++s) {
@@ -1634,6 +1663,37 @@ int odeintr_set_stream(odeintr_system_t h, void* cuda_stream) {
 int odeintr_set_max_tries(odeintr_system_t h, long long max_tries) {
   if (!h || max_tries < 1) return fail(ODEINTR_E_INVALID, "max_tries must be >= 1");
   h->max_tries = max_tries;
+  return ODEINTR_OK;
+}
+
+int odeintr_set_instance_order(odeintr_system_t h, int mode, const int* perm, size_t n) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (mode == ODEINTR_ORDER_INDEX || mode == ODEINTR_ORDER_COST_PROXY) {
+    h->order_mode = mode;
+    return ODEINTR_OK;
+  }
+  if (mode != ODEINTR_ORDER_PERMUTATION || !perm || n == 0 || n >= (1ull << 31))
+    return fail(ODEINTR_E_INVALID, "Invalid instance order");
+  std::vector<unsigned char> seen(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    if (perm[i] < 0 || (size_t)perm[i] >= n || seen[(size_t)perm[i]]) return fail(ODEINTR_E_INVALID, "Invalid instance order: not a permutation");
+    seen[(size_t)perm[i]] = 1;
+  }
+  CU_TRY(h->perm.reserve(n));
+  if ((rc = upload(h, h->perm.p, perm, n * sizeof(int)))) return rc;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->perm_m = n;
+  h->order_mode = mode;
+  return ODEINTR_OK;
+}
+
+int odeintr_get_instance_order(odeintr_system_t h, int* perm, size_t n) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!perm || h->perm.cap < n || n == 0) return fail(ODEINTR_E_STATE, "no instance order has been computed");
+  CU_TRY(cudaMemcpyAsync(perm, h->perm.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
   return ODEINTR_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "builtin_kernels.h"
 
 namespace odeintr_b200 {
@@ -133,6 +135,27 @@ void launch_copy_probe(const void* src, void* dst, long long bytes, unsigned blo
 
 void philox_host(unsigned long long counter, unsigned block, unsigned long long seed, unsigned out[4]) {
   philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), block, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+
+// ---- K6: instance order by a cost proxy --------------------------------------------------------------------
+__global__ void iota_kernel(int* v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int)i;
+}
+
+size_t sort_pairs_temp_bytes(long long n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, (int)n);
+  return bytes;
+}
+
+int launch_sort_by_key(void* temp, size_t temp_bytes, const unsigned* keys_in, unsigned* keys_out, int* vals_in,
+                       int* vals_out, long long n, cudaStream_t st) {
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vals_in, n);
+  // least-significant-digit radix sort: stable, so instances with equal keys keep their original order
+  return (int)cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, (const int*)vals_in, vals_out, (int)n,
+                                              0, 32, st);
 }
 
 }  // namespace odeintr_b200

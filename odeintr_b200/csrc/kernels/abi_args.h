@@ -80,6 +80,9 @@ struct odeintr_adaptive_args {
   int* rows;                  // per-instance observer calls (may be null)
   int* fail_flags;            // one word: OR of every instance's non-zero status (may be null)
   int* rows_min;              // one word: minimum over instances of the observer calls made (may be null)
+  const int* perm;            // K6 instance order: thread j integrates instance perm[j] (null: instance j).  Results
+                              // land where the instance lives, so the order changes which trajectories share a warp
+                              // and nothing else
 };
 
 // Large coupled system ("lattice") fused Runge-Kutta stage launch, SURVEY.md §8(d) config 5:

@@ -13,6 +13,11 @@
 #pragma once
 #include "odeintr_b200/integrate_device.cuh"
 
+namespace odeintr_b200 {
+template <bool B, class T> struct enable_if_c {};
+template <class T> struct enable_if_c<true, T> { typedef T type; };
+}  // namespace odeintr_b200
+
 // Register budget: measured on a B200 (scripts/explore_regs.py, 10 M instances) 5 resident blocks of 128 threads
 // per SM (<= 96 registers, a few spilled words in L1) beats the uncapped build by 3 % (dopri5, 104 registers) to
 // 12 % (rosenbrock4, 156 registers); tighter caps lose again.
@@ -25,9 +30,11 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
   constexpr int N = ODEINTR_SYS_SIZE;
   typedef odeintr::system_type Sys;
   typedef odeintr_b200::ODEINTR_STEPPER<Sys, N> Stepper;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.m) return;
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.m) return;
   const unsigned live = __activemask();  // lanes of this warp that own an instance
+  // K6: with a cost-proxy order (odeintr_set_instance_order) neighbouring lanes hold trajectories that step alike
+  const long long i = a.perm ? static_cast<long long>(a.perm[slot]) : slot;
 
   Sys sys;
   sys.load_params(a.pars, a.par_ld, i * a.par_inc);
@@ -88,4 +95,58 @@ odeintr_adaptive_ensemble(const odeintr_adaptive_args a) {
     const int least = __reduce_min_sync(live, obs.rows);
     if ((threadIdx.x & 31) == (__ffs(live) - 1)) atomicMin(a.rows_min, least);
   }
+}
+
+namespace odeintr_b200 {
+// step size after `attempts` step attempts from (x, t0, dt0): dense-output steppers ...
+template <class St, class Sys, int N>
+ODEINTR_DEV typename enable_if_c<St::is_dense, double>::type pilot_step_size(St& st, Sys& sys, vec<N>& x, const double t0,
+                                                                            const double dt0, const int attempts) {
+  st.initialize(x, t0, dt0);
+  bool in_step = false;
+  for (int k = 0; k < attempts; ++k) {
+    if (!in_step) { st.begin_step(sys); in_step = true; }
+    const int r = st.try_once(sys);
+    if (r > 0) in_step = false;
+    else if (r < 0) break;
+  }
+  return st.dt;
+}
+// ... and controlled steppers
+template <class St, class Sys, int N>
+ODEINTR_DEV typename enable_if_c<!St::is_dense, double>::type pilot_step_size(St& st, Sys& sys, vec<N>& x, const double t0,
+                                                                             const double dt0, const int attempts) {
+  double t = t0, dt = dt0;
+  for (int k = 0; k < attempts; ++k) {
+    if (st.counters().exhausted()) break;
+    st.try_step(sys, x, t, dt);
+  }
+  return dt;
+}
+}  // namespace odeintr_b200
+
+// K6 pilot: the first `attempts` step attempts of every instance on a scratch copy of its state; key[i] = the step
+// size the controller has settled on by then (bit pattern of |dt| as a float: positive floats order like unsigned
+// integers).  Trajectories with the same key advance at the same rate -- they reject, accept and cross their sample
+// times together -- so sorting the instances by it (odeintr_set_instance_order) restores the lane coherence of a sorted
+// parameter sweep for ensembles that arrive shuffled.  Nothing is written back but the key.
+extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK, ODEINTR_ADAPTIVE_MIN_BLOCKS)
+odeintr_adaptive_pilot(const odeintr_adaptive_args a, unsigned* key, const int attempts) {
+  constexpr int N = ODEINTR_SYS_SIZE;
+  typedef odeintr::system_type Sys;
+  typedef odeintr_b200::ODEINTR_STEPPER<Sys, N> Stepper;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.m) return;
+  Sys sys;
+  sys.load_params(a.pars, a.par_ld, i * a.par_inc);
+  Stepper st;
+  st.setup(a.atol, a.rtol);
+  st.counters().budget = a.max_tries;
+  odeintr_b200::vec<N> x;
+#pragma unroll
+  for (int v = 0; v < N; ++v) x[v] = a.x[v * a.ld + i];
+  const double dt = odeintr_b200::pilot_step_size(st, sys, x, a.t0, a.dt, attempts);
+  const float mag = fabsf(static_cast<float>(dt));
+  // near-equal step sizes tie (the low mantissa bits are dropped) and a stable sort keeps their original order
+  key[i] = (mag == mag) ? (__float_as_uint(mag) >> 10) : 0xffffffffu;
 }

@@ -347,6 +347,25 @@ class CompiledSystem:
                      [start + self.last_steps() * step_size])
         return EnsembleRecord(t, out), x_final
 
+    def set_instance_order(self, order="index"):
+        """How the instances of an ensemble are dealt to the lanes by the adaptive steppers (odeintr_set_instance_order):
+        "index" (default), "cost" (sorted by a pilot's cost proxy before every integrate call: for shuffled / random
+        ensembles) or an explicit permutation.  Results do not depend on it, only the time."""
+        if isinstance(order, str):
+            mode = {"index": _abi.ORDER_INDEX, "cost": _abi.ORDER_COST_PROXY}.get(order)
+            if mode is None:
+                raise OdeintrError("Invalid instance order")
+            self._check(self._lib.odeintr_set_instance_order(self._h, mode, None, 0))
+            return
+        perm = np.ascontiguousarray(np.asarray(order, dtype=np.int32).reshape(-1))
+        self._check(self._lib.odeintr_set_instance_order(self._h, _abi.ORDER_PERMUTATION,
+                                                         perm.ctypes.data_as(_abi.c_int_p), perm.size))
+
+    def get_instance_order(self):
+        perm = np.empty(self.n_instances, dtype=np.int32)
+        self._check(self._lib.odeintr_get_instance_order(self._h, perm.ctypes.data_as(_abi.c_int_p), perm.size))
+        return perm
+
     def set_halo(self, halo: int, fields: int = 1):
         """Stencil radius of a large system for the tiled rk4 kernels: declared (> 0), measured (< 0) or
         none (0 = stage-per-launch kernels) -- odeintr_lattice_set_halo."""

@@ -207,6 +207,16 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
  * of x_dev receive the ring neighbours' boundary cells (what odeintr_lattice_shard_run does between rounds).  For
  * callers that step with odeintr_lattice_shard_step, and for timing the exchange alone.  Collective over the ranks. */
 int odeintr_lattice_exchange(odeintr_system_t h);
+/* Adaptive steppers on a sharded large system (compile_sys_openmp's default method rk5_i, and rk5_a): after
+ * odeintr_lattice_shard the ordinary integrate calls -- odeintr_integrate_const / _times / _adaptive -- run on this
+ * rank's slab.  They are COLLECTIVE: every rank calls them with the same arguments.  An attempted step is one
+ * temporally blocked pass per slab (6 * halo ghost cells of x and of its derivative on either side, refreshed by the
+ * ring exchange after every accepted step) and one 16-byte ncclAllReduce(max) of the error norm, so all ranks take
+ * the same decisions with the controller the single-GPU run uses: the result is bit-identical to it.
+ * The observer records whole slabs; odeintr_lattice_shard_get_output returns the owned cells of every recorded row:
+ * out[(row * fields + f) * n_local + c], rows = odeintr_output_rows(h), Time column from odeintr_get_output_times,
+ * step counts (global, identical on all ranks) from odeintr_get_stats(h, ..., 1). */
+int odeintr_lattice_shard_get_output(odeintr_system_t h, double* out, size_t n_values);
 
 /* ---- observer record ------------------------------------------------------------------------ */
 
@@ -251,6 +261,13 @@ int odeintr_kernel_attributes(odeintr_system_t h, const char* kernel, int* regs,
 /* pinned host memory for end-to-end transfers */
 void* odeintr_host_alloc(size_t bytes);
 int odeintr_host_free(void* p);
+
+/* Self-test of the correctly rounded repeated-divisor division the exact-mode kernels use (kernels/exact_div.cuh:
+ * rosenbrock4's divisions by the step size and the LU pivots, dopri5's dense-output constants): `pairs` quotients
+ * a / b -- random and adversarial significands, exponents inside and outside the guarded window -- are computed both
+ * ways on the device and compared bit for bit; *mismatches receives the count (0 = identical). */
+int odeintr_selftest_exact_division(int device, unsigned long long pairs, unsigned long long seed,
+                                    unsigned long long* mismatches);
 
 /* FP64-pipe issue-rate probe (roofline denominator for the compute-bound ensembles): returns DP
  * instructions per second summed over the device; kind 0 = DFMA, 1 = DADD/DMUL mix (no FMA). */

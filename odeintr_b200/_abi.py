@@ -58,6 +58,7 @@ SIGNATURES = {
     "odeintr_lattice_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "odeintr_lattice_shard_run": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_double, C.c_double]),
     "odeintr_lattice_exchange": (C.c_int, [C.c_void_p]),
+    "odeintr_lattice_shard_get_output": (C.c_int, [C.c_void_p, c_dbl_p, C.c_size_t]),
     "odeintr_reset_observer": (C.c_int, [C.c_void_p]),
     "odeintr_release_record": (C.c_int, [C.c_void_p]),
     "odeintr_output_rows": (C.c_size_t, [C.c_void_p]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "odeintr_kernel_attributes": (C.c_int, [C.c_void_p, C.c_char_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "odeintr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "odeintr_host_free": (C.c_int, [C.c_void_p]),
+    "odeintr_selftest_exact_division": (C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "odeintr_fp64_probe": (C.c_int, [C.c_int, C.c_int, c_dbl_p, c_dbl_p]),
     "odeintr_hbm_probe": (C.c_int, [C.c_int, C.c_size_t, c_dbl_p]),
     "odeintr_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, c_int_p, c_int_p, c_int_p,

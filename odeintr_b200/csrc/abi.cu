@@ -52,6 +52,7 @@ struct nccl_api {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -75,6 +76,7 @@ int load_nccl() {
   ODEINTR_NCCL_SYM(GroupEnd, "ncclGroupEnd")
   ODEINTR_NCCL_SYM(Send, "ncclSend")
   ODEINTR_NCCL_SYM(Recv, "ncclRecv")
+  ODEINTR_NCCL_SYM(AllReduce, "ncclAllReduce")
   ODEINTR_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef ODEINTR_NCCL_SYM
   g_nccl.ok = true;
@@ -238,6 +240,9 @@ struct odeintr_system_s {
   dev_buf<unsigned> order_keys, order_keys_sorted;
   dev_buf<unsigned char> sort_temp;
   size_t perm_m = 0;            // instances the resident permutation was made for (mode 2)
+  size_t lat_vec_len = 0;       // doubles per state-like vector of the adaptive large-system loops (N, or a slab)
+  std::vector<const double*> slab_fresh;  // slab vectors whose ghost cells hold the neighbours' current values
+  dev_buf<double> lat_negzero;  // -0.0 everywhere: (-0.0) + k == k bit for bit (RHS alone through the stage kernel)
   bool tiled_on = false;        // rk4 steps of this system go through the temporally blocked kernels
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
@@ -1139,6 +1144,73 @@ int tiled5_decide(odeintr_system_t h) {
   return ODEINTR_OK;
 }
 
+// ghost cells <- ring neighbours' boundary cells, every field of every buffer, one NCCL group (or local copies for one
+// rank)
+int lattice_exchange_many(odeintr_system_t h, double* const* bufs, int nb, cudaStream_t stream) {
+  const long long g = h->sh_ghost, n = h->sh_n, pitch = h->sh_pitch;
+  if (g == 0 || nb == 0) return ODEINTR_OK;
+  const int world = h->comm_world, rank = h->comm_rank;
+  const long long pad = h->sh_pad;
+  // per field: owned cells live at [pad, pad + n); ghost cells at [pad - g, pad) and [pad + n, pad + n + g)
+  if (world == 1) {
+    for (int b = 0; b < nb; ++b)
+      for (int f = 0; f < h->sh_fields; ++f) {
+        double* own = bufs[b] + (long long)f * pitch + pad;
+        CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      }
+    return ODEINTR_OK;
+  }
+  if (!h->comm) return fail(ODEINTR_E_STATE, "odeintr_lattice_comm_init has not been called");
+  const int left = (rank + world - 1) % world, right = (rank + 1) % world;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int b = 0; b < nb; ++b)
+    for (int f = 0; f < h->sh_fields; ++f) {
+      double* own = bufs[b] + (long long)f * pitch + pad;
+      // order matters when left == right (two ranks): sends (to right, to left) pair with recvs (from left, from right)
+      NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, stream));
+      NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, stream));
+      NCCL_TRY(g_nccl.Send(own, (size_t)g, ncclDouble, left, h->comm, stream));
+      NCCL_TRY(g_nccl.Recv(own + n, (size_t)g, ncclDouble, right, h->comm, stream));
+    }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return ODEINTR_OK;
+}
+int lattice_exchange(odeintr_system_t h, double* buf, cudaStream_t stream) {
+  double* bufs[1] = {buf};
+  return lattice_exchange_many(h, bufs, 1, stream);
+}
+
+// ---- slab vectors of a sharded adaptive run: which of them have current ghost cells ------------------------------
+bool slab_is_fresh(odeintr_system_t h, const double* p) {
+  return std::find(h->slab_fresh.begin(), h->slab_fresh.end(), p) != h->slab_fresh.end();
+}
+void slab_mark(odeintr_system_t h, const double* p, bool fresh) {
+  auto it = std::find(h->slab_fresh.begin(), h->slab_fresh.end(), p);
+  if (fresh && it == h->slab_fresh.end()) h->slab_fresh.push_back(p);
+  if (!fresh && it != h->slab_fresh.end()) h->slab_fresh.erase(it);
+}
+// make the ghost cells of (up to two) slab vectors current: one ring exchange for those that are stale
+int slab_refresh(odeintr_system_t h, const double* a, const double* b) {
+  double* stale[2];
+  int n = 0;
+  if (a && !slab_is_fresh(h, a)) stale[n++] = const_cast<double*>(a);
+  if (b && b != a && !slab_is_fresh(h, b)) stale[n++] = const_cast<double*>(b);
+  if (!n) return ODEINTR_OK;
+  const int rc = lattice_exchange_many(h, stale, n, h->stream);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) slab_mark(h, stale[i], true);
+  return ODEINTR_OK;
+}
+// max over the ranks of the two words (error bits, reach flag) the attempt kernel left in lat_err
+int slab_allreduce_err(odeintr_system_t h) {
+  if (h->comm_world <= 1) return ODEINTR_OK;
+  if (!h->comm) return fail(ODEINTR_E_STATE, "odeintr_lattice_comm_init has not been called");
+  // non-negative doubles order like their bit patterns: the max of the patterns is the pattern of the max
+  NCCL_TRY(g_nccl.AllReduce(h->lat_err.p, h->lat_err.p, 2, ncclUint64, ncclMax, h->comm, h->stream));
+  return ODEINTR_OK;
+}
+
 #include "lattice_adaptive.h"
 
 // Fixed-step Cash-Karp (method "rk54") on a large system: six combo launches, the result replaces the state.
@@ -1220,14 +1292,38 @@ int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt) {
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
   if (!h->k_combo) return fail(ODEINTR_E_STATE, "system was not compiled for adaptive stepping of a large system");
-  if (h->m != 1) return fail(ODEINTR_E_STATE, "Invalid initial state");
   if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
-  const size_t N = (size_t)h->N;
+  // One GPU: the state is h->x (N doubles).  After odeintr_lattice_shard the same loops run on this rank's slab of the
+  // lattice -- every rank makes the same calls with the same arguments (collective): the error norm of an attempt is
+  // the maximum over all slabs, so all ranks take the same decisions and the same steps.
+  const bool slab = h->sharded;
+  if (slab) {
+    if (h->lattice_method != 1 && h->lattice_method != 2)
+      return fail(ODEINTR_E_STATE, "sharded adaptive stepping is provided for rk5_i and rk5_a");
+    if (!h->k_lattice_sharded) return fail(ODEINTR_E_STATE, "the generated translation unit has no sharded stage kernel");
+  } else if (h->m != 1) {
+    return fail(ODEINTR_E_STATE, "Invalid initial state");
+  }
+  const size_t N = slab ? (size_t)h->sh_fields * (size_t)h->sh_pitch : (size_t)h->N;
+  double* const xstate = slab ? h->sh_x : h->x.p;
+  h->lat_vec_len = N;
+  h->slab_fresh.clear();
   CU_TRY(h->lat_work.reserve((h->lattice_method == 4 ? 18 : 13) * N));
   CU_TRY(h->lat_err.reserve(2));  // max-norm error bits, reach flag
   {
     const int rc5 = tiled5_decide(h);
     if (rc5) return rc5;
+  }
+  if (slab) {
+    if (h->tiled5 != 1)
+      return fail(ODEINTR_E_STATE, "sharded adaptive stepping needs the temporally blocked dopri5 kernel (stencil radius <= 16)");
+    if (h->sh_ghost < 6 * h->tiled5_halo)
+      return fail(ODEINTR_E_INVALID, "ghost zone narrower than 6 x the stencil radius (" + std::to_string(h->tiled5_halo) +
+                                         "): declare the radius to odeintr_lattice_shard");
+    CU_TRY(h->lat_negzero.reserve(N));
+    CU_TRY(cudaMemsetAsync(h->lat_negzero.p, 0, N * sizeof(double), h->stream));
+    odeintr_b200::launch_fill_negzero(h->lat_negzero.p, (long long)N, h->stream);
+    g_total_launches += 1;
   }
   double* w = h->lat_work.p;
   // state-like vectors start as copies of x, derivative-like ones as zeros: entries no user loop writes keep
@@ -1235,7 +1331,7 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   double* state_like[5];
   for (int j = 0; j < 5; ++j) {
     state_like[j] = w + (size_t)j * N;
-    CU_TRY(cudaMemcpyAsync(state_like[j], h->x.p, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(state_like[j], xstate, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
   CU_TRY(cudaMemsetAsync(w + 5 * N, 0, 8 * N * sizeof(double), h->stream));
   double* deriv_like[8];
@@ -1243,6 +1339,7 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
 
   lattice_dopri5 core;
   core.h = h;
+  core.slab = slab;
   core.xtA = state_like[0]; core.xtB = state_like[1];
   core.k2 = deriv_like[0]; core.k3 = deriv_like[1]; core.k4 = deriv_like[2]; core.k5 = deriv_like[3];
   core.k6 = deriv_like[4];
@@ -1251,14 +1348,14 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   if (record) {
     size_t guess = mode == ODEINTR_MODE_TIMES ? n_times : 16;
     if (mode == ODEINTR_MODE_CONST) guess = (size_t)const_step_count(t0, t1, dt) + 2;
-    int rc = reserve_out(h, guess);
-    if (rc) return rc;
+    cudaError_t ce = h->out.reserve(guess * N);
+    if (ce != cudaSuccess) return fail(ODEINTR_E_CUDA, std::string("cannot allocate observer record: ") + cudaGetErrorString(ce));
     cap_rows = h->out.cap / N;
   }
   lattice_observer obs{h, &rec_t, cap_rows};
   odeintr_b200::null_observer nobs;
   lat_sys sys;
-  lat_state x(h, h->x.p);
+  lat_state x(h, xstate);
   int rc;
   if ((rc = begin_timing(h))) return rc;
   bool ok = true;  // failures are carried by the counters' status word
@@ -1621,7 +1718,7 @@ int odeintr_destroy(odeintr_system_t h) {
   h->work_counter.release();
   h->perm.release(); h->perm_iota.release(); h->order_keys.release(); h->order_keys_sorted.release(); h->sort_temp.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
-  h->lat_work.release(); h->lat_err.release(); h->lat_flag.release(); h->pipe_bcast.release();
+  h->lat_work.release(); h->lat_err.release(); h->lat_flag.release(); h->pipe_bcast.release(); h->lat_negzero.release();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
@@ -1871,9 +1968,9 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
     return fail(ODEINTR_E_INVALID, "Invalid shard specification");
   if ((long long)fields * cells_total != (long long)h->N) return fail(ODEINTR_E_INVALID, "fields * cells_total must equal sys_dim");
   if (!x_dev) return fail(ODEINTR_E_INVALID, "null state pointer");
-  h->sh_tiled = slab_tiled_possible(h, halo) && cells_total == h->lat_cells_ct && tiled_configure(h, halo, fields);
+  h->sh_tiled = !h->lattice_method && slab_tiled_possible(h, halo) && cells_total == h->lat_cells_ct && tiled_configure(h, halo, fields);
   h->sh_steps_per_exchange = h->sh_tiled ? h->sh_interval : 1;
-  const long long ghost = (long long)halo * h->lattice_stages * h->sh_steps_per_exchange;
+  const long long ghost = odeintr_lattice_ghost_width(h, halo);
   if (n_local + 2 * ghost > cells_total && n_local != cells_total)
     return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
   if (n_local < ghost) return fail(ODEINTR_E_INVALID, "slab too small for the halo width");
@@ -1883,8 +1980,10 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
   h->sh_pitch = odeintr_lattice_pitch(h, halo, n_local);
   h->sh_x = x_dev;
   const size_t total = (size_t)fields * (size_t)h->sh_pitch;
-  CU_TRY(h->lat_buf_a.reserve(total));
-  if (!h->sh_tiled) { CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total)); }
+  if (!h->lattice_method) {  // (adaptive steppers keep their work vectors in lat_work)
+    CU_TRY(h->lat_buf_a.reserve(total));
+    if (!h->sh_tiled) { CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total)); }
+  }
   CU_TRY(h->lat_flag.reserve(8));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
   h->sh_primed = false;
@@ -1894,6 +1993,8 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
 
 long long odeintr_lattice_ghost_width(odeintr_system_t h, int halo) {
   if (!h) return 0;
+  // adaptive dopri5 (rk5_i / rk5_a): an attempt forms six neighbour-dependent stages; exchanged after every accepted step
+  if (h->lattice_method) return 7LL * halo;
   return (long long)halo * h->lattice_stages * (slab_tiled_possible(h, halo) ? h->sh_interval : 1);
 }
 
@@ -2052,37 +2153,6 @@ int odeintr_lattice_comm_init(odeintr_system_t h, int world, int rank, const voi
   return ODEINTR_OK;
 }
 
-namespace {
-// ghost cells <- ring neighbours' boundary cells, every field, one NCCL group (or local copies for one rank)
-int lattice_exchange(odeintr_system_t h, double* buf, cudaStream_t stream) {
-  const long long g = h->sh_ghost, n = h->sh_n, pitch = h->sh_pitch;
-  if (g == 0) return ODEINTR_OK;
-  const int world = h->comm_world, rank = h->comm_rank;
-  const long long pad = h->sh_pad;
-  // per field: owned cells live at [pad, pad + n); ghost cells at [pad - g, pad) and [pad + n, pad + n + g)
-  if (world == 1) {
-    for (int f = 0; f < h->sh_fields; ++f) {
-      double* own = buf + (long long)f * pitch + pad;
-      CU_TRY(cudaMemcpyAsync(own - g, own + n - g, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-      CU_TRY(cudaMemcpyAsync(own + n, own, g * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-    }
-    return ODEINTR_OK;
-  }
-  if (!h->comm) return fail(ODEINTR_E_STATE, "odeintr_lattice_comm_init has not been called");
-  const int left = (rank + world - 1) % world, right = (rank + 1) % world;
-  NCCL_TRY(g_nccl.GroupStart());
-  for (int f = 0; f < h->sh_fields; ++f) {
-    double* own = buf + (long long)f * pitch + pad;
-    // order matters when left == right (two ranks): sends (to right, to left) pair with recvs (from left, from right)
-    NCCL_TRY(g_nccl.Send(own + n - g, (size_t)g, ncclDouble, right, h->comm, stream));
-    NCCL_TRY(g_nccl.Recv(own - g, (size_t)g, ncclDouble, left, h->comm, stream));
-    NCCL_TRY(g_nccl.Send(own, (size_t)g, ncclDouble, left, h->comm, stream));
-    NCCL_TRY(g_nccl.Recv(own + n, (size_t)g, ncclDouble, right, h->comm, stream));
-  }
-  NCCL_TRY(g_nccl.GroupEnd());
-  return ODEINTR_OK;
-}
-}  // namespace
 
 int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long long n_steps, double t0, double dt) {
   int rc = activate(h);
@@ -2165,6 +2235,20 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
   h->last_launches = launches;
   if ((rc = end_timing(h))) return rc;
   h->last_steps = n_steps;
+  return ODEINTR_OK;
+}
+
+int odeintr_lattice_shard_get_output(odeintr_system_t h, double* out, size_t n_values) {
+  int rc = activate(h);
+  if (rc) return rc;
+  if (!h->sharded) return fail(ODEINTR_E_STATE, "odeintr_lattice_shard has not been called");
+  const size_t rows = h->rows, nl = (size_t)h->sh_n, pitch = (size_t)h->sh_pitch, fields = (size_t)h->sh_fields;
+  if (n_values != rows * fields * nl || (!out && n_values)) return fail(ODEINTR_E_INVALID, "Invalid output buffer");
+  if (!n_values) return ODEINTR_OK;
+  // record rows are whole slabs [field][pitch]; the caller gets the owned cells [row][field][n_local]
+  CU_TRY(cudaMemcpy2DAsync(out, nl * sizeof(double), h->out.p + h->sh_pad, pitch * sizeof(double), nl * sizeof(double),
+                           rows * fields, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
   return ODEINTR_OK;
 }
 
@@ -2264,7 +2348,8 @@ int odeintr_get_output_times_per_instance(odeintr_system_t h, double* t, size_t 
 int odeintr_get_stats(odeintr_system_t h, long long* accepted, long long* rejected, int* status, size_t n_inst) {
   int rc = activate(h);
   if (rc) return rc;
-  if (n_inst != h->m || h->accepted.cap < h->m) return fail(ODEINTR_E_STATE, "no adaptive statistics recorded");
+  const size_t have = h->sharded && h->lattice_method ? 1 : h->m;  // a slab run counts the (global) steps once
+  if (n_inst != have || h->accepted.cap < have) return fail(ODEINTR_E_STATE, "no adaptive statistics recorded");
   if (accepted) CU_TRY(cudaMemcpyAsync(accepted, h->accepted.p, n_inst * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   if (rejected) CU_TRY(cudaMemcpyAsync(rejected, h->rejected.p, n_inst * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   if (status) CU_TRY(cudaMemcpyAsync(status, h->status.p, n_inst * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -2319,6 +2404,26 @@ void* odeintr_host_alloc(size_t bytes) {
 }
 int odeintr_host_free(void* p) {
   if (p) CU_TRY(cudaFreeHost(p));
+  return ODEINTR_OK;
+}
+
+int odeintr_selftest_exact_division(int device, unsigned long long pairs, unsigned long long seed,
+                                    unsigned long long* mismatches) {
+  CU_TRY(cudaSetDevice(device));
+  if (!mismatches) return fail(ODEINTR_E_INVALID, "null argument");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  unsigned long long* dev = nullptr;
+  CU_TRY(cudaMalloc(&dev, sizeof(unsigned long long)));
+  CU_TRY(cudaMemset(dev, 0, sizeof(unsigned long long)));
+  const unsigned blocks = (unsigned)prop.multiProcessorCount * 8u;
+  const unsigned long long threads = (unsigned long long)blocks * 256ull;
+  const unsigned long long per_thread = ((pairs + threads - 1) / threads + 7) / 8 * 8;
+  odeintr_b200::launch_exact_div_check(per_thread, blocks, seed, dev, 0);
+  g_total_launches += 1;
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpy(mismatches, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(dev);
   return ODEINTR_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "builtin_kernels.h"
+#include "kernels/exact_div.cuh"
 
 namespace odeintr_b200 {
 
@@ -157,5 +158,49 @@ int launch_sort_by_key(void* temp, size_t temp_bytes, const unsigned* keys_in, u
   return (int)cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, (const int*)vals_in, vals_out, (int)n,
                                               0, 32, st);
 }
+
+// ---- self-test of exact_div.cuh: divisor::under(a) against a / b, bit for bit ----------------------------------
+// Pair k of thread i: significands from Philox; every fourth pair an adversarial one (divisor significand close to
+// all ones / all zeros, numerator significand just below the divisor's: the worst case for the first quotient estimate);
+// exponents spread over +-300 so that the guarded window is crossed as well.  One divisor serves 8 numerators.
+__global__ void exact_div_check_kernel(unsigned long long pairs_per_thread, unsigned long long seed,
+                                       unsigned long long* mismatches) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long bad = 0;
+  for (unsigned long long k = 0; k < pairs_per_thread; k += 8) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)k, (uint32_t)(k >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    unsigned long long mb = (((unsigned long long)r[0] << 32) | r[1]) & 0xfffffffffffffull;
+    const int kind = r[2] & 3;
+    if (kind == 1) mb |= 0xfffffffffff00ull;        // significand 1.111...1xx
+    else if (kind == 2) mb &= 0x00000000000ffull;   // significand 1.000...0xx
+    const int eb = (int)(r[3] % 601) - 300;
+    const double b = __longlong_as_double((long long)(((unsigned long long)(1023 + eb) << 52) | mb)) * ((r[2] & 4) ? -1.0 : 1.0);
+    const divisor d(b);
+    for (int j = 0; j < 8; ++j) {
+      uint32_t q[4];
+      philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)(k + j), 0x9e3779b9u, (uint32_t)seed, (uint32_t)(seed >> 32), q);
+      unsigned long long ma = (((unsigned long long)q[0] << 32) | q[1]) & 0xfffffffffffffull;
+      if ((q[2] & 3) == 1) ma = mb - 1 - (q[2] >> 28);  // just below the divisor's significand
+      ma &= 0xfffffffffffffull;
+      const int ea = (int)(q[3] % 601) - 300;
+      const double a = __longlong_as_double((long long)(((unsigned long long)(1023 + ea) << 52) | ma)) * ((q[2] & 4) ? -1.0 : 1.0);
+      const double want = a / b, got = d.under(a);
+      if (__double_as_longlong(want) != __double_as_longlong(got)) ++bad;
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+void launch_exact_div_check(unsigned long long pairs_per_thread, unsigned blocks, unsigned long long seed,
+                            unsigned long long* mismatches_dev, cudaStream_t st) {
+  exact_div_check_kernel<<<blocks, 256, 0, st>>>(pairs_per_thread, seed, mismatches_dev);
+}
+
+__global__ void fill_negzero_kernel(double* v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = -0.0;
+}
+void launch_fill_negzero(double* v, long long n, cudaStream_t st) { fill_negzero_kernel<<<1184, 256, 0, st>>>(v, n); }
 
 }  // namespace odeintr_b200

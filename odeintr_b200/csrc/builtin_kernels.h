@@ -16,5 +16,8 @@ void launch_copy_probe(const void* src, void* dst, long long bytes, unsigned blo
 size_t sort_pairs_temp_bytes(long long n);
 int launch_sort_by_key(void* temp, size_t temp_bytes, const unsigned* keys_in, unsigned* keys_out, int* vals_in,
                        int* vals_out, long long n, cudaStream_t st);
+void launch_exact_div_check(unsigned long long pairs_per_thread, unsigned blocks, unsigned long long seed,
+                            unsigned long long* mismatches_dev, cudaStream_t st);
+void launch_fill_negzero(double* v, long long n, cudaStream_t st);
 void philox_host(unsigned long long counter, unsigned block, unsigned long long seed, unsigned out[4]);
 }  // namespace odeintr_b200

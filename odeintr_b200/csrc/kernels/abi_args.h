@@ -144,6 +144,12 @@ struct odeintr_lattice_dopri5_args {
   double eps_abs, eps_rel, adt;
   unsigned long long* err_max;  // bit pattern of the max-norm error (atomicMax)
   int* flag;                  // set to 1 when the snippet reaches beyond the halo
+  // Slab of a sharded run (one process per GPU): the launch produces the cells [own_lo, own_hi) (global numbering);
+  // entry (field f, global cell c) of every array sits at f * pitch + (c - c0), ghost cells -- the ring neighbours'
+  // cells, periodic images at the ends of the ring -- at the offsets beyond the owned range.  One GPU: own = [0, L),
+  // c0 = 0, pitch = L, sharded = 0 (the window is then loaded with the cell index wrapped periodically).
+  long long own_lo, own_hi, c0, pitch;
+  int sharded;
 };
 
 // Ensemble of wider systems, one trajectory per block (lattice_ensemble.cuh): the fixed-step schedule of

@@ -50,11 +50,12 @@ ODEINTR_DEV void lattice_dopri5_tiled_general(const odeintr_lattice_dopri5_args&
 #pragma unroll
   for (int f = 0; f < F; ++f) fld[f] = static_cast<int>(off[f] / L);
   const long long start = sys.cell_start(), bound = sys.cell_bound();
-  const long long tile_lo = (long long)blockIdx.x * T;
+  const long long tile_lo = a.own_lo + (long long)blockIdx.x * T;
 
-  // window position, distance from the tile (0 inside), global cell (wrapped) and role of each of the thread's cells
+  // window position, distance from the tile (0 inside), global cell (wrapped), place in the arrays and role of each of
+  // the thread's cells
   int jj[NC], dist[NC];
-  long long cg[NC];
+  long long cg[NC], at[NC];
   bool live[NC], store[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
@@ -63,11 +64,14 @@ ODEINTR_DEV void lattice_dopri5_tiled_general(const odeintr_lattice_dopri5_args&
     else if (tid < 2 * margin) { jj[k] = T + (tid - margin); dist[k] = tid - margin + 1; }
     else { jj[k] = 0; dist[k] = 1 << 20; }  // no margin cell
     long long c = tile_lo + jj[k];
+    const bool owned = c < a.own_hi;
+    at[k] = c - a.c0;  // a slab holds the periodic images in its ghost cells ...
     c %= L;
     if (c < 0) c += L;
+    if (!a.sharded) at[k] = c;  // ... one GPU wraps the index
     cg[k] = c;
     live[k] = dist[k] <= margin && c >= start && c < bound;
-    store[k] = k < C && tile_lo + jj[k] < L && live[k];
+    store[k] = k < C && owned && live[k];
   }
 
   double x[NC][F], k1[NC][F], k2[NC][F], k3[NC][F], k4[NC][F], k5[NC][F], k6[NC][F], y[NC][F];
@@ -77,8 +81,8 @@ ODEINTR_DEV void lattice_dopri5_tiled_general(const odeintr_lattice_dopri5_args&
     for (int f = 0; f < F; ++f) {
       x[k][f] = k1[k][f] = 0.0;
       if (dist[k] <= margin) {
-        x[k][f] = __ldg(a.x_in + fld[f] * L + cg[k]);
-        k1[k][f] = __ldg(a.d_in + fld[f] * L + cg[k]);
+        x[k][f] = __ldg(a.x_in + fld[f] * a.pitch + at[k]);
+        k1[k][f] = __ldg(a.d_in + fld[f] * a.pitch + at[k]);
       }
     }
 
@@ -133,7 +137,7 @@ ODEINTR_DEV void lattice_dopri5_tiled_general(const odeintr_lattice_dopri5_args&
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         const int q = fld[f] * W + margin + jj[k];
-        const long long g = fld[f] * L + cg[k];
+        const long long g = fld[f] * a.pitch + at[k];
         double v;
         if (stage == 2) {
           k2[k][f] = kk[f];
@@ -220,9 +224,10 @@ ODEINTR_DEV void lattice_dopri5_tiled_fast(const odeintr_lattice_dopri5_args& a)
   constexpr int margin = 6 * H, W = T + 2 * margin;
   Sys sys;
   const long long start = sys.cell_start(), bound = sys.cell_bound();
-  const long long tile_lo = (long long)blockIdx.x * T;
-  // block-uniform: the whole window lies inside the lattice and inside the user loop's range
-  if (!(tile_lo - margin >= (start > 0 ? start : 0) && tile_lo + T + margin <= (bound < L ? bound : L))) {
+  const long long tile_lo = a.own_lo + (long long)blockIdx.x * T;
+  // block-uniform: a full tile whose whole window lies inside the lattice and inside the user loop's range
+  if (!(tile_lo - margin >= (start > 0 ? start : 0) && tile_lo + T + margin <= (bound < L ? bound : L) &&
+        tile_lo + T <= a.own_hi)) {
     lattice_dopri5_tiled_general(a);
     return;
   }
@@ -246,8 +251,8 @@ ODEINTR_DEV void lattice_dopri5_tiled_fast(const odeintr_lattice_dopri5_args& a)
   double xm[F], m1[F], m2[F], m3[F], m4[F], m5[F], ym[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    const double* gx = a.x_in + fld[f] * L + tile_lo;
-    const double* gd = a.d_in + fld[f] * L + tile_lo;
+    const double* gx = a.x_in + fld[f] * a.pitch + (tile_lo - a.c0);
+    const double* gd = a.d_in + fld[f] * a.pitch + (tile_lo - a.c0);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
       x[k][f] = __ldg(gx + tid + k * 256);
@@ -347,7 +352,7 @@ ODEINTR_DEV void lattice_dopri5_tiled_fast(const odeintr_lattice_dopri5_args& a)
       sys.cell(view, kk, idx, ts);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
-        const long long g = fld[f] * L + tile_lo + j;
+        const long long g = fld[f] * a.pitch + (tile_lo - a.c0) + j;
         const double v = combine(f, x[k][f], k1[k][f], k2[k][f], k3[k][f], k4[k][f], k5[k][f], k6[k][f], kk[f]);
         if (stage == 2) k2[k][f] = kk[f];
         if (stage == 3) k3[k][f] = kk[f];

@@ -7,6 +7,7 @@
 #pragma once
 #include "odeintr_b200/abi_args.h"
 #include "odeintr_b200/time_compare.cuh"
+#include "odeintr_b200/exact_div.cuh"
 
 #ifndef ODEINTR_BLOCK
 #define ODEINTR_BLOCK 128

@@ -20,8 +20,10 @@ struct lat_state {
   lat_state(odeintr_system_t h_, double* p_) : h(h_), p(p_) {}
   lat_state(const lat_state&) = default;
   lat_state& operator=(const lat_state& o) {
-    if (p != o.p && p && o.p)
-      cudaMemcpyAsync(p, o.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    if (p != o.p && p && o.p) {
+      cudaMemcpyAsync(p, o.p, h->lat_vec_len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+      if (h->sharded) slab_mark(h, p, slab_is_fresh(h, o.p));  // ghost cells travel with the copy
+    }
     return *this;
   }
 };
@@ -80,11 +82,25 @@ struct lattice_dopri5 {
     a.eps_abs = h->atol; a.eps_rel = h->rtol; a.adt = 1.0 * std::fabs(dt);
     a.err_max = h->lat_err.p;
     a.flag = reinterpret_cast<int*>(h->lat_err.p + 1);
+    if (slab) {  // the attempt reads 6 * halo ghost cells of x and k1 on either side: bring them up to date
+      const int erc = slab_refresh(h, in, d_in);
+      if (erc) { if (!rc) rc = erc; return -1.0; }
+      if (out) slab_mark(h, out, false);
+      if (d_out) slab_mark(h, d_out, false);
+      if (dense_out) slab_mark(h, dense_out, false);
+    }
     cudaMemsetAsync(h->lat_err.p, 0, 2 * sizeof(unsigned long long), h->stream);
     const long long L = h->lat_cells_ct;
     const long long tile = 256LL * tile5_cpt((int)((long long)h->N / L));
+    long long cells = L;
+    if (slab) {  // sharded run: this rank's cells, addressed through its slab (ghost cells hold the neighbours')
+      a.own_lo = h->sh_c0; a.own_hi = h->sh_c0 + h->sh_n; a.c0 = h->sh_c0 - h->sh_pad; a.pitch = h->sh_pitch; a.sharded = 1;
+      cells = h->sh_n;
+    } else {
+      a.own_lo = 0; a.own_hi = L; a.c0 = 0; a.pitch = L; a.sharded = 0;
+    }
     void* params[1] = {&a};
-    if (cudaLaunchKernel((const void*)h->k_dopri5_tiled, dim3((unsigned)((L + tile - 1) / tile)), dim3(256), params,
+    if (cudaLaunchKernel((const void*)h->k_dopri5_tiled, dim3((unsigned)((cells + tile - 1) / tile)), dim3(256), params,
                          h->tiled5_smem, h->stream) != cudaSuccess) {
       if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_tiled failed");
       return -1.0;
@@ -92,6 +108,10 @@ struct lattice_dopri5 {
     h->last_launches += 1;
     g_total_launches += 1;
     if (dense_out) return 0.0;  // nothing to read back: the attempt it repeats has already been vetted
+    if (slab) {  // error norm over the whole lattice: max over the ranks' slabs (one small all-reduce per attempt)
+      const int erc = slab_allreduce_err(h);
+      if (erc) { if (!rc) rc = erc; return -1.0; }
+    }
     unsigned long long words[2] = {0, 0};
     cudaMemcpyAsync(words, h->lat_err.p, sizeof(words), cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -100,6 +120,8 @@ struct lattice_dopri5 {
     std::memcpy(&err, &words[0], sizeof(err));
     return err;
   }
+
+  bool slab = false;  // the vectors are slabs of a sharded run (odeintr_lattice_shard): [field][pitch] with ghost cells
 
   // runge_kutta_dopri5::do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt, xerr) + default_error_checker::error
   // returns the max-norm error (A.2); out / dxdt_out must not alias in / dxdt_in
@@ -112,7 +134,16 @@ struct lattice_dopri5 {
         return e;
       }
       if (rc) return 0.0;
+      if (slab) {
+        rc = fail(ODEINTR_E_INVALID, "the system definition reads x further than the measured stencil radius; sharded "
+                                     "adaptive stepping has no stage-per-launch path");
+        return 0.0;
+      }
       h->tiled5 = 0;  // the stage-per-launch path below has no reach limit
+    }
+    if (slab) {
+      rc = fail(ODEINTR_E_STATE, "sharded adaptive stepping needs the temporally blocked dopri5 kernel (stencil radius <= 16)");
+      return 0.0;
     }
     k_valid = true;
     const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
@@ -204,7 +235,23 @@ struct lattice_dopri5 {
   }
 
   // dxdt = f(x, t)
-  void rhs(const double* x, double* dxdt, double t) { combo(x, nullptr, 0, nullptr, nullptr, 1.0, nullptr, dxdt, t); }
+  void rhs(const double* x, double* dxdt, double t) {
+    if (!slab) { combo(x, nullptr, 0, nullptr, nullptr, 1.0, nullptr, dxdt, t); return; }
+    // slab: the sharded stage kernel with acc = (-0.0) + 1.0 * k, i.e. k itself bit for bit, on the owned cells
+    int erc = slab_refresh(h, x, nullptr);
+    if (erc) { if (!rc) rc = erc; return; }
+    odeintr_lattice_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.pars = h->P ? h->pars.p : nullptr;
+    a.n = h->sh_n; a.n_total = h->sh_total; a.c0 = h->sh_c0; a.ghost = h->sh_ghost; a.pitch = h->sh_pitch;
+    a.xs = x + h->sh_pad; a.x = x + h->sh_pad; a.xt = nullptr;
+    a.acc_in = h->lat_negzero.p + h->sh_pad; a.acc_out = dxdt + h->sh_pad;
+    a.t = t; a.a_dt = 0.0; a.b_dt = 1.0;
+    a.lo = h->sh_c0; a.hi = h->sh_c0 + h->sh_n; a.halo = h->sh_halo;
+    erc = launch(h, h->k_lattice_sharded, h->stream, (unsigned)h->sm_count * 8u, 256u, &a);
+    if (erc && !rc) rc = erc;
+    slab_mark(h, dxdt, false);
+  }
 };
 
 // default_step_adjuster on the host: glibc pow, i.e. exactly what the CPU reference evaluates
@@ -308,7 +355,7 @@ struct lattice_ck54_controlled {
     t += dt;
     dt = lat_increase_step(dt, err, 5);
     cnt.accepted++;
-    cudaMemcpyAsync(x.p, xnew, (size_t)core.h->N * sizeof(double), cudaMemcpyDeviceToDevice, core.h->stream);
+    cudaMemcpyAsync(x.p, xnew, core.h->lat_vec_len * sizeof(double), cudaMemcpyDeviceToDevice, core.h->stream);
     return true;
   }
 };
@@ -398,7 +445,7 @@ struct lattice_rkf78_controlled {
     t += dt;
     dt = lat_increase_step(dt, err, 8);
     cnt.accepted++;
-    cudaMemcpyAsync(x.p, xnew, (size_t)rk.core.h->N * sizeof(double), cudaMemcpyDeviceToDevice, rk.core.h->stream);
+    cudaMemcpyAsync(x.p, xnew, rk.core.h->lat_vec_len * sizeof(double), cudaMemcpyDeviceToDevice, rk.core.h->stream);
     return true;
   }
 };
@@ -429,8 +476,9 @@ struct lattice_dopri5_controlled {
     if (first) { core.rhs(x.p, dxdt, t); first = false; }
     const bool ok = try_step_full(x.p, dxdt, t, xnew, dnew, dt);
     if (ok) {
-      const size_t bytes = (size_t)core.h->N * sizeof(double);
+      const size_t bytes = core.h->lat_vec_len * sizeof(double);
       cudaMemcpyAsync(x.p, xnew, bytes, cudaMemcpyDeviceToDevice, core.h->stream);
+      if (core.slab) slab_mark(core.h, x.p, slab_is_fresh(core.h, xnew));
       std::swap(dxdt, dnew);
     }
     return ok;
@@ -476,7 +524,7 @@ struct lattice_observer {
   size_t cap_rows;
   int rc = 0;
   void operator()(const lat_state& x, double t) {
-    const size_t N = (size_t)h->N, row = rec_t->size();
+    const size_t N = h->lat_vec_len, row = rec_t->size();
     if (row >= cap_rows) {  // grow the record, keeping what is there
       const size_t new_cap = std::max<size_t>(16, cap_rows * 2);
       double* bigger = nullptr;

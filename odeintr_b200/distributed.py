@@ -161,6 +161,46 @@ class ShardedLattice:
                 self.steps += 1
                 self.t = t0 + self.steps * dt  # integrate_const time rule
 
+    # -- adaptive steppers (rk5_i, the default of compile_sys_openmp, and rk5_a): collective calls --------------------------
+    def _record(self):
+        rows = int(self.lib.odeintr_output_rows(self.system._h))
+        t = np.empty(rows, dtype=np.float64)
+        if self.lib.odeintr_get_output_times(self.system._h, t.ctypes.data_as(_abi.c_dbl_p), rows) != 0:
+            raise OdeintrError(_abi.last_error())
+        x = np.empty((rows, self.fields, self.n_local), dtype=np.float64)
+        if self.lib.odeintr_lattice_shard_get_output(self.system._h, x.ctypes.data_as(_abi.c_dbl_p), x.size) != 0:
+            raise OdeintrError(_abi.last_error())
+        return t, x
+
+    def integrate_times(self, times, step_size=1.0):
+        """NAME_at() on the sharded lattice (every rank calls it with the same arguments): returns (Time, x) with x
+        [rows, fields, n_local] = this rank's cells of every recorded row.  The state stays in the slab."""
+        tt = np.ascontiguousarray(np.asarray(times, dtype=np.float64).reshape(-1))
+        self.stream.synchronize()
+        if self.lib.odeintr_integrate_times(self.system._h, tt.ctypes.data_as(_abi.c_dbl_p), tt.size, step_size) != 0:
+            raise OdeintrError(_abi.last_error())
+        return self._record()
+
+    def integrate_const(self, duration, step_size=1.0, start=0.0):
+        """NAME() on the sharded lattice: observer every step_size."""
+        self.stream.synchronize()
+        if self.lib.odeintr_integrate_const(self.system._h, start, start + duration, step_size, 1, 1) != 0:
+            raise OdeintrError(_abi.last_error())
+        return self._record()
+
+    def no_record(self, duration, step_size=1.0, start=0.0):
+        """NAME_no_record() on the sharded lattice: integrate_adaptive without observer; the slab holds the result."""
+        self.stream.synchronize()
+        if self.lib.odeintr_integrate_adaptive(self.system._h, start, start + duration, step_size, 0) != 0:
+            raise OdeintrError(_abi.last_error())
+
+    def stats(self):
+        """(accepted, rejected) step counts of the last adaptive call: global, identical on every rank."""
+        acc, rej, st = (C.c_longlong * 1)(), (C.c_longlong * 1)(), (C.c_int * 1)()
+        if self.lib.odeintr_get_stats(self.system._h, acc, rej, st, 1) != 0:
+            raise OdeintrError(_abi.last_error())
+        return int(acc[0]), int(rej[0])
+
     def local_state(self):
         return self.x[:, self.pad:self.pad + self.n_local]
 

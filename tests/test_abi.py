@@ -59,3 +59,22 @@ def test_python_flag_constants_match_the_header():
         assert getattr(_abi, "FLAG_" + name) == value, name
     assert len(set(flags.values())) == len(flags)  # one bit each
     assert all(v & (v - 1) == 0 for v in flags.values())
+
+
+def test_rcpp_glue_compiles_against_the_header():
+    # src/gpu_glue.cpp is the reference-side binding (the Rcpp translation unit that replaces the module sourceCpp used
+    # to build).  R and Rcpp do not exist in this image: type-check it against include/odeintr_b200.h with a mock of the
+    # Rcpp interface it uses, so that the glue cannot drift away from the C-ABI unnoticed.
+    import subprocess
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", str(root / "include"),
+                        "-I", str(root / "tests" / "mock_rcpp"), str(root / "src" / "gpu_glue.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every generated function of compile_sys_template.cpp:58-171 has its export in the glue and its closure in R/
+    glue = (root / "src" / "gpu_glue.cpp").read_text()
+    rsrc = (root / "R" / "odeintr_gpu.R").read_text()
+    for fn in ("run", "adap", "at", "continue_at", "no_record", "reset_observer", "get_state", "set_state", "get_output",
+               "set_params", "get_params"):
+        assert "odeintr_gpu_%s(" % fn in glue and "odeintr_gpu_%s(" % fn in rsrc, fn

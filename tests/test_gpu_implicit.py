@@ -105,3 +105,18 @@ def test_reciprocal_fast_mode_stays_within_the_stated_tolerance():
     assert np.all(st["status"] == 0)
     print("accepted steps, fast mode vs oracle:", int(st["accepted"].sum()), int(e["accepted"].sum()))
     assert abs(int(st["accepted"].sum()) - int(e["accepted"].sum())) <= 0.01 * e["accepted"].sum()
+
+
+def test_repeated_divisor_division_is_correctly_rounded():
+    # kernels/exact_div.cuh replaces Boost's / uBLAS' repeated divisions by one reciprocal + two FMA corrections per
+    # quotient; Markstein's theorem says the quotients are the correctly rounded ones.  2^28 of them, random and
+    # adversarial, against the device's IEEE division: not one bit may differ.
+    import ctypes as C
+
+    from odeintr_b200 import _abi
+
+    lib = _abi.load()
+    for seed in (20260101, 7):
+        bad = C.c_ulonglong(12345)
+        assert lib.odeintr_selftest_exact_division(0, 1 << 28, seed, C.byref(bad)) == 0, _abi.last_error()
+        assert bad.value == 0, bad.value

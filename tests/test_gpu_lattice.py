@@ -591,3 +591,46 @@ def test_native_shard_run_overlapped_exchange_matches_unsharded(case, spe, steps
         torch.cuda.synchronize()
         got = lat.gather_state().cpu().numpy().reshape(-1)
         assert np.array_equal(bits(got), bits(ref)), (case, spe, overlap)
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a"])
+@pytest.mark.parametrize("case", ["bistable", "chain", "fixed_ends"])
+def test_sharded_adaptive_dopri5_single_rank_matches_unsharded(case, method):
+    # compile_sys_openmp's default method on a slab (odeintr_lattice_shard + the ordinary integrate calls): the attempt
+    # kernel addresses the slab with its ghost cells, the derivative alone comes from the sharded stage kernel, ghost
+    # cells are refreshed after every accepted step.  With one rank the ring closes on the slab itself; the result must
+    # be the unsharded run's (hence the oracle's) bit for bit, step counts included.
+    import torch
+
+    from odeintr_b200.distributed import ShardedLattice
+
+    if case == "chain":
+        n_cells, fields, src, pars, glob = 5003, 2, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(n_cells) / n_cells), 0.2 * np.cos(2 * np.pi * 5 * np.arange(n_cells) / n_cells)])
+    else:
+        n_cells, fields, pars, glob = 9001, 1, BISTABLE_PARS, ""
+        src = BISTABLE_1D if case == "bistable" else \
+            "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + a * x[i] * (1 - x[i]) * (x[i] - b);"
+        x0 = np.random.default_rng(45).uniform(0, 1, n_cells)
+    kw = dict(method=method, sys_dim=fields * n_cells, globals=glob, atol=1e-7, rtol=1e-7)
+    env = {}
+    ref_sys = odeintr_b200.compile_sys_openmp("ref", src, pars, True, env=env, **kw).system
+    at = np.array([0.0, 0.5, 1.0 + 1e-3, 2.75])
+    ref = env["ref_at"](x0, at, 0.1)
+    ref_stats = ref_sys.stats()
+    lat = ShardedLattice(odeintr_b200.compile_sys_openmp("sh", src, pars, True, **kw).system, n_cells, fields=fields,
+                         halo=1, rank=0, world=1, native=True)
+    lat.set_state_from(lambda f, cells: x0[f * n_cells + cells])
+    t, x = lat.integrate_times(at, 0.1)
+    assert np.array_equal(t, at) and x.shape == (4, fields, n_cells)
+    assert np.array_equal(bits(x.reshape(4, -1)), bits(cols(ref)))
+    acc, rej = lat.stats()
+    assert acc == ref_stats["accepted"][0] and rej == ref_stats["rejected"][0]
+    # the slab keeps the final state: continue with NAME_no_record / NAME on it
+    fin_ref = env["ref_no_record"](cols(ref)[-1], 0.7, 0.05, 2.75)
+    lat.no_record(0.7, 0.05, start=2.75)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(lat.gather_state().cpu().numpy().reshape(-1)), bits(fin_ref))
+    rec_ref = env["ref"](fin_ref, 1.0, 0.25, 3.45)
+    t, x = lat.integrate_const(1.0, 0.25, start=3.45)
+    assert np.array_equal(t, rec_ref["Time"].to_numpy()) and np.array_equal(bits(x.reshape(len(t), -1)), bits(cols(rec_ref)))

@@ -343,7 +343,21 @@ def main():
         barrier()
         wall_e2e = max_over_ranks(time.perf_counter() - t0)
         t_e2e = max_over_ranks(t_e2e)
+        # the box's ceiling for this traffic: the same pinned buffers moved by bare back-to-back copies, every rank at the
+        # same moment (N ranks share the host's PCIe root complexes and memory controllers)
+        ceiling = None
+        if hasattr(lib, "odeintr_pcie_probe"):
+            secs = C.c_double()
+            t_probe = []
+            for _ in range(2):
+                barrier()
+                if lib.odeintr_pcie_probe(local_rank, px, n_x * 8, po, n_out * 8, C.byref(secs)) != 0:
+                    raise RuntimeError(_abi.last_error())
+                t_probe.append(max_over_ranks(secs.value))
+            ceiling = min(t_probe)
         # spot check: the record of the last pass starts at the inputs and its last row is a propagated state
+        lib.odeintr_synchronize(h)
+        e2e_pass()
         assert np.array_equal(out_host[0, :, :4096], x_host[:, :4096])
         assert np.all(np.isfinite(out_host[10, :, :4096])) and not np.array_equal(out_host[10, :, :4096], x_host[:, :4096])
         e2e = {
@@ -353,6 +367,13 @@ def main():
             "device_ms_per_step": 1e3 * t_e2e / k_e2e,
             "api": "odeintr_integrate_const_host (pinned host buffers, chunked 3-stream copy/compute overlap)",
         }
+        if ceiling:
+            e2e["pcie_ceiling"] = {
+                "ms_per_step": 1e3 * ceiling, "d2h_GBps_per_gpu": n_out * 8 / ceiling / 1e9,
+                "aggregate_GBps": world * (n_out + n_x) * 8 / ceiling / 1e9,
+                "how": "odeintr_pcie_probe: this step's h2d + d2h bytes through the same pinned buffers as bare 256 MiB "
+                       "copies on two streams, all %d rank(s) at once, device-timed, max over ranks, best of 2" % world}
+            e2e["frac_of_pcie_ceiling"] = ceiling / (wall_e2e / k_e2e)
         lib.odeintr_host_free(px); lib.odeintr_host_free(po)
 
     # ---- secondary: the other BASELINE.json configs, reported beside the headline, never instead of it -------------

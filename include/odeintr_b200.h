@@ -274,6 +274,11 @@ int odeintr_selftest_exact_division(int device, unsigned long long pairs, unsign
 int odeintr_fp64_probe(int kind, int device, double* dp_instr_per_s, double* ms);
 /* device-to-device copy bandwidth probe in bytes (read + write) per second */
 int odeintr_hbm_probe(int device, size_t bytes, double* bytes_per_s);
+/* Ceiling of the host-buffer path (odeintr_integrate_const_host): moves the pinned host range host_in to the device
+ * and a device buffer to the pinned host range host_out, both at once, in back-to-back 256 MiB copies, and reports the
+ * device-timed duration.  With every rank of a box calling it at the same moment this is what the host's PCIe / memory
+ * system lets N GPUs move concurrently -- the denominator of bench.py's e2e.frac_of_pcie_ceiling. */
+int odeintr_pcie_probe(int device, void* host_in, size_t bytes_in, void* host_out, size_t bytes_out, double* seconds);
 int odeintr_device_info(int device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
                         size_t* total_mem);
 

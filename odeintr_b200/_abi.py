@@ -82,6 +82,7 @@ SIGNATURES = {
     "odeintr_selftest_exact_division": (C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "odeintr_fp64_probe": (C.c_int, [C.c_int, C.c_int, c_dbl_p, c_dbl_p]),
     "odeintr_hbm_probe": (C.c_int, [C.c_int, C.c_size_t, c_dbl_p]),
+    "odeintr_pcie_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, c_dbl_p]),
     "odeintr_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, c_int_p, c_int_p, c_int_p,
                                       C.POINTER(C.c_size_t)]),
 }

@@ -525,7 +525,29 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
         raise OdeintrError("large systems must pass sys_dim (loop-indexed dxdt has no literal index; "
                            "R/odeintr.R:403)")
     sys_dim = int(math.ceil(sys_dim))
-    loops = parse_cell_loops(sys)
+    mode = "dense" if method.endswith("_i") else ("controlled" if method.endswith("_a") else "plain")
+    try:
+        loops = parse_cell_loops(sys)
+    except OdeintrError:
+        # Not a set of loops over the cells (nested loops, a reduction ahead of the loop, statements outside any
+        # loop ...): the reference compiles any C++ into sys() (compile_sys_openmp_template.cpp:39-43).  So does the
+        # general form: the snippet verbatim, evaluated by one thread; only the steppers' vector algebra runs in
+        # parallel.  Correct for everything the reference accepts, fast for nothing.
+        body = "\n".join(l for l in _strip_comments(sys).split("\n") if not l.strip().startswith("#pragma"))
+        code = _fill(read_template("compile_sys_openmp_generic_template"), {
+            "__FUNCNAME__": name,
+            "__SYS_SIZE__": str(sys_dim),
+            "__NPARS__": str(p.n_runtime),
+            "__STEPPER_TYPE__": _LATTICE_STEPPERS[method],
+            "__HEADERS__": headers,
+            "__GLOBALS__": p.globals + globals,
+            "__LOAD_PARS__": p.load,
+            "__SYS__": body,
+            "__FOOTERS__": footers,
+        })
+        spec = StepperSpec(method, base, mode, boost_type, make_stepper_constr(method, atol, rtol), "lattice_rk.cuh",
+                           "lattice_" + base)
+        return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol), 1)
     cell = []
     for var, body in zip(loops.var_names, loops.bodies):
         cell.append("{ const auto %s = odeintr_b200::loop_index<%s>(odeintr_c); %s }" % (var, loops.var_type, body))
@@ -547,7 +569,6 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     code = code.replace("__NFIELDS__", str(len(loops.offsets)))
     code = code.replace("__CELL_START__", loops.start).replace("__CELL_BOUND__", loops.bound)
     code = code.replace("__FIELD_OFFSETS__", offs)
-    mode = "dense" if method.endswith("_i") else ("controlled" if method.endswith("_a") else "plain")
     spec = StepperSpec(method, base, mode, boost_type, make_stepper_constr(method, atol, rtol), "lattice_rk.cuh",
                        "lattice_" + base)
     return Generated(code, name, sys_dim, p, spec, "lattice", float(atol), float(rtol), len(loops.offsets))

@@ -234,6 +234,7 @@ struct odeintr_system_s {
   cudaStream_t stream2 = nullptr;        // sharded runs: the halo exchange travels here, beside the interior kernels
   cudaEvent_t ev_edges = nullptr, ev_xchg = nullptr;
   cudaKernel_t k_pilot = nullptr;
+  cudaKernel_t k_serial = nullptr;  // general large-system snippet: the right-hand side is one serial kernel (correctness path)
   int order_mode = 0;           // K6: 0 = instances in index order, 1 = sorted by the pilot's cost proxy, 2 = caller's permutation
   int pilot_attempts = 12;
   dev_buf<int> perm, perm_iota;
@@ -626,6 +627,7 @@ struct lattice_window {      // which cells a launch computes and how local buff
 int lattice_ck54_fixed_step(odeintr_system_t h, double t, double dt);  // after lattice_adaptive.h
 int lattice_rkf78_fixed_step(odeintr_system_t h, double t, double dt);
 int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt);
+int lattice_serial_fixed_step(odeintr_system_t h, double t, double dt);
 
 // launch descriptor of the tiled rk4 kernels for one step x_in -> x_out of the window w
 void tiled_args_init(odeintr_system_t h, const lattice_window& w, const double* x_in, double* x_out, double t, double dt,
@@ -735,6 +737,10 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
   double* acc = h->lat_acc;
   const unsigned grid = (unsigned)h->sm_count * 8u, block = 256u;
   int rc;
+  if (h->k_serial && (h->lattice_stages == 4 || h->lattice_stages == 1)) {
+    if (w.sharded) return fail(ODEINTR_E_STATE, "general (non-cell-loop) snippets cannot be sharded");
+    return lattice_serial_fixed_step(h, t, dt);
+  }
   if (h->lattice_stages == 4 && h->tiled2d_on && h->k_tiled2d && !w.sharded) {
     // M x M lattice with a short reach: the whole rk4 step in one temporally blocked pass over 32 x 64 tiles
     odeintr_lattice_tiled_args ta;
@@ -1288,6 +1294,40 @@ int lattice_rk5_fixed_step(odeintr_system_t h, double t, double dt) {
   return ODEINTR_OK;
 }
 
+// rk4 / euler of a GENERAL large-system snippet (odeintr_lattice_serial_rhs): Boost's own unfused schedule -- every
+// stage derivative is a stored vector, the combinations are odeintr_lattice_combo launches in scale_sumN's order
+// (coefficient * dt first, left to right, zero tableau entries skipped like everywhere else).
+int lattice_serial_fixed_step(odeintr_system_t h, double t, double dt) {
+  const size_t N = (size_t)h->N;
+  CU_TRY(h->lat_work.reserve(7 * N));
+  CU_TRY(h->lat_err.reserve(2));
+  double* w = h->lat_work.p;
+  if (!h->lat_work_primed) {
+    for (int j = 0; j < 3; ++j)
+      CU_TRY(cudaMemcpyAsync(w + (size_t)j * N, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemsetAsync(w + 3 * N, 0, 4 * N * sizeof(double), h->stream));
+    h->lat_work_primed = true;
+  }
+  lattice_dopri5 core;
+  core.h = h;
+  double *xtA = w, *xtB = w + N, *xnew = w + 2 * N, *k1 = w + 3 * N, *k2 = w + 4 * N, *k3 = w + 5 * N, *k4 = w + 6 * N;
+  const double* x = h->lat_x;
+  if (h->lattice_stages == 1) {  // euler: x + dt * f(x)
+    core.combo(x, x, 0, nullptr, nullptr, dt, xnew, k1, t);
+  } else {
+    const double half = 1.0 / 2.0, b1 = 1.0 / 6.0, b2 = 1.0 / 3.0;
+    core.combo(x, x, 0, nullptr, nullptr, half * dt, xtA, k1, t);
+    core.combo(xtA, x, 0, nullptr, nullptr, half * dt, xtB, k2, t + half * dt);
+    core.combo(xtB, x, 0, nullptr, nullptr, 1.0 * dt, xtA, k3, t + half * dt);
+    const double* v[] = {k1, k2, k3};
+    const double c[] = {b1 * dt, b2 * dt, b2 * dt};
+    core.combo(xtA, x, 3, v, c, b1 * dt, xnew, k4, t + 1.0 * dt);
+  }
+  if (core.rc) return core.rc;
+  CU_TRY(cudaMemcpyAsync(h->lat_x, xnew, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return ODEINTR_OK;
+}
+
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
@@ -1680,6 +1720,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_dopri5_tiled_h[2], h->lib, "odeintr_lattice_dopri5_tiled_h2") != cudaSuccess)
     h->k_dopri5_tiled_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
+  if (cudaLibraryGetKernel(&h->k_serial, h->lib, "odeintr_lattice_serial_rhs") != cudaSuccess) h->k_serial = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;
   (void)cudaGetLastError();
   if (!h->k_plain && !h->k_adaptive && !h->k_lattice) {
@@ -2481,6 +2522,42 @@ int odeintr_hbm_probe(int device, size_t bytes, double* bytes_per_s) {
   CU_TRY(cudaGetLastError());
   if (bytes_per_s) *bytes_per_s = 2.0 * (double)bytes / ((double)best * 1e-3);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+  return ODEINTR_OK;
+}
+
+int odeintr_pcie_probe(int device, void* host_in, size_t bytes_in, void* host_out, size_t bytes_out, double* seconds) {
+  // Ceiling of the host-buffer path: the same pinned host ranges an odeintr_integrate_*_host call reads (host_in, H2D)
+  // and writes (host_out, D2H), moved by back-to-back 256 MiB cudaMemcpyAsync copies on two streams at once -- what
+  // the chunk pipeline could reach if the kernels took no time.  Either range may be null.
+  CU_TRY(cudaSetDevice(device));
+  if (!seconds) return fail(ODEINTR_E_INVALID, "null argument");
+  const size_t chunk = (size_t)256 << 20;
+  char *dev_in = nullptr, *dev_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e_in = nullptr;
+  CU_TRY(cudaMalloc(&dev_in, chunk)); CU_TRY(cudaMalloc(&dev_out, chunk));
+  CU_TRY(cudaMemset(dev_out, 0, chunk));
+  CU_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)); CU_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreateWithFlags(&e_in, cudaEventDisableTiming));
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaEventRecord(e0, s_out));
+  CU_TRY(cudaStreamWaitEvent(s_in, e0, 0));
+  if (host_in)
+    for (size_t o = 0; o < bytes_in; o += chunk)
+      CU_TRY(cudaMemcpyAsync(dev_in, (const char*)host_in + o, std::min(chunk, bytes_in - o), cudaMemcpyHostToDevice, s_in));
+  if (host_out)
+    for (size_t o = 0; o < bytes_out; o += chunk)
+      CU_TRY(cudaMemcpyAsync((char*)host_out + o, dev_out, std::min(chunk, bytes_out - o), cudaMemcpyDeviceToHost, s_out));
+  CU_TRY(cudaEventRecord(e_in, s_in));
+  CU_TRY(cudaStreamWaitEvent(s_out, e_in, 0));
+  CU_TRY(cudaEventRecord(e1, s_out));
+  CU_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  *seconds = (double)ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e_in);
+  cudaStreamDestroy(s_in); cudaStreamDestroy(s_out);
+  cudaFree(dev_in); cudaFree(dev_out);
   return ODEINTR_OK;
 }
 

@@ -48,9 +48,38 @@ struct lattice_dopri5 {
             double adt = 0.0) {
     odeintr_lattice_combo_args a;
     std::memset(&a, 0, sizeof(a));
+    if (xs && h->k_serial) {
+      // general snippet: k = f(xs) by the serial kernel into k_out (or a scratch vector), then the same sum with k as
+      // its last stored term -- the order of the additions is unchanged
+      double* kdst = k_out;
+      if (!kdst) {
+        if (h->lat_negzero.reserve((size_t)h->N) != cudaSuccess) { if (!rc) rc = fail(ODEINTR_E_CUDA, "out of device memory"); return rc; }
+        kdst = h->lat_negzero.p;
+        cudaMemsetAsync(kdst, 0, (size_t)h->N * sizeof(double), h->stream);
+      }
+      const double* pars = h->P ? h->pars.p : nullptr;
+      void* params[4] = {(void*)&xs, (void*)&kdst, (void*)&pars, (void*)&t};
+      if (cudaLaunchKernel((const void*)h->k_serial, dim3(1), dim3(32), params, 0, h->stream) != cudaSuccess) {
+        if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_serial_rhs failed");
+        return rc;
+      }
+      h->last_launches += 1;
+      g_total_launches += 1;
+      const double* in2[12];
+      double c2[12];
+      for (int j = 0; j < nin; ++j) { in2[j] = in[j]; c2[j] = c[j]; }
+      int n2 = nin;
+      if (ck != 0.0) { in2[n2] = kdst; c2[n2] = ck; ++n2; }  // (a zero weight is a skipped tableau entry)
+      if (!out && !err_x) return 0;  // the derivative alone was asked for
+      xs = nullptr; in = in2; c = c2; nin = n2; ck = 0.0; k_out = nullptr;
+      a.xs = nullptr; a.base = base; a.nin = nin;
+      for (int j = 0; j < nin; ++j) { a.in[j] = in[j]; a.c[j] = c[j]; }
+      a.ck = 0.0; a.out = out; a.k_out = nullptr;
+    } else {
     a.xs = xs; a.base = base; a.nin = nin;
     for (int j = 0; j < nin; ++j) { a.in[j] = in[j]; a.c[j] = c[j]; }
     a.ck = ck; a.out = out; a.k_out = k_out;
+    }
     a.err_x = err_x; a.err_d = err_d; a.eps_abs = h->atol; a.eps_rel = h->rtol; a.adt = adt;
     a.err_max = err_x ? h->lat_err.p : nullptr;
     a.pars = h->P ? h->pars.p : nullptr;

@@ -84,8 +84,6 @@ def test_oscillator_chain_two_fields_runtime_parameters(halo):
 def test_large_system_errors():
     with pytest.raises(odeintr_b200.OdeintrError, match="sys_dim"):
         odeintr_b200.compile_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method="rk4")
-    with pytest.raises(odeintr_b200.OdeintrError, match="loops over the cells"):
-        odeintr_b200.compile_sys_openmp("b", "dxdt[0] = x[1]; dxdt[1] = -x[0];", method="rk4", sys_dim=2)
     with pytest.raises(odeintr_b200.OdeintrError, match="Invalid integration method"):
         odeintr_b200.compile_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method="rk4_a", sys_dim=64)
 
@@ -634,3 +632,50 @@ def test_sharded_adaptive_dopri5_single_rank_matches_unsharded(case, method):
     rec_ref = env["ref"](fin_ref, 1.0, 0.25, 3.45)
     t, x = lat.integrate_const(1.0, 0.25, start=3.45)
     assert np.array_equal(t, rec_ref["Time"].to_numpy()) and np.array_equal(bits(x.reshape(len(t), -1)), bits(cols(rec_ref)))
+
+
+MEAN_FIELD = """
+double m = 0.0;
+for (int i = 0; i < N; ++i) m += x[i];
+m /= N;
+#pragma omp parallel for
+for (int i = 0; i < N; ++i) dxdt[i] = -x[i] + K * (m - x[i]) * x[i];
+dxdt[0] += 0.1 * std::sin(t);
+"""
+NESTED_2D = """
+for (int i = 0; i < M; ++i)
+  for (int j = 0; j < M; ++j)
+    dxdt[i * M + j] = D * laplace2D(x, i, j) + x[i * M + j] * (1 - x[i * M + j]) * (x[i * M + j] - 0.5);
+"""
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler", "rk5_i", "rk5_a", "rk54_a", "rk78", "rk5"])
+@pytest.mark.parametrize("case", ["mean_field", "nested_2d", "straight_line"])
+def test_general_snippets_take_the_serial_rhs_path(case, method):
+    # compile_sys_openmp pastes ANY C++ into sys() (inst/templates/compile_sys_openmp_template.cpp:39-43).  Snippets
+    # that are not loops over the cells -- a reduction ahead of the loop (mean-field coupling), nested i / j loops,
+    # statements outside any loop, no loop at all -- cannot be dealt out one cell per thread; they run on the general
+    # path: the snippet verbatim in one thread (the reference's own evaluation order), the steppers' vector algebra in
+    # parallel on stored stage derivatives.  Same bits as the oracle, for every method of the large-system table.
+    if case == "mean_field":
+        n, src, pars = 777, MEAN_FIELD, {"K": 0.5}
+    elif case == "nested_2d":
+        n, src, pars = 24 * 24, NESTED_2D, {"D": 0.1}
+    else:
+        n, src, pars = 2, "dxdt[0] = x[1]; dxdt[1] = -x[0] - 0.1 * x[1];", None
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("g", src, pars, True, method=method, sys_dim=n, env=env)
+    assert "odeintr_lattice_serial_rhs" in code.code
+    ora = bo.build(src, pars, True, method, sys_dim=n)
+    x0 = np.random.default_rng(n).uniform(0, 1, n)
+    df = env["g"](x0, 2.0, 0.25)
+    ref = ora.integrate_const(x0, 0, 2.0, 0.25)
+    assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    at = np.array([0.5, 1.0, 2.2])
+    df = env["g_at"](x0, at, 0.1)
+    adv = ora.integrate_const(x0, 0.0, at[0], 0.1, record=False)
+    ref = ora.integrate_times(adv["x"], at, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["g_no_record"](x0, 1.05, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.05, 0.1)["x"]))

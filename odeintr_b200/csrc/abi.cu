@@ -160,6 +160,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TILE_CPT")) o.push_back(std::string("-DODEINTR_TILE_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
+  if (const char* c = std::getenv("ODEINTR_WARP_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE5_CPT")) o.push_back(std::string("-DODEINTR_TILE5_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE5_MIN_BLOCKS=") + c);

@@ -60,13 +60,7 @@ struct lu_factors {
     for (int n = 0; n < N; ++n) inv_diag[n] = 1.0 / m(n, n);
   }
 #else
-  // exact mode: the same quotients as uBLAS' divisions, bit for bit, from the pivots' correctly rounded reciprocals
-  // (exact_div.cuh): N true divisions per attempt instead of 6 N
-  divisor pivot[N];
-  ODEINTR_DEV void prepare() {
-#pragma unroll
-    for (int n = 0; n < N; ++n) pivot[n] = divisor(m(n, n));
-  }
+  ODEINTR_DEV void prepare() {}
 #endif
 
   // uBLAS lu_substitute: row swaps, unit-lower forward solve, upper backward solve (column oriented)
@@ -92,7 +86,9 @@ struct lu_factors {
 #ifdef ODEINTR_RECIPROCAL
       const double t = v[n] *= inv_diag[n];
 #else
-      const double t = v[n] = pivot[n].under(v[n]);
+      // (a corrected-reciprocal quotient, exact_div.cuh, was measured here in round 2: bit-identical but no faster than
+      //  the device's division sequence, and it costs registers -- 0.94e10 against 1.02e10 accepted steps/s)
+      const double t = v[n] /= m(n, n);
 #endif
 #pragma unroll
       for (int r = 0; r < n; ++r) v[r] -= t * m(r, n);
@@ -163,8 +159,7 @@ struct rosenbrock4_dense {
     const double rh = 1.0 / h;
 #define ODEINTR_OVER_H(e) ((e) * rh)
 #else
-    const divisor over_h(h);  // fifteen divisions by the step size per attempt, one reciprocal
-#define ODEINTR_OVER_H(e) (over_h.under(e))
+#define ODEINTR_OVER_H(e) ((e) / h)
 #endif
 #pragma unroll
     for (int i = 0; i < N; ++i) g1[i] = dxdt[i] + h * K::d1 * dfdt[i];

@@ -665,7 +665,7 @@ def test_general_snippets_take_the_serial_rhs_path(case, method):
         n, src, pars = 2, "dxdt[0] = x[1]; dxdt[1] = -x[0] - 0.1 * x[1];", None
     env = {}
     code = odeintr_b200.compile_sys_openmp("g", src, pars, True, method=method, sys_dim=n, env=env)
-    assert "odeintr_lattice_serial_rhs" in code.code
+    assert "odeintr_lattice_serial_rhs" in code
     ora = bo.build(src, pars, True, method, sys_dim=n)
     x0 = np.random.default_rng(n).uniform(0, 1, n)
     df = env["g"](x0, 2.0, 0.25)

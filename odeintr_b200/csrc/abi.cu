@@ -266,6 +266,7 @@ struct odeintr_system_s {
   dev_buf<int> lat_flag;
   int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a, 4 = rk78_a
   dev_buf<double> lat_work;
+  bool lat_mid_primed = false;   // the intermediate state of fused step pairs holds x on the cells no loop writes
   bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 / rk78 / rk5 paths hold copies of x / zeros
   int lat_rk5_parity = 0;        // which of the two derivative vectors holds k1 of the next rk5 step
   dev_buf<unsigned long long> lat_err;
@@ -687,7 +688,9 @@ int tiled_produce(odeintr_system_t h, odeintr_lattice_tiled_args ta, long long l
   int mode = 0;  // 1 = warp kernel, 2 = block-tiled interior kernels
   if (interior && h->k_warp && h->warp_blocks > 0 && !std::getenv("ODEINTR_NO_WARP")) {
     const long long P = 32LL * h->warp_cpt - 8LL * h->warp_halo;
-    long long wlo = ilo, whi = ihi;
+    // the warp kernel evaluates EVERY cell of its windows, the outermost (discarded) ones included: keep their own
+    // neighbours inside the user loop's range as well, so that an absolute index never reaches across the seam
+    long long wlo = std::max(ilo, glo + margin + h->lattice_halo), whi = std::min(ihi, ghi - margin - h->lattice_halo);
     const bool tma = even_fields && !std::getenv("ODEINTR_NO_TMA");
     if (tma) {
       if ((wlo - ta.c0) & 1) ++wlo;
@@ -723,6 +726,58 @@ int tiled_produce(odeintr_system_t h, odeintr_lattice_tiled_args ta, long long l
     }
     return tiled_launch(h, h->k_tiled_int, (unsigned)n_full, h->tiled_int_smem, ta);
   }
+  return ODEINTR_OK;
+}
+
+// Two rk4 steps of a 1-D large system in ONE pass of the warp kernel (a.nsub = 2): the interior goes x -> x'' without
+// the intermediate state ever reaching HBM (8 B per cell and step instead of 16); the few hundred cells at the ends of
+// the loop range / the periodic seam take the general kernel twice, through an intermediate array.  Pays when a single
+// step is bound by HBM (several fields).  Same operations per cell as two separate steps: bit-identical.
+enum { LATTICE_NOT_FUSED = -1001 };
+int lattice_step_pair(odeintr_system_t h, const lattice_window& w, double t, double t2, double dt) {
+  const char* knob = std::getenv("ODEINTR_FUSE");
+  const int fields = h->lat_cells_ct > 0 ? (int)((long long)h->N / h->lat_cells_ct) : 1;
+  const bool want = knob ? std::atoi(knob) != 0 : fields >= 2;
+  if (!want || w.sharded || h->lattice_stages != 4 || !h->tiled_on || h->tiled2d_on || !h->k_tiled || !h->k_warp ||
+      h->warp_blocks <= 0 || h->k_serial || std::getenv("ODEINTR_NO_WARP") || std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
+    return LATTICE_NOT_FUSED;
+  odeintr_lattice_tiled_args ta;
+  tiled_args_init(h, w, h->lat_x, h->lat_a, t, dt, ta);
+  if (h->lat_cells_ct != ta.n_total) return LATTICE_NOT_FUSED;
+  const long long glo = h->lat_start > 0 ? h->lat_start : 0;
+  const long long ghi = h->lat_bound < ta.n_total ? h->lat_bound : ta.n_total;
+  const long long m1 = 4 * h->lattice_halo;  // margin of one step
+  const long long P = 32LL * h->warp_cpt - 16LL * h->warp_halo;
+  long long ilo = glo + 2 * m1 + h->lattice_halo, ihi = ghi - 2 * m1 - h->lattice_halo;
+  const bool tma = (reinterpret_cast<uintptr_t>(ta.x_in) % 16 == 0) && (reinterpret_cast<uintptr_t>(ta.x_out) % 16 == 0) &&
+                   (fields == 1 || ta.pitch % 2 == 0) && !std::getenv("ODEINTR_NO_TMA");
+  if (tma) {
+    if (ilo & 1) ++ilo;
+    if (ihi & 1) --ihi;
+  }
+  if (P < 32 || ihi - ilo < P) return LATTICE_NOT_FUSED;
+  const size_t N = (size_t)h->N;
+  CU_TRY(h->lat_buf_acc.reserve(N));
+  double* mid = h->lat_buf_acc.p;
+  const bool covers_all = h->lat_cells_ct > 0 && h->lat_start <= 0 && h->lat_bound >= h->lat_cells_ct;
+  if (!covers_all && !h->lat_mid_primed)  // cells no loop writes never change: one copy per integrate call
+    CU_TRY(cudaMemcpyAsync(mid, h->lat_x, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->lat_mid_primed = true;
+  int rc;
+  // the ends, first step: x -> mid on the end ranges widened by one step's margin (what the second step reads)
+  odeintr_lattice_tiled_args e1 = ta;
+  e1.x_out = mid;
+  if ((rc = tiled_general(h, e1, glo, std::min(ilo + m1, ghi), std::max(ihi - m1, glo), ghi))) return rc;
+  // the ends, second step: mid -> x_out
+  odeintr_lattice_tiled_args e2 = ta;
+  e2.x_in = mid; e2.t = t2;
+  if ((rc = tiled_general(h, e2, glo, ilo, ihi, ghi))) return rc;
+  // the interior: both steps in registers
+  ta.lo = ilo; ta.hi = ihi; ta.sharded = 0; ta.tma = tma ? 1 : 0; ta.nsub = 2; ta.t2 = t2;
+  const long long warp_tiles = (ihi - ilo + P - 1) / P;
+  const unsigned grid = (unsigned)std::min<long long>((warp_tiles + 7) / 8, (long long)h->sm_count * h->warp_blocks);
+  if ((rc = tiled_launch(h, h->k_warp, grid, h->warp_smem, ta))) return rc;
+  std::swap(h->lat_x, h->lat_a);
   return ODEINTR_OK;
 }
 
@@ -980,6 +1035,7 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
   CU_TRY(h->lat_flag.reserve(1));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
   h->lat_work_primed = false;
+  h->lat_mid_primed = false;
   if ((rc = begin_timing(h))) return rc;
   size_t row = 0;
   auto observe = [&]() -> int {
@@ -993,9 +1049,19 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
     if (!sc.uniform) t = sc.t[(size_t)s];
     if (sc.record && (sc.uniform || sc.obs[(size_t)s])) if ((rc = observe())) return rc;
     const long long nfull = sc.uniform ? sc.nfull_uniform : sc.nfull[(size_t)s];
-    for (long long k = 0; k < nfull; ++k) {
+    for (long long k = 0; k < nfull;) {
+      if (k + 1 < nfull) {  // two steps in one pass where that pays (lattice_step_pair)
+        const double t_b = (sc.time_rule == ODEINTR_TIME_CONST) ? sc.t0 + static_cast<double>(step + 1) * sc.dt : t + sc.dt;
+        rc = lattice_step_pair(h, w, t, t_b, sc.dt);
+        if (rc == ODEINTR_OK) {
+          step += 2; k += 2;
+          t = (sc.time_rule == ODEINTR_TIME_CONST) ? sc.t0 + static_cast<double>(step) * sc.dt : t_b + sc.dt;
+          continue;
+        }
+        if (rc != LATTICE_NOT_FUSED) return rc;
+      }
       if ((rc = lattice_step(h, w, t, sc.dt, 0))) return rc;
-      ++step;
+      ++step; ++k;
       t = (sc.time_rule == ODEINTR_TIME_CONST) ? sc.t0 + static_cast<double>(step) * sc.dt : t + sc.dt;
     }
     if (!sc.uniform && sc.hrem[(size_t)s] != 0.0) {

@@ -183,4 +183,6 @@ struct odeintr_lattice_tiled_args {
   long long lo2;              // general kernel: a second range of cells [lo2, hi2) after [lo, hi) -- what is left on
   long long hi2;              // either side of the cells the interior / warp kernel produces
   int tma;                    // warp kernel: windows are 16-byte aligned, move them with the TMA engine
+  int nsub;                   // warp kernel: rk4 steps per pass (1, or 2: the second one at time t2)
+  double t2;
 };

@@ -29,10 +29,10 @@
 #include "odeintr_b200/lattice_tiled.cuh"
 
 #ifndef ODEINTR_WARP_CPT  // cells per lane: odd (bank-conflict-free lane stride), >= the radius
-#define ODEINTR_WARP_CPT (ODEINTR_NFIELDS > 2 ? 3 : (ODEINTR_NFIELDS > 1 ? 5 : 7))
+#define ODEINTR_WARP_CPT (ODEINTR_NFIELDS > 2 ? 3 : (ODEINTR_NFIELDS > 1 ? 5 : 11))
 #endif
 #ifndef ODEINTR_WARP_MIN_BLOCKS
-#define ODEINTR_WARP_MIN_BLOCKS (ODEINTR_NFIELDS > 1 ? 2 : 3)
+#define ODEINTR_WARP_MIN_BLOCKS 2  // 128 registers: the compiler interleaves the lane's independent cells (measured: 3 blocks of 85 registers lose 8 %)
 #endif
 
 #if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
@@ -90,7 +90,12 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
   constexpr int F = ODEINTR_NFIELDS;
   constexpr int C = ODEINTR_WARP_CPT;
   constexpr int WC = 32 * C;      // cells of a warp's window
-  constexpr int P = WC - 8 * H;   // cells of the new state it yields
+  // Steps per pass: a.nsub = 2 takes TWO rk4 steps (at a.t and a.t2) before anything goes back to HBM -- 8 bytes per
+  // cell and step instead of 16 for systems whose single step is bound by HBM (the two-field oscillator chain), at
+  // the price of a margin twice as wide.
+  const int nsub = a.nsub > 1 ? 2 : 1;
+  const int M4 = 4 * H * nsub;    // margin: cells on either side of the window that do not survive the pass
+  const int P = WC - 2 * M4;      // cells of the new state a warp tile yields
   constexpr int S = C + 2 * H;
   constexpr int WPB = 8;          // warps per block
   constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
@@ -129,7 +134,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
   };
   const unsigned bytes = static_cast<unsigned>(WC * sizeof(double));
   auto prefetch = [&](const long long w, const int b) {  // lane 0: window of tile w -> input buffer b
-    const long long ws = tile_start(w) - 4 * H;
+    const long long ws = tile_start(w) - M4;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' reads of this buffer come first
     mbar_expect_tx(bar + b, bytes * F);
 #pragma unroll
@@ -152,7 +157,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
   int it = 0;
   for (long long w = first; w < n_tiles; w += stride, ++it) {
     const int b = it & 1;
-    const long long s = tile_start(w), ws = s - 4 * H;
+    const long long s = tile_start(w), ws = s - M4;
     double* in = in0 + b * F * WC;
     if (tma) {
       mbar_wait(bar + b, (it >> 1) & 1);
@@ -180,11 +185,14 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
     __syncwarp();  // every lane has its cells: the input buffer is free for the tile after the next
     if (tma && lane == 0 && w + 2 * stride < n_tiles) prefetch(w + 2 * stride, b);
 
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+    const double t_step = sub == 0 ? a.t : a.t2;
 #pragma unroll
     for (int stage = 1; stage <= 4; ++stage) {
       const double a_dt = stage == 1 ? half * dt : (stage == 2 ? half * dt : 1.0 * dt);
       const double b_dt = stage == 1 ? b1 * dt : (stage == 2 ? b2 * dt : (stage == 3 ? b2 * dt : b1 * dt));
-      const double ts = stage == 1 ? a.t : (stage == 4 ? a.t + 1.0 * dt : a.t + half * dt);
+      const double ts = stage == 1 ? t_step : (stage == 4 ? t_step + 1.0 * dt : t_step + half * dt);
       // register window of the stage input: own cells + H cells of either neighbour lane
       double ext[F][S];
 #pragma unroll
@@ -212,8 +220,18 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
         }
       }
     }
+    if (sub + 1 < nsub) {  // the state after the first step is the start of the second
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          xs[k][f] = acc[k][f];
+          own[k][fld[f]] = acc[k][f];
+        }
+    }
+    }
 
-    // new state -> staging buffer -> HBM (the window's outer 4 H cells on each side are not part of it)
+    // new state -> staging buffer -> HBM (the window's outer 4 H cells per step on each side are not part of it)
     double* out = out0 + b * F * WC;
     if (tma) {
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued from `out` two tiles ago
@@ -229,7 +247,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
       if (lane == 0) {
 #pragma unroll
         for (int f = 0; f < F; ++f)
-          tma_store_1d(a.x_out + fld[f] * a.pitch + (s - a.c0), out + fld[f] * WC + 4 * H, static_cast<unsigned>(P * sizeof(double)));
+          tma_store_1d(a.x_out + fld[f] * a.pitch + (s - a.c0), out + fld[f] * WC + M4, static_cast<unsigned>(P * sizeof(double)));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     } else {
@@ -237,7 +255,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         double* g = a.x_out + fld[f] * a.pitch + (s - a.c0);
-        for (int j = lane; j < P; j += 32) g[j] = out[fld[f] * WC + 4 * H + j];
+        for (int j = lane; j < P; j += 32) g[j] = out[fld[f] * WC + M4 + j];
       }
       __syncwarp();
     }

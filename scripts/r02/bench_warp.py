@@ -24,8 +24,9 @@ for name in (sys.argv[2:] or ["bistable", "chain"]):
     if x0 is None: x0 = x_chain
     s = odeintr_b200.compile_sys_openmp(name, src, pars, True, method="rk4", sys_dim=n, globals=glob).system
     digests = {}
-    for label, env in (("warp_tma", {}), ("warp_plain", {"ODEINTR_NO_TMA": "1"}), ("block_tma", {"ODEINTR_NO_WARP": "1"})):
-        for k in ("ODEINTR_NO_TMA", "ODEINTR_NO_WARP"):
+    for label, env in (("warp_tma", {"ODEINTR_FUSE": "0"}), ("warp_tma_two_steps_per_pass", {"ODEINTR_FUSE": "1"}),
+                       ("warp_plain", {"ODEINTR_NO_TMA": "1", "ODEINTR_FUSE": "0"}), ("block_tma", {"ODEINTR_NO_WARP": "1"})):
+        for k in ("ODEINTR_NO_TMA", "ODEINTR_NO_WARP", "ODEINTR_FUSE"):
             os.environ.pop(k, None)
         os.environ.update(env)
         best = None
@@ -37,7 +38,7 @@ for name in (sys.argv[2:] or ["bistable", "chain"]):
         digests[label] = hashlib.sha1(fin.tobytes()).hexdigest()
         rate = n * steps / best * 1e3
         print(json.dumps({"case": name, "path": label, "ms_per_step": best / steps, "rate": rate, "fp64_frac": rate * dpi / dp.value,
-                          "hbm_GBps": rate * 16 / 1e9, "launches": s.last_launches(), "sha1": digests[label][:12]}), flush=True)
+                          "hbm_GBps": rate * (8 if "two_steps" in label else 16) / 1e9, "launches": s.last_launches(), "sha1": digests[label][:12]}), flush=True)
     print(name, "all paths bit-identical:", len(set(digests.values())) == 1, flush=True)
     for k in ("odeintr_lattice_rk4_warp_h1", "odeintr_lattice_rk4_tiled_tma"):
         print(k, s.kernel_attributes(k), flush=True)

@@ -679,3 +679,46 @@ def test_general_snippets_take_the_serial_rhs_path(case, method):
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
     fin = env["g_no_record"](x0, 1.05, 0.1)
     assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 1.05, 0.1)["x"]))
+
+
+@pytest.mark.parametrize("case", ["bistable", "chain", "fixed_ends", "radius_2"])
+def test_two_rk4_steps_per_pass_bit_exact(case, monkeypatch):
+    # lattice_step_pair: the warp kernel takes two rk4 steps per pass (the state between them never reaches HBM), the
+    # cells at the ends of the loop range / the periodic seam go through the general kernel twice via an intermediate
+    # array.  Odd step counts leave a single step at the end; observers between steps break the pairs up; loops that
+    # leave cells alone need those cells in the intermediate array too.  Forced on here (by default it is used where a
+    # single step is HBM-bound: several fields); every case must give the oracle's bits.
+    monkeypatch.setenv("ODEINTR_FUSE", "1")
+    pars, glob = BISTABLE_PARS, ""
+    if case == "chain":
+        L = 20010
+        n, src, pars, glob = 2 * L, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
+        x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(L) / L), 0.1 * np.cos(2 * np.pi * 3 * np.arange(L) / L)])
+    elif case == "bistable":
+        n, src = 30011, BISTABLE_1D
+        x0 = np.random.default_rng(101).uniform(0, 1, n)
+    elif case == "fixed_ends":
+        n = 30011
+        src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + a * x[i] * (1 - x[i]) * (x[i] - b);"
+        x0 = np.random.default_rng(102).uniform(0, 1, n)
+    else:
+        n = 30011
+        src = ("for (int i = 0; i < N; ++i) dxdt[i] = D * (x[(i + N - 2) % N] + x[(i + 2) % N] + x[(i + N - 1) % N] "
+               "+ x[(i + 1) % N] - 4.0 * x[i]) - 0.2 * x[i];")
+        x0 = np.random.default_rng(103).uniform(0, 1, n)
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("f2", src, pars, True, method="rk4", sys_dim=n, globals=glob, env=env)
+    ora = bo.build(src, pars, True, "rk4", sys_dim=n, globals=glob)
+    fin = env["f2_no_record"](x0, 0.7, 0.1)  # 7 steps: three pairs and a single step
+    launches = code.system.last_launches()
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0.0, 0.7, 0.1)["x"]))
+    assert launches <= 3 * 3 + 3, launches  # a pair costs at most three launches (two for the ends, one for the interior)
+    # observer every third step (obs_stride through the C-ABI): pairs inside a segment, a single step left over
+    s = code.system
+    s.set_state(x0)
+    s.reset_observer()
+    from odeintr_b200 import _abi
+    assert s._lib.odeintr_integrate_const(s._h, 0.0, 0.9, 0.1, 3, 1) == 0, _abi.last_error()
+    rec = s.get_output()
+    ref = ora.integrate_const(x0, 0.0, 0.9, 0.1)
+    assert np.array_equal(bits(cols(rec)), bits(ref["rec"][::3]))

@@ -23,15 +23,17 @@ def sm_count():
     return torch.cuda.get_device_properties(0).multi_processor_count
 
 
-@pytest.mark.parametrize("case", ["one_field", "two_fields", "one_field_odd_start"])
-def test_persistent_tiled_rk4_many_tiles_per_block_bit_exact(case):
+@pytest.mark.parametrize("case", ["one_field", "two_fields", "one_field_odd_start", "one_field_two_steps_per_pass"])
+def test_persistent_tiled_rk4_many_tiles_per_block_bit_exact(case, monkeypatch):
     # 2^21 + 6 cells: > 2000 tiles of 1024 cells (> 8000 warp tiles) on at most 148 x 4 resident blocks, so every
     # persistent block walks through several tiles; the ragged end and the periodic seam go to the general kernel
     if case == "two_fields":
         L = (1 << 20) + 2  # even distance between the fields: TMA-aligned windows
         n, src, pars, glob = 2 * L, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
         x0 = np.concatenate([np.sin(2 * np.pi * 8 * np.arange(L) / L), 0.1 * np.cos(2 * np.pi * 3 * np.arange(L) / L)])
-    elif case == "one_field":
+    elif case in ("one_field", "one_field_two_steps_per_pass"):
+        if case != "one_field":
+            monkeypatch.setenv("ODEINTR_FUSE", "1")  # (the default for several fields: "two_fields" above)
         n, src, pars, glob = (1 << 21) + 6, BISTABLE_1D, BISTABLE_PARS, ""
         x0 = np.random.default_rng(81).uniform(0, 1, n)
     else:

@@ -251,6 +251,9 @@ struct odeintr_system_s {
   bool tiled_pending = false;   // measure the radius at the next integrate call
   bool tiled2d_on = false;      // M x M lattice: rk4 steps go through odeintr_lattice_rk4_tiled2d
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
+  cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
+  int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
+  size_t warp5_smem = 0;
   long long tiled5_halo = 0;
   size_t tiled5_smem = 0;
   long long lat_side = 0;       // M when the snippet addresses an M x M lattice (one field), else 0
@@ -1215,6 +1218,26 @@ int tiled5_decide(odeintr_system_t h) {
   h->tiled5_halo = reach;
   h->tiled5_smem = smem;
   h->tiled5 = 1;
+  // radius <= 2: the interior cells of an attempt go to the warp-autonomous kernel (lattice_dopri5_warp.cuh)
+  h->k_warp5 = nullptr; h->warp5_blocks = 0;
+  const int wh = reach < 1 ? 1 : reach;
+  if (wh <= 2 && h->k_warp5_h[wh] && h->k_warp5_info && !std::getenv("ODEINTR_NO_WARP")) {
+    void* wout = h->lat_flag.p;
+    void* wparams[1] = {&wout};
+    int cpt = 0;
+    CU_TRY(cudaLaunchKernel((const void*)h->k_warp5_info, dim3(1), dim3(1), wparams, 0, h->stream));
+    CU_TRY(cudaMemcpyAsync(&cpt, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    const size_t wsmem = 8 * (8 * (size_t)fields * 32 * (size_t)cpt * sizeof(double) + 2 * sizeof(unsigned long long));
+    int nb = 0;
+    if (cpt >= wh && (cpt & 1) && 32 * cpt > 12 * wh && wsmem <= 220 * 1024 &&
+        cudaFuncSetAttribute((const void*)h->k_warp5_h[wh], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_warp5_h[wh], 256, wsmem) == cudaSuccess && nb > 0) {
+      h->k_warp5 = h->k_warp5_h[wh];
+      h->warp5_cpt = cpt; h->warp5_halo = wh; h->warp5_smem = wsmem; h->warp5_blocks = nb;
+    }
+    (void)cudaGetLastError();
+  }
   return ODEINTR_OK;
 }
 
@@ -1787,6 +1810,9 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
     h->k_dopri5_tiled_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_dopri5_tiled_h[2], h->lib, "odeintr_lattice_dopri5_tiled_h2") != cudaSuccess)
     h->k_dopri5_tiled_h[2] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp5_h[1], h->lib, "odeintr_lattice_dopri5_warp_h1") != cudaSuccess) h->k_warp5_h[1] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp5_h[2], h->lib, "odeintr_lattice_dopri5_warp_h2") != cudaSuccess) h->k_warp5_h[2] = nullptr;
+  if (cudaLibraryGetKernel(&h->k_warp5_info, h->lib, "odeintr_lattice_dopri5_warp_info") != cudaSuccess) h->k_warp5_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_serial, h->lib, "odeintr_lattice_serial_rhs") != cudaSuccess) h->k_serial = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;

@@ -150,6 +150,7 @@ struct odeintr_lattice_dopri5_args {
   // c0 = 0, pitch = L, sharded = 0 (the window is then loaded with the cell index wrapped periodically).
   long long own_lo, own_hi, c0, pitch;
   int sharded;
+  int tma;                    // warp kernel (lattice_dopri5_warp.cuh): 16-byte aligned windows, move them with the TMA engine
 };
 
 // Ensemble of wider systems, one trajectory per block (lattice_ensemble.cuh): the fixed-step schedule of

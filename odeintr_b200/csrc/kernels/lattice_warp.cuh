@@ -35,16 +35,16 @@
 #define ODEINTR_WARP_MIN_BLOCKS 2  // 128 registers: the compiler interleaves the lane's independent cells (measured: 3 blocks of 85 registers lose 8 %)
 #endif
 
-#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC)
 
 namespace odeintr_b200 {
 
 // View of one stage's input for cell k of a lane: `e` points at (field 0, cell k) inside the lane's register window
 // ext[field][C + 2 H] (H neighbour cells on each side of its C own cells).  Field and displacement of every access
 // of an ordinary stencil are compile-time constants after inlining, so the select chain below folds to one register.
-template <int H>
+template <int H, int C>
 struct lattice_reg_view {
-  static constexpr int S = ODEINTR_WARP_CPT + 2 * H;  // doubles between fields
+  static constexpr int S = C + 2 * H;  // doubles between fields
   const double* e;
   long long n_total;  // cells per field
   int centre;         // global number of the cell being computed (absolute-index path)
@@ -83,6 +83,14 @@ ODEINTR_DEV void tma_store_1d(void* gdst, const void* ssrc, const unsigned bytes
                : "memory");
 }
 
+}  // namespace odeintr_b200
+
+#endif
+
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
+
+namespace odeintr_b200 {
+
 // Shared memory of a block of 8 warps: per warp two input windows and two output staging windows of F * 32 C doubles,
 // then two mbarriers per warp.
 template <int H>
@@ -100,7 +108,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
   constexpr int WPB = 8;          // warps per block
   constexpr long long L = static_cast<long long>(ODEINTR_SYS_SIZE) / ODEINTR_NFIELDS;
   static_assert(C % 2 == 1 && C >= H, "cells per lane: odd and at least the stencil radius");
-  typedef odeintr::system_type_t<lattice_reg_view<H> > Sys;
+  typedef odeintr::system_type_t<lattice_reg_view<H, C> > Sys;
   extern __shared__ __align__(128) double smem_w[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* in0 = smem_w + warp * (4 * F * WC);
@@ -146,7 +154,7 @@ ODEINTR_DEV void lattice_rk4_warp_body(const odeintr_lattice_tiled_args& a) {
     if (first + stride < n_tiles) prefetch(first + stride, 1);
   }
 
-  lattice_reg_view<H> view;
+  lattice_reg_view<H, C> view;
   view.n_total = L; view.bad = 0;
   rel_index idx;
   idx.off = 0; idx.cells = static_cast<int>(L); idx.rel = true;

@@ -128,14 +128,56 @@ struct lattice_dopri5 {
     } else {
       a.own_lo = 0; a.own_hi = L; a.c0 = 0; a.pitch = L; a.sharded = 0;
     }
-    void* params[1] = {&a};
-    if (cudaLaunchKernel((const void*)h->k_dopri5_tiled, dim3((unsigned)((cells + tile - 1) / tile)), dim3(256), params,
-                         h->tiled5_smem, h->stream) != cudaSuccess) {
-      if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_tiled failed");
-      return -1.0;
+    // one launch of the block-tiled kernel over the cells [lo, hi)
+    auto launch_tiled = [&](long long lo, long long hi) -> bool {
+      if (hi <= lo) return true;
+      odeintr_lattice_dopri5_args at = a;
+      at.own_lo = lo; at.own_hi = hi;
+      void* params[1] = {&at};
+      if (cudaLaunchKernel((const void*)h->k_dopri5_tiled, dim3((unsigned)((hi - lo + tile - 1) / tile)), dim3(256), params,
+                           h->tiled5_smem, h->stream) != cudaSuccess) {
+        if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_tiled failed");
+        return false;
+      }
+      h->last_launches += 1;
+      g_total_launches += 1;
+      return true;
+    };
+    (void)cells;
+    // Interior cells -- the whole window of 6 * halo (+ halo: the warp kernel evaluates its outermost cells too) around
+    // them inside the user loop's range, away from the periodic seam -- go to the warp-autonomous kernel.
+    bool warp_done = false;
+    if (h->k_warp5 && h->warp5_blocks > 0) {
+      const long long hh = h->warp5_halo, m6 = 6 * hh + h->tiled5_halo;
+      const long long glo = h->lat_start > 0 ? h->lat_start : 0, ghi = h->lat_bound < L ? h->lat_bound : L;
+      long long ilo = std::max(a.own_lo, glo + m6), ihi = std::min(a.own_hi, ghi - m6);
+      const int nf = (int)((long long)h->N / L);
+      const double* outs[2] = {dense_out ? dense_out : out, dense_out ? dense_out : d_out};
+      bool tma = !std::getenv("ODEINTR_NO_TMA") && (nf == 1 || a.pitch % 2 == 0) &&
+                 reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(d_in) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(outs[0]) % 16 == 0 && reinterpret_cast<uintptr_t>(outs[1]) % 16 == 0;
+      if (tma) {
+        if ((ilo - a.c0) & 1) ++ilo;
+        if ((ihi - a.c0) & 1) --ihi;
+      }
+      const long long P = 32LL * h->warp5_cpt - 12LL * hh;
+      if (ihi - ilo >= P) {
+        odeintr_lattice_dopri5_args aw = a;
+        aw.own_lo = ilo; aw.own_hi = ihi; aw.tma = tma ? 1 : 0;
+        const long long warp_tiles = (ihi - ilo + P - 1) / P;
+        const unsigned grid = (unsigned)std::min<long long>((warp_tiles + 7) / 8, (long long)h->sm_count * h->warp5_blocks);
+        void* params[1] = {&aw};
+        if (cudaLaunchKernel((const void*)h->k_warp5, dim3(grid), dim3(256), params, h->warp5_smem, h->stream) != cudaSuccess) {
+          if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_warp failed");
+          return -1.0;
+        }
+        h->last_launches += 1;
+        g_total_launches += 1;
+        if (!launch_tiled(a.own_lo, ilo) || !launch_tiled(ihi, a.own_hi)) return -1.0;
+        warp_done = true;
+      }
     }
-    h->last_launches += 1;
-    g_total_launches += 1;
+    if (!warp_done && !launch_tiled(a.own_lo, a.own_hi)) return -1.0;
     if (dense_out) return 0.0;  // nothing to read back: the attempt it repeats has already been vetted
     if (slab) {  // error norm over the whole lattice: max over the ranks' slabs (one small all-reduce per attempt)
       const int erc = slab_allreduce_err(h);

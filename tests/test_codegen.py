@@ -145,7 +145,8 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
     for method in ("rk5_i", "rk5_a", "rk5"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
-        assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2"}
+        assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2",
+                              "odeintr_lattice_dopri5_warp_h1", "odeintr_lattice_dopri5_warp_h2", "odeintr_lattice_dopri5_warp_info"}
     for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged

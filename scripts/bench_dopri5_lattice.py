@@ -12,7 +12,7 @@ lib = _abi.load()
 logn = int(os.environ.get("LOGN", "26"))
 n = 1 << logn
 x0 = np.random.default_rng(1).uniform(0, 1, n)
-tag = "staged" if os.environ.get("ODEINTR_NO_TILED") else "tiled"
+tag = "staged" if os.environ.get("ODEINTR_NO_TILED") else ("tiled_block" if os.environ.get("ODEINTR_NO_WARP") else "tiled_warp")
 for method in ("rk5_i", "rk5_a"):
     s = odeintr_b200.compile_sys_openmp("b1d", BISTABLE_1D, BISTABLE_PARS, True, method=method, sys_dim=n).system
     for rep in range(2):

@@ -390,6 +390,7 @@ def main():
         if world == 1:
             os.sched_setaffinity(0, _ALL_CPUS)  # the CPU samples inside the secondaries get every host core
             table = (("vdp_dopri5", vdp_secondary), ("robertson_rosenbrock4", robertson_secondary),
+                     ("heterogeneous_vdp_k6", heterogeneous_secondary),
                      ("lattice_rk4", lattice_secondary), ("lattice_chain_rk4", chain_secondary),
                      ("lattice2d_rk4", lattice2d_secondary), ("lattice_ensemble_rk4", lattice_ensemble_secondary))
             for key, fn in table:
@@ -713,6 +714,48 @@ def robertson_secondary(lib, dp_peak):
         DP_INSTR_PER_TRY_ROBERTSON,
         "BASELINE.json configs[3]: Robertson alpha-sweep, 10 M instances, compile_implicit rosenbrock4 (exact mode: Boost's "
         "divisions), symbolic Jacobian, name_at at 41 log-spaced times", "robertson_rosenbrock4_accepted_steps_per_s")
+
+
+def heterogeneous_secondary(lib, dp_peak):
+    """K6: a heterogeneous adaptive ensemble -- the Van der Pol sweep with mu SHUFFLED over [0.1, 10] (1 Mi instances,
+    dopri5 dense output, 101 samples): neighbouring lanes hold unrelated trajectories, which reject, accept and cross
+    their sample times at different moments.  Index order against odeintr_set_instance_order(COST_PROXY) (pilot + radix
+    sort + index map inside the timed call); per-instance results and step counts must be identical."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    m = 1 << 20
+    s = odeintr_b200.compile_sys("vpol", VDP, "mu", method="rk5_i", atol=1e-8, rtol=1e-8).system
+    try:
+        mus = np.random.default_rng(0).uniform(0.1, 10.0, m)
+        s.set_params(mu=mus)
+        tt = np.arange(0, 20.0001, 0.2)
+        X = np.repeat(np.array([2.0, 0.0])[:, None], m, axis=1)
+        res = {}
+        for order in ("index", "cost"):
+            s.set_instance_order(order)
+            ms = []
+            for rep in range(3):
+                s.set_state(X)
+                if lib.odeintr_integrate_times(s._h, tt.ctypes.data_as(_abi.c_dbl_p), tt.size, 0.01) != 0:
+                    raise RuntimeError(_abi.last_error())
+                if rep:
+                    ms.append(s.last_kernel_ms())
+            st = s.stats()
+            res[order] = (statistics.mean(ms), st["accepted"].copy(), st["rejected"].copy(), s.get_state().copy())
+        same = bool(np.array_equal(res["index"][3].view(np.uint64), res["cost"][3].view(np.uint64)) and
+                    np.array_equal(res["index"][1], res["cost"][1]) and np.array_equal(res["index"][2], res["cost"][2]))
+        tries = int(res["cost"][1].sum() + res["cost"][2].sum())
+        return {"workload": "Van der Pol, mu shuffled over [0.1, 10], %d instances, dopri5 dense output at 101 times" % m,
+                "metric": "heterogeneous_vdp_attempts_per_s", "value": tries / res["cost"][0] * 1e3, "unit": "step attempts/s",
+                "ms_index_order": res["index"][0], "ms_cost_proxy_order": res["cost"][0],
+                "speedup": res["index"][0] / res["cost"][0], "identical_results_and_step_counts": same,
+                "roofline": {"bound": "fp64", "frac": tries / res["cost"][0] * 1e3 * DP_INSTR_PER_TRY_VDP / dp_peak,
+                             "note": "step attempts x DP instructions per attempt against the measured issue peak"}}
+    finally:
+        s.close()
 
 
 def lattice_sharded_secondary(lib, dp_peak, rank, world, local_rank, dist):

@@ -392,6 +392,7 @@ def main():
             table = (("vdp_dopri5", vdp_secondary), ("robertson_rosenbrock4", robertson_secondary),
                      ("heterogeneous_vdp_k6", heterogeneous_secondary),
                      ("lattice_rk4", lattice_secondary), ("lattice_chain_rk4", chain_secondary),
+                     ("lattice_dopri5", lattice_dopri5_secondary),
                      ("lattice2d_rk4", lattice2d_secondary), ("lattice_ensemble_rk4", lattice_ensemble_secondary))
             for key, fn in table:
                 t_sec = time.perf_counter()
@@ -513,7 +514,7 @@ def lattice_secondary(lib, dp_peak):
                          "frac": rate * 50.0 / dp_peak,
                          "hbm": {"bytes_per_cell_step": 16, "achieved_GBps": rate * 16.0 / 1e9, "peak_GBps": hbm,
                                  "frac": rate * 16.0 / 1e9 / hbm},
-                         "kernel": s.lattice_kernel_name() if hasattr(s, "lattice_kernel_name") else "odeintr_lattice_rk4_tiled_tma",
+                         "kernel": "odeintr_lattice_rk4_warp_h1",
                          "note": "the stage-per-launch schedule (odeintr_lattice_stage) moves 128 B per cell and step "
                                  "and is HBM-bound at 0.90 of the peak = 4.6e10 cell-steps/s; temporal blocking "
                                  "leaves 16 B and an FP64-bound step"},
@@ -714,6 +715,62 @@ def robertson_secondary(lib, dp_peak):
         DP_INSTR_PER_TRY_ROBERTSON,
         "BASELINE.json configs[3]: Robertson alpha-sweep, 10 M instances, compile_implicit rosenbrock4 (exact mode: Boost's "
         "divisions), symbolic Jacobian, name_at at 41 log-spaced times", "robertson_rosenbrock4_accepted_steps_per_s")
+
+
+def lattice_dopri5_secondary(lib, dp_peak):
+    """The reference's documented large-system call on its DEFAULT method: bistable_at(inic, c(0, 1, 5, 10)) with rk5_i
+    (R/odeintr.R:393-421) on a 1-D lattice of 2^26 cells: adaptive dopri5, one temporally blocked pass per attempted
+    step (warp-autonomous kernel), controller on the host, dense output by repeating the accepted attempt.
+    111 DP instructions per cell and attempt (6 x 9 RHS + 57 stage algebra), 32 bytes per cell and attempt."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    n = 1 << 26
+    s = odeintr_b200.compile_sys_openmp("b1d", BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, sys_dim=n).system
+    try:
+        x0 = np.random.default_rng(1).uniform(0, 1, n)
+        at = np.array([0.0, 1.0, 5.0, 10.0])
+        ms = []
+        for rep in range(3):
+            s.set_state(x0)
+            if lib.odeintr_integrate_times(s._h, at.ctypes.data_as(_abi.c_dbl_p), at.size, 0.1) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        st = s.stats()
+        acc, rej = int(st["accepted"][0]), int(st["rejected"][0])
+        tries = acc + rej + (at.size - 1)  # every interpolated observation repeats one attempt
+        t = statistics.mean(ms) * 1e-3
+        rate = n * tries / t
+        # parity + CPU sample at 2^20 cells: same call through the oracle
+        from oracle import build_oracle
+
+        ns = 1 << 20
+        env = {}
+        ss = odeintr_b200.compile_sys_openmp("b1s", BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, sys_dim=ns, env=env).system
+        xs = x0[:ns].copy()
+        got = env["b1s_at"](xs, at, 0.1).iloc[:, 1:].to_numpy()
+        sst = ss.stats()
+        ss.close()
+        ora = build_oracle.build(BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, "rk5_i", sys_dim=ns)
+        t0 = time.perf_counter()
+        ref = ora.integrate_times(xs, at, 0.1)
+        tc = time.perf_counter() - t0
+        return {"workload": "bistable_at(inic, c(0, 1, 5, 10)) with the default method rk5_i on a 1-D lattice of 2^26 cells "
+                            "(adaptive dopri5, atol = rtol = 1e-6)",
+                "metric": "lattice_dopri5_cell_attempts_per_s", "value": rate, "unit": "cell-attempts/s",
+                "ms_per_call": 1e3 * t, "accepted": acc, "rejected": rej, "gpu_launches": s.last_launches(),
+                "parity": {"bit_exact_vs_oracle_2^20_cells": bool(np.array_equal(got.view(np.uint64), ref["rec"].view(np.uint64))),
+                           "step_counts_equal": bool(sst["accepted"][0] == ref["accepted"] and sst["rejected"][0] == ref["rejected"])},
+                "roofline": {"bound": "fp64", "achieved": rate * 111.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 111.0 / dp_peak, "kernel": "odeintr_lattice_dopri5_warp_h1"},
+                "cpu_baseline": {"value": ns * (ref["accepted"] + ref["rejected"]) / tc, "unit": "cell-attempts/s",
+                                 "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                                 "sample": "2^20 cells, same call (%.1f s)" % tc}}
+    finally:
+        s.close()
 
 
 def heterogeneous_secondary(lib, dp_peak):

@@ -160,6 +160,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TILE_CPT")) o.push_back(std::string("-DODEINTR_TILE_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_WARP5_CPT")) o.push_back(std::string("-DODEINTR_WARP5_CPT=") + c);
+  if (const char* c = std::getenv("ODEINTR_WARP5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP5_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE2_MIN_BLOCKS=") + c);
@@ -740,7 +742,10 @@ enum { LATTICE_NOT_FUSED = -1001 };
 int lattice_step_pair(odeintr_system_t h, const lattice_window& w, double t, double t2, double dt) {
   const char* knob = std::getenv("ODEINTR_FUSE");
   const int fields = h->lat_cells_ct > 0 ? (int)((long long)h->N / h->lat_cells_ct) : 1;
-  const bool want = knob ? std::atoi(knob) != 0 : fields >= 2;
+  // measured (profiles/r02_lattice_warp.md): two fields 0.74 -> 0.61 ms per step (HBM-bound otherwise), one field
+  // 0.90 -> 0.85: on by default; ODEINTR_FUSE=0 switches it off for A/B measurements
+  const bool want = knob ? std::atoi(knob) != 0 : true;
+  (void)fields;
   if (!want || w.sharded || h->lattice_stages != 4 || !h->tiled_on || h->tiled2d_on || !h->k_tiled || !h->k_warp ||
       h->warp_blocks <= 0 || h->k_serial || std::getenv("ODEINTR_NO_WARP") || std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
     return LATTICE_NOT_FUSED;

@@ -28,11 +28,16 @@
 #pragma once
 #include "odeintr_b200/lattice_tiled.cuh"
 
-#ifndef ODEINTR_WARP_CPT  // cells per lane: odd (bank-conflict-free lane stride), >= the radius
-#define ODEINTR_WARP_CPT (ODEINTR_NFIELDS > 2 ? 3 : (ODEINTR_NFIELDS > 1 ? 5 : 11))
+// Cells per lane C: odd (bank-conflict-free lane stride), >= the radius.  Measured on a B200 (2^28 states, profiles/
+// r02_lattice_warp.md): more cells per lane amortise the per-tile work of lane 0 (TMA issue) and shrink the margins'
+// share, and with one block of 8 warps per SM the compiler may keep all C independent cells in flight (no register
+// cap): one field C = 7 / 3 blocks 1.00 ms per step, 11 / 2 blocks 0.95, 13 / 1 block 0.90; two fields 5 / 2 blocks
+// 0.81, 9 / 1 block 0.74.
+#ifndef ODEINTR_WARP_CPT
+#define ODEINTR_WARP_CPT (ODEINTR_NFIELDS > 2 ? 5 : (ODEINTR_NFIELDS > 1 ? 9 : 13))
 #endif
 #ifndef ODEINTR_WARP_MIN_BLOCKS
-#define ODEINTR_WARP_MIN_BLOCKS 2  // 128 registers: the compiler interleaves the lane's independent cells (measured: 3 blocks of 85 registers lose 8 %)
+#define ODEINTR_WARP_MIN_BLOCKS 1
 #endif
 
 #if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC)

@@ -242,7 +242,8 @@ def test_tiled_dopri5_attempt_bit_exact(case, method, monkeypatch):
     if case == "bistable_staged":
         assert launches > 6 * tries        # seven stage launches per attempt
     else:
-        assert launches < 3 * tries + 20   # one launch per attempt (+ one per interpolated observation)
+        assert launches < 3 * (tries + len(df)) + 20   # an attempt (and an interpolated observation) is one pass: the warp
+                                                       # kernel for the interior + at most two launches for the ends
     at = np.array([0.5, 1.0, 1.0 + 1e-3, 2.75])
     df = env["d5_at"](x0, at, 0.1)
     adv = ora.integrate_const(x0, 0.0, at[0], 0.1, record=False)

@@ -162,6 +162,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP5_CPT")) o.push_back(std::string("-DODEINTR_WARP5_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP5_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
+  if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_TILE2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TILE2_MIN_BLOCKS=") + c);
@@ -252,6 +254,8 @@ struct odeintr_system_s {
   bool tiled_auto = false;      // the radius was measured by the probe (a violation falls back to the staged kernels)
   bool tiled_pending = false;   // measure the radius at the next integrate call
   bool tiled2d_on = false;      // M x M lattice: rk4 steps go through odeintr_lattice_rk4_tiled2d
+  cudaKernel_t k_stream2d = nullptr, k_stream2d_info = nullptr;  // M x M lattices, radius 1: streaming rk4 step (lattice_stream2d.cuh)
+  int stream2d_rows = 0, stream2d_blocks = 0;
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
@@ -817,6 +821,18 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
     ta.t = t; ta.dt = dt;
     ta.flag = h->lat_flag.p;
     const long long side = h->lat_side;
+    if (h->stream2d_blocks > 0 && h->lattice_halo == 1) {
+      // strips of 56 columns x segments of stream2d_rows rows, one warp each, strips fastest (neighbouring warps walk
+      // down neighbouring strips: whole rows of the lattice are touched together)
+      const long long tasks = ((side + 55) / 56) * ((side + h->stream2d_rows - 1) / h->stream2d_rows);
+      const unsigned sgrid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)h->sm_count * h->stream2d_blocks);
+      void* sparams[1] = {&ta};
+      CU_TRY(cudaLaunchKernel((const void*)h->k_stream2d, dim3(sgrid), dim3(256), sparams, 0, h->stream));
+      h->last_launches += 1;
+      g_total_launches += 1;
+      std::swap(h->lat_x, h->lat_a);
+      return ODEINTR_OK;
+    }
     const long long th = tile2_rows();
     const unsigned tiles = (unsigned)(((side + 63) / 64) * ((side + th - 1) / th));
     void* params[1] = {&ta};
@@ -953,6 +969,25 @@ bool tiled2d_configure(odeintr_system_t h, long long halo) {
   }
   h->tiled2d_smem = bytes;
   h->lattice_halo = halo;
+  // radius 1, even M, a loop over all cells: the streaming kernel (lattice_stream2d.cuh) takes the step
+  h->stream2d_blocks = 0;
+  const bool covers_all = h->lat_start <= 0 && h->lat_bound >= (long long)h->N;
+  if (halo == 1 && h->k_stream2d && h->k_stream2d_info && h->lat_side % 2 == 0 && h->lat_side >= 64 && covers_all &&
+      !std::getenv("ODEINTR_NO_STREAM2D")) {
+    if (h->lat_flag.reserve(10) == cudaSuccess) {
+      void* wout = h->lat_flag.p;
+      void* wparams[1] = {&wout};
+      int rows = 0, nb = 0;
+      if (cudaLaunchKernel((const void*)h->k_stream2d_info, dim3(1), dim3(1), wparams, 0, h->stream) == cudaSuccess &&
+          cudaMemcpyAsync(&rows, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+          cudaStreamSynchronize(h->stream) == cudaSuccess && rows > 0 &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_stream2d, 256, 0) == cudaSuccess && nb > 0) {
+        h->stream2d_rows = rows;
+        h->stream2d_blocks = nb;
+      }
+      (void)cudaGetLastError();
+    }
+  }
   return true;
 }
 
@@ -1818,6 +1853,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp5_h[1], h->lib, "odeintr_lattice_dopri5_warp_h1") != cudaSuccess) h->k_warp5_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp5_h[2], h->lib, "odeintr_lattice_dopri5_warp_h2") != cudaSuccess) h->k_warp5_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp5_info, h->lib, "odeintr_lattice_dopri5_warp_info") != cudaSuccess) h->k_warp5_info = nullptr;
+  if (cudaLibraryGetKernel(&h->k_stream2d, h->lib, "odeintr_lattice_rk4_stream2d") != cudaSuccess) h->k_stream2d = nullptr;
+  if (cudaLibraryGetKernel(&h->k_stream2d_info, h->lib, "odeintr_lattice_stream2d_info") != cudaSuccess) h->k_stream2d_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_serial, h->lib, "odeintr_lattice_serial_rhs") != cudaSuccess) h->k_serial = nullptr;
   if (cudaLibraryGetKernel(&h->k_probe, h->lib, "odeintr_lattice_probe") != cudaSuccess) h->k_probe = nullptr;

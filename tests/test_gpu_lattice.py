@@ -723,3 +723,30 @@ def test_two_rk4_steps_per_pass_bit_exact(case, monkeypatch):
     rec = s.get_output()
     ref = ora.integrate_const(x0, 0.0, 0.9, 0.1)
     assert np.array_equal(bits(cols(rec)), bits(ref["rec"][::3]))
+
+
+@pytest.mark.parametrize("case", ["laplace2D_330", "nine_point_128_short_segments", "laplace4_doc_200"])
+def test_2d_lattice_streaming_rk4_bit_exact(case, monkeypatch):
+    # M x M lattices with radius 1, even M >= 64 and a loop over all cells step through the streaming kernel
+    # (lattice_stream2d.cuh): strips of 56 columns (ragged last strip, columns wrapping across the seam), row segments
+    # (ragged last one, 8 rows of pipeline fill wrapping across the seam), the 9-point stencil's diagonal neighbours.
+    # Must give the oracle's bits, and the block-tiled kernel (ODEINTR_NO_STREAM2D) must too.
+    pars = BISTABLE_PARS
+    if case == "laplace2D_330":
+        m, src = 330, BISTABLE_2D          # 6 strips (5.9), 2 row segments (256 + 74)
+    elif case == "nine_point_128_short_segments":
+        m, src = 128, NINE_POINT_AUTO
+        monkeypatch.setenv("ODEINTR_STREAM2_ROWS", "24")   # 6 segments, the last one ragged
+    else:
+        m, src = 200, BISTABLE_DOC
+    ora = bo.build(src, pars, True, "rk4", sys_dim=m * m)
+    x0 = np.random.default_rng(m).uniform(0, 1, m * m)
+    ref = ora.integrate_adaptive(x0, 0.0, 0.7, 0.1)["x"]
+    for stream in (True, False):
+        if not stream:
+            monkeypatch.setenv("ODEINTR_NO_STREAM2D", "1")
+        env = {}
+        code = odeintr_b200.compile_sys_openmp("s2", src, pars, True, method="rk4", sys_dim=m * m, env=env)
+        fin = env["s2_no_record"](x0, 0.7, 0.1)
+        assert code.system.get_halo() == 1
+        assert np.array_equal(bits(fin), bits(ref)), (case, stream)

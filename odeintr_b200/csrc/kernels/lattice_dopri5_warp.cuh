@@ -19,7 +19,7 @@
 #if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 7
 
 #ifndef ODEINTR_WARP5_CPT  // cells per lane: odd, >= the radius
-#define ODEINTR_WARP5_CPT (ODEINTR_NFIELDS > 1 ? 3 : 5)
+#define ODEINTR_WARP5_CPT (ODEINTR_NFIELDS > 1 ? 3 : 7)  // measured (profiles/r02_sweep_dopri5_warp.log): 7 cells / 2 blocks per SM best
 #endif
 #ifndef ODEINTR_WARP5_MIN_BLOCKS
 #define ODEINTR_WARP5_MIN_BLOCKS 2

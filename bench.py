@@ -42,9 +42,12 @@ LO = (-20.0, -25.0, 5.0)
 HI = (20.0, 25.0, 45.0)
 T_END, DT, STRIDE = 1.0, 0.001, 100
 DP_INSTR_PER_STEP = 78.0      # exact mode: 4 RHS x 9 + 3 components x 14 (mul and add issue separately)
-# DP instructions per step ATTEMPT of the adaptive kernels (counted by ncu, profiles/r02_adaptive.md)
-DP_INSTR_PER_TRY_VDP = 250.0
-DP_INSTR_PER_TRY_ROBERTSON = 330.0
+# FP64-pipe instructions per step ATTEMPT of the adaptive kernels, derived from ncu (FP64 pipe active % x cycles x 16
+# lanes per scheduler and clock / attempts; profiles/r02_adaptive.md): Van der Pol dopri5 with dense output ~280 (RHS 30,
+# stage algebra ~120, error norm with 2 divisions ~30, controller pow ~100), Robertson rosenbrock4 ~1000 (47 IEEE divisions
+# at ~10 pipe instructions each are half of it).  With these the roofline fraction below IS the pipe utilisation.
+DP_INSTR_PER_TRY_VDP = 280.0
+DP_INSTR_PER_TRY_ROBERTSON = 1000.0
 METRIC = "lorenz_rk4_ensemble_trajectory_steps_per_s"
 UNIT = "trajectory-steps/s"
 
@@ -419,6 +422,8 @@ def main():
                "sample": "%d of the 100 M instances x 1000 rk4 steps, observer every 100 steps, OpenMP over instances "
                          "(%.1f s)" % (inst, secs)}
 
+    # DRAM bytes per launch of the headline kernel: from the committed ncu --set full capture of this kernel (the spec's
+    # definition of `traffic`; a run cannot count DRAM bytes itself), scaled to this run's instance count
     traffic = None
     tfile = ROOT / "profiles" / "rk4_ensemble_traffic.json"
     if tfile.exists():
@@ -442,6 +447,8 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved_dp / 1e12, "peak": dp_peak.value / 1e12, "unit": "TFLOP/s",
                 "frac": achieved_dp / dp_peak.value, "traffic": traffic,
+                "traffic_source": "profiles/rk4_ensemble_traffic.json (ncu --set full capture of odeintr_plain_ensemble, "
+                                  "dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes are in `hbm`)",
                 "kernel": "odeintr_plain_ensemble<rk4_stepper, N=3>",
                 "kernel_ms": kern_avg_ms,
                 "note": "compute-bound on the FP64 pipe (north_star: FP64 pipe utilisation). achieved = 78 DP "
@@ -675,8 +682,8 @@ def _adaptive_secondary(lib, dp_peak, name, build_system, build_oracle_fn, par_l
                              "unit": "TFLOP/s", "frac": tries / t * dp_instr_per_try / dp_peak,
                              "dp_instr_per_attempt": dp_instr_per_try, "kernel": "odeintr_adaptive_ensemble (%s)" % name,
                              "registers": attrs["registers"], "local_bytes": attrs["local_bytes"],
-                             "note": "DP instructions per step attempt counted by ncu (smsp__inst_executed_pipe_fp64 x 32 / "
-                                     "attempts, profiles/r02_adaptive.md); unit is DP instructions, not flops"},
+                             "note": "FP64-pipe instructions per step attempt derived from ncu (pipe active % x cycles x "
+                                     "lanes / attempts, profiles/r02_adaptive.md); unit is DP instructions, not flops"},
                 "cpu_baseline": {"value": float(ec["accepted"].sum()) / tc, "unit": "accepted steps/s", "cores": threads,
                                  "kind": "port", "sample": "%d instances of the sweep (%.1f s), OpenMP over instances" % (mc, tc)}}
     finally:

@@ -162,6 +162,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_TMA_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_TMA_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP5_CPT")) o.push_back(std::string("-DODEINTR_WARP5_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP5_MIN_BLOCKS=") + c);
+  if (const char* c = std::getenv("ODEINTR_STREAM2_L2_AHEAD")) o.push_back(std::string("-DODEINTR_STREAM2_L2_AHEAD=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);

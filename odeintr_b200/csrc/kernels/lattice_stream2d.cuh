@@ -7,29 +7,35 @@
 // four-stage pipeline held in registers:
 //     row j   : x                       (loaded)
 //     row j-1 : k1 = f(x rows j-2..j)            -> stage-1 state, running sum
-//     row j-3 : k2 = f(stage-1 rows j-4..j-2)    -> stage-2 state, running sum
-//     row j-5 : k3 = f(stage-2 rows j-6..j-4)    -> stage-3 state, running sum
-//     row j-7 : k4 = f(stage-3 rows j-8..j-6)    -> new state of row j-7 (stored)
-// (the stages work two rows apart, so within one iteration none of them waits for another: four independent
-// right-hand sides per lane and row) so every loaded row yields one finished row: the rows above / below a cell are the lane's own registers (each stage
+//     row j-2 : k2 = f(stage-1 rows j-3..j-1)    -> stage-2 state, running sum
+//     row j-3 : k3 = f(stage-2 rows j-4..j-2)    -> stage-3 state, running sum
+//     row j-4 : k4 = f(stage-3 rows j-5..j-3)    -> new state of row j-4 (stored)
+// so every loaded row yields one finished row: the rows above / below a cell are the lane's own registers (each stage
 // keeps a window of three rows), the columns left / right of a lane's pair come from the neighbouring lanes by
 // shuffles -- once per row and stage, kept with the row.  Only the strip's outer 4 columns on either side are
-// redundant (a strip yields 56 of its 64 columns: what the edge lanes lack spoils one more column per stage), plus 11
+// redundant (a strip yields 56 of its 64 columns: what the edge lanes lack spoils one more column per stage), plus 8
 // rows of pipeline fill per row segment.  HBM sees every cell once for reading (x 64/56) and once for writing, as
 // coalesced 16-byte accesses per lane; the next rows are prefetched into registers.
 // Rows and columns wrap periodically in the address arithmetic, so every strip is treated alike.
 // Radius 1 (the 5- and 9-point stencils), loops over all cells, even M; everything else stays with K4t2.
 // Every cell goes through exactly the operations of the staged schedule (Boost's order, no FMA): bit-identical.
+// Measured variants (profiles/r02_stream2d.md): 2 blocks of 128 registers per SM 1.50-1.53e11 cell-steps/s at 8192^2
+// (K4t2: 1.30e11), 1 block of 138 registers 1.07-1.09e11; stages two rows apart (four independent right-hand sides per
+// iteration, 196 registers, one block per SM) 1.06e11 with long_scoreboard the top stall -- the wider live set costs
+// more in occupancy than the independence gains; with a 128-register cap it spills (5.7e10).  Kept: this form.
 #pragma once
 #include "odeintr_b200/lattice_tiled2d.cuh"
 
 #if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1 && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
 
 #ifndef ODEINTR_STREAM2_ROWS  // rows of a segment (one warp task): 8 more are computed to fill the pipeline
-#define ODEINTR_STREAM2_ROWS 256
+#define ODEINTR_STREAM2_ROWS 512
 #endif
-#ifndef ODEINTR_STREAM2_MIN_BLOCKS
-#define ODEINTR_STREAM2_MIN_BLOCKS 1
+#ifndef ODEINTR_STREAM2_MIN_BLOCKS  // measured (profiles/r02_stream2d.md): 2 blocks of 128 registers beat 1 block of 138
+#define ODEINTR_STREAM2_MIN_BLOCKS 2
+#endif
+#ifndef ODEINTR_STREAM2_L2_AHEAD  // rows ahead of the register prefetch queue that are pulled into L2
+#define ODEINTR_STREAM2_L2_AHEAD 12
 #endif
 
 namespace odeintr_b200 {
@@ -107,22 +113,18 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
 
     // windows of the four stage inputs: rows (oldest, middle, newest), each [left, c0, c1, right]
     double W[4][3][RS];
-    double xq[3][2];                           // x of rows j-3, j-4, j-5 (what stages 2 and 3 add their k to)
-    double a1q[2][2], a2q[2][2], a3q[2][2];    // running sums on their way from stage to stage (two iterations each)
+    double x3[2], acc1[2], acc2[2], acc3[2];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int q = 0; q < RS; ++q) W[s][r][q] = 0.0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) xq[r][0] = xq[r][1] = 0.0;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) a1q[r][0] = a1q[r][1] = a2q[r][0] = a2q[r][1] = a3q[r][0] = a3q[r][1] = 0.0;
+    x3[0] = x3[1] = acc1[0] = acc1[1] = acc2[0] = acc2[1] = acc3[0] = acc3[1] = 0.0;
 
     // prefetch queue of input rows
     double2 pf[PF];
-    const int j0 = r_lo - 4, j1 = r_hi + 7;   // rows [j0, j1) enter the pipeline; row j - 7 leaves it
+    const int j0 = r_lo - 4, j1 = r_hi + 4;   // rows [j0, j1) enter the pipeline
 #pragma unroll
     for (int p = 0; p < PF; ++p)
       pf[p] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j0 + p)) * MM + col0));
@@ -151,44 +153,48 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
       k1v = kk[0];
     };
 
-    // The stages of one iteration work on rows two apart (j-1, j-3, j-5, j-7), so each of them reads only what EARLIER
-    // iterations produced: the four right-hand sides (8 cells per lane) are independent and overlap in the pipe.
     for (int j = j0; j < j1; ++j) {
       const double2 xin = pf[0];
 #pragma unroll
       for (int p = 0; p + 1 < PF; ++p) pf[p] = pf[p + 1];
       if (j + PF < j1)
         pf[PF - 1] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j + PF)) * MM + col0));
+      // HBM latency is longer than three iterations of two warps per scheduler: pull the rows further ahead into L2
+      // (one request per 128-byte line: every eighth lane), so that the register queue above is served from L2
+      if (ODEINTR_STREAM2_L2_AHEAD > 0 && (lane & 7) == 0 && j + PF + ODEINTR_STREAM2_L2_AHEAD < j1)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_in + static_cast<long long>(wrap(j + PF + ODEINTR_STREAM2_L2_AHEAD)) * MM + col0));
 
-      // x of row j-3 leaves the x window: keep it for stages 2 (row j-3) and 3 (row j-5)
-      xq[2][0] = xq[1][0]; xq[2][1] = xq[1][1];
-      xq[1][0] = xq[0][0]; xq[1][1] = xq[0][1];
-      xq[0][0] = W[0][0][1]; xq[0][1] = W[0][0][2];
+      // x of row j - 3 leaves the x window after this push: stage 3 needs it
+      x3[0] = W[0][0][1]; x3[1] = W[0][0][2];
       push(0, xin.x, xin.y);                       // x rows j-2, j-1, j
-      double k10, k11, k20, k21, k30, k31, k40, k41;
-      rhs(0, j - 1, t1, k10, k11);                 // stage 1 at row j-1: x rows j-2 .. j
-      rhs(1, j - 3, t2, k20, k21);                 // stage 2 at row j-3: stage-1 states of rows j-4 .. j-2
-      rhs(2, j - 5, t2, k30, k31);                 // stage 3 at row j-5: stage-2 states of rows j-6 .. j-4
-      rhs(3, j - 7, t4, k40, k41);                 // stage 4 at row j-7: stage-3 states of rows j-8 .. j-6
-      const double s1a = W[0][1][1] + (half * dt) * k10, s1b = W[0][1][2] + (half * dt) * k11;
-      const double n1a = W[0][1][1] + (b1 * dt) * k10, n1b = W[0][1][2] + (b1 * dt) * k11;  // the running sum starts from x
-      const double s2a = xq[0][0] + (half * dt) * k20, s2b = xq[0][1] + (half * dt) * k21;
-      const double n2a = a1q[1][0] + (b2 * dt) * k20, n2b = a1q[1][1] + (b2 * dt) * k21;
-      const double s3a = xq[2][0] + (1.0 * dt) * k30, s3b = xq[2][1] + (1.0 * dt) * k31;
-      const double n3a = a2q[1][0] + (b2 * dt) * k30, n3b = a2q[1][1] + (b2 * dt) * k31;
-      const double o0 = a3q[1][0] + (b1 * dt) * k40, o1 = a3q[1][1] + (b1 * dt) * k41;
-      const int ro = j - 7;
+      double k0, k1v;
+      // stage 1 at row j-1
+      rhs(0, j - 1, t1, k0, k1v);
+      const double s1a = W[0][1][1] + (half * dt) * k0, s1b = W[0][1][2] + (half * dt) * k1v;
+      const double n1a = W[0][1][1] + (b1 * dt) * k0, n1b = W[0][1][2] + (b1 * dt) * k1v;   // the running sum starts from x
+      push(1, s1a, s1b);                           // stage-1 states of rows j-3, j-2, j-1
+      // stage 2 at row j-2
+      rhs(1, j - 2, t2, k0, k1v);
+      const double s2a = W[0][0][1] + (half * dt) * k0, s2b = W[0][0][2] + (half * dt) * k1v;
+      const double n2a = acc1[0] + (b2 * dt) * k0, n2b = acc1[1] + (b2 * dt) * k1v;
+      push(2, s2a, s2b);                           // stage-2 states of rows j-4, j-3, j-2
+      // stage 3 at row j-3
+      rhs(2, j - 3, t2, k0, k1v);
+      const double s3a = x3[0] + (1.0 * dt) * k0, s3b = x3[1] + (1.0 * dt) * k1v;
+      const double n3a = acc2[0] + (b2 * dt) * k0, n3b = acc2[1] + (b2 * dt) * k1v;
+      push(3, s3a, s3b);                           // stage-3 states of rows j-5, j-4, j-3
+      // stage 4 at row j-4: the new state
+      rhs(3, j - 4, t4, k0, k1v);
+      const double o0 = acc3[0] + (b1 * dt) * k0, o1 = acc3[1] + (b1 * dt) * k1v;
+      const int ro = j - 4;
       if (keeps && ro >= r_lo && ro < r_hi) {
         double2 o;
         o.x = o0; o.y = o1;
         *reinterpret_cast<double2*>(a.x_out + static_cast<long long>(ro) * MM + col0) = o;
       }
-      push(1, s1a, s1b);                           // stage-1 states of rows j-3, j-2, j-1
-      push(2, s2a, s2b);                           // stage-2 states of rows j-5, j-4, j-3
-      push(3, s3a, s3b);                           // stage-3 states of rows j-7, j-6, j-5
-      a3q[1][0] = a3q[0][0]; a3q[1][1] = a3q[0][1]; a3q[0][0] = n3a; a3q[0][1] = n3b;
-      a2q[1][0] = a2q[0][0]; a2q[1][1] = a2q[0][1]; a2q[0][0] = n2a; a2q[0][1] = n2b;
-      a1q[1][0] = a1q[0][0]; a1q[1][1] = a1q[0][1]; a1q[0][0] = n1a; a1q[0][1] = n1b;
+      acc3[0] = n3a; acc3[1] = n3b;
+      acc2[0] = n2a; acc2[1] = n2b;
+      acc1[0] = n1a; acc1[1] = n1b;
     }
     (void)col_left; (void)col_right;
   }

@@ -53,6 +53,7 @@ enum {
 #define ODEINTR_FLAG_LATTICE_CK54 64u   /* large-system TU stepped with Cash-Karp 5(4) (rk54; rk54_a with LATTICE_ADAPTIVE): set by the generator */
 #define ODEINTR_FLAG_LATTICE_RKF78 128u /* large-system TU stepped with Fehlberg 7(8) (rk78; rk78_a with LATTICE_ADAPTIVE): set by the generator */
 #define ODEINTR_FLAG_LATTICE_RK5 256u   /* large-system TU stepped with dopri5 as a plain fixed-step stepper (rk5): set by the generator */
+#define ODEINTR_FLAG_LATTICE_BS 512u    /* large-system TU stepped with Bulirsch-Stoer (bs with LATTICE_ADAPTIVE; bsd with DENSE_OUTPUT too): set by the generator */
 #define ODEINTR_FLAG_DENSE_OUTPUT 4u    /* the TU instantiates a dense-output stepper (rk5_i, rosenbrock4): set by the generator */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

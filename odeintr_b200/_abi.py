@@ -96,6 +96,7 @@ FLAG_LATTICE_EULER = 8
 FLAG_LATTICE_ADAPTIVE = 16
 FLAG_LATTICE_CK54 = 64  # large-system TU stepped with Cash-Karp (rk54 / rk54_a): set by the generator
 FLAG_LATTICE_RKF78 = 128  # large-system TU stepped with Fehlberg 7(8) (rk78 / rk78_a): set by the generator
+FLAG_LATTICE_BS = 512  # large-system TU stepped with Bulirsch-Stoer (bs; bsd with DENSE_OUTPUT): set by the generator
 FLAG_LATTICE_RK5 = 256  # large-system TU stepped with dopri5 as a plain fixed-step stepper (rk5): set by the generator
 FLAG_RECIPROCAL = 32  # rosenbrock4 fast mode: reciprocals instead of repeated divisions (not bit-compatible)
 

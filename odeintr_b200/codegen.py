@@ -504,7 +504,8 @@ def parse_cell_loops(sys_src: str) -> CellLoops:
     return CellLoops(vtype, start, bound, bodies, names, offsets)
 
 
-_LATTICE_STEPPERS = {"rk4": "4", "euler": "1", "rk5_a": "7", "rk5_i": "7", "rk54": "6", "rk54_a": "6", "rk78": "13", "rk78_a": "13", "rk5": "7"}
+_LATTICE_STEPPERS = {"rk4": "4", "euler": "1", "rk5_a": "7", "rk5_i": "7", "rk54": "6", "rk54_a": "6", "rk78": "13", "rk78_a": "13", "rk5": "7",
+                     "bs": "2", "bsd": "2"}  # (the stage count selects the kernels a TU instantiates; bs / bsd use the combo kernel alone)
 
 
 def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: str = "rk5_i", sys_dim: int = -1,
@@ -517,7 +518,7 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
     base = re.sub(r"_i$|_a$", "", method)
     if method not in _LATTICE_STEPPERS:
         raise OdeintrError("method '%s' is not yet provided for large systems by odeintr_b200 "
-                           "(euler, rk4, rk5, rk54, rk78, rk5_a, rk54_a, rk78_a and the default rk5_i are)" % method)
+                           "(euler, rk4, rk5, rk54, rk78, rk5_a, rk54_a, rk78_a, bs, bsd and the default rk5_i are)" % method)
     sys = _join(sys)
     if sys_dim is None or math.ceil(sys_dim) < 1:
         sys_dim = get_sys_dim(sys)
@@ -526,6 +527,8 @@ def generate_sys_openmp(name: str, sys, pars=None, const: bool = False, method: 
                            "R/odeintr.R:403)")
     sys_dim = int(math.ceil(sys_dim))
     mode = "dense" if method.endswith("_i") else ("controlled" if method.endswith("_a") else "plain")
+    if base in ("bs", "bsd"):  # a controlled / a dense-output stepper by type (R/utils.R:57-58)
+        mode = "controlled" if base == "bs" else "dense"
     try:
         loops = parse_cell_loops(sys)
     except OdeintrError:

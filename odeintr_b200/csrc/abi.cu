@@ -274,8 +274,10 @@ struct odeintr_system_s {
   long long lat_start = 0, lat_bound = 0;  // range of the user's cell loop (odeintr_lattice_info)
   long long lat_cells_ct = 0;   // cells per field compiled into the interior kernel
   dev_buf<int> lat_flag;
-  int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a, 4 = rk78_a
+  int lattice_method = 0;  // 0 = fixed step (rk4 / euler / rk54), 1 = rk5_a, 2 = rk5_i, 3 = rk54_a, 4 = rk78_a, 5 = bs, 6 = bsd
   dev_buf<double> lat_work;
+  std::vector<double*> lat_pool;  // work vectors of the Bulirsch-Stoer steppers (their number depends on the orders reached)
+  size_t lat_pool_len = 0, lat_pool_used = 0;
   bool lat_mid_primed = false;   // the intermediate state of fused step pairs holds x on the cells no loop writes
   bool lat_work_primed = false;  // the work vectors of the fixed-step rk54 / rk78 / rk5 paths hold copies of x / zeros
   int lat_rk5_parity = 0;        // which of the two derivative vectors holds k1 of the next rk5 step
@@ -1807,6 +1809,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   h->lattice_method = (flags & ODEINTR_FLAG_LATTICE_ADAPTIVE) ? ((flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 2 : 1) : 0;
   if ((flags & ODEINTR_FLAG_LATTICE_CK54) && h->lattice_method) h->lattice_method = 3;
   if ((flags & ODEINTR_FLAG_LATTICE_RKF78) && h->lattice_method) h->lattice_method = 4;
+  if ((flags & ODEINTR_FLAG_LATTICE_BS) && h->lattice_method) h->lattice_method = (flags & ODEINTR_FLAG_DENSE_OUTPUT) ? 6 : 5;
   std::vector<char> image;
   int rc = nvrtc_to_cubin(cuda_src, flags, image, h->log);
   if (rc) { delete h; return rc; }
@@ -1897,6 +1900,8 @@ int odeintr_destroy(odeintr_system_t h) {
   h->perm.release(); h->perm_iota.release(); h->order_keys.release(); h->order_keys_sorted.release(); h->sort_temp.release();
   h->lat_buf_a.release(); h->lat_buf_b.release(); h->lat_buf_acc.release();
   h->lat_work.release(); h->lat_err.release(); h->lat_flag.release(); h->pipe_bcast.release(); h->lat_negzero.release();
+  for (double* v : h->lat_pool) cudaFree(v);
+  h->lat_pool.clear();
   for (int s = 0; s < 3; ++s) {
     h->pipe_x[s].release(); h->pipe_out[s].release(); h->pipe_pars[s].release();
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);

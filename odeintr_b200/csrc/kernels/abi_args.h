@@ -128,6 +128,8 @@ struct odeintr_lattice_combo_args {
   const double* pars;
   long long n_total;
   double t;
+  int all;  // also form the sum for the entries no user loop writes (their k is zero): Bulirsch-Stoer's extrapolation
+            // tables do not reproduce such entries by x + c * 0
 };
 
 // One attempted dopri5 step of a large 1-D system in one launch (lattice_dopri5_tiled.cuh).

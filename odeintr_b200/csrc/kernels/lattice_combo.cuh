@@ -5,6 +5,7 @@
 //     v    = base + c0*in0 + c1*in1 + ... + ck*k           (left to right, like Boost's scale_sumN)
 //     out  = v ;  k_out = k
 //     err  = max over cells of |v| / (eps_abs + eps_rel * (|err_x| + adt * |err_d|))      (optional)
+// With `all` set the same sum is formed for the entries no user loop writes (k = 0 there).
 // One launch per Runge-Kutta stage; the error norm of default_error_checker is reduced in the same pass that
 // forms the embedded error estimate (warp shuffle max + one atomicMax per warp on the bit pattern, which is
 // order preserving for non-negative doubles).
@@ -53,6 +54,30 @@ odeintr_lattice_combo(const odeintr_lattice_combo_args a) {
           const double e = fabs(v) / (a.eps_abs + a.eps_rel * (1.0 * fabs(a.err_x[idx]) + a.adt * fabs(a.err_d[idx])));
           emax = fmax(emax, e);
         }
+      }
+    }
+  }
+  // the entries no user loop writes (fixed ends, gaps between fields): their derivative is zero
+  if (a.all && !(F == 1 && off[0] == 0 && first <= 0 && last >= a.n_total)) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n_total; idx += (long long)gridDim.x * blockDim.x) {
+      bool covered = false;
+#pragma unroll
+      for (int f = 0; f < F; ++f) covered = covered || (idx - off[f] >= first && idx - off[f] < last);
+      if (covered) continue;
+      double v;
+      int j = 0;
+      if (a.base) v = a.base[idx];
+      else if (a.nin > 0) { v = a.c[0] * a.in[0][idx]; j = 1; }
+      else v = 0.0;
+      for (; j < a.nin; ++j) v = v + a.c[j] * a.in[j][idx];
+      if (a.xs) {
+        if (a.ck != 0.0) v = v + a.ck * 0.0;
+        if (a.k_out) a.k_out[idx] = 0.0;
+      }
+      if (a.out) a.out[idx] = v;
+      if (a.err_max) {
+        const double e = fabs(v) / (a.eps_abs + a.eps_rel * (1.0 * fabs(a.err_x[idx]) + a.adt * fabs(a.err_d[idx])));
+        emax = fmax(emax, e);
       }
     }
   }

@@ -34,17 +34,18 @@
 #ifndef ODEINTR_STREAM2_MIN_BLOCKS  // measured (profiles/r02_stream2d.md): 2 blocks of 128 registers beat 1 block of 138
 #define ODEINTR_STREAM2_MIN_BLOCKS 2
 #endif
-#ifndef ODEINTR_STREAM2_L2_AHEAD  // rows ahead of the register prefetch queue that are pulled into L2
-#define ODEINTR_STREAM2_L2_AHEAD 12
+#ifndef ODEINTR_STREAM2_L2_AHEAD  // rows ahead of the register prefetch queue that are pulled into L2 (measured: -3 %, off)
+#define ODEINTR_STREAM2_L2_AHEAD 0
 #endif
 
 namespace odeintr_b200 {
 
 // One stage's input around the cell being computed: three rows (above, own, below) of the lane's two columns plus the
-// column on either side, in registers.  `e` points at the cell's entry of the middle row; rows are RS doubles apart.
+// column on either side, in registers.  `up` / `mid` / `dn` point at the cell's entry of the row above / its own row /
+// the row below (the three rows of a window rotate through three register rows: no row is ever moved).
 struct lattice_reg2_view {
   static constexpr int RS = 4;  // left neighbour, the lane's two columns, right neighbour
-  const double* e;
+  const double *up, *mid, *dn;
   int row, col, side;
   mutable int bad;
 
@@ -58,16 +59,16 @@ struct lattice_reg2_view {
     for (int r = -1; r <= 1; ++r)
 #pragma unroll
       for (int c = -1; c <= 1; ++c)
-        if (dr == r && dc == c) v = e[r * RS + c];  // never a run-time register index
+        if (dr == r && dc == c) v = (r < 0 ? up : r > 0 ? dn : mid)[c];  // never a run-time register index
     return v;
   }
   ODEINTR_DEV double operator[](const rel_cell2& c) const {
     if (c.rel && c.has_row && c.has_col) return at2(c.dr, c.dc);
     return (*this)[c.abs];
   }
-  ODEINTR_DEV double operator[](const rel_index2&) const { return e[0]; }
+  ODEINTR_DEV double operator[](const rel_index2&) const { return mid[0]; }
   ODEINTR_DEV double operator[](const long long g) const {
-    if (g < 0 || g >= static_cast<long long>(side) * side) { bad = 1; return e[0]; }
+    if (g < 0 || g >= static_cast<long long>(side) * side) { bad = 1; return mid[0]; }
     const long long r = g / side;
     return at2(min_image(r - row, side), min_image(g - r * side - col, side));
   }
@@ -111,7 +112,9 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
     const bool keeps = lane >= 2 && lane < 30 && c_out + 2 * (lane - 2) < MM;  // the lane's pair belongs to the output
     const int col_left = wrap(col0 - 1), col_right = wrap(col0 + 2);
 
-    // windows of the four stage inputs: rows (oldest, middle, newest), each [left, c0, c1, right]
+    // windows of the four stage inputs: three rows each, [left, c0, c1, right].  The rows ROTATE through the three
+    // register rows (the row loop is unrolled by three with compile-time slots), so a new row overwrites the oldest
+    // one and nothing is shifted: the row entering in phase ph lives in slot ph, the one above it in slot (ph + 2) % 3
     double W[4][3][RS];
     double x3[2], acc1[2], acc2[2], acc3[2];
 #pragma unroll
@@ -122,79 +125,79 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
         for (int q = 0; q < RS; ++q) W[s][r][q] = 0.0;
     x3[0] = x3[1] = acc1[0] = acc1[1] = acc2[0] = acc2[1] = acc3[0] = acc3[1] = 0.0;
 
-    // prefetch queue of input rows
+    // prefetch queue of input rows (slot = phase)
     double2 pf[PF];
-    const int j0 = r_lo - 4, j1 = r_hi + 4;   // rows [j0, j1) enter the pipeline
+    const int j0 = r_lo - 4;
+    const int j1 = j0 + (r_hi + 4 - j0 + 2) / 3 * 3;   // rows [j0, j1) enter the pipeline: a multiple of three
 #pragma unroll
     for (int p = 0; p < PF; ++p)
       pf[p] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j0 + p)) * MM + col0));
 
-    // a new row enters stage window s: shift, insert, fetch the neighbouring lanes' edge columns
-    auto push = [&](const int s, const double v0, const double v1) {
+    for (int jb = j0; jb < j1; jb += 3) {
 #pragma unroll
-      for (int q = 0; q < RS; ++q) { W[s][0][q] = W[s][1][q]; W[s][1][q] = W[s][2][q]; }
-      W[s][2][1] = v0; W[s][2][2] = v1;
-      W[s][2][0] = __shfl_up_sync(full, v1, 1);    // the left neighbour's second column
-      W[s][2][3] = __shfl_down_sync(full, v0, 1);  // the right neighbour's first column
-    };
-    // k of the lane's two cells in the middle row of window s (global row `row`)
-    auto rhs = [&](const int s, const int row, const double ts, double& k0, double& k1v) {
-      const int rw = wrap(row);
-      double kk[1];
-      kk[0] = 0.0;
-      view.e = &W[s][1][1];
-      view.row = idx.row = rw; view.col = idx.col = col0; idx.centre = rw * MM + col0;
-      sys.cell(view, kk, idx, ts);
-      k0 = kk[0];
-      kk[0] = 0.0;
-      view.e = &W[s][1][2];
-      view.col = idx.col = col0 + 1; idx.centre = rw * MM + col0 + 1;
-      sys.cell(view, kk, idx, ts);
-      k1v = kk[0];
-    };
+      for (int ph = 0; ph < 3; ++ph) {
+        const int j = jb + ph;
+        const int nw = ph, md = (ph + 2) % 3, ol = (ph + 1) % 3;  // slots of the newest / middle / oldest row after a push
+        // a new row enters stage window s (over the row that leaves it); the neighbouring lanes' edge columns with it
+        auto push = [&](const int s, const double v0, const double v1) {
+          W[s][nw][1] = v0; W[s][nw][2] = v1;
+          W[s][nw][0] = __shfl_up_sync(full, v1, 1);    // the left neighbour's second column
+          W[s][nw][3] = __shfl_down_sync(full, v0, 1);  // the right neighbour's first column
+        };
+        // k of the lane's two cells in the middle row of window s (global row `row`)
+        auto rhs = [&](const int s, const int row, const double ts, double& k0, double& k1v) {
+          const int rw = wrap(row);
+          double kk[1];
+          kk[0] = 0.0;
+          view.up = &W[s][ol][1]; view.mid = &W[s][md][1]; view.dn = &W[s][nw][1];
+          view.row = idx.row = rw; view.col = idx.col = col0; idx.centre = rw * MM + col0;
+          sys.cell(view, kk, idx, ts);
+          k0 = kk[0];
+          kk[0] = 0.0;
+          view.up = &W[s][ol][2]; view.mid = &W[s][md][2]; view.dn = &W[s][nw][2];
+          view.col = idx.col = col0 + 1; idx.centre = rw * MM + col0 + 1;
+          sys.cell(view, kk, idx, ts);
+          k1v = kk[0];
+        };
 
-    for (int j = j0; j < j1; ++j) {
-      const double2 xin = pf[0];
-#pragma unroll
-      for (int p = 0; p + 1 < PF; ++p) pf[p] = pf[p + 1];
-      if (j + PF < j1)
-        pf[PF - 1] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j + PF)) * MM + col0));
-      // HBM latency is longer than three iterations of two warps per scheduler: pull the rows further ahead into L2
-      // (one request per 128-byte line: every eighth lane), so that the register queue above is served from L2
-      if (ODEINTR_STREAM2_L2_AHEAD > 0 && (lane & 7) == 0 && j + PF + ODEINTR_STREAM2_L2_AHEAD < j1)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_in + static_cast<long long>(wrap(j + PF + ODEINTR_STREAM2_L2_AHEAD)) * MM + col0));
+        const double2 xin = pf[ph];
+        if (j + PF < j1)
+          pf[ph] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j + PF)) * MM + col0));
+        if (ODEINTR_STREAM2_L2_AHEAD > 0 && (lane & 7) == 0 && j + PF + ODEINTR_STREAM2_L2_AHEAD < j1)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_in + static_cast<long long>(wrap(j + PF + ODEINTR_STREAM2_L2_AHEAD)) * MM + col0));
 
-      // x of row j - 3 leaves the x window after this push: stage 3 needs it
-      x3[0] = W[0][0][1]; x3[1] = W[0][0][2];
-      push(0, xin.x, xin.y);                       // x rows j-2, j-1, j
-      double k0, k1v;
-      // stage 1 at row j-1
-      rhs(0, j - 1, t1, k0, k1v);
-      const double s1a = W[0][1][1] + (half * dt) * k0, s1b = W[0][1][2] + (half * dt) * k1v;
-      const double n1a = W[0][1][1] + (b1 * dt) * k0, n1b = W[0][1][2] + (b1 * dt) * k1v;   // the running sum starts from x
-      push(1, s1a, s1b);                           // stage-1 states of rows j-3, j-2, j-1
-      // stage 2 at row j-2
-      rhs(1, j - 2, t2, k0, k1v);
-      const double s2a = W[0][0][1] + (half * dt) * k0, s2b = W[0][0][2] + (half * dt) * k1v;
-      const double n2a = acc1[0] + (b2 * dt) * k0, n2b = acc1[1] + (b2 * dt) * k1v;
-      push(2, s2a, s2b);                           // stage-2 states of rows j-4, j-3, j-2
-      // stage 3 at row j-3
-      rhs(2, j - 3, t2, k0, k1v);
-      const double s3a = x3[0] + (1.0 * dt) * k0, s3b = x3[1] + (1.0 * dt) * k1v;
-      const double n3a = acc2[0] + (b2 * dt) * k0, n3b = acc2[1] + (b2 * dt) * k1v;
-      push(3, s3a, s3b);                           // stage-3 states of rows j-5, j-4, j-3
-      // stage 4 at row j-4: the new state
-      rhs(3, j - 4, t4, k0, k1v);
-      const double o0 = acc3[0] + (b1 * dt) * k0, o1 = acc3[1] + (b1 * dt) * k1v;
-      const int ro = j - 4;
-      if (keeps && ro >= r_lo && ro < r_hi) {
-        double2 o;
-        o.x = o0; o.y = o1;
-        *reinterpret_cast<double2*>(a.x_out + static_cast<long long>(ro) * MM + col0) = o;
+        // x of row j - 3 leaves the x window with this push: stage 3 needs it
+        x3[0] = W[0][nw][1]; x3[1] = W[0][nw][2];
+        push(0, xin.x, xin.y);                       // x rows j-2, j-1, j
+        double k0, k1v;
+        // stage 1 at row j-1
+        rhs(0, j - 1, t1, k0, k1v);
+        const double s1a = W[0][md][1] + (half * dt) * k0, s1b = W[0][md][2] + (half * dt) * k1v;
+        const double n1a = W[0][md][1] + (b1 * dt) * k0, n1b = W[0][md][2] + (b1 * dt) * k1v;   // the running sum starts from x
+        push(1, s1a, s1b);                           // stage-1 states of rows j-3, j-2, j-1
+        // stage 2 at row j-2
+        rhs(1, j - 2, t2, k0, k1v);
+        const double s2a = W[0][ol][1] + (half * dt) * k0, s2b = W[0][ol][2] + (half * dt) * k1v;
+        const double n2a = acc1[0] + (b2 * dt) * k0, n2b = acc1[1] + (b2 * dt) * k1v;
+        push(2, s2a, s2b);                           // stage-2 states of rows j-4, j-3, j-2
+        // stage 3 at row j-3
+        rhs(2, j - 3, t2, k0, k1v);
+        const double s3a = x3[0] + (1.0 * dt) * k0, s3b = x3[1] + (1.0 * dt) * k1v;
+        const double n3a = acc2[0] + (b2 * dt) * k0, n3b = acc2[1] + (b2 * dt) * k1v;
+        push(3, s3a, s3b);                           // stage-3 states of rows j-5, j-4, j-3
+        // stage 4 at row j-4: the new state
+        rhs(3, j - 4, t4, k0, k1v);
+        const double o0 = acc3[0] + (b1 * dt) * k0, o1 = acc3[1] + (b1 * dt) * k1v;
+        const int ro = j - 4;
+        if (keeps && ro >= r_lo && ro < r_hi) {
+          double2 o;
+          o.x = o0; o.y = o1;
+          *reinterpret_cast<double2*>(a.x_out + static_cast<long long>(ro) * MM + col0) = o;
+        }
+        acc3[0] = n3a; acc3[1] = n3b;
+        acc2[0] = n2a; acc2[1] = n2b;
+        acc1[0] = n1a; acc1[1] = n1b;
       }
-      acc3[0] = n3a; acc3[1] = n3b;
-      acc2[0] = n2a; acc2[1] = n2b;
-      acc1[0] = n1a; acc1[1] = n1b;
     }
     (void)col_left; (void)col_right;
   }

@@ -42,6 +42,8 @@ struct lattice_dopri5 {
   odeintr_system_t h;
   double *k2, *k3, *k4, *k5, *k6, *xtA, *xtB;
   int rc = 0;  // first launch error, reported by the caller
+  double eps_abs_o = -1.0, eps_rel_o = -1.0;  // tolerances of the error norm when they are not the handle's (bs / bsd: 1e-6)
+  int all = 0;                                 // combos also cover the entries no user loop writes (bs / bsd)
 
   int combo(const double* xs, const double* base, int nin, const double* const* in, const double* c, double ck,
             double* out, double* k_out, double t, const double* err_x = nullptr, const double* err_d = nullptr,
@@ -80,7 +82,9 @@ struct lattice_dopri5 {
     for (int j = 0; j < nin; ++j) { a.in[j] = in[j]; a.c[j] = c[j]; }
     a.ck = ck; a.out = out; a.k_out = k_out;
     }
-    a.err_x = err_x; a.err_d = err_d; a.eps_abs = h->atol; a.eps_rel = h->rtol; a.adt = adt;
+    a.err_x = err_x; a.err_d = err_d; a.adt = adt;
+    a.eps_abs = eps_abs_o >= 0.0 ? eps_abs_o : h->atol; a.eps_rel = eps_rel_o >= 0.0 ? eps_rel_o : h->rtol;
+    a.all = all;
     a.err_max = err_x ? h->lat_err.p : nullptr;
     a.pars = h->P ? h->pars.p : nullptr;
     a.n_total = h->N;
@@ -585,6 +589,402 @@ struct lattice_dopri5_dense {
   }
   void calc_state(double tq, lat_state& x) {
     ctl.core.calc_state(tq, x.p, x_old.p, d_old, t_old, d_cur, t);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bulirsch-Stoer on large systems (methods "bs" and "bsd", R/utils.R:57-58): Boost's bulirsch_stoer /
+// bulirsch_stoer_dense_out over device vectors.  Every vector operation of modified_midpoint, the extrapolation
+// tables, the finite differences and the Taylor polynomial of the dense output is one launch of odeintr_lattice_combo
+// (left-to-right sums, Boost's order); the midpoint steps fuse the right-hand side with the update that uses it.  The
+// order / step-size controller runs on the host (glibc pow, like the oracle).  The reference default-constructs these
+// steppers: tolerances 1e-6 / 1e-6 whatever atol / rtol say.  Extrapolating an entry no user loop writes does not
+// reproduce it bit for bit ((1 + c) x - c x), so these combos cover every entry of the vectors (`all`).
+// Same control flow as the per-trajectory steppers kernels/bulirsch_stoer.cuh, bulirsch_stoer_dense.cuh.
+struct lattice_bs_common {
+  static constexpr int K_MAX = 8;
+  lattice_dopri5 core;
+  lat_counters cnt;
+  bool dense_sequence = false;  // interval sequence 2, 6, 10, ... (bsd) instead of 2, 4, 6, ... (bs)
+  bool last_step_rejected = false, first = true;
+  int k_opt = 4;
+  double coeff[K_MAX + 1][K_MAX + 1];
+  long long seq[K_MAX + 1], cost[K_MAX + 1];
+  double facmin_table[K_MAX + 1];
+  double* table[K_MAX] = {nullptr};
+  double* mm[3] = {nullptr, nullptr, nullptr};
+
+  // a work vector of lat_vec_len doubles from the handle's pool (kept across calls)
+  double* vec() {
+    odeintr_system_t h = core.h;
+    if (h->lat_pool_used < h->lat_pool.size()) return h->lat_pool[h->lat_pool_used++];
+    double* p = nullptr;
+    if (cudaMalloc(&p, h->lat_pool_len * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      if (!core.rc) core.rc = fail(ODEINTR_E_CUDA, "out of device memory for the Bulirsch-Stoer work vectors");
+      return h->lat_pool.empty() ? nullptr : h->lat_pool[0];  // keep the launches harmless; the call fails with core.rc
+    }
+    h->lat_pool.push_back(p);
+    h->lat_pool_used++;
+    return p;
+  }
+  void setup(bool dense) {
+    dense_sequence = dense;
+    core.eps_abs_o = 1e-6; core.eps_rel_o = 1e-6; core.all = 1;
+    for (int i = 0; i <= K_MAX; ++i) {
+      seq[i] = dense ? 2 + 4 * i : 2 * (i + 1);
+      cost[i] = i == 0 ? seq[i] : cost[i - 1] + seq[i];
+      for (int k = 0; k < i; ++k) {
+        const double r = static_cast<double>(seq[i]) / static_cast<double>(seq[k]);
+        coeff[i][k] = 1.0 / (r * r - 1.0);
+      }
+      facmin_table[i] = std::pow(0.02, 1.0 / static_cast<double>(2 * i + 1));
+    }
+    for (int i = 0; i < 3; ++i) mm[i] = vec();
+  }
+  double* table_row(int j) {
+    if (!table[j]) table[j] = vec();
+    return table[j];
+  }
+  void copy(double* dst, const double* src) {
+    cudaMemcpyAsync(dst, src, core.h->lat_vec_len * sizeof(double), cudaMemcpyDeviceToDevice, core.h->stream);
+  }
+  // out = c0 * a + c1 * b  (out may be a or b: every entry is read before it is written, by the same thread)
+  void lin2(double* out, double c0, const double* a, double c1, const double* b) {
+    const double* v[] = {a, b};
+    const double c[] = {c0, c1};
+    core.combo(nullptr, nullptr, 2, v, c, 0.0, out, nullptr, 0.0);
+  }
+  // modified_midpoint(_dense_out)::do_step: `steps` substeps from (in, dxdt) over dt; derivs / x_mp only for bsd
+  void midpoint(const double* in, const double* dxdt, double t, double* out, double dt, int steps, double* x_mp,
+                double* const* derivs) {
+    const double h = dt / static_cast<double>(steps);
+    const double h2 = 2.0 * h;
+    double th = t + h;
+    {
+      const double* v[] = {dxdt};
+      const double c[] = {h};
+      core.combo(nullptr, in, 1, v, c, 0.0, mm[0], nullptr, t);  // x1 = in + h * dxdt
+    }
+    const double* x0 = in;
+    double* x1 = mm[0];
+    int i1 = 0, i0 = -1;
+    if (x_mp && steps == 2) copy(x_mp, x1);
+    for (int i = 1; i != steps; ++i) {
+      int in_ = 0;
+      while (in_ == i1 || in_ == i0) ++in_;
+      // d = f(x1, th); x1' = x0 + h2 * d; x0' = x1 -- the derivative and the update it feeds in one launch
+      core.combo(x1, x0, 0, nullptr, nullptr, h2, mm[in_], derivs ? derivs[i - 1] : nullptr, th);
+      x0 = x1; i0 = i1;
+      x1 = mm[in_]; i1 = in_;
+      if (x_mp && i == steps / 2 - 1) copy(x_mp, x1);
+      th += h;
+    }
+    const double* v[] = {x0, x1};
+    const double c[] = {1.0 / 2.0, 1.0 / 2.0};
+    core.combo(x1, nullptr, 2, v, c, (1.0 / 2.0) * h, out, derivs ? derivs[steps - 1] : nullptr, th);
+  }
+  void extrapolate(int k, double* xest) {
+    for (int j = k - 1; j > 0; --j) lin2(table[j - 1], 1.0 + coeff[k][j], table[j], -coeff[k][j], table[j - 1]);
+    lin2(xest, 1.0 + coeff[k][0], table[0], -coeff[k][0], xest);
+  }
+  // default_error_checker::error(in, dxdt, out - table[0], dt)
+  double error_of(const double* in, const double* dxdt, const double* out, double dt) {
+    cudaMemsetAsync(core.h->lat_err.p, 0, sizeof(unsigned long long), core.h->stream);
+    const double* v[] = {out, table[0]};
+    const double c[] = {1.0, -1.0};
+    core.combo(nullptr, nullptr, 2, v, c, 0.0, nullptr, nullptr, 0.0, in, dxdt, 1.0 * std::fabs(dt));
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(&bits, core.h->lat_err.p, sizeof(bits), cudaMemcpyDeviceToHost, core.h->stream);
+    cudaStreamSynchronize(core.h->stream);
+    double err;
+    std::memcpy(&err, &bits, sizeof(err));
+    return err;
+  }
+  double calc_h_opt(double h, double error, int k) const {
+    const double STEPFAC1 = 0.65, STEPFAC2 = 0.94, STEPFAC4 = 4.0;
+    const double expo = 1.0 / (2 * k + 1);
+    const double facmin = facmin_table[k];
+    double fac;
+    if (error == 0.0) fac = 1.0 / facmin;
+    else {
+      fac = STEPFAC2 / std::pow(error / STEPFAC1, expo);
+      fac = std::max(facmin / STEPFAC4, std::min(1.0 / facmin, fac));
+    }
+    return h * fac;
+  }
+  bool should_reject(double error, int k) const {
+    if (k == k_opt - 1) {
+      const double d = static_cast<double>(seq[k_opt] * seq[k_opt + 1] / (seq[0] * seq[0]));  // (integer arithmetic, as in Boost)
+      return error > d * d;
+    } else if (k == k_opt) {
+      const double d = static_cast<double>(seq[k_opt] / seq[0]);
+      return error > d * d;
+    }
+    return error > 1.0;
+  }
+  // the order / step-size decisions after column k of the tableau (identical in bs and bsd); true = leave the k loop
+  bool decide(int k, double error, const double* h_opt, const double* work, bool& reject, double& new_h) {
+    const double KFAC2 = 0.9;
+    if ((k == k_opt - 1) || first) {  // convergence before k_opt
+      if (error < 1.0) {
+        reject = false;
+        if ((work[k] < KFAC2 * work[k - 1]) || (k_opt <= 2)) {
+          k_opt = std::min(K_MAX - 1, std::max(2, k + 1));
+          new_h = h_opt[k];
+          new_h *= static_cast<double>(cost[k + 1]) / static_cast<double>(cost[k]);
+        } else {
+          k_opt = std::min(K_MAX - 1, std::max(2, k));
+          new_h = h_opt[k];
+        }
+        return true;
+      } else if (should_reject(error, k) && !first) {
+        reject = true;
+        new_h = h_opt[k];
+        return true;
+      }
+    }
+    if (k == k_opt) {  // convergence at k_opt
+      if (error < 1.0) {
+        reject = false;
+        if (work[k - 1] < KFAC2 * work[k]) {
+          k_opt = std::max(2, k_opt - 1);
+          new_h = h_opt[k_opt];
+        } else if ((work[k] < KFAC2 * work[k - 1]) && !last_step_rejected) {
+          k_opt = std::min(K_MAX - 1, k_opt + 1);
+          new_h = h_opt[k];
+          new_h *= static_cast<double>(cost[k_opt]) / static_cast<double>(cost[k]);
+        } else
+          new_h = h_opt[k_opt];
+        return true;
+      } else if (should_reject(error, k)) {
+        reject = true;
+        new_h = h_opt[k_opt];
+        return true;
+      }
+    }
+    if (k == k_opt + 1) {  // convergence at k_opt + 1
+      if (error < 1.0) {
+        reject = false;
+        if (work[k - 2] < KFAC2 * work[k - 1]) k_opt = std::max(2, k_opt - 1);
+        if ((work[k] < KFAC2 * work[k_opt]) && !last_step_rejected) k_opt = std::min(K_MAX - 1, k);
+        new_h = h_opt[k_opt];
+      } else {
+        reject = true;
+        new_h = h_opt[k_opt];
+      }
+      return true;
+    }
+    return false;
+  }
+};
+
+// bulirsch_stoer< state_type, double, state_type, double, openmp_range_algebra > (controlled stepper, method "bs")
+struct lattice_bs_controlled : lattice_bs_common {
+  static constexpr bool is_dense = false;
+  double *dxdt = nullptr, *xnew = nullptr;
+  double dt_last = 0.0;
+  lat_counters& counters() { return cnt; }
+  void reset() { first = true; last_step_rejected = false; k_opt = 4; }
+  void restart() { reset(); dt_last = 0.0; }  // integrate_const hands every interval a fresh copy of the stepper
+  void init() { setup(false); dxdt = vec(); xnew = vec(); }
+  bool try_step(lat_sys&, lat_state& x, double& t, double& dt) {
+    core.rhs(x.p, dxdt, t);
+    if (dt != dt_last) reset();  // step size changed from outside -> reset
+    bool reject = true;
+    double h_opt[K_MAX + 1], work[K_MAX + 1];
+    double new_h = dt;
+    for (int k = 0; k <= k_opt + 1; ++k) {
+      if (k == 0) {
+        midpoint(x.p, dxdt, t, xnew, dt, (int)seq[k], nullptr, nullptr);
+      } else {
+        midpoint(x.p, dxdt, t, table_row(k - 1), dt, (int)seq[k], nullptr, nullptr);
+        extrapolate(k, xnew);
+        const double error = error_of(x.p, dxdt, xnew, dt);
+        if (core.rc) return true;  // the caller reports core.rc
+        h_opt[k] = calc_h_opt(dt, error, k);
+        work[k] = static_cast<double>(cost[k]) / h_opt[k];
+        if (decide(k, error, h_opt, work, reject, new_h)) break;
+      }
+    }
+    if (!reject) t += dt;
+    if (!last_step_rejected || odeintr_b200::less_with_sign(new_h, dt, dt)) {
+      dt_last = new_h;
+      dt = new_h;
+    }
+    last_step_rejected = reject;
+    first = false;
+    if (reject) { cnt.rejected++; return false; }
+    copy(x.p, xnew);
+    cnt.accepted++;
+    return true;
+  }
+};
+
+// bulirsch_stoer_dense_out< ... > (dense-output stepper, method "bsd"): the derivatives of every midpoint run are kept,
+// their finite differences at the interval centre extrapolated, the dense output is the Taylor polynomial about the
+// centre in theta = -1 ... 1
+struct lattice_bsd_dense : lattice_bs_common {
+  static constexpr bool is_dense = true;
+  lat_state x_cur, x_old;
+  double *d_cur = nullptr, *d_old = nullptr;
+  double t = 0, t_old = 0, dt = 0;
+  int k_final = 0;
+  double* mp_states[K_MAX + 1] = {nullptr};
+  std::vector<double*> derivs[K_MAX + 1];
+  std::vector<double*> diffs[2 * K_MAX + 2];
+  lat_counters& counters() { return cnt; }
+  void init() {
+    setup(true);
+    x_cur.h = x_old.h = core.h;
+    x_cur.p = vec(); x_old.p = vec(); d_cur = vec(); d_old = vec();
+    for (int i = 0; i <= K_MAX; ++i) derivs[i].assign((size_t)seq[i], nullptr);
+    int num = 1;
+    for (int i = 2 * K_MAX + 1; i >= 0; --i) {
+      diffs[i].assign((size_t)num, nullptr);
+      num += (i + 1) % 2;
+    }
+  }
+  void reset() { first = true; last_step_rejected = false; }
+  void initialize(const lat_state& x0, double t0, double dt0) {
+    x_cur = x0;  // value copy (no-op when x0 is the current state itself)
+    t = t0; dt = dt0;
+    reset();
+  }
+  const lat_state& current_state() const { return x_cur; }
+  double* mp(int k) { if (!mp_states[k]) mp_states[k] = vec(); return mp_states[k]; }
+  double* dv(int k, int i) { if (!derivs[k][i]) derivs[k][i] = vec(); return derivs[k][i]; }
+  double* df(int kappa, int j) { if (!diffs[kappa][j]) diffs[kappa][j] = vec(); return diffs[kappa][j]; }
+  static double binomial(int n, int k) {
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * static_cast<double>(n - k + i) / static_cast<double>(i);
+    return std::floor(r + 0.5);
+  }
+  // out = sum of c_j v_j, left to right, in launches of at most 12 terms (later launches continue from out)
+  void sum_terms(double* out, const double* base, const std::vector<const double*>& v, const std::vector<double>& c) {
+    size_t done = 0;
+    const double* b = base;
+    while (true) {
+      const double* vv[12];
+      double cc[12];
+      int n = 0;
+      if (!b && done > 0) { vv[n] = out; cc[n] = 1.0; ++n; }  // 1.0 * out: exact
+      while (done < v.size() && n < 12) { vv[n] = v[done]; cc[n] = c[done]; ++n; ++done; }
+      core.combo(nullptr, b, n, vv, cc, 0.0, out, nullptr, 0.0);
+      if (done >= v.size()) break;
+      b = nullptr;
+      if (base) b = out;  // continue from what is there: base + ... (the base enters with weight one)
+    }
+  }
+  void calculate_finite_difference(int j, int kappa, double fac, const double* dxdt) {
+    const int m = static_cast<int>(seq[j] / 2) - 1;
+    if (kappa == 0) {  // no calculation required for the 0th derivative of f
+      const double* v[] = {dv(j, m)};
+      const double c[] = {fac};
+      core.combo(nullptr, nullptr, 1, v, c, 0.0, df(0, j), nullptr, 0.0);
+      return;
+    }
+    const int j_diffs = j - kappa / 2;
+    std::vector<const double*> v;
+    std::vector<double> c;
+    v.push_back(dv(j, m + kappa)); c.push_back(fac);
+    double sign = -1.0;
+    int cc = 1;
+    for (int i = m + kappa - 2; i >= m - kappa; i -= 2) {
+      if (i >= 0) { v.push_back(dv(j, i)); c.push_back(sign * fac * binomial(kappa, cc)); }
+      else { v.push_back(dxdt); c.push_back(sign * fac); }
+      sign *= -1;
+      ++cc;
+    }
+    sum_terms(df(kappa, j_diffs), nullptr, v, c);
+  }
+  template <class Get>
+  void extrapolate_dense_out(int k, Get get, int order_start_index) {
+    for (int j = k; j > 1; --j) {
+      const double cf = coeff[k + order_start_index][j + order_start_index - 1];
+      lin2(get(j - 1), 1.0 + cf, get(j), -cf, get(j - 1));
+    }
+    const double cf = coeff[k + order_start_index][order_start_index];
+    lin2(get(0), 1.0 + cf, get(1), -cf, get(0));
+  }
+  void prepare_dense_output(int k, const double* dxdt_start, double dt_) {
+    for (int j = 0; j <= k; ++j) {
+      const double d = static_cast<double>(seq[j]) / (2.0 * dt_);
+      double f = 1.0;
+      for (int kappa = 0; kappa <= 2 * j + 1; ++kappa) {
+        calculate_finite_difference(j, kappa, f, dxdt_start);
+        f *= d;
+      }
+      if (j > 0) extrapolate_dense_out(j, [&](int q) { return mp(q); }, 0);
+    }
+    double d = dt_ / 2;
+    for (int kappa = 0; kappa <= 2 * k + 1; ++kappa) {
+      for (int j = 1; j <= (k - kappa / 2); ++j) extrapolate_dense_out(j, [&](int q) { return df(kappa, q); }, kappa / 2);
+      const double* v[] = {df(kappa, 0)};
+      const double c[] = {d};
+      core.combo(nullptr, nullptr, 1, v, c, 0.0, df(kappa, 0), nullptr, 0.0);  // (dt/2)^(kappa+1) / (kappa+1)!
+      d *= dt_ / (2 * (kappa + 2));
+    }
+  }
+  bool try_step(const double* in, const double* dxdt, double& tt, double* out, double* dxdt_new, double& dtt) {
+    bool reject = true;
+    double h_opt[K_MAX + 1], work[K_MAX + 1];
+    k_final = 0;
+    double new_h = dtt;
+    for (int k = 0; k <= k_opt + 1; ++k) {
+      const int steps = (int)seq[k];
+      double* dptr[40];
+      for (int i = 0; i < steps; ++i) dptr[i] = dv(k, i);
+      if (k == 0) {
+        midpoint(in, dxdt, tt, out, dtt, steps, mp(k), dptr);
+      } else {
+        midpoint(in, dxdt, tt, table_row(k - 1), dtt, steps, mp(k), dptr);
+        extrapolate(k, out);
+        const double error = error_of(in, dxdt, out, dtt);
+        if (core.rc) return true;
+        h_opt[k] = calc_h_opt(dtt, error, k);
+        work[k] = static_cast<double>(cost[k]) / h_opt[k];
+        k_final = k;
+        if (decide(k, error, h_opt, work, reject, new_h)) break;
+      }
+    }
+    if (!reject) {
+      core.rhs(out, dxdt_new, tt + dtt);  // dxdt for the next step and the dense output
+      prepare_dense_output(k_final, dxdt, dtt);  // (no interpolation control in the default-constructed stepper)
+      tt += dtt;
+    }
+    if (!last_step_rejected || (new_h < dtt)) dtt = new_h;
+    last_step_rejected = reject;
+    if (reject) cnt.rejected++; else cnt.accepted++;
+    return !reject;
+  }
+  bool do_step(lat_sys&) {
+    if (first) core.rhs(x_cur.p, d_cur, t);
+    t_old = t;
+    int fails = 0;
+    if (cnt.exhausted()) return false;
+    while (true) {
+      const bool ok = try_step(x_cur.p, d_cur, t, x_old.p, d_old, dt);
+      first = false;
+      if (core.rc) return false;
+      if (ok) break;
+      if (++fails >= ODEINTR_MAX_FAILED_STEPS) { cnt.status |= ODEINTR_STATUS_STEP_OVERFLOW; return false; }
+      if (cnt.exhausted()) return false;
+    }
+    std::swap(x_cur.p, x_old.p);
+    std::swap(d_cur, d_old);
+    return true;
+  }
+  void calc_state(double tq, lat_state& x) {
+    const double theta = 2 * ((tq - t_old) / (t - t_old)) - 1;  // interpolation polynomial on theta = -1 ... 1
+    std::vector<const double*> v;
+    std::vector<double> c;
+    double theta_pow = theta;
+    for (int i = 0; i <= 2 * k_final + 1; ++i) {
+      v.push_back(df(i, 0)); c.push_back(theta_pow);
+      theta_pow *= theta;
+    }
+    sum_terms(x.p, mp(0), v, c);
   }
 };
 

@@ -94,6 +94,8 @@ class CompiledSystem:
             flags |= _abi.FLAG_LATTICE_CK54
         if gen.family == "lattice" and gen.stepper.base == "rk78":
             flags |= _abi.FLAG_LATTICE_RKF78
+        if gen.family == "lattice" and gen.stepper.base in ("bs", "bsd"):
+            flags |= _abi.FLAG_LATTICE_BS
         if gen.family == "lattice" and gen.stepper.mode != "plain":
             flags |= _abi.FLAG_LATTICE_ADAPTIVE
         rc = self._lib.odeintr_compile(gen.code.encode(), gen.name.encode(), self.N, self.P, gen.atol, gen.rtol,

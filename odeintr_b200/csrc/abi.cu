@@ -1482,7 +1482,16 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   double* const xstate = slab ? h->sh_x : h->x.p;
   h->lat_vec_len = N;
   h->slab_fresh.clear();
-  CU_TRY(h->lat_work.reserve((h->lattice_method == 4 ? 18 : 13) * N));
+  const bool bs_family = h->lattice_method == 5 || h->lattice_method == 6;
+  if (bs_family) {  // Bulirsch-Stoer: work vectors from a pool that grows with the orders the controller reaches
+    if (h->lat_pool_len != N) {
+      for (double* v : h->lat_pool) cudaFree(v);
+      h->lat_pool.clear();
+      h->lat_pool_len = N;
+    }
+    h->lat_pool_used = 0;
+  }
+  CU_TRY(h->lat_work.reserve((bs_family ? 0 : h->lattice_method == 4 ? 18 : 13) * N + 1));
   CU_TRY(h->lat_err.reserve(2));  // max-norm error bits, reach flag
   {
     const int rc5 = tiled5_decide(h);
@@ -1502,14 +1511,16 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   double* w = h->lat_work.p;
   // state-like vectors start as copies of x, derivative-like ones as zeros: entries no user loop writes keep
   // their value / a zero derivative through every stage
-  double* state_like[5];
-  for (int j = 0; j < 5; ++j) {
-    state_like[j] = w + (size_t)j * N;
-    CU_TRY(cudaMemcpyAsync(state_like[j], xstate, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  double* state_like[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* deriv_like[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!bs_family) {
+    for (int j = 0; j < 5; ++j) {
+      state_like[j] = w + (size_t)j * N;
+      CU_TRY(cudaMemcpyAsync(state_like[j], xstate, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CU_TRY(cudaMemsetAsync(w + 5 * N, 0, 8 * N * sizeof(double), h->stream));
+    for (int j = 0; j < 8; ++j) deriv_like[j] = w + (size_t)(5 + j) * N;
   }
-  CU_TRY(cudaMemsetAsync(w + 5 * N, 0, 8 * N * sizeof(double), h->stream));
-  double* deriv_like[8];
-  for (int j = 0; j < 8; ++j) deriv_like[j] = w + (size_t)(5 + j) * N;
 
   lattice_dopri5 core;
   core.h = h;
@@ -1534,7 +1545,42 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   if ((rc = begin_timing(h))) return rc;
   bool ok = true;  // failures are carried by the counters' status word
   lat_counters cnt;
-  if (h->lattice_method == 2) {
+  if (h->lattice_method == 5) {
+    lattice_bs_controlled st;
+    st.core = core;
+    st.cnt.budget = h->max_tries;
+    st.init();
+    if (st.core.rc) return st.core.rc;
+    double dtc = dt, tc = t0;
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, obs)
+                  : odeintr_b200::integrate_times_controlled(st, sys, x, times, (long long)n_times, dtc, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, obs)
+                  : odeintr_b200::integrate_const_controlled(st, sys, x, t0, t1, dtc, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, obs)
+                  : odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, nobs);
+    cnt = st.cnt;
+    if (st.core.rc) return st.core.rc;
+  } else if (h->lattice_method == 6) {
+    lattice_bsd_dense st;
+    st.core = core;
+    st.cnt.budget = h->max_tries;
+    st.init();
+    if (st.core.rc) return st.core.rc;
+    if (mode == ODEINTR_MODE_TIMES)
+      ok = record ? odeintr_b200::integrate_times_dense(st, sys, x, times, (long long)n_times, dt, obs)
+                  : odeintr_b200::integrate_times_dense(st, sys, x, times, (long long)n_times, dt, nobs);
+    else if (mode == ODEINTR_MODE_CONST)
+      ok = record ? odeintr_b200::integrate_const_dense(st, sys, x, t0, t1, dt, obs)
+                  : odeintr_b200::integrate_const_dense(st, sys, x, t0, t1, dt, nobs);
+    else
+      ok = record ? odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, obs)
+                  : odeintr_b200::integrate_adaptive_dense(st, sys, x, t0, t1, dt, nobs);
+    cnt = st.cnt;
+    if (st.core.rc) return st.core.rc;
+  } else if (h->lattice_method == 2) {
     lattice_dopri5_dense st;
     st.ctl.core = core;
     st.ctl.cnt.budget = h->max_tries;
@@ -2166,6 +2212,7 @@ int odeintr_lattice_shard(odeintr_system_t h, long long cells_total, long long f
   if (!h->lattice_method) {  // (adaptive steppers keep their work vectors in lat_work)
     CU_TRY(h->lat_buf_a.reserve(total));
     if (!h->sh_tiled) { CU_TRY(h->lat_buf_b.reserve(total)); CU_TRY(h->lat_buf_acc.reserve(total)); }
+    else if (h->sh_steps_per_exchange >= 2 && h->k_warp && h->warp_blocks > 0) CU_TRY(h->lat_buf_acc.reserve(total));  // fused step pairs
   }
   CU_TRY(h->lat_flag.reserve(8));
   CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
@@ -2229,6 +2276,64 @@ int slab_tiled_step(odeintr_system_t h, double* cur, double* other, double t, do
   return tiled_produce(h, ta, e_lo, e_hi, glo, ghi, true);
 }
 
+// Two consecutive rk4 steps of the slab (phases `phase` and `phase + 1` of one round) as ONE pass of the warp kernel over
+// the middle of the slab (x -> x'' in registers, 8 B per cell and step: what lattice_step_pair does on one GPU); the
+// edges -- everything between the window of the step and the middle -- take the general kernel twice through `mid`.
+// part = SLAB_EDGES: both edge steps (the second one's results are what an exchange after the pair sends);
+// part = SLAB_MIDDLE: the fused pass.  slab_pair_possible decides once per run.
+bool slab_pair_possible(odeintr_system_t h, long long* ilo_out, long long* ihi_out, bool* tma_out, const double* cur,
+                        const double* other) {
+  const char* knob = std::getenv("ODEINTR_FUSE");
+  if (knob && std::atoi(knob) == 0) return false;
+  if (h->lattice_stages != 4 || !h->sh_tiled || !h->k_tiled || !h->k_warp || h->warp_blocks <= 0 || h->k_serial ||
+      h->sh_steps_per_exchange < 2 || std::getenv("ODEINTR_NO_WARP") || std::getenv("ODEINTR_TILED_GENERAL_ONLY"))
+    return false;
+  if (h->lat_cells_ct != h->sh_total) return false;
+  const long long g = h->sh_ghost, m1 = 4 * (long long)h->sh_halo;
+  const long long glo = h->lat_start > 0 ? h->lat_start : 0;
+  const long long ghi = h->lat_bound < h->sh_total ? h->lat_bound : h->sh_total;
+  const long long e_lo = h->sh_c0 + g, e_hi = h->sh_c0 + h->sh_n - g;
+  // the fused pass reads 2 * m1 (+ one radius: it evaluates its outermost cells too) beyond what it produces: owned
+  // cells only, so that it can start before the ghost cells arrive, and inside the user loop's range
+  long long ilo = std::max(std::max(e_lo, h->sh_c0 + 2 * m1 + h->sh_halo), glo + 2 * m1 + h->sh_halo);
+  long long ihi = std::min(std::min(e_hi, h->sh_c0 + h->sh_n - 2 * m1 - h->sh_halo), ghi - 2 * m1 - h->sh_halo);
+  const bool tma = reinterpret_cast<uintptr_t>(cur) % 16 == 0 && reinterpret_cast<uintptr_t>(other) % 16 == 0 &&
+                   (h->sh_fields == 1 || h->sh_pitch % 2 == 0) && !std::getenv("ODEINTR_NO_TMA");
+  if (tma) {
+    if ((ilo - h->sh_c0) & 1) ++ilo;
+    if ((ihi - h->sh_c0) & 1) --ihi;
+  }
+  const long long P = 32LL * h->warp_cpt - 16LL * h->warp_halo;
+  if (P < 32 || ihi - ilo < 4 * P) return false;
+  *ilo_out = ilo; *ihi_out = ihi; *tma_out = tma;
+  return true;
+}
+
+int slab_tiled_pair(odeintr_system_t h, double* cur, double* mid, double* other, double t, double t2, double dt, int phase,
+                    int part, long long ilo, long long ihi, bool tma) {
+  const long long g = h->sh_ghost, pad = h->sh_pad, m1 = 4 * (long long)h->sh_halo;
+  lattice_window w = {h->sh_n, h->sh_total, h->sh_c0, g, h->sh_pitch, 1, 0, 0};
+  const long long lo1 = h->sh_c0 - g + m1 * (phase + 1), hi1 = h->sh_c0 + h->sh_n + g - m1 * (phase + 1);
+  const long long lo2 = lo1 + m1, hi2 = hi1 - m1;
+  int rc;
+  if (part == SLAB_EDGES) {
+    // first step of the edges: cur -> mid on everything the second step of the edges reads
+    odeintr_lattice_tiled_args e1;
+    tiled_args_init(h, w, cur + pad, mid + pad, t, dt, e1);
+    if ((rc = tiled_general(h, e1, lo1, std::min(ilo + m1, hi1), std::max(ihi - m1, lo1), hi1))) return rc;
+    odeintr_lattice_tiled_args e2;
+    tiled_args_init(h, w, mid + pad, other + pad, t2, dt, e2);
+    return tiled_general(h, e2, lo2, ilo, ihi, hi2);
+  }
+  odeintr_lattice_tiled_args ta;
+  tiled_args_init(h, w, cur + pad, other + pad, t, dt, ta);
+  ta.lo = ilo; ta.hi = ihi; ta.sharded = 0; ta.tma = tma ? 1 : 0; ta.nsub = 2; ta.t2 = t2;
+  const long long P = 32LL * h->warp_cpt - 16LL * h->warp_halo;
+  const long long warp_tiles = (ihi - ilo + P - 1) / P;
+  const unsigned grid = (unsigned)std::min<long long>((warp_tiles + 7) / 8, (long long)h->sm_count * h->warp_blocks);
+  return tiled_launch(h, h->k_warp, grid, h->warp_smem, ta);
+}
+
 int slab_check_reach(odeintr_system_t h) {
   int flag = 0;
   CU_TRY(cudaMemcpyAsync(&flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -2244,6 +2349,8 @@ int slab_prime(odeintr_system_t h) {
   if (h->sh_primed) return ODEINTR_OK;
   const size_t total = (size_t)h->sh_fields * (size_t)h->sh_pitch;
   CU_TRY(cudaMemcpyAsync(h->lat_buf_a.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (h->sh_tiled && h->lat_buf_acc.p && h->lat_buf_acc.cap >= total)  // intermediate state of fused step pairs
+    CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   if (!h->sh_tiled) {
     CU_TRY(cudaMemcpyAsync(h->lat_buf_b.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CU_TRY(cudaMemcpyAsync(h->lat_buf_acc.p, h->sh_x, total * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -2372,10 +2479,42 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
       CU_TRY(cudaEventRecord(h->ev_xchg, h->stream2));
       return ODEINTR_OK;
     };
+    long long p_ilo = 0, p_ihi = 0;
+    bool p_tma = false;
+    double* mid = h->lat_buf_acc.p;
+    const bool pairs = mid && h->lat_buf_acc.cap >= (size_t)h->sh_fields * (size_t)h->sh_pitch &&
+                       slab_pair_possible(h, &p_ilo, &p_ihi, &p_tma, cur, other);
     for (long long s = 0; s < n_steps; ++s) {
       const int phase = (int)(s % spe);
       const double t = t0 + static_cast<double>(first_step + s) * dt;
       h->last_launches = 0;
+      if (pairs && phase + 1 < spe && s + 1 < n_steps) {
+        // two steps of one round in one pass over the middle of the slab (the state between them stays in registers)
+        const double t2 = t0 + static_cast<double>(first_step + s + 1) * dt;
+        const bool first_of_round = phase == 0;
+        const bool feeds_exchange = phase + 1 == spe - 1 && s + 2 < n_steps;  // the step after the pair starts a round
+        if (!overlap) {
+          if (first_of_round && (rc = lattice_exchange(h, cur, h->stream))) return rc;
+          if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
+          if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
+        } else {
+          if (s == 0 && (rc = exchange_async(cur))) return rc;
+          if (first_of_round) {
+            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
+            CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_xchg, 0));
+            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
+            if (feeds_exchange && (rc = exchange_async(other))) return rc;  // a round of two steps
+          } else {
+            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
+            if (feeds_exchange && (rc = exchange_async(other))) return rc;
+            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
+          }
+        }
+        launches += h->last_launches;
+        std::swap(cur, other);
+        ++s;
+        continue;
+      }
       if (!overlap) {
         if (phase == 0 && (rc = lattice_exchange(h, cur, h->stream))) return rc;
         if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_ALL))) return rc;

@@ -161,6 +161,8 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
         };
 
         const double2 xin = pf[ph];
+        // (measured: loading unconditionally -- rows wrap, the rows past the segment's end exist -- removes the
+        // predicated copy that ncu shows waiting for the load, but costs a spill at 128 registers: 1.72e11 vs 1.75e11)
         if (j + PF < j1)
           pf[ph] = __ldg(reinterpret_cast<const double2*>(a.x_in + static_cast<long long>(wrap(j + PF)) * MM + col0));
         if (ODEINTR_STREAM2_L2_AHEAD > 0 && (lane & 7) == 0 && j + PF + ODEINTR_STREAM2_L2_AHEAD < j1)

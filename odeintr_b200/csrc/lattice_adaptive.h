@@ -617,13 +617,20 @@ struct lattice_bs_common {
   // a work vector of lat_vec_len doubles from the handle's pool (kept across calls)
   double* vec() {
     odeintr_system_t h = core.h;
-    if (h->lat_pool_used < h->lat_pool.size()) return h->lat_pool[h->lat_pool_used++];
+    // handed out zeroed: a general snippet's right-hand side leaves the entries it does not write alone, and in the
+    // reference those are the zeros of a freshly resized vector
+    if (h->lat_pool_used < h->lat_pool.size()) {
+      double* q = h->lat_pool[h->lat_pool_used++];
+      cudaMemsetAsync(q, 0, h->lat_pool_len * sizeof(double), h->stream);
+      return q;
+    }
     double* p = nullptr;
     if (cudaMalloc(&p, h->lat_pool_len * sizeof(double)) != cudaSuccess) {
       cudaGetLastError();
       if (!core.rc) core.rc = fail(ODEINTR_E_CUDA, "out of device memory for the Bulirsch-Stoer work vectors");
       return h->lat_pool.empty() ? nullptr : h->lat_pool[0];  // keep the launches harmless; the call fails with core.rc
     }
+    cudaMemsetAsync(p, 0, h->lat_pool_len * sizeof(double), h->stream);
     h->lat_pool.push_back(p);
     h->lat_pool_used++;
     return p;
@@ -801,7 +808,7 @@ struct lattice_bs_controlled : lattice_bs_common {
         midpoint(x.p, dxdt, t, table_row(k - 1), dt, (int)seq[k], nullptr, nullptr);
         extrapolate(k, xnew);
         const double error = error_of(x.p, dxdt, xnew, dt);
-        if (core.rc) return true;  // the caller reports core.rc
+        if (core.rc) { cnt.budget = 0; return true; }  // the loops stop at their next budget check; the caller reports core.rc
         h_opt[k] = calc_h_opt(dt, error, k);
         work[k] = static_cast<double>(cost[k]) / h_opt[k];
         if (decide(k, error, h_opt, work, reject, new_h)) break;

@@ -147,7 +147,7 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2",
                               "odeintr_lattice_dopri5_warp_h1", "odeintr_lattice_dopri5_warp_h2", "odeintr_lattice_dopri5_warp_info"}
-    for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a"):
+    for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a", "bs", "bsd"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged
     for src in (BISTABLE_2D, BISTABLE_DOC):
@@ -194,5 +194,8 @@ def test_cell_loop_parser():
         codegen.parse_cell_loops("for (int i = 0; i < N; ++i) dxdt[i] = 1; for (int i = 1; i < N; ++i) dxdt[i] += 1;")
     g = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8)  # default rk5_i
     assert g.stepper.method == "rk5_i" and g.stepper.mode == "dense" and _cubin(g.code) > 1000
-    with pytest.raises(OdeintrError, match="not yet provided for large systems"):
-        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method="bs")
+    for method, mode in (("bs", "controlled"), ("bsd", "dense")):  # steppers by type, not by suffix (R/utils.R:57-58)
+        g = codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method=method)
+        assert g.stepper.mode == mode and _cubin(g.code) > 1000
+    with pytest.raises(OdeintrError, match="multistep"):
+        codegen.generate_sys_openmp("b", "for (int i = 0; i < N; ++i) dxdt[i] = -x[i];", sys_dim=8, method="abm4")

@@ -650,7 +650,7 @@ for (int i = 0; i < M; ++i)
 """
 
 
-@pytest.mark.parametrize("method", ["rk4", "euler", "rk5_i", "rk5_a", "rk54_a", "rk78", "rk5"])
+@pytest.mark.parametrize("method", ["rk4", "euler", "rk5_i", "rk5_a", "rk54_a", "rk78", "rk5", "bs", "bsd"])
 @pytest.mark.parametrize("case", ["mean_field", "nested_2d", "straight_line"])
 def test_general_snippets_take_the_serial_rhs_path(case, method):
     # compile_sys_openmp pastes ANY C++ into sys() (inst/templates/compile_sys_openmp_template.cpp:39-43).  Snippets
@@ -750,3 +750,40 @@ def test_2d_lattice_streaming_rk4_bit_exact(case, monkeypatch):
         fin = env["s2_no_record"](x0, 0.7, 0.1)
         assert code.system.get_halo() == 1
         assert np.array_equal(bits(fin), bits(ref)), (case, stream)
+
+
+FIXED_ENDS = """
+for (int i = 1; i < N - 1; ++i)
+  dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]) + a * x[i] * (1 - x[i]) * (x[i] - b);
+"""
+
+
+@pytest.mark.parametrize("method", ["bs", "bsd"])
+@pytest.mark.parametrize("case", ["periodic", "fixed_ends", "chain"])
+def test_large_system_bulirsch_stoer(case, method):
+    # bs / bsd on large systems (R/utils.R:57-58 with openmp_range_algebra): modified-midpoint runs, extrapolation
+    # tables, finite differences and the dense-output polynomial as odeintr_lattice_combo launches in Boost's order, the
+    # order / step-size controller on the host (glibc pow, like the oracle): bit-exact, step counts included.  The
+    # fixed-ends case has entries no loop writes: the extrapolation (1 + c) x - c x does not reproduce them exactly, so
+    # the combos cover every entry.
+    if case == "chain":
+        n, src, pars, glob = 2 * 700, CHAIN, CHAIN_PARS, CHAIN_GLOBALS
+    else:
+        n, src, pars, glob = 2003, (BISTABLE_1D if case == "periodic" else FIXED_ENDS), BISTABLE_PARS, ""
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("bsl", src, pars, True, method=method, sys_dim=n, env=env, globals=glob)
+    ora = bo.build(src, pars, True, method, sys_dim=n, globals=glob)
+    x0 = np.random.default_rng(77).uniform(0.1, 1, n)
+    df = env["bsl"](x0, 3.0, 0.25)
+    ref = ora.integrate_const(x0, 0, 3.0, 0.25)
+    assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    st = code.system.stats()
+    assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
+    at = np.array([0.5, 1.0, 2.2, 7.0])
+    df = env["bsl_at"](x0, at, 0.1)
+    adv = ora.integrate_const(x0, 0.0, at[0], 0.1, record=False)
+    ref = ora.integrate_times(adv["x"], at, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["bsl_no_record"](x0, 4.05, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 4.05, 0.1)["x"]))

@@ -260,6 +260,8 @@ struct odeintr_system_s {
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
+  cudaKernel_t k_stream5 = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
+  int stream5_blocks = 0, stream5_rows = 0;
   size_t warp5_smem = 0;
   long long tiled5_halo = 0;
   size_t tiled5_smem = 0;
@@ -1234,6 +1236,45 @@ int tiled5_decide(odeintr_system_t h) {
   if (h->tiled5 >= 0) return ODEINTR_OK;
   if (h->P && !h->pars.p) return ODEINTR_OK;  // no parameters yet: the probe would have nothing to read
   h->tiled5 = 0;
+  if (h->lat_side > 0) {
+    // M x M lattice (one field): radius 1, even M >= 64, a loop over all cells -> the streaming attempt kernel
+    const bool covers_all = h->lat_start <= 0 && h->lat_bound >= (long long)h->N;
+    if (!h->k_stream5 || !h->k_probe || h->lat_side % 2 != 0 || h->lat_side < 64 || !covers_all ||
+        h->lat_cells_ct != (long long)h->N || h->lat_cells_ct >= (1LL << 31) || std::getenv("ODEINTR_NO_TILED") ||
+        std::getenv("ODEINTR_NO_STREAM2D"))
+      return ODEINTR_OK;
+    CU_TRY(h->lat_flag.reserve(10));
+    CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+    const double* pars = h->P ? h->pars.p : nullptr;
+    double t = 0.0;
+    int* out = h->lat_flag.p;
+    void* params[3] = {&pars, &t, &out};
+    CU_TRY(cudaLaunchKernel((const void*)h->k_probe, dim3((unsigned)h->sm_count * 8u), dim3(256), params, 0, h->stream));
+    int reach = 0, nb = 0;
+    CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (reach > 1) return ODEINTR_OK;  // (the probe reports the larger of the row and column reach)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_stream5, 256, 0) != cudaSuccess || nb <= 0) {
+      (void)cudaGetLastError();
+      return ODEINTR_OK;
+    }
+    // rows per warp task: the fewest waves of tasks (strips x segments) over the resident warps with segments of at
+    // most 512 rows (12 rows of pipeline fill each), so that the last wave is a full one
+    const long long strips = (h->lat_side + 51) / 52, slots = (long long)h->sm_count * nb * 8;
+    long long rows = 256;
+    if (const char* c = std::getenv("ODEINTR_STREAM5_ROWS")) rows = std::atoll(c);
+    else
+      for (long long wv = 1; wv <= 64; ++wv) {
+        const long long segs = wv * slots / strips;
+        if (segs < 1) continue;
+        const long long r = (h->lat_side + segs - 1) / segs;
+        if (r <= 512) { rows = r < 48 ? 48 : r; break; }
+      }
+    h->stream5_blocks = nb; h->stream5_rows = (int)rows;
+    h->tiled5_halo = 1;
+    h->tiled5 = 2;
+    return ODEINTR_OK;
+  }
   if (!h->k_dopri5_tiled || !h->k_probe || h->lat_cells_ct <= 0 || h->lat_cells_ct >= (1LL << 31) ||
       std::getenv("ODEINTR_NO_TILED"))
     return ODEINTR_OK;
@@ -1903,6 +1944,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp5_h[1], h->lib, "odeintr_lattice_dopri5_warp_h1") != cudaSuccess) h->k_warp5_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp5_h[2], h->lib, "odeintr_lattice_dopri5_warp_h2") != cudaSuccess) h->k_warp5_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp5_info, h->lib, "odeintr_lattice_dopri5_warp_info") != cudaSuccess) h->k_warp5_info = nullptr;
+  if (cudaLibraryGetKernel(&h->k_stream5, h->lib, "odeintr_lattice_dopri5_stream2d") != cudaSuccess) h->k_stream5 = nullptr;
   if (cudaLibraryGetKernel(&h->k_stream2d, h->lib, "odeintr_lattice_rk4_stream2d") != cudaSuccess) h->k_stream2d = nullptr;
   if (cudaLibraryGetKernel(&h->k_stream2d_info, h->lib, "odeintr_lattice_stream2d_info") != cudaSuccess) h->k_stream2d_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;

@@ -153,6 +153,17 @@ struct odeintr_lattice_dopri5_args {
   long long own_lo, own_hi, c0, pitch;
   int sharded;
   int tma;                    // warp kernel (lattice_dopri5_warp.cuh): 16-byte aligned windows, move them with the TMA engine
+  int seg_rows;               // streaming M x M kernel (lattice_dopri5_stream2d.cuh): rows per warp task
+  double cf[32];              //   and its coefficient * dt products, formed once on the host (odeintr_dopri5_cf below): as
+                              //   kernel parameters they are constant-bank operands, not registers
+};
+// index of the products in odeintr_lattice_dopri5_args::cf
+enum odeintr_dopri5_cf {
+  ODEINTR_CF_B21 = 0, ODEINTR_CF_B31, ODEINTR_CF_B32, ODEINTR_CF_B41, ODEINTR_CF_B42, ODEINTR_CF_B43, ODEINTR_CF_B51,
+  ODEINTR_CF_B52, ODEINTR_CF_B53, ODEINTR_CF_B54, ODEINTR_CF_B61, ODEINTR_CF_B62, ODEINTR_CF_B63, ODEINTR_CF_B64,
+  ODEINTR_CF_B65, ODEINTR_CF_C1, ODEINTR_CF_C3, ODEINTR_CF_C4, ODEINTR_CF_C5, ODEINTR_CF_C6,
+  ODEINTR_CF_E1, ODEINTR_CF_E3, ODEINTR_CF_E4, ODEINTR_CF_E5, ODEINTR_CF_E6, ODEINTR_CF_E7,  // error weights * dt, or the dense-output weights
+  ODEINTR_CF_T2, ODEINTR_CF_T3, ODEINTR_CF_T4, ODEINTR_CF_T5, ODEINTR_CF_T6                   // stage times
 };
 
 // Ensemble of wider systems, one trajectory per block (lattice_ensemble.cuh): the fixed-step schedule of

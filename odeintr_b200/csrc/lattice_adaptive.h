@@ -123,6 +123,60 @@ struct lattice_dopri5 {
       if (dense_out) slab_mark(h, dense_out, false);
     }
     cudaMemsetAsync(h->lat_err.p, 0, 2 * sizeof(unsigned long long), h->stream);
+    if (h->tiled5 == 2) {  // M x M lattice: the streaming kernel, one warp per (strip of 52 columns, segment of rows)
+      a.own_lo = 0; a.own_hi = (long long)h->N; a.c0 = 0; a.pitch = (long long)h->N; a.sharded = 0;
+      a.seg_rows = h->stream5_rows;
+      {  // coefficient * dt products (left to right sums use them as they are: the same doubles the other paths form)
+        const double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
+        const double b21 = 1.0 / 5.0;
+        const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+        const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+        const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+        const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
+                     b65 = -5103.0 / 18656.0;
+        const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+        const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
+                     dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+        volatile double vdt = dt;  // (keeps the host compiler from folding or contracting anything: plain IEEE products)
+        const double d = vdt;
+        double* cf = a.cf;
+        cf[ODEINTR_CF_B21] = d * b21;
+        cf[ODEINTR_CF_B31] = d * b31; cf[ODEINTR_CF_B32] = d * b32;
+        cf[ODEINTR_CF_B41] = d * b41; cf[ODEINTR_CF_B42] = d * b42; cf[ODEINTR_CF_B43] = d * b43;
+        cf[ODEINTR_CF_B51] = d * b51; cf[ODEINTR_CF_B52] = d * b52; cf[ODEINTR_CF_B53] = d * b53; cf[ODEINTR_CF_B54] = d * b54;
+        cf[ODEINTR_CF_B61] = d * b61; cf[ODEINTR_CF_B62] = d * b62; cf[ODEINTR_CF_B63] = d * b63; cf[ODEINTR_CF_B64] = d * b64;
+        cf[ODEINTR_CF_B65] = d * b65;
+        cf[ODEINTR_CF_C1] = d * c1; cf[ODEINTR_CF_C3] = d * c3; cf[ODEINTR_CF_C4] = d * c4; cf[ODEINTR_CF_C5] = d * c5;
+        cf[ODEINTR_CF_C6] = d * c6;
+        if (dense_out) {
+          cf[ODEINTR_CF_E1] = dcoef[0]; cf[ODEINTR_CF_E3] = dcoef[1]; cf[ODEINTR_CF_E4] = dcoef[2];
+          cf[ODEINTR_CF_E5] = dcoef[3]; cf[ODEINTR_CF_E6] = dcoef[4]; cf[ODEINTR_CF_E7] = dcoef[5];
+        } else {
+          cf[ODEINTR_CF_E1] = d * dc1; cf[ODEINTR_CF_E3] = d * dc3; cf[ODEINTR_CF_E4] = d * dc4;
+          cf[ODEINTR_CF_E5] = d * dc5; cf[ODEINTR_CF_E6] = d * dc6; cf[ODEINTR_CF_E7] = d * dc7;
+        }
+        cf[ODEINTR_CF_T2] = t + d * a2; cf[ODEINTR_CF_T3] = t + d * a3; cf[ODEINTR_CF_T4] = t + d * a4;
+        cf[ODEINTR_CF_T5] = t + d * a5; cf[ODEINTR_CF_T6] = t + d;
+      }
+      const long long side = h->lat_side;
+      const long long tasks = ((side + 51) / 52) * ((side + h->stream5_rows - 1) / h->stream5_rows);
+      const unsigned grid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)h->sm_count * h->stream5_blocks);
+      void* params[1] = {&a};
+      if (cudaLaunchKernel((const void*)h->k_stream5, dim3(grid), dim3(256), params, 0, h->stream) != cudaSuccess) {
+        if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_stream2d failed");
+        return -1.0;
+      }
+      h->last_launches += 1;
+      g_total_launches += 1;
+      if (dense_out) return 0.0;
+      unsigned long long words2[2] = {0, 0};
+      cudaMemcpyAsync(words2, h->lat_err.p, sizeof(words2), cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (words2[1] & 0xffffffffull) return -1.0;  // a read beyond radius 1: not this kernel's system
+      double err2;
+      std::memcpy(&err2, &words2[0], sizeof(err2));
+      return err2;
+    }
     const long long L = h->lat_cells_ct;
     const long long tile = 256LL * tile5_cpt((int)((long long)h->N / L));
     long long cells = L;
@@ -201,7 +255,7 @@ struct lattice_dopri5 {
   // runge_kutta_dopri5::do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt, xerr) + default_error_checker::error
   // returns the max-norm error (A.2); out / dxdt_out must not alias in / dxdt_in
   double step_with_error(const double* in, const double* d_in, double t, double* out, double* d_out, double dt) {
-    if (h->tiled5 == 1) {
+    if (h->tiled5 >= 1) {
       const double e = tiled_attempt(in, d_in, t, out, d_out, dt);
       if (e >= 0.0) {
         k_valid = false;
@@ -738,8 +792,9 @@ struct lattice_bs_common {
         reject = false;
         if ((work[k] < KFAC2 * work[k - 1]) || (k_opt <= 2)) {
           k_opt = std::min(K_MAX - 1, std::max(2, k + 1));
-          new_h = h_opt[k];
-          new_h *= static_cast<double>(cost[k + 1]) / static_cast<double>(cost[k]);
+          // (Boost writes the two steppers' products differently: bs scales by the ratio, bsd multiplies, then divides)
+          if (dense_sequence) new_h = h_opt[k] * static_cast<double>(cost[k + 1]) / static_cast<double>(cost[k]);
+          else { new_h = h_opt[k]; new_h *= static_cast<double>(cost[k + 1]) / static_cast<double>(cost[k]); }
         } else {
           k_opt = std::min(K_MAX - 1, std::max(2, k));
           new_h = h_opt[k];
@@ -759,8 +814,8 @@ struct lattice_bs_common {
           new_h = h_opt[k_opt];
         } else if ((work[k] < KFAC2 * work[k - 1]) && !last_step_rejected) {
           k_opt = std::min(K_MAX - 1, k_opt + 1);
-          new_h = h_opt[k];
-          new_h *= static_cast<double>(cost[k_opt]) / static_cast<double>(cost[k]);
+          if (dense_sequence) new_h = h_opt[k] * static_cast<double>(cost[k_opt]) / static_cast<double>(cost[k]);
+          else { new_h = h_opt[k]; new_h *= static_cast<double>(cost[k_opt]) / static_cast<double>(cost[k]); }
         } else
           new_h = h_opt[k_opt];
         return true;

@@ -787,3 +787,42 @@ def test_large_system_bulirsch_stoer(case, method):
     assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
     fin = env["bsl_no_record"](x0, 4.05, 0.1)
     assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 4.05, 0.1)["x"]))
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk5"])
+@pytest.mark.parametrize("case", ["laplace2D_128", "documented_192", "laplace2D_66", "staged_128"])
+def test_2d_lattice_streaming_dopri5_bit_exact(case, method, monkeypatch):
+    # The reference's documented large-system example (R/odeintr.R:393-421: an M x M bistable lattice, default method
+    # rk5_i) through K4ds2: one attempted dopri5 step per launch, warps streaming down strips of 64 columns with the
+    # six neighbour-dependent stages as a register pipeline and partial sums in place of stored stage derivatives.
+    # Same bits as the oracle (controller on the host: glibc pow), same accepted / rejected counts; M = 192 and 66 are
+    # not multiples of the 52 columns a strip yields (ragged last strip, wrap across the seam); the staged case pins
+    # the seven-launch path beside it.
+    m = {"laplace2D_128": 128, "documented_192": 192, "laplace2D_66": 66, "staged_128": 128}[case]
+    src = BISTABLE_DOC if case == "documented_192" else BISTABLE_2D
+    if case == "staged_128":
+        monkeypatch.setenv("ODEINTR_NO_STREAM2D", "1")
+    n = m * m
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("d2", src, BISTABLE_PARS, True, method=method, sys_dim=n, env=env)
+    ora = bo.build(src, BISTABLE_PARS, True, method, sys_dim=n)
+    x0 = np.random.default_rng(m).uniform(0, 1, n)
+    df = env["d2"](x0, 3.0, 0.25)
+    ref = ora.integrate_const(x0, 0, 3.0, 0.25)
+    assert df.shape == (ref["rows"], n + 1) and np.array_equal(df["Time"].to_numpy(), ref["t"])
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    st = code.system.stats()
+    if method != "rk5":
+        assert st["accepted"][0] == ref["accepted"] and st["rejected"][0] == ref["rejected"]
+        tries = ref["accepted"] + ref["rejected"]
+        launches = code.system.last_launches()
+        if case == "staged_128":
+            assert launches >= 7 * tries
+        else:  # one launch per attempt (+ the dense-output evaluations and the first derivative)
+            assert launches <= tries + ref["rows"] + 2, (launches, tries)
+    at = np.array([0.0, 1.0, 10.0 ** 0.5, 10.0])  # bistable_at(inic, 10^(0:3))-style call
+    df = env["d2_at"](x0, at, 0.1)
+    ref = ora.integrate_times(x0, at, 0.1)
+    assert np.array_equal(bits(cols(df)), bits(ref["rec"]))
+    fin = env["d2_no_record"](x0, 2.05, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 2.05, 0.1)["x"]))

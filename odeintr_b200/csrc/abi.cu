@@ -260,6 +260,7 @@ struct odeintr_system_s {
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
+  cudaKernel_t k_lat_ens_dense = nullptr, k_lat_ens_ctl = nullptr;  // adaptive ensembles of wider systems (lattice_ensemble_adaptive.cuh)
   cudaKernel_t k_stream5 = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
   int stream5_blocks = 0, stream5_rows = 0;
   size_t warp5_smem = 0;
@@ -1503,6 +1504,8 @@ int lattice_serial_fixed_step(odeintr_system_t h, double t, double dt) {
   return ODEINTR_OK;
 }
 
+int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times, size_t n_times,
+                 bool record, bool wide);
 // Large system under an adaptive stepper: the shared integrate loops run on the host over device vectors.
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
@@ -1516,6 +1519,12 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
     if (h->lattice_method != 1 && h->lattice_method != 2)
       return fail(ODEINTR_E_STATE, "sharded adaptive stepping is provided for rk5_i and rk5_a");
     if (!h->k_lattice_sharded) return fail(ODEINTR_E_STATE, "the generated translation unit has no sharded stage kernel");
+  } else if (h->m > 1) {
+    // an ensemble of large systems: one warp / block per trajectory, every trajectory with its own step sizes
+    if (h->lattice_method != 1 && h->lattice_method != 2)
+      return fail(ODEINTR_E_STATE, "adaptive ensembles of large systems are provided for rk5_i and rk5_a");
+    return run_adaptive(h, mode, mode == ODEINTR_MODE_TIMES ? times[0] : t0, mode == ODEINTR_MODE_TIMES ? times[n_times - 1] : t1,
+                        dt, times, n_times, record, true);
   } else if (h->m != 1) {
     return fail(ODEINTR_E_STATE, "Invalid initial state");
   }
@@ -1746,14 +1755,51 @@ std::vector<double> dense_const_times(double t0, double t1, double dt, bool* opt
 
 // Controlled / dense-output steppers: one launch, per-instance step control inside the kernel.
 int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times, size_t n_times,
-                 bool record) {
-  if (!h->k_adaptive) return fail(ODEINTR_E_STATE, "system was not compiled with an adaptive stepper");
+                 bool record, bool wide) {
+  // wide: an ensemble of compile_sys_openmp systems under rk5_i / rk5_a, one warp / block per trajectory
+  cudaKernel_t kern = wide ? (h->lattice_method == 2 ? h->k_lat_ens_dense : h->k_lat_ens_ctl) : h->k_adaptive;
+  if (!kern)
+    return fail(ODEINTR_E_STATE, wide ? "adaptive ensembles of large systems are provided for rk5_i / rk5_a on 1-D lattices of "
+                                        "3 ... 2048 cells with at most 4 states per thread (fields x cells / threads)"
+                                      : "system was not compiled with an adaptive stepper");
   if (h->m == 0) return fail(ODEINTR_E_STATE, "Invalid initial state");
   const size_t m = h->m, N = (size_t)h->N;
-  odeintr_adaptive_args a;
-  std::memset(&a, 0, sizeof(a));
+  odeintr_lattice_ensemble_adaptive_args wa;
+  std::memset(&wa, 0, sizeof(wa));
+  odeintr_adaptive_args& a = wa.p;
   int rc = param_view(h, a.pars, a.par_ld, a.par_inc);
   if (rc) return rc;
+  unsigned wide_block = 0, wide_grid = 0;
+  size_t wide_smem = 0;
+  if (wide) {
+    if ((rc = tiled5_decide(h))) return rc;
+    if (h->tiled5 != 1) return fail(ODEINTR_E_INVALID, "ensembles of large systems need a stencil radius of at most 16 cells");
+    const long long L = h->lat_cells_ct, halo = h->tiled5_halo < 1 ? 1 : h->tiled5_halo;
+    const int fields = (int)((long long)h->N / L);
+    if (2 * halo + 1 > L) return fail(ODEINTR_E_INVALID, "stencil radius too wide for the lattice");
+    // threads per trajectory and trajectories per block, as lattice_ensemble.cuh derives them from the lattice length
+    const unsigned nt = (unsigned)(L > 2048 ? 512 : (L >= 256 ? 256 : (L + 31) / 32 * 32));
+    const unsigned group = nt == 32 ? 4 : 1;
+    wide_smem = group * (2 * (size_t)fields * (size_t)(L + 2 * halo) + 2 * (nt / 32)) * sizeof(double);
+    if (wide_smem > 200 * 1024) return fail(ODEINTR_E_INVALID, "lattice too large for one block's shared memory");
+    CU_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
+    wide_block = nt * group;
+    wide_grid = (unsigned)((m + group - 1) / group);
+    CU_TRY(h->lat_flag.reserve(10));
+    CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+    wa.halo = halo;
+    wa.flag = h->lat_flag.p;
+  }
+  auto run_kernel = [&](odeintr_adaptive_args& args, unsigned grid, unsigned block) -> int {
+    if (!wide) return launch(h, kern, h->stream, grid, block, &args);
+    odeintr_lattice_ensemble_adaptive_args w2 = wa;
+    w2.p = args;
+    void* params[1] = {&w2};
+    CU_TRY(cudaLaunchKernel((const void*)kern, dim3(wide_grid), dim3(wide_block), params, wide_smem, h->stream));
+    h->last_launches += 1;
+    g_total_launches += 1;
+    return ODEINTR_OK;
+  };
   CU_TRY(h->accepted.reserve(m)); CU_TRY(h->rejected.reserve(m)); CU_TRY(h->status.reserve(m));
   CU_TRY(h->rows_inst.reserve(m)); CU_TRY(h->fail_flags.reserve(1));
   std::vector<double> rec_t;
@@ -1791,7 +1837,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   CU_TRY(cudaMemsetAsync(h->fail_flags.p, 0, sizeof(int), h->stream));
   if ((rc = begin_timing(h))) return rc;
   // K6: instance order.  The pilot and the sort are part of the call (and of its device time).
-  if (h->order_mode == 1 && h->k_pilot && m >= 64 && m < (1ull << 31)) {
+  if (!wide && h->order_mode == 1 && h->k_pilot && m >= 64 && m < (1ull << 31)) {
     CU_TRY(h->order_keys.reserve(m)); CU_TRY(h->order_keys_sorted.reserve(m));
     CU_TRY(h->perm.reserve(m)); CU_TRY(h->perm_iota.reserve(m));
     const size_t tb = odeintr_b200::sort_pairs_temp_bytes((long long)m);
@@ -1807,7 +1853,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
       return fail(ODEINTR_E_CUDA, "instance-order sort failed");
     g_total_launches += 2;
     a.perm = h->perm.p;
-  } else if (h->order_mode == 2 && h->perm_m == m) {
+  } else if (!wide && h->order_mode == 2 && h->perm_m == m) {
     a.perm = h->perm.p;
   }
   bool ragged = false;
@@ -1819,7 +1865,7 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
     CU_TRY(cudaMemcpyAsync(h->stage.p, h->x.p, N * m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     odeintr_adaptive_args dry = a;
     dry.x = h->stage.p;
-    if ((rc = launch(h, h->k_adaptive, h->stream, grid, block, &dry))) return rc;
+    if ((rc = run_kernel(dry, grid, block))) return rc;
     std::vector<int> rows_host(m);
     CU_TRY(cudaMemcpyAsync(rows_host.data(), h->rows_inst.p, m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1834,8 +1880,16 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
     a.out = h->out.p;
     a.max_rows = (int)rec_t.size();
   }
-  if ((rc = launch(h, h->k_adaptive, h->stream, grid, block, &a))) return rc;
+  if ((rc = run_kernel(a, grid, block))) return rc;
   if ((rc = end_timing(h))) return rc;
+  if (wide) {
+    int reach_flag = 0;
+    CU_TRY(cudaMemcpyAsync(&reach_flag, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (reach_flag)
+      return fail(ODEINTR_E_INVALID, "the system definition reads x further than the stencil radius (" +
+                                         std::to_string(wa.halo) + " cells) from the cell it computes");
+  }
   int flags = 0, rows_min = 0x7fffffff;
   CU_TRY(cudaMemcpyAsync(&flags, h->fail_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (optional_last) CU_TRY(cudaMemcpyAsync(&rows_min, h->rows_min.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1932,6 +1986,8 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp_h[2], h->lib, "odeintr_lattice_rk4_warp_h2") != cudaSuccess) h->k_warp_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp_info, h->lib, "odeintr_lattice_warp_info") != cudaSuccess) h->k_warp_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lat_ens_dense, h->lib, "odeintr_lattice_ensemble_dopri5_dense") != cudaSuccess) h->k_lat_ens_dense = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lat_ens_ctl, h->lib, "odeintr_lattice_ensemble_dopri5_controlled") != cudaSuccess) h->k_lat_ens_ctl = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[1], h->lib, "odeintr_lattice_rk4_tiled2d_h1") != cudaSuccess) h->k_tiled2d_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[2], h->lib, "odeintr_lattice_rk4_tiled2d_h2") != cudaSuccess) h->k_tiled2d_h[2] = nullptr;
   h->k_tiled2d = h->k_tiled2d_h[1];
@@ -2172,7 +2228,7 @@ int odeintr_integrate_const(odeintr_system_t h, double t0, double t1, double dt,
   }
   if (h->k_adaptive) {
     if (obs_stride != 1) return fail(ODEINTR_E_INVALID, "obs_stride applies to fixed-step steppers only");
-    return run_adaptive(h, ODEINTR_MODE_CONST, t0, t1, dt, nullptr, 0, record != 0);
+    return run_adaptive(h, ODEINTR_MODE_CONST, t0, t1, dt, nullptr, 0, record != 0, false);
   }
   return fail(ODEINTR_E_STATE, "integrate_const: no kernel for this stepper family");
 }
@@ -2189,7 +2245,7 @@ int odeintr_integrate_times(odeintr_system_t h, const double* times, size_t n_ti
     schedule_times(sc, times, n_times, dt);
     return h->k_lattice ? run_lattice(h, sc) : run_plain(h, sc);
   }
-  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_TIMES, times[0], times[n_times - 1], dt, times, n_times, true);
+  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_TIMES, times[0], times[n_times - 1], dt, times, n_times, true, false);
   return fail(ODEINTR_E_STATE, "integrate_times: no kernel for this stepper family");
 }
 
@@ -2204,7 +2260,7 @@ int odeintr_integrate_adaptive(odeintr_system_t h, double t0, double t1, double 
     schedule_adaptive(sc, t0, t1, dt, record != 0);
     return h->k_lattice ? run_lattice(h, sc) : run_plain(h, sc);
   }
-  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_ADAPTIVE, t0, t1, dt, nullptr, 0, record != 0);
+  if (h->k_adaptive) return run_adaptive(h, ODEINTR_MODE_ADAPTIVE, t0, t1, dt, nullptr, 0, record != 0, false);
   return fail(ODEINTR_E_STATE, "integrate_adaptive: no kernel for this stepper family");
 }
 

@@ -85,6 +85,13 @@ struct odeintr_adaptive_args {
                               // and nothing else
 };
 
+// Ensemble of wider systems under an adaptive stepper, one warp / block per trajectory (lattice_ensemble_adaptive.cuh)
+struct odeintr_lattice_ensemble_adaptive_args {
+  odeintr_adaptive_args p;
+  long long halo;             // stencil radius (ghost cells per side of the shared-memory rings)
+  int* flag;                  // set to 1 when the snippet reaches beyond the halo
+};
+
 // Large coupled system ("lattice") fused Runge-Kutta stage launch, SURVEY.md §8(d) config 5:
 //   k = f(xs)[cell];  xt = x + a_dt*k (if xt != null);  acc_out = acc_in + b_dt*k
 // All pointers address local cell 0 of field 0; on a sharded run ghost cells sit at negative offsets and

@@ -26,6 +26,11 @@ struct step_counters {
   }
 };
 
+// A system whose state vector is spread over the threads of a trajectory (lattice_ensemble_adaptive.cuh) completes the
+// error norm across them; an ordinary system's norm is complete as it is.
+template <class Sys> ODEINTR_DEV auto reduce_error(Sys& s, const double e, int) -> decltype(s.block_max(e)) { return s.block_max(e); }
+template <class Sys> ODEINTR_DEV double reduce_error(Sys&, const double e, long) { return e; }
+
 // controlled_runge_kutta< runge_kutta_dopri5 > (FSAL): method "rk5_a"
 template <class Sys, int N>
 struct dopri5_controlled {
@@ -45,7 +50,7 @@ struct dopri5_controlled {
     vec<N> xerr;
     core.do_step_impl(sys, in, dxdt_in, t, out, dxdt_out, dt);
     core.calc_error(dxdt_in, dxdt_out, dt, xerr);
-    const double err = error_norm<N>(in, dxdt_in, xerr, dt, eps_abs, eps_rel);
+    const double err = reduce_error(sys, error_norm<N>(in, dxdt_in, xerr, dt, eps_abs, eps_rel), 0);
     const double dt_used = dt;
     if (!adjust_step(err, dt, 4, 5, 0.00032)) {
       cnt.rejected++;

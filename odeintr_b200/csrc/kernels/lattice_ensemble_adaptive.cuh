@@ -1,0 +1,235 @@
+// odeintr_b200/csrc/kernels/lattice_ensemble_adaptive.cuh
+// K5a: ensembles of WIDER systems under the adaptive steppers -- compile_sys_openmp's default method rk5_i
+// (dense-output dopri5) and rk5_a (controlled dopri5), one WARP or one BLOCK per trajectory (lattice_ensemble.cuh has
+// the fixed-step rk4 form).  In the reference: an R loop around NAME_set_params() + NAME() / NAME_at()
+// (README.md:157-163) over a system compiled with compile_sys_openmp's defaults (R/odeintr.R:418-421).
+//
+// The threads of a trajectory run Boost's integrate_const / integrate_times / integrate_adaptive loops
+// (integrate_loops.cuh) and the per-trajectory steppers of adaptive_steppers.cuh UNCHANGED -- the same code every
+// thread of K2 runs for its own small system -- on a distributed state: a thread's "state vector" holds the entries of
+// its own cells (CPT cells x fields, in registers, k1 .. k7 and the dense-output history included).  Two things make
+// the distributed vectors behave like the whole one:
+//   * the right-hand side publishes the stage state to a shared-memory ring (ghost cells hold the periodic images),
+//     waits for the trajectory's threads and evaluates the user's loop body for the thread's cells (two rings
+//     alternate, so one barrier per evaluation is enough);
+//   * the error norm is the maximum over the trajectory's threads (shuffles, and shared memory between warps), handed
+//     back to every thread: all of them take the controller's decisions with the same numbers, so step sizes, accepted /
+//     rejected counts and the control flow are uniform across the trajectory.
+// HBM sees the initial state, the requested samples and the final state.  Every trajectory follows the oracle's step
+// sequence up to the controller's pow() (libdevice vs glibc), like K2: results within 10 x rtol, in practice 1e-13.
+#pragma once
+#include "odeintr_b200/lattice_ensemble.cuh"
+
+// registers: ~13 doubles per owned entry (x, k1, x_new, k7, x_old, k1_old, k2 .. k6, stage state, error estimate)
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 7 && \
+    ODEINTR_ENS_CPT * ODEINTR_NFIELDS <= 4 && ODEINTR_ENS_CELLS >= 3 && ODEINTR_ENS_CELLS <= 2048
+#define ODEINTR_HAVE_ENS_ADAPTIVE 1
+#include "odeintr_b200/integrate_device.cuh"
+
+namespace odeintr_b200 {
+
+// the user's system as the steppers see it: vec<NE> holds the calling thread's entries of a distributed vector
+template <class UserSys>
+struct block_system {
+  static constexpr int F = ODEINTR_NFIELDS;
+  static constexpr int L = ODEINTR_ENS_CELLS;
+  static constexpr int NT = ODEINTR_ENS_THREADS;
+  static constexpr int C = ODEINTR_ENS_CPT;
+  static constexpr int NE = C * F;
+  typedef lattice_rel_view<true> View;
+  UserSys user;
+  View view;
+  rel_index idx;
+  double* ring[2];   // stage-state rings of this trajectory (fields x (L + 2 halo))
+  double* red;       // per-warp partial maxima, two alternating rows
+  int phase, rphase;
+  int tid, h, W;
+  int fld[F];
+  bool live[C];
+
+  ODEINTR_DEV void barrier() const {
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+  }
+  ODEINTR_DEV void sys(const vec<NE>& x, vec<NE>& k, const double t) {
+    double* const R = ring[phase];
+    phase ^= 1;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = tid + c * NT;
+      if (j < L) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          double* r = R + fld[f] * W + h;
+          const double v = x[c * F + f];
+          r[j] = v;
+          if (j < h) r[L + j] = v;
+          if (j >= L - h) r[j - L] = v;
+        }
+      }
+    }
+    barrier();
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = tid + c * NT;
+      double kk[F], own[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) { kk[f] = 0.0; own[fld[f]] = x[c * F + f]; }
+      if (live[c]) {
+        view.p = R + h + j;
+        view.own = own;
+        view.centre = idx.centre = j;
+        user.cell(view, kk, idx, t);
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) k[c * F + f] = kk[f];
+    }
+  }
+  // maximum over the trajectory's threads, known to all of them afterwards
+  ODEINTR_DEV double block_max(double e) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, s));
+    if (NT == 32) return e;
+    double* const row = red + rphase * (NT / 32);
+    rphase ^= 1;
+    if ((tid & 31) == 0) row[tid >> 5] = e;
+    __syncthreads();
+    double m = row[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) m = fmax(m, row[w]);
+    return m;  // (the other row is written next: no second barrier)
+  }
+};
+
+// observer of a distributed state: every thread stores its own entries of the sample row
+template <int NE>
+struct block_sample_writer {
+  double* out;   // this instance's column of sample 0, or null
+  double* t_rec; // this instance's sample times (ragged records), or null
+  long long ld;
+  int rows, max_rows;
+  int tid;
+  const int* fld;
+  ODEINTR_DEV void operator()(const vec<NE>& x, const double t) {
+    constexpr int F = ODEINTR_NFIELDS, L = ODEINTR_ENS_CELLS, NT = ODEINTR_ENS_THREADS, C = ODEINTR_ENS_CPT;
+    if (out && rows < max_rows) {
+      double* row = out + static_cast<long long>(rows) * ODEINTR_SYS_SIZE * ld;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = tid + c * NT;
+        if (j < L) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) store_stream(row + (static_cast<long long>(fld[f]) * L + j) * ld, x[c * F + f]);
+        }
+      }
+      if (t_rec && tid == 0) store_stream(t_rec + static_cast<long long>(rows) * ld, t);
+    }
+    ++rows;
+  }
+};
+
+template <template <class, int> class Stepper>
+ODEINTR_DEV void lattice_ensemble_adaptive_body(const odeintr_lattice_ensemble_adaptive_args& b) {
+  typedef odeintr::system_type_t<lattice_rel_view<true> > UserSys;
+  typedef block_system<UserSys> Sys;
+  constexpr int F = Sys::F, L = Sys::L, NT = Sys::NT, C = Sys::C, NE = Sys::NE;
+  constexpr int G = ODEINTR_ENS_GROUP;
+  typedef Stepper<Sys, NE> St;
+  const odeintr_adaptive_args& a = b.p;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x % NT, grp = threadIdx.x / NT;
+  const int h = static_cast<int>(b.halo);
+  const int W = L + 2 * h;
+  const long long inst = static_cast<long long>(blockIdx.x) * G + grp;
+  if (inst >= a.m) return;  // only whole warps of a grouped block (they never meet a block barrier)
+
+  Sys sys;
+  sys.user.load_params(a.pars, a.par_ld, inst * a.par_inc);
+  sys.ring[0] = smem + grp * (2 * F * W + 2 * (NT / 32));
+  sys.ring[1] = sys.ring[0] + F * W;
+  sys.red = sys.ring[1] + F * W;
+  sys.phase = 0; sys.rphase = 0;
+  sys.tid = tid; sys.h = h; sys.W = W;
+  {
+    long long off[F];
+    sys.user.field_offsets(off, 0);
+#pragma unroll
+    for (int f = 0; f < F; ++f) sys.fld[f] = static_cast<int>(off[f] / L);
+  }
+  const long long start = sys.user.cell_start(), bound = sys.user.cell_bound();
+  sys.view.n_total = L; sys.view.width = W; sys.view.halo = h; sys.view.bad = 0;
+  sys.idx.off = 0; sys.idx.cells = L; sys.idx.rel = true;
+
+  vec<NE> x;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = tid + c * NT;
+    sys.live[c] = j < L && j >= start && j < bound;
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+      x[c * F + f] = j < L ? a.x[(static_cast<long long>(sys.fld[f]) * L + j) * a.ld + inst] : 0.0;
+  }
+
+  St st;
+  st.setup(a.atol, a.rtol);
+  st.counters().budget = a.max_tries;
+  block_sample_writer<NE> obs;
+  obs.out = a.out ? a.out + inst : nullptr;
+  obs.t_rec = a.t_rec ? a.t_rec + inst : nullptr;
+  obs.ld = a.ld; obs.rows = 0; obs.max_rows = a.max_rows; obs.tid = tid; obs.fld = sys.fld;
+
+  bool ok;
+  if constexpr (St::is_dense) {
+    if (a.mode == ODEINTR_MODE_TIMES) ok = integrate_times_dense(st, sys, x, a.times, a.n_times, a.dt, obs);
+    else if (a.mode == ODEINTR_MODE_CONST) ok = integrate_const_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+    else ok = integrate_adaptive_dense(st, sys, x, a.t0, a.t1, a.dt, obs);
+  } else {
+    double dt = a.dt;
+    if (a.mode == ODEINTR_MODE_TIMES) ok = integrate_times_controlled(st, sys, x, a.times, a.n_times, dt, obs);
+    else if (a.mode == ODEINTR_MODE_CONST) ok = integrate_const_controlled(st, sys, x, a.t0, a.t1, dt, obs);
+    else {
+      double t = a.t0;
+      ok = integrate_adaptive_controlled(st, sys, x, t, a.t1, dt, obs);
+    }
+  }
+  (void)ok;  // the status word carries the failure
+
+  bool finite = true;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = tid + c * NT;
+    if (j < L) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        a.x[(static_cast<long long>(sys.fld[f]) * L + j) * a.ld + inst] = x[c * F + f];
+        finite = finite && isfinite(x[c * F + f]);
+      }
+    }
+  }
+  step_counters& cnt = st.counters();
+  const double worst = sys.block_max(finite ? 0.0 : 1.0);
+  if (tid == 0) {
+    if (a.accepted) a.accepted[inst] = cnt.accepted;
+    if (a.rejected) a.rejected[inst] = cnt.rejected;
+    int status = cnt.status;
+    if (worst > 0.0 && status == ODEINTR_STATUS_OK) status = ODEINTR_STATUS_NONFINITE;
+    if (a.status) a.status[inst] = status;
+    if (status != ODEINTR_STATUS_OK && a.fail_flags) atomicOr(a.fail_flags, status);
+    if (a.rows) a.rows[inst] = obs.rows;
+    if (a.rows_min) atomicMin(a.rows_min, obs.rows);
+  }
+  if (sys.view.bad) *b.flag = 1;
+}
+
+}  // namespace odeintr_b200
+
+extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)
+odeintr_lattice_ensemble_dopri5_dense(const odeintr_lattice_ensemble_adaptive_args a) {
+  odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::dopri5_dense>(a);
+}
+extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)
+odeintr_lattice_ensemble_dopri5_controlled(const odeintr_lattice_ensemble_adaptive_args a) {
+  odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::dopri5_controlled>(a);
+}
+
+#endif  // adaptive ensembles of wider systems

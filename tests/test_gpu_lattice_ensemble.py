@@ -96,3 +96,70 @@ def test_ensemble_limits_are_reported():
                                     method="rk4", sys_dim=64, env=env)
     with pytest.raises(odeintr_b200.OdeintrError, match="further than the stencil radius"):
         env["far"](np.random.default_rng(1).uniform(0, 2, (64, 5)), 1.0, 0.1)
+
+
+@pytest.mark.parametrize("method", ["rk5_i", "rk5_a"])
+@pytest.mark.parametrize("cells", [32, 37, 300, 1024])
+def test_adaptive_ensemble_of_wider_systems(cells, method):
+    # K5a: compile_sys_openmp's default method (rk5_i) and rk5_a on an ensemble of lattices, one warp / block per
+    # trajectory running the per-trajectory integrate loops on a distributed state (error norm = max over the
+    # trajectory's threads).  Every trajectory against the oracle run one at a time: within 10 x rtol as stated, and --
+    # the operation sequence being the same up to the controller's pow() -- within the 1e-11 regression bound, with the
+    # same accepted / rejected counts.
+    from test_gpu_adaptive import close
+
+    m = 23
+    rng = np.random.default_rng(cells + 1)
+    x0 = rng.uniform(0, 1, (cells, m))
+    D = rng.uniform(0.05, 0.3, m)
+    b = rng.uniform(0.3, 0.7, m)
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("bis", BISTABLE_1D, BISTABLE_PARS, False, method=method, sys_dim=cells, env=env)
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, False, method, sys_dim=cells)
+    env["bis_set_params"](D=D, a=1.0, b=b)
+    rec = env["bis"](x0, 4.0, 0.5)
+    st = code.system.stats()
+    for i in (range(m) if cells <= 300 else (0, 7, 22)):
+        ref = ora.integrate_const(x0[:, i].copy(), 0, 4.0, 0.5, pars=[D[i], 1.0, b[i]])
+        assert rec.x.shape[0] >= ref["rows"] - 1
+        rows = min(rec.x.shape[0], ref["rows"])
+        close(rec.x[:rows, :, i], ref["rec"][:rows], 1e-6)
+        assert st["accepted"][i] == ref["accepted"] and st["rejected"][i] == ref["rejected"], i
+    at = np.array([0.0, 1.0, 10.0 ** 0.5, 5.0])
+    rec = env["bis_at"](x0, at, 0.2)
+    i = m - 1
+    ref = ora.integrate_times(x0[:, i].copy(), at, 0.2, pars=[D[i], 1.0, b[i]])
+    close(rec.x[:, :, i], ref["rec"], 1e-6)
+    fin = env["bis_no_record"](x0, 2.05, 0.1)
+    ref = ora.integrate_adaptive(x0[:, 3].copy(), 0, 2.05, 0.1, pars=[D[3], 1.0, b[3]])
+    close(fin[:, 3], ref["x"], 1e-6)
+
+
+def test_adaptive_ensemble_two_fields_and_fixed_ends():
+    from test_gpu_adaptive import close
+
+    n, m = 2 * 48, 9
+    L = n // 2
+    rng = np.random.default_rng(8)
+    amp = rng.uniform(0.5, 1.5, m)
+    x0 = np.concatenate([np.sin(2 * np.pi * 3 * np.arange(L) / L)[:, None] * amp[None, :], np.zeros((L, m))])
+    K = rng.uniform(0.2, 0.8, m)
+    env = {}
+    odeintr_b200.compile_sys_openmp("chain", CHAIN, CHAIN_PARS, False, sys_dim=n, globals=CHAIN_GLOBALS, env=env)  # default rk5_i
+    ora = bo.build(CHAIN, CHAIN_PARS, False, "rk5_i", sys_dim=n, globals=CHAIN_GLOBALS)
+    env["chain_set_params"](beta=1.0, K=K)
+    rec = env["chain"](x0, 2.0, 0.25)
+    for i in range(m):
+        ref = ora.integrate_const(x0[:, i].copy(), 0, 2.0, 0.25, pars=[1.0, K[i]])
+        rows = min(rec.x.shape[0], ref["rows"])
+        close(rec.x[:rows, :, i], ref["rec"][:rows], 1e-6)
+    src = "for (int i = 1; i < N - 1; ++i) dxdt[i] = D * (x[i - 1] + x[i + 1] - 2.0 * x[i]);"
+    cells = 129
+    x0 = rng.uniform(0, 1, (cells, m))
+    env = {}
+    odeintr_b200.compile_sys_openmp("heat", src, {"D": 0.2}, True, method="rk5_a", sys_dim=cells, env=env)
+    ora = bo.build(src, {"D": 0.2}, True, "rk5_a", sys_dim=cells)
+    fin = env["heat_no_record"](x0, 1.5, 0.1)
+    for i in range(m):
+        close(fin[:, i], ora.integrate_adaptive(x0[:, i].copy(), 0, 1.5, 0.1)["x"], 1e-6)
+    assert np.array_equal(fin[0], x0[0]) and np.array_equal(fin[-1], x0[-1])  # the ends are not cells of the loop

@@ -396,7 +396,8 @@ def main():
                      ("heterogeneous_vdp_k6", heterogeneous_secondary),
                      ("lattice_rk4", lattice_secondary), ("lattice_chain_rk4", chain_secondary),
                      ("lattice_dopri5", lattice_dopri5_secondary),
-                     ("lattice2d_rk4", lattice2d_secondary), ("lattice_ensemble_rk4", lattice_ensemble_secondary))
+                     ("lattice2d_rk4", lattice2d_secondary), ("lattice2d_dopri5", lattice2d_dopri5_secondary),
+                     ("lattice_ensemble_rk4", lattice_ensemble_secondary))
             for key, fn in table:
                 t_sec = time.perf_counter()
                 try:
@@ -929,8 +930,8 @@ for (int i = 0; i < N; ++i)
 
 def lattice2d_secondary(lib, dp_peak):
     """The reference's documented large-system example (R/odeintr.R:393-413): periodic M x M bistable lattice through
-    laplace2D, M = 8192, rk4, plain compile_sys_openmp call (2-D temporally blocked kernel).  66 DP instructions per
-    cell and step (4 x 13 RHS + 14)."""
+    laplace2D, M = 8192, rk4, plain compile_sys_openmp call (K4s2: warps streaming down strips of 64 columns, the four
+    stages as a register pipeline).  66 DP instructions per cell and step (4 x 13 RHS + 14)."""
     import numpy as np
 
     import odeintr_b200
@@ -955,7 +956,68 @@ def lattice2d_secondary(lib, dp_peak):
                 "metric": "lattice_rk4_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
                 "ms_per_step": 1e3 * t / steps, "halo": s.get_halo(), "gpu_launches": s.last_launches(),
                 "roofline": {"bound": "fp64", "achieved": rate * 66.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
-                             "frac": rate * 66.0 / dp_peak, "kernel": "odeintr_lattice_rk4_tiled2d_h1"}}
+                             "frac": rate * 66.0 / dp_peak, "kernel": "odeintr_lattice_rk4_stream2d"}}
+    finally:
+        s.close()
+
+
+def lattice2d_dopri5_secondary(lib, dp_peak):
+    """The reference's documented large-system example exactly as documented: bistable_at(inic, times) on the periodic
+    M x M lattice with compile_sys_openmp's DEFAULT method rk5_i (R/odeintr.R:393-421), M = 8192.  K4ds2: one attempted
+    dopri5 step per launch, warps streaming down strips of 64 columns, the six neighbour-dependent stages as a register
+    pipeline with partial sums in place of stored stage derivatives; controller on the host.  135 DP instructions per
+    cell and attempt (6 x 13 RHS + 57 stage algebra), 32 bytes per cell and attempt."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    m = 8192
+    n = m * m
+    pars = {"D": 0.1, "a": 1.0, "b": 0.5}
+    s = odeintr_b200.compile_sys_openmp("b2d5", BISTABLE_2D, pars, True, sys_dim=n).system
+    try:
+        x0 = np.random.default_rng(1).uniform(0, 1, n)
+        at = np.array([0.0, 1.0, 5.0, 10.0])
+        ms = []
+        for rep in range(3):
+            s.set_state(x0)
+            if lib.odeintr_integrate_times(s._h, at.ctypes.data_as(_abi.c_dbl_p), at.size, 0.1) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        st = s.stats()
+        acc, rej = int(st["accepted"][0]), int(st["rejected"][0])
+        tries = acc + rej + (at.size - 1)  # every interpolated observation repeats one attempt
+        t = statistics.mean(ms) * 1e-3
+        rate = n * tries / t
+        launches = s.last_launches()
+        # parity + CPU sample on a 1024 x 1024 lattice: the same call through the oracle
+        from oracle import build_oracle
+
+        ms_ = 1024
+        ns = ms_ * ms_
+        env = {}
+        ss = odeintr_b200.compile_sys_openmp("b2s5", BISTABLE_2D, pars, True, sys_dim=ns, env=env).system
+        xs = x0[:ns].copy()
+        got = env["b2s5_at"](xs, at, 0.1).iloc[:, 1:].to_numpy()
+        sst = ss.stats()
+        ss.close()
+        ora = build_oracle.build(BISTABLE_2D, pars, True, "rk5_i", sys_dim=ns)
+        t0 = time.perf_counter()
+        ref = ora.integrate_times(xs, at, 0.1)
+        tc = time.perf_counter() - t0
+        return {"workload": "bistable_at(inic, c(0, 1, 5, 10)) with the default method rk5_i on the periodic 8192 x 8192 lattice "
+                            "through laplace2D (adaptive dopri5, atol = rtol = 1e-6)",
+                "metric": "lattice_dopri5_cell_attempts_per_s", "value": rate, "unit": "cell-attempts/s",
+                "ms_per_call": 1e3 * t, "accepted": acc, "rejected": rej, "gpu_launches": launches,
+                "parity": {"bit_exact_vs_oracle_1024x1024": bool(np.array_equal(got.view(np.uint64), ref["rec"].view(np.uint64))),
+                           "step_counts_equal": bool(sst["accepted"][0] == ref["accepted"] and sst["rejected"][0] == ref["rejected"])},
+                "roofline": {"bound": "fp64", "achieved": rate * 135.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 135.0 / dp_peak, "kernel": "odeintr_lattice_dopri5_stream2d"},
+                "cpu_baseline": {"value": ns * (ref["accepted"] + ref["rejected"]) / tc, "unit": "cell-attempts/s",
+                                 "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                                 "sample": "1024 x 1024 cells, same call (%.1f s)" % tc}}
     finally:
         s.close()
 

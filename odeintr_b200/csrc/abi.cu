@@ -163,6 +163,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_WARP5_CPT")) o.push_back(std::string("-DODEINTR_WARP5_CPT=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP5_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_L2_AHEAD")) o.push_back(std::string("-DODEINTR_STREAM2_L2_AHEAD=") + c);
+  if (std::getenv("ODEINTR_STREAM5_LATE_NORM")) o.push_back("-DODEINTR_STREAM5_LATE_NORM=1");
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
@@ -1510,6 +1511,13 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
 int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times,
                          size_t n_times, bool record) {
   if (!h->k_combo) return fail(ODEINTR_E_STATE, "system was not compiled for adaptive stepping of a large system");
+  if (h->m > 1 && !h->sharded) {
+    // an ensemble of large systems: one warp / block per trajectory, every trajectory with its own step sizes
+    if (h->lattice_method != 1 && h->lattice_method != 2)
+      return fail(ODEINTR_E_STATE, "adaptive ensembles of large systems are provided for rk5_i and rk5_a");
+    return run_adaptive(h, mode, mode == ODEINTR_MODE_TIMES ? times[0] : t0, mode == ODEINTR_MODE_TIMES ? times[n_times - 1] : t1,
+                        dt, times, n_times, record, true);
+  }
   if (h->P && h->par_sets != 1) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
   // One GPU: the state is h->x (N doubles).  After odeintr_lattice_shard the same loops run on this rank's slab of the
   // lattice -- every rank makes the same calls with the same arguments (collective): the error norm of an attempt is
@@ -1519,12 +1527,6 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
     if (h->lattice_method != 1 && h->lattice_method != 2)
       return fail(ODEINTR_E_STATE, "sharded adaptive stepping is provided for rk5_i and rk5_a");
     if (!h->k_lattice_sharded) return fail(ODEINTR_E_STATE, "the generated translation unit has no sharded stage kernel");
-  } else if (h->m > 1) {
-    // an ensemble of large systems: one warp / block per trajectory, every trajectory with its own step sizes
-    if (h->lattice_method != 1 && h->lattice_method != 2)
-      return fail(ODEINTR_E_STATE, "adaptive ensembles of large systems are provided for rk5_i and rk5_a");
-    return run_adaptive(h, mode, mode == ODEINTR_MODE_TIMES ? times[0] : t0, mode == ODEINTR_MODE_TIMES ? times[n_times - 1] : t1,
-                        dt, times, n_times, record, true);
   } else if (h->m != 1) {
     return fail(ODEINTR_E_STATE, "Invalid initial state");
   }

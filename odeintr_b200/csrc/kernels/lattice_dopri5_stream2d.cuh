@@ -171,6 +171,17 @@ ODEINTR_DEV void lattice_dopri5_stream2d_body(const odeintr_lattice_dopri5_args&
           pfx[ph % PF] = __ldg(reinterpret_cast<const double2*>(a.x_in + o));
           pfk[ph % PF] = __ldg(reinterpret_cast<const double2*>(a.d_in + o));
         }
+        // |x| and |k1| of the row that leaves the pipeline in this iteration (error norm): asked for now, used at the end
+        double2 xo, ko;
+        {
+          const int ro = j - 6;
+          const bool want = !dense && keeps && ro >= r_lo && ro < r_hi;
+          const long long o = static_cast<long long>(want ? ro : r_lo) * MM + col0;
+#ifndef ODEINTR_STREAM5_LATE_NORM
+          xo = __ldg(reinterpret_cast<const double2*>(a.x_in + o));
+          ko = __ldg(reinterpret_cast<const double2*>(a.d_in + o));
+#endif
+        }
         double k0, k1v;
         // s2 of row j (pointwise)
         W[0][nw][0] = xin.x + cf[ODEINTR_CF_B21] * kin.x; W[0][nw][1] = xin.y + cf[ODEINTR_CF_B21] * kin.y;
@@ -243,8 +254,10 @@ ODEINTR_DEV void lattice_dopri5_stream2d_body(const odeintr_lattice_dopri5_args&
             } else {
               w.x = k0; w.y = k1v;
               *reinterpret_cast<double2*>(a.d_out + o) = w;
-              const double2 xo = __ldg(reinterpret_cast<const double2*>(a.x_in + o));
-              const double2 ko = __ldg(reinterpret_cast<const double2*>(a.d_in + o));
+#ifdef ODEINTR_STREAM5_LATE_NORM
+              xo = __ldg(reinterpret_cast<const double2*>(a.x_in + o));
+              ko = __ldg(reinterpret_cast<const double2*>(a.d_in + o));
+#endif
               const double ea = fabs(v0) / (a.eps_abs + a.eps_rel * (1.0 * fabs(xo.x) + a.adt * fabs(ko.x)));
               const double eb = fabs(v1) / (a.eps_abs + a.eps_rel * (1.0 * fabs(xo.y) + a.adt * fabs(ko.y)));
               emax = fmax(emax, fmax(ea, eb));

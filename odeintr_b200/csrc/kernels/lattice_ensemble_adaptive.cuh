@@ -51,7 +51,9 @@ struct block_system {
     if (NT == 32) __syncwarp();
     else __syncthreads();
   }
-  ODEINTR_DEV void sys(const vec<NE>& x, vec<NE>& k, const double t) {
+  // (not inlined: the steppers call it seven times per attempt and every integrate loop instantiates them -- inlined
+  // the translation unit grows to 20 MB and takes a minute to compile; the call costs nothing next to the barrier)
+  __device__ __noinline__ void sys(const vec<NE>& x, vec<NE>& k, const double t) {
     double* const R = ring[phase];
     phase ^= 1;
 #pragma unroll

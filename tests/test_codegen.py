@@ -143,10 +143,14 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
     k = _kernels(codegen.generate_sys_openmp("c", CHAIN, CHAIN_PARS, True, "rk4", sys_dim=2 * 300, globals=CHAIN_GLOBALS).code)
     assert k == staged | tiled | {"odeintr_lattice_ensemble"}
+    dopri5 = {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2",
+              "odeintr_lattice_dopri5_warp_h1", "odeintr_lattice_dopri5_warp_h2", "odeintr_lattice_dopri5_warp_info"}
     for method in ("rk5_i", "rk5_a", "rk5"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
-        assert k == staged | {"odeintr_lattice_dopri5_tiled", "odeintr_lattice_dopri5_tiled_h1", "odeintr_lattice_dopri5_tiled_h2",
-                              "odeintr_lattice_dopri5_warp_h1", "odeintr_lattice_dopri5_warp_h2", "odeintr_lattice_dopri5_warp_info"}
+        assert k == staged | dopri5
+    # lattices one block can hold also get the adaptive one-warp / one-block-per-trajectory kernels (K5a)
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk5_i", sys_dim=1024).code)
+    assert k == staged | dopri5 | {"odeintr_lattice_ensemble_dopri5_dense", "odeintr_lattice_ensemble_dopri5_controlled"}
     for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a", "bs", "bsd"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged
@@ -155,7 +159,7 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
         assert k == staged | {"odeintr_lattice_rk4_tiled2d_h1", "odeintr_lattice_rk4_tiled2d_h2",
                               "odeintr_lattice_rk4_stream2d", "odeintr_lattice_stream2d_info"}
     k = _kernels(codegen.generate_sys_openmp("b2", BISTABLE_2D, BISTABLE_PARS, True, "rk5_i", sys_dim=96 * 96).code)
-    assert k == staged
+    assert k == staged | {"odeintr_lattice_dopri5_stream2d"}
 
 
 def test_snippets_that_treat_the_loop_variable_as_an_int_still_build():

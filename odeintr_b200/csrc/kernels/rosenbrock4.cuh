@@ -140,7 +140,14 @@ struct rosenbrock4_dense {
   ODEINTR_DEV const vec<N>& current_state() const { return x_cur; }
 
   // rosenbrock4::do_step(sys, x, t, xout, dt, xerr)
-  ODEINTR_DEV void stage_step(Sys& sys, const vec<N>& x, const double tt, vec<N>& xout, const double h, vec<N>& xerr) {
+  // ODEINTR_K3_OUTLINE: one copy of the attempt instead of one per integrate loop (the kernel instantiates the const /
+  // times / adaptive loops; inlined, it is 157 KB of code and ncu shows no_instruction among the top stalls)
+#ifdef ODEINTR_K3_OUTLINE
+  __device__ __noinline__
+#else
+  ODEINTR_DEV
+#endif
+  void stage_step(Sys& sys, const vec<N>& x, const double tt, vec<N>& xout, const double h, vec<N>& xerr) {
     vec<N> dxdt, dfdt, dn, xt;
     lu_factors<N> lu;
     sys.sys(x, dxdt, tt);

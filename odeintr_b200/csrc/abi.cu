@@ -164,7 +164,8 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_WARP5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_WARP5_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_L2_AHEAD")) o.push_back(std::string("-DODEINTR_STREAM2_L2_AHEAD=") + c);
   if (std::getenv("ODEINTR_STREAM5_LATE_NORM")) o.push_back("-DODEINTR_STREAM5_LATE_NORM=1");
-  if (std::getenv("ODEINTR_K3_OUTLINE")) o.push_back("-DODEINTR_K3_OUTLINE=1");
+  if (const char* c = std::getenv("ODEINTR_STREAM5_THREADS")) o.push_back(std::string("-DODEINTR_STREAM5_THREADS=") + c);
+  if (const char* c = std::getenv("ODEINTR_STREAM5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM5_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
@@ -263,8 +264,8 @@ struct odeintr_system_s {
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
   cudaKernel_t k_lat_ens_dense = nullptr, k_lat_ens_ctl = nullptr;  // adaptive ensembles of wider systems (lattice_ensemble_adaptive.cuh)
-  cudaKernel_t k_stream5 = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
-  int stream5_blocks = 0, stream5_rows = 0;
+  cudaKernel_t k_stream5 = nullptr, k_stream5_info = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
+  int stream5_blocks = 0, stream5_rows = 0, stream5_threads = 256;
   size_t warp5_smem = 0;
   long long tiled5_halo = 0;
   size_t tiled5_smem = 0;
@@ -1257,13 +1258,24 @@ int tiled5_decide(odeintr_system_t h) {
     CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (reach > 1) return ODEINTR_OK;  // (the probe reports the larger of the row and column reach)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_stream5, 256, 0) != cudaSuccess || nb <= 0) {
+    int threads = 256;
+    if (h->k_stream5_info) {  // threads per block the kernel was compiled for
+      void* wout = h->lat_flag.p;
+      void* wparams[1] = {&wout};
+      if (cudaLaunchKernel((const void*)h->k_stream5_info, dim3(1), dim3(1), wparams, 0, h->stream) == cudaSuccess &&
+          cudaMemcpyAsync(&threads, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess)
+        cudaStreamSynchronize(h->stream);
+      (void)cudaGetLastError();
+      if (threads < 32 || threads > 1024 || threads % 32) threads = 256;
+    }
+    h->stream5_threads = threads;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)h->k_stream5, threads, 0) != cudaSuccess || nb <= 0) {
       (void)cudaGetLastError();
       return ODEINTR_OK;
     }
     // rows per warp task: the fewest waves of tasks (strips x segments) over the resident warps with segments of at
     // most 512 rows (12 rows of pipeline fill each), so that the last wave is a full one
-    const long long strips = (h->lat_side + 51) / 52, slots = (long long)h->sm_count * nb * 8;
+    const long long strips = (h->lat_side + 51) / 52, slots = (long long)h->sm_count * nb * (threads / 32);
     long long rows = 256;
     if (const char* c = std::getenv("ODEINTR_STREAM5_ROWS")) rows = std::atoll(c);
     else
@@ -2004,6 +2016,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp5_h[2], h->lib, "odeintr_lattice_dopri5_warp_h2") != cudaSuccess) h->k_warp5_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp5_info, h->lib, "odeintr_lattice_dopri5_warp_info") != cudaSuccess) h->k_warp5_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_stream5, h->lib, "odeintr_lattice_dopri5_stream2d") != cudaSuccess) h->k_stream5 = nullptr;
+  if (cudaLibraryGetKernel(&h->k_stream5_info, h->lib, "odeintr_lattice_dopri5_stream2d_info") != cudaSuccess) h->k_stream5_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_stream2d, h->lib, "odeintr_lattice_rk4_stream2d") != cudaSuccess) h->k_stream2d = nullptr;
   if (cudaLibraryGetKernel(&h->k_stream2d_info, h->lib, "odeintr_lattice_stream2d_info") != cudaSuccess) h->k_stream2d_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_info, h->lib, "odeintr_lattice_info") != cudaSuccess) h->k_info = nullptr;

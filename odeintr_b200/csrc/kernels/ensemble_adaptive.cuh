@@ -21,8 +21,14 @@ template <class T> struct enable_if_c<true, T> { typedef T type; };
 // Register budget: measured on a B200 (scripts/explore_regs.py, 10 M instances) 5 resident blocks of 128 threads
 // per SM (<= 96 registers, a few spilled words in L1) beats the uncapped build by 3 % (dopri5, 104 registers) to
 // 12 % (rosenbrock4, 156 registers); tighter caps lose again.
+// Round 2 (profiles/r02_bench_outline.log): rosenbrock4 is better off with 4 blocks of 128 registers (88 B of spills
+// instead of 240: 1.02e10 -> 1.09e10 accepted steps/s on config 4); dopri5 keeps 5 (4.23e10 against 4.05e10).
 #ifndef ODEINTR_ADAPTIVE_MIN_BLOCKS
+#ifdef ODEINTR_IMPLICIT_SYSTEM
+#define ODEINTR_ADAPTIVE_MIN_BLOCKS ((ODEINTR_MIN_BLOCKS) > 1 ? (ODEINTR_MIN_BLOCKS) : (ODEINTR_BLOCK == 128 ? 4 : 1))
+#else
 #define ODEINTR_ADAPTIVE_MIN_BLOCKS ((ODEINTR_MIN_BLOCKS) > 1 ? (ODEINTR_MIN_BLOCKS) : (ODEINTR_BLOCK == 128 ? 5 : 1))
+#endif
 #endif
 
 extern "C" __global__ void __launch_bounds__(ODEINTR_BLOCK, ODEINTR_ADAPTIVE_MIN_BLOCKS)

@@ -32,6 +32,9 @@
 #ifndef ODEINTR_STREAM5_MIN_BLOCKS
 #define ODEINTR_STREAM5_MIN_BLOCKS 1
 #endif
+#ifndef ODEINTR_STREAM5_THREADS  // threads per block (the host launches what odeintr_lattice_dopri5_stream2d_info reports)
+#define ODEINTR_STREAM5_THREADS 256
+#endif
 
 namespace odeintr_b200 {
 
@@ -280,7 +283,9 @@ ODEINTR_DEV void lattice_dopri5_stream2d_body(const odeintr_lattice_dopri5_args&
 
 }  // namespace odeintr_b200
 
-extern "C" __global__ void __launch_bounds__(256, ODEINTR_STREAM5_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(ODEINTR_STREAM5_THREADS, ODEINTR_STREAM5_MIN_BLOCKS)
 odeintr_lattice_dopri5_stream2d(const odeintr_lattice_dopri5_args a) { odeintr_b200::lattice_dopri5_stream2d_body(a); }
+
+extern "C" __global__ void odeintr_lattice_dopri5_stream2d_info(int* out) { out[0] = ODEINTR_STREAM5_THREADS; }
 
 #endif  // dopri5 on an M x M lattice

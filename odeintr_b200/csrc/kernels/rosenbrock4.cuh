@@ -140,14 +140,11 @@ struct rosenbrock4_dense {
   ODEINTR_DEV const vec<N>& current_state() const { return x_cur; }
 
   // rosenbrock4::do_step(sys, x, t, xout, dt, xerr)
-  // ODEINTR_K3_OUTLINE: one copy of the attempt instead of one per integrate loop (the kernel instantiates the const /
-  // times / adaptive loops; inlined, it is 157 KB of code and ncu shows no_instruction among the top stalls)
-#ifdef ODEINTR_K3_OUTLINE
-  __device__ __noinline__
-#else
-  ODEINTR_DEV
-#endif
-  void stage_step(Sys& sys, const vec<N>& x, const double tt, vec<N>& xout, const double h, vec<N>& xerr) {
+  // (the kernel instantiates the const / times / adaptive loops, each with its own inlined copy of the attempt: 157 KB of
+  //  code, and ncu shows no_instruction among the top stalls.  Measured, profiles/r02_bench_outline.log: ONE out-of-line
+  //  copy halves the code but passes the vectors through local memory: 1.02e10 -> 0.96e10 accepted steps/s; kept inline.
+  //  What did help is one resident block fewer: 4 blocks of 128 registers, 88 B of spills instead of 240: 1.09e10.)
+  ODEINTR_DEV void stage_step(Sys& sys, const vec<N>& x, const double tt, vec<N>& xout, const double h, vec<N>& xerr) {
     vec<N> dxdt, dfdt, dn, xt;
     lu_factors<N> lu;
     sys.sys(x, dxdt, tt);

@@ -160,9 +160,10 @@ struct lattice_dopri5 {
       }
       const long long side = h->lat_side;
       const long long tasks = ((side + 51) / 52) * ((side + h->stream5_rows - 1) / h->stream5_rows);
-      const unsigned grid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)h->sm_count * h->stream5_blocks);
+      const long long wpb = h->stream5_threads / 32;
+      const unsigned grid = (unsigned)std::min<long long>((tasks + wpb - 1) / wpb, (long long)h->sm_count * h->stream5_blocks);
       void* params[1] = {&a};
-      if (cudaLaunchKernel((const void*)h->k_stream5, dim3(grid), dim3(256), params, 0, h->stream) != cudaSuccess) {
+      if (cudaLaunchKernel((const void*)h->k_stream5, dim3(grid), dim3((unsigned)h->stream5_threads), params, 0, h->stream) != cudaSuccess) {
         if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_stream2d failed");
         return -1.0;
       }

@@ -20,6 +20,7 @@ ODEINTR_FLAG_LATTICE_ADAPTIVE = 16L
 ODEINTR_FLAG_LATTICE_CK54 = 64L
 ODEINTR_FLAG_LATTICE_RKF78 = 128L
 ODEINTR_FLAG_LATTICE_RK5 = 256L
+ODEINTR_FLAG_LATTICE_BS = 512L
 
 # device stepper named by a method string (replaces make_stepper_type / make_stepper_constr, R/utils.R:22-60:
 # the Boost type and constructor strings become the name of a hand-written device stepper)
@@ -179,6 +180,7 @@ compile_sys_openmp_gpu = function(name, sys, pars = NULL, const = FALSE, method 
     if (stepper$method == "rk5") flags = bitwOr(flags, ODEINTR_FLAG_LATTICE_RK5)
     if (stepper$base == "rk54") flags = bitwOr(flags, ODEINTR_FLAG_LATTICE_CK54)
     if (stepper$base == "rk78") flags = bitwOr(flags, ODEINTR_FLAG_LATTICE_RKF78)
+    if (stepper$base %in% c("bs", "bsd")) flags = bitwOr(flags, ODEINTR_FLAG_LATTICE_BS)
     h = try(odeintr_gpu_compile(code, name, ceiling(sys_dim), gpu_n_runtime_pars(pars, const), atol, rtol, flags))
     if (!inherits(h, "try-error"))
     {

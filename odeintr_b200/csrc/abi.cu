@@ -166,6 +166,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (std::getenv("ODEINTR_STREAM5_LATE_NORM")) o.push_back("-DODEINTR_STREAM5_LATE_NORM=1");
   if (const char* c = std::getenv("ODEINTR_STREAM5_THREADS")) o.push_back(std::string("-DODEINTR_STREAM5_THREADS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM5_MIN_BLOCKS=") + c);
+  if (std::getenv("ODEINTR_STREAM2_LAZY")) o.push_back("-DODEINTR_STREAM2_LAZY=1");
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);

@@ -24,7 +24,7 @@
 // iteration, 196 registers, one block per SM) 1.06e11 with long_scoreboard the top stall -- the wider live set costs
 // more in occupancy than the independence gains; with a 128-register cap it spills (5.7e10).  Kept: this form.
 #pragma once
-#include "odeintr_b200/lattice_tiled2d.cuh"
+#include "odeintr_b200/lattice_lazy2_view.cuh"
 
 #if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1 && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
 
@@ -75,12 +75,22 @@ struct lattice_reg2_view {
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(side) * side; }
 };
 
+#ifdef ODEINTR_STREAM2_LAZY  // windows of 2 doubles per row, own-row neighbours by two shuffles per evaluation (A/B)
+typedef lattice_lazy2_view stream2_view;
+#else
+typedef lattice_reg2_view stream2_view;
+#endif
+
 ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) {
-  typedef odeintr::system_type_t<lattice_reg2_view> Sys;
+  typedef odeintr::system_type_t<stream2_view> Sys;
   constexpr int MM = isqrt(ODEINTR_SYS_SIZE);
   constexpr int CW = 64, USE = CW - 8;      // columns of a strip, columns it yields
   constexpr int RSEG = ODEINTR_STREAM2_ROWS;
-  constexpr int RS = lattice_reg2_view::RS;
+#ifdef ODEINTR_STREAM2_LAZY
+  constexpr int RS = 2, C0 = 0;   // a window row: the lane's two columns
+#else
+  constexpr int RS = lattice_reg2_view::RS, C0 = 1;  // a window row: left neighbour, the two columns, right neighbour
+#endif
   constexpr int PF = 3;                     // rows prefetched ahead
   constexpr int n_strips = (MM + USE - 1) / USE, n_segs = (MM + RSEG - 1) / RSEG;
   const int lane = threadIdx.x & 31;
@@ -91,7 +101,7 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
 
   Sys sys;
   sys.load_params(a.pars, 1, 0);
-  lattice_reg2_view view;
+  stream2_view view;
   view.side = MM; view.bad = 0;
   rel_index2 idx;
   idx.side = MM;
@@ -140,21 +150,34 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
         const int nw = ph, md = (ph + 2) % 3, ol = (ph + 1) % 3;  // slots of the newest / middle / oldest row after a push
         // a new row enters stage window s (over the row that leaves it); the neighbouring lanes' edge columns with it
         auto push = [&](const int s, const double v0, const double v1) {
-          W[s][nw][1] = v0; W[s][nw][2] = v1;
+          W[s][nw][C0] = v0; W[s][nw][C0 + 1] = v1;
+#ifndef ODEINTR_STREAM2_LAZY
           W[s][nw][0] = __shfl_up_sync(full, v1, 1);    // the left neighbour's second column
           W[s][nw][3] = __shfl_down_sync(full, v0, 1);  // the right neighbour's first column
+#endif
         };
         // k of the lane's two cells in the middle row of window s (global row `row`)
         auto rhs = [&](const int s, const int row, const double ts, double& k0, double& k1v) {
           const int rw = wrap(row);
           double kk[1];
           kk[0] = 0.0;
+#ifdef ODEINTR_STREAM2_LAZY
+          view.up = W[s][ol]; view.mid = W[s][md]; view.dn = W[s][nw];
+          view.left = __shfl_up_sync(full, W[s][md][1], 1);     // the left neighbour's second column
+          view.right = __shfl_down_sync(full, W[s][md][0], 1);  // the right neighbour's first column
+          view.ci = 0;
+#else
           view.up = &W[s][ol][1]; view.mid = &W[s][md][1]; view.dn = &W[s][nw][1];
+#endif
           view.row = idx.row = rw; view.col = idx.col = col0; idx.centre = rw * MM + col0;
           sys.cell(view, kk, idx, ts);
           k0 = kk[0];
           kk[0] = 0.0;
+#ifdef ODEINTR_STREAM2_LAZY
+          view.ci = 1;
+#else
           view.up = &W[s][ol][2]; view.mid = &W[s][md][2]; view.dn = &W[s][nw][2];
+#endif
           view.col = idx.col = col0 + 1; idx.centre = rw * MM + col0 + 1;
           sys.cell(view, kk, idx, ts);
           k1v = kk[0];
@@ -169,17 +192,17 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_in + static_cast<long long>(wrap(j + PF + ODEINTR_STREAM2_L2_AHEAD)) * MM + col0));
 
         // x of row j - 3 leaves the x window with this push: stage 3 needs it
-        x3[0] = W[0][nw][1]; x3[1] = W[0][nw][2];
+        x3[0] = W[0][nw][C0]; x3[1] = W[0][nw][C0 + 1];
         push(0, xin.x, xin.y);                       // x rows j-2, j-1, j
         double k0, k1v;
         // stage 1 at row j-1
         rhs(0, j - 1, t1, k0, k1v);
-        const double s1a = W[0][md][1] + (half * dt) * k0, s1b = W[0][md][2] + (half * dt) * k1v;
-        const double n1a = W[0][md][1] + (b1 * dt) * k0, n1b = W[0][md][2] + (b1 * dt) * k1v;   // the running sum starts from x
+        const double s1a = W[0][md][C0] + (half * dt) * k0, s1b = W[0][md][C0 + 1] + (half * dt) * k1v;
+        const double n1a = W[0][md][C0] + (b1 * dt) * k0, n1b = W[0][md][C0 + 1] + (b1 * dt) * k1v;   // the running sum starts from x
         push(1, s1a, s1b);                           // stage-1 states of rows j-3, j-2, j-1
         // stage 2 at row j-2
         rhs(1, j - 2, t2, k0, k1v);
-        const double s2a = W[0][ol][1] + (half * dt) * k0, s2b = W[0][ol][2] + (half * dt) * k1v;
+        const double s2a = W[0][ol][C0] + (half * dt) * k0, s2b = W[0][ol][C0 + 1] + (half * dt) * k1v;
         const double n2a = acc1[0] + (b2 * dt) * k0, n2b = acc1[1] + (b2 * dt) * k1v;
         push(2, s2a, s2b);                           // stage-2 states of rows j-4, j-3, j-2
         // stage 3 at row j-3

@@ -166,7 +166,6 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (std::getenv("ODEINTR_STREAM5_LATE_NORM")) o.push_back("-DODEINTR_STREAM5_LATE_NORM=1");
   if (const char* c = std::getenv("ODEINTR_STREAM5_THREADS")) o.push_back(std::string("-DODEINTR_STREAM5_THREADS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM5_MIN_BLOCKS=") + c);
-  if (std::getenv("ODEINTR_STREAM2_LAZY")) o.push_back("-DODEINTR_STREAM2_LAZY=1");
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM2_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_WARP_CPT")) o.push_back(std::string("-DODEINTR_WARP_CPT=") + c);
@@ -1719,6 +1718,10 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
                   : odeintr_b200::integrate_adaptive_controlled(st, sys, x, tc, t1, dtc, nobs);
     cnt = st.cnt;
     if (st.core.rc) return st.core.rc;
+    if (x.p != xstate) {  // accepted steps swap the state vector with the stepper's: bring the result home
+      CU_TRY(cudaMemcpyAsync(xstate, x.p, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      if (slab) slab_mark(h, xstate, slab_is_fresh(h, x.p));
+    }
   }
   if (!ok && cnt.status == ODEINTR_STATUS_OK) cnt.status = ODEINTR_STATUS_NONFINITE;
   if ((rc = end_timing(h))) return rc;

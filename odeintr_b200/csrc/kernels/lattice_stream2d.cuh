@@ -24,7 +24,7 @@
 // iteration, 196 registers, one block per SM) 1.06e11 with long_scoreboard the top stall -- the wider live set costs
 // more in occupancy than the independence gains; with a 128-register cap it spills (5.7e10).  Kept: this form.
 #pragma once
-#include "odeintr_b200/lattice_lazy2_view.cuh"
+#include "odeintr_b200/lattice_tiled2d.cuh"
 
 #if defined(ODEINTR_LATTICE_2D) && ODEINTR_NFIELDS == 1 && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 4
 
@@ -75,22 +75,14 @@ struct lattice_reg2_view {
   ODEINTR_DEV std::size_t size() const { return static_cast<std::size_t>(side) * side; }
 };
 
-#ifdef ODEINTR_STREAM2_LAZY  // windows of 2 doubles per row, own-row neighbours by two shuffles per evaluation (A/B)
-typedef lattice_lazy2_view stream2_view;
-#else
-typedef lattice_reg2_view stream2_view;
-#endif
+typedef lattice_reg2_view stream2_view;  // (measured: the lazy two-doubles-per-row view of K4ds2 loses here, 1.66e11 vs 1.75e11)
 
 ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) {
   typedef odeintr::system_type_t<stream2_view> Sys;
   constexpr int MM = isqrt(ODEINTR_SYS_SIZE);
   constexpr int CW = 64, USE = CW - 8;      // columns of a strip, columns it yields
   constexpr int RSEG = ODEINTR_STREAM2_ROWS;
-#ifdef ODEINTR_STREAM2_LAZY
-  constexpr int RS = 2, C0 = 0;   // a window row: the lane's two columns
-#else
   constexpr int RS = lattice_reg2_view::RS, C0 = 1;  // a window row: left neighbour, the two columns, right neighbour
-#endif
   constexpr int PF = 3;                     // rows prefetched ahead
   constexpr int n_strips = (MM + USE - 1) / USE, n_segs = (MM + RSEG - 1) / RSEG;
   const int lane = threadIdx.x & 31;
@@ -151,33 +143,20 @@ ODEINTR_DEV void lattice_rk4_stream2d_body(const odeintr_lattice_tiled_args& a) 
         // a new row enters stage window s (over the row that leaves it); the neighbouring lanes' edge columns with it
         auto push = [&](const int s, const double v0, const double v1) {
           W[s][nw][C0] = v0; W[s][nw][C0 + 1] = v1;
-#ifndef ODEINTR_STREAM2_LAZY
           W[s][nw][0] = __shfl_up_sync(full, v1, 1);    // the left neighbour's second column
           W[s][nw][3] = __shfl_down_sync(full, v0, 1);  // the right neighbour's first column
-#endif
         };
         // k of the lane's two cells in the middle row of window s (global row `row`)
         auto rhs = [&](const int s, const int row, const double ts, double& k0, double& k1v) {
           const int rw = wrap(row);
           double kk[1];
           kk[0] = 0.0;
-#ifdef ODEINTR_STREAM2_LAZY
-          view.up = W[s][ol]; view.mid = W[s][md]; view.dn = W[s][nw];
-          view.left = __shfl_up_sync(full, W[s][md][1], 1);     // the left neighbour's second column
-          view.right = __shfl_down_sync(full, W[s][md][0], 1);  // the right neighbour's first column
-          view.ci = 0;
-#else
           view.up = &W[s][ol][1]; view.mid = &W[s][md][1]; view.dn = &W[s][nw][1];
-#endif
           view.row = idx.row = rw; view.col = idx.col = col0; idx.centre = rw * MM + col0;
           sys.cell(view, kk, idx, ts);
           k0 = kk[0];
           kk[0] = 0.0;
-#ifdef ODEINTR_STREAM2_LAZY
-          view.ci = 1;
-#else
           view.up = &W[s][ol][2]; view.mid = &W[s][md][2]; view.dn = &W[s][nw][2];
-#endif
           view.col = idx.col = col0 + 1; idx.centre = rw * MM + col0 + 1;
           sys.cell(view, kk, idx, ts);
           k1v = kk[0];

@@ -606,9 +606,9 @@ struct lattice_dopri5_controlled {
     if (first) { core.rhs(x.p, dxdt, t); first = false; }
     const bool ok = try_step_full(x.p, dxdt, t, xnew, dnew, dt);
     if (ok) {
-      const size_t bytes = core.h->lat_vec_len * sizeof(double);
-      cudaMemcpyAsync(x.p, xnew, bytes, cudaMemcpyDeviceToDevice, core.h->stream);
-      if (core.slab) slab_mark(core.h, x.p, slab_is_fresh(core.h, xnew));
+      // the new state and its derivative trade places with the old ones (no copy: the caller moves the final state
+      // home when the loops are over); ghost-cell freshness is tracked per vector and travels with the pointers
+      std::swap(x.p, xnew);
       std::swap(dxdt, dnew);
     }
     return ok;

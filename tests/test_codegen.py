@@ -159,7 +159,7 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
         assert k == staged | {"odeintr_lattice_rk4_tiled2d_h1", "odeintr_lattice_rk4_tiled2d_h2",
                               "odeintr_lattice_rk4_stream2d", "odeintr_lattice_stream2d_info"}
     k = _kernels(codegen.generate_sys_openmp("b2", BISTABLE_2D, BISTABLE_PARS, True, "rk5_i", sys_dim=96 * 96).code)
-    assert k == staged | {"odeintr_lattice_dopri5_stream2d"}
+    assert k == staged | {"odeintr_lattice_dopri5_stream2d", "odeintr_lattice_dopri5_stream2d_info"}
 
 
 def test_snippets_that_treat_the_loop_variable_as_an_int_still_build():

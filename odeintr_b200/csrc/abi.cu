@@ -263,7 +263,7 @@ struct odeintr_system_s {
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
-  cudaKernel_t k_lat_ens_dense = nullptr, k_lat_ens_ctl = nullptr;  // adaptive ensembles of wider systems (lattice_ensemble_adaptive.cuh)
+  cudaKernel_t k_lat_ens_a[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // adaptive ensembles of wider systems (lattice_ensemble_adaptive.cuh), by lattice_method
   cudaKernel_t k_stream5 = nullptr, k_stream5_info = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
   int stream5_blocks = 0, stream5_rows = 0, stream5_threads = 256;
   size_t warp5_smem = 0;
@@ -1526,8 +1526,6 @@ int run_lattice_adaptive(odeintr_system_t h, int mode, double t0, double t1, dou
   if (!h->k_combo) return fail(ODEINTR_E_STATE, "system was not compiled for adaptive stepping of a large system");
   if (h->m > 1 && !h->sharded) {
     // an ensemble of large systems: one warp / block per trajectory, every trajectory with its own step sizes
-    if (h->lattice_method != 1 && h->lattice_method != 2)
-      return fail(ODEINTR_E_STATE, "adaptive ensembles of large systems are provided for rk5_i and rk5_a");
     return run_adaptive(h, mode, mode == ODEINTR_MODE_TIMES ? times[0] : t0, mode == ODEINTR_MODE_TIMES ? times[n_times - 1] : t1,
                         dt, times, n_times, record, true);
   }
@@ -1776,10 +1774,10 @@ std::vector<double> dense_const_times(double t0, double t1, double dt, bool* opt
 int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, const double* times, size_t n_times,
                  bool record, bool wide) {
   // wide: an ensemble of compile_sys_openmp systems under rk5_i / rk5_a, one warp / block per trajectory
-  cudaKernel_t kern = wide ? (h->lattice_method == 2 ? h->k_lat_ens_dense : h->k_lat_ens_ctl) : h->k_adaptive;
+  cudaKernel_t kern = wide ? (h->lattice_method >= 1 && h->lattice_method <= 6 ? h->k_lat_ens_a[h->lattice_method] : nullptr) : h->k_adaptive;
   if (!kern)
-    return fail(ODEINTR_E_STATE, wide ? "adaptive ensembles of large systems are provided for rk5_i / rk5_a on 1-D lattices of "
-                                        "3 ... 2048 cells with at most 4 states per thread (fields x cells / threads)"
+    return fail(ODEINTR_E_STATE, wide ? "adaptive ensembles of large systems are provided on 1-D lattices of 3 ... 2048 cells with at "
+                                        "most 4 states per thread (fields x cells / threads); run the trajectories one at a time"
                                       : "system was not compiled with an adaptive stepper");
   if (h->m == 0) return fail(ODEINTR_E_STATE, "Invalid initial state");
   const size_t m = h->m, N = (size_t)h->N;
@@ -1791,9 +1789,23 @@ int run_adaptive(odeintr_system_t h, int mode, double t0, double t1, double dt, 
   unsigned wide_block = 0, wide_grid = 0;
   size_t wide_smem = 0;
   if (wide) {
-    if ((rc = tiled5_decide(h))) return rc;
-    if (h->tiled5 != 1) return fail(ODEINTR_E_INVALID, "ensembles of large systems need a stencil radius of at most 16 cells");
-    const long long L = h->lat_cells_ct, halo = h->tiled5_halo < 1 ? 1 : h->tiled5_halo;
+    // stencil radius of the loop body, measured with the system's parameters in place (odeintr_lattice_probe)
+    if (!h->k_probe || h->lat_cells_ct <= 0) return fail(ODEINTR_E_STATE, "the generated translation unit has no probe kernel");
+    if (h->P && !h->pars.p) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
+    int reach = 0;
+    {
+      CU_TRY(h->lat_flag.reserve(10));
+      CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+      const double* ppars = h->P ? h->pars.p : nullptr;
+      double pt = 0.0;
+      int* pout = h->lat_flag.p;
+      void* pparams[3] = {&ppars, &pt, &pout};
+      CU_TRY(cudaLaunchKernel((const void*)h->k_probe, dim3((unsigned)h->sm_count * 8u), dim3(256), pparams, 0, h->stream));
+      CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (reach > 32) return fail(ODEINTR_E_INVALID, "ensembles of large systems need a stencil radius of at most 32 cells");
+    const long long L = h->lat_cells_ct, halo = reach < 1 ? 1 : reach;
     const int fields = (int)((long long)h->N / L);
     if (2 * halo + 1 > L) return fail(ODEINTR_E_INVALID, "stencil radius too wide for the lattice");
     // threads per trajectory and trajectories per block, as lattice_ensemble.cuh derives them from the lattice length
@@ -2005,8 +2017,13 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp_h[2], h->lib, "odeintr_lattice_rk4_warp_h2") != cudaSuccess) h->k_warp_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp_info, h->lib, "odeintr_lattice_warp_info") != cudaSuccess) h->k_warp_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
-  if (cudaLibraryGetKernel(&h->k_lat_ens_dense, h->lib, "odeintr_lattice_ensemble_dopri5_dense") != cudaSuccess) h->k_lat_ens_dense = nullptr;
-  if (cudaLibraryGetKernel(&h->k_lat_ens_ctl, h->lib, "odeintr_lattice_ensemble_dopri5_controlled") != cudaSuccess) h->k_lat_ens_ctl = nullptr;
+  {
+    static const char* const names[7] = {nullptr, "odeintr_lattice_ensemble_dopri5_controlled", "odeintr_lattice_ensemble_dopri5_dense",
+                                         "odeintr_lattice_ensemble_rk54_controlled", "odeintr_lattice_ensemble_rk78_controlled",
+                                         "odeintr_lattice_ensemble_bs_controlled", "odeintr_lattice_ensemble_bsd_dense"};
+    for (int k = 1; k < 7; ++k)
+      if (cudaLibraryGetKernel(&h->k_lat_ens_a[k], h->lib, names[k]) != cudaSuccess) h->k_lat_ens_a[k] = nullptr;
+  }
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[1], h->lib, "odeintr_lattice_rk4_tiled2d_h1") != cudaSuccess) h->k_tiled2d_h[1] = nullptr;
   if (cudaLibraryGetKernel(&h->k_tiled2d_h[2], h->lib, "odeintr_lattice_rk4_tiled2d_h2") != cudaSuccess) h->k_tiled2d_h[2] = nullptr;
   h->k_tiled2d = h->k_tiled2d_h[1];

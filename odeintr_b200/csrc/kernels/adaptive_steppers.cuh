@@ -123,7 +123,7 @@ struct rk54_controlled {
         xnew[i] = x[i] + e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e6 * k6[i];
       }
     }
-    const double err = error_norm<N>(x, k1, xerr, dt, eps_abs, eps_rel);
+    const double err = reduce_error(sys, error_norm<N>(x, k1, xerr, dt, eps_abs, eps_rel), 0);
     const double dt_used = dt;
     if (!adjust_step(err, dt, 4, 5, 0.00032)) {
       cnt.rejected++;

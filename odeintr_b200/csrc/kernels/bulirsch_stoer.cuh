@@ -118,7 +118,7 @@ struct bs_controlled {
           }
 #pragma unroll
           for (int i = 0; i < N; ++i) err[i] = out[i] + (-1.0) * table[0][i];
-          const double error = error_norm<N>(x, dxdt, err, dt, eps_abs, eps_rel);
+          const double error = reduce_error(sys, error_norm<N>(x, dxdt, err, dt, eps_abs, eps_rel), 0);
           h_opt[k] = calc_h_opt(dt, error, k);
           work[k] = cost(k) / h_opt[k];
           if ((k == k_opt - 1) || first) {  // convergence before k_opt

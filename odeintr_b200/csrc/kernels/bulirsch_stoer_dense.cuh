@@ -206,7 +206,7 @@ struct bsd_dense {
       }
 #pragma unroll
       for (int q = 0; q < N; ++q) err[q] = out[q] + (-1.0) * table[0][q];
-      const double error = error_norm<N>(in, dxdt, err, h, eps_abs, eps_rel);
+      const double error = reduce_error(sys, error_norm<N>(in, dxdt, err, h, eps_abs, eps_rel), 0);
       h_opt[k] = calc_h_opt(h, error, k);
       work[k] = cost(k) / h_opt[k];
       k_final = k;

@@ -1,6 +1,6 @@
 // odeintr_b200/csrc/kernels/lattice_ensemble_adaptive.cuh
 // K5a: ensembles of WIDER systems under the adaptive steppers -- compile_sys_openmp's default method rk5_i
-// (dense-output dopri5) and rk5_a (controlled dopri5), one WARP or one BLOCK per trajectory (lattice_ensemble.cuh has
+// (dense-output dopri5), rk5_a, rk54_a, rk78_a, bs and bsd --, one WARP or one BLOCK per trajectory (lattice_ensemble.cuh has
 // the fixed-step rk4 form).  In the reference: an R loop around NAME_set_params() + NAME() / NAME_at()
 // (README.md:157-163) over a system compiled with compile_sys_openmp's defaults (R/odeintr.R:418-421).
 //
@@ -21,7 +21,8 @@
 #include "odeintr_b200/lattice_ensemble.cuh"
 
 // registers: ~13 doubles per owned entry (x, k1, x_new, k7, x_old, k1_old, k2 .. k6, stage state, error estimate)
-#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && ODEINTR_LATTICE_STAGES == 7 && \
+#if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && \
+    (ODEINTR_LATTICE_STAGES == 7 || ODEINTR_LATTICE_STAGES == 6 || ODEINTR_LATTICE_STAGES == 13 || ODEINTR_LATTICE_STAGES == 2) && \
     ODEINTR_ENS_CPT * ODEINTR_NFIELDS <= 4 && ODEINTR_ENS_CELLS >= 3 && ODEINTR_ENS_CELLS <= 2048
 #define ODEINTR_HAVE_ENS_ADAPTIVE 1
 #include "odeintr_b200/integrate_device.cuh"
@@ -225,13 +226,23 @@ ODEINTR_DEV void lattice_ensemble_adaptive_body(const odeintr_lattice_ensemble_a
 
 }  // namespace odeintr_b200
 
-extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)
-odeintr_lattice_ensemble_dopri5_dense(const odeintr_lattice_ensemble_adaptive_args a) {
-  odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::dopri5_dense>(a);
-}
-extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)
-odeintr_lattice_ensemble_dopri5_controlled(const odeintr_lattice_ensemble_adaptive_args a) {
-  odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::dopri5_controlled>(a);
-}
+// one kernel per stepper the translation unit's method can ask for (the stage count is how the generator names it)
+#define ODEINTR_ENS_ADAPTIVE_KERNEL(NAME, STEPPER)                                                  \
+  extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)             \
+  NAME(const odeintr_lattice_ensemble_adaptive_args a) {                                            \
+    odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::STEPPER>(a);                         \
+  }
+#if ODEINTR_LATTICE_STAGES == 7    // rk5_i, rk5_a
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_dopri5_dense, dopri5_dense)
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_dopri5_controlled, dopri5_controlled)
+#elif ODEINTR_LATTICE_STAGES == 6  // rk54_a
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_rk54_controlled, rk54_controlled)
+#elif ODEINTR_LATTICE_STAGES == 13  // rk78_a
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_rk78_controlled, rk78_controlled)
+#else                              // bs, bsd
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_bs_controlled, bs_controlled)
+ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_bsd_dense, bsd_dense)
+#endif
+#undef ODEINTR_ENS_ADAPTIVE_KERNEL
 
 #endif  // adaptive ensembles of wider systems

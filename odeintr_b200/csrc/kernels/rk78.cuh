@@ -103,7 +103,7 @@ struct rk78_controlled {
     vec<N> k1, xn, xe;
     sys.sys(x, k1, t);
     rkf78_step<Sys, N, true>(sys, x, k1, t, dt, xn, xe);
-    const double err = error_norm<N>(x, k1, xe, dt, eps_abs, eps_rel);
+    const double err = reduce_error(sys, error_norm<N>(x, k1, xe, dt, eps_abs, eps_rel), 0);
     const double dt_used = dt;
     if (!adjust_step(err, dt, 7, 8, 2.56e-6)) {
       cnt.rejected++;

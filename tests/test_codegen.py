@@ -154,6 +154,10 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
     for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a", "bs", "bsd"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk78_a", sys_dim=300).code)
+    assert k == staged | {"odeintr_lattice_ensemble_rk78_controlled"}
+    k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "bs", sys_dim=300).code)
+    assert k == staged | {"odeintr_lattice_ensemble_bs_controlled", "odeintr_lattice_ensemble_bsd_dense"}
     for src in (BISTABLE_2D, BISTABLE_DOC):
         k = _kernels(codegen.generate_sys_openmp("b2", src, BISTABLE_PARS, True, "rk4", sys_dim=96 * 96).code)
         assert k == staged | {"odeintr_lattice_rk4_tiled2d_h1", "odeintr_lattice_rk4_tiled2d_h2",

@@ -263,6 +263,7 @@ struct odeintr_system_s {
   int tiled5 = -1;              // dopri5 attempts go through odeintr_lattice_dopri5_tiled: -1 undecided, 0 no, 1 yes
   cudaKernel_t k_warp5_h[3] = {nullptr, nullptr, nullptr}, k_warp5 = nullptr, k_warp5_info = nullptr;
   int warp5_cpt = 0, warp5_halo = 0, warp5_blocks = 0;  // warp-autonomous dopri5 attempt (lattice_dopri5_warp.cuh)
+  cudaKernel_t k_lat_ens_plain = nullptr;  // ensembles of wider systems under euler / rk54 / rk5 / rk78 (fixed step)
   cudaKernel_t k_lat_ens_a[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // adaptive ensembles of wider systems (lattice_ensemble_adaptive.cuh), by lattice_method
   cudaKernel_t k_stream5 = nullptr, k_stream5_info = nullptr;  // M x M lattices, radius 1: streaming dopri5 attempt (lattice_dopri5_stream2d.cuh); tiled5 == 2
   int stream5_blocks = 0, stream5_rows = 0, stream5_threads = 256;
@@ -1145,16 +1146,35 @@ int run_lattice_once(odeintr_system_t h, const plain_schedule& sc) {
 // Ensemble of wider systems (m > 1 trajectories of a compile_sys_openmp system): one block per trajectory, the
 // whole integrate call in one launch of odeintr_lattice_ensemble (lattice_ensemble.cuh).
 int run_lattice_ensemble(odeintr_system_t h, const plain_schedule& sc) {
-  if (!h->k_lat_ens)
-    return fail(ODEINTR_E_STATE, "ensembles of large systems are provided for fixed-step rk4 and at most 8192 / fields "
-                                 "cells per field; run the trajectories one at a time");
+  // rk4: the register-blocked kernel of lattice_ensemble.cuh; euler / rk54 / rk5 / rk78: the plain steppers on a
+  // distributed state (lattice_ensemble_adaptive.cuh)
+  const bool other = h->lattice_stages != 4;
+  cudaKernel_t kern = other ? h->k_lat_ens_plain : h->k_lat_ens;
+  if (!kern)
+    return fail(ODEINTR_E_STATE, "ensembles of large systems are provided for 1-D lattices of at most 8192 / fields cells per "
+                                 "field (rk4) or 2048 cells and 4 states per thread (the other methods); run the trajectories "
+                                 "one at a time");
   if (h->lat_cells_ct <= 0) return fail(ODEINTR_E_STATE, "system was not compiled with compile_sys_openmp");
   if (h->P && !h->pars.p) return fail(ODEINTR_E_INVALID, "Invalid parameter vector");
   int rc;
   // stencil radius: declared, or measured by the probe (parameters of instance 0; index expressions that depend on
   // parameters or state are caught by the per-access check)
   long long halo = h->lattice_halo;
-  if (!h->tiled_on) {
+  if (other) {
+    if (!h->k_probe) return fail(ODEINTR_E_STATE, "the generated translation unit has no probe kernel");
+    int reach = 0;
+    CU_TRY(h->lat_flag.reserve(10));
+    CU_TRY(cudaMemsetAsync(h->lat_flag.p, 0, sizeof(int), h->stream));
+    const double* ppars = h->P ? h->pars.p : nullptr;
+    double pt = 0.0;
+    int* pout = h->lat_flag.p;
+    void* pparams[3] = {&ppars, &pt, &pout};
+    CU_TRY(cudaLaunchKernel((const void*)h->k_probe, dim3((unsigned)h->sm_count * 8u), dim3(256), pparams, 0, h->stream));
+    CU_TRY(cudaMemcpyAsync(&reach, h->lat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (reach > 32) return fail(ODEINTR_E_INVALID, "ensembles of large systems need a stencil radius of at most 32 cells");
+    halo = reach < 1 ? 1 : reach;
+  } else if (!h->tiled_on) {
     const bool pending = h->tiled_pending, was_auto = h->tiled_auto;
     if ((rc = tiled_autodetect(h))) return rc;  // sets lattice_halo when a tile can hold the reach
     if (!h->tiled_on) {
@@ -1183,14 +1203,14 @@ int run_lattice_ensemble(odeintr_system_t h, const plain_schedule& sc) {
   // threads per trajectory and trajectories per block, as lattice_ensemble.cuh derives them from the lattice length
   const unsigned nt = (unsigned)(L > 2048 ? 512 : (L >= 256 ? 256 : (L + 31) / 32 * 32));
   const unsigned group = nt == 32 ? 4 : 1;
-  const size_t smem = group * 2 * (size_t)fields * (size_t)(L + 2 * halo) * sizeof(double);
+  const size_t smem = group * (2 * (size_t)fields * (size_t)(L + 2 * halo) + (other ? 2 * (nt / 32) : 0)) * sizeof(double);
   if (smem > 200 * 1024) return fail(ODEINTR_E_INVALID, "lattice too large for one block's shared memory");
-  CU_TRY(cudaFuncSetAttribute((const void*)h->k_lat_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned block = nt * group;
   const unsigned grid = (unsigned)((h->m + group - 1) / group);
   if ((rc = begin_timing(h))) return rc;
   void* params[1] = {&a};
-  CU_TRY(cudaLaunchKernel((const void*)h->k_lat_ens, dim3(grid), dim3(block), params, smem, h->stream));
+  CU_TRY(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(block), params, smem, h->stream));
   h->last_launches += 1;
   g_total_launches += 1;
   if ((rc = end_timing(h))) return rc;
@@ -2017,6 +2037,7 @@ int odeintr_compile(const char* cuda_src, const char* name, int sys_dim, int n_p
   if (cudaLibraryGetKernel(&h->k_warp_h[2], h->lib, "odeintr_lattice_rk4_warp_h2") != cudaSuccess) h->k_warp_h[2] = nullptr;
   if (cudaLibraryGetKernel(&h->k_warp_info, h->lib, "odeintr_lattice_warp_info") != cudaSuccess) h->k_warp_info = nullptr;
   if (cudaLibraryGetKernel(&h->k_lat_ens, h->lib, "odeintr_lattice_ensemble") != cudaSuccess) h->k_lat_ens = nullptr;
+  if (cudaLibraryGetKernel(&h->k_lat_ens_plain, h->lib, "odeintr_lattice_ensemble_plain") != cudaSuccess) h->k_lat_ens_plain = nullptr;
   {
     static const char* const names[7] = {nullptr, "odeintr_lattice_ensemble_dopri5_controlled", "odeintr_lattice_ensemble_dopri5_dense",
                                          "odeintr_lattice_ensemble_rk54_controlled", "odeintr_lattice_ensemble_rk78_controlled",

@@ -22,10 +22,12 @@
 
 // registers: ~13 doubles per owned entry (x, k1, x_new, k7, x_old, k1_old, k2 .. k6, stage state, error estimate)
 #if !defined(ODEINTR_LATTICE_2D) && !defined(ODEINTR_NO_SYMBOLIC) && \
-    (ODEINTR_LATTICE_STAGES == 7 || ODEINTR_LATTICE_STAGES == 6 || ODEINTR_LATTICE_STAGES == 13 || ODEINTR_LATTICE_STAGES == 2) && \
+    (ODEINTR_LATTICE_STAGES == 7 || ODEINTR_LATTICE_STAGES == 6 || ODEINTR_LATTICE_STAGES == 13 || ODEINTR_LATTICE_STAGES == 2 || \
+     ODEINTR_LATTICE_STAGES == 1) && \
     ODEINTR_ENS_CPT * ODEINTR_NFIELDS <= 4 && ODEINTR_ENS_CELLS >= 3 && ODEINTR_ENS_CELLS <= 2048
 #define ODEINTR_HAVE_ENS_ADAPTIVE 1
 #include "odeintr_b200/integrate_device.cuh"
+#include "odeintr_b200/steppers_plain.cuh"
 
 namespace odeintr_b200 {
 
@@ -224,7 +226,103 @@ ODEINTR_DEV void lattice_ensemble_adaptive_body(const odeintr_lattice_ensemble_a
   if (sys.view.bad) *b.flag = 1;
 }
 
+// The fixed-step methods other than rk4 (euler, rk54, rk5, rk78; rk4 has the register-blocked kernel of
+// lattice_ensemble.cuh) on the same distributed state: K1's host-computed step schedule, the plain steppers of K1.
+template <template <class, int> class Stepper>
+ODEINTR_DEV void lattice_ensemble_plain_body(const odeintr_lattice_ensemble_args& b) {
+  typedef odeintr::system_type_t<lattice_rel_view<true> > UserSys;
+  typedef block_system<UserSys> Sys;
+  constexpr int F = Sys::F, L = Sys::L, NT = Sys::NT, C = Sys::C, NE = Sys::NE;
+  constexpr int G = ODEINTR_ENS_GROUP;
+  const odeintr_plain_args& a = b.p;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x % NT, grp = threadIdx.x / NT;
+  const int h = static_cast<int>(b.halo);
+  const int W = L + 2 * h;
+  const long long inst = b.first + static_cast<long long>(blockIdx.x) * G + grp;
+  if (inst >= a.m) return;
+
+  Sys sys;
+  sys.user.load_params(a.pars, a.par_ld, inst * a.par_inc);
+  sys.ring[0] = smem + grp * (2 * F * W + 2 * (NT / 32));
+  sys.ring[1] = sys.ring[0] + F * W;
+  sys.red = sys.ring[1] + F * W;
+  sys.phase = 0; sys.rphase = 0;
+  sys.tid = tid; sys.h = h; sys.W = W;
+  {
+    long long off[F];
+    sys.user.field_offsets(off, 0);
+#pragma unroll
+    for (int f = 0; f < F; ++f) sys.fld[f] = static_cast<int>(off[f] / L);
+  }
+  const long long start = sys.user.cell_start(), bound = sys.user.cell_bound();
+  sys.view.n_total = L; sys.view.width = W; sys.view.halo = h; sys.view.bad = 0;
+  sys.idx.off = 0; sys.idx.cells = L; sys.idx.rel = true;
+  vec<NE> x;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = tid + c * NT;
+    sys.live[c] = j < L && j >= start && j < bound;
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+      x[c * F + f] = j < L ? a.x[(static_cast<long long>(sys.fld[f]) * L + j) * a.ld + inst] : 0.0;
+  }
+  Stepper<Sys, NE> stepper;
+  stepper.reset();
+  block_sample_writer<NE> obs;
+  obs.out = a.out ? a.out + inst : nullptr;
+  obs.t_rec = nullptr;
+  obs.ld = a.ld; obs.rows = 0; obs.max_rows = 0x7fffffff; obs.tid = tid; obs.fld = sys.fld;
+
+  // the schedule of odeintr_plain_ensemble (ensemble_plain.cuh): observe, full steps, remainder step, per segment
+  const double dt = a.dt;
+  double t = a.t0;
+  long long step = 0;
+  for (long long s = 0; s < a.n_seg; ++s) {
+    if (a.seg_t) t = a.seg_t[s];
+    if (obs.out && (!a.seg_obs || a.seg_obs[s])) obs(x, t);
+    const long long nfull = a.seg_nfull ? a.seg_nfull[s] : a.nfull_uniform;
+    for (long long q = 0; q < nfull; ++q) {
+      stepper.do_step(sys, x, t, dt);
+      ++step;
+      t = (a.time_rule == ODEINTR_TIME_CONST) ? a.t0 + static_cast<double>(step) * dt : t + dt;
+    }
+    if (a.seg_hrem) {  // remainder step that lands exactly on the next observation / end time
+      const double hr = a.seg_hrem[s];
+      if (hr != 0.0) {
+        stepper.do_step(sys, x, t, hr);
+        t += hr;
+      }
+    }
+  }
+  if (obs.out && a.record_final) obs(x, t);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = tid + c * NT;
+    if (j < L) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) a.x[(static_cast<long long>(sys.fld[f]) * L + j) * a.ld + inst] = x[c * F + f];
+    }
+  }
+  if (sys.view.bad) *b.flag = 1;
+}
+
 }  // namespace odeintr_b200
+
+#if ODEINTR_LATTICE_STAGES != 2  // (bs / bsd are never plain steppers)
+extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)
+odeintr_lattice_ensemble_plain(const odeintr_lattice_ensemble_args a) {
+#if ODEINTR_LATTICE_STAGES == 1
+  odeintr_b200::lattice_ensemble_plain_body<odeintr_b200::euler_stepper>(a);
+#elif ODEINTR_LATTICE_STAGES == 6
+  odeintr_b200::lattice_ensemble_plain_body<odeintr_b200::rk54_stepper>(a);
+#elif ODEINTR_LATTICE_STAGES == 7
+  odeintr_b200::lattice_ensemble_plain_body<odeintr_b200::rk5_stepper>(a);
+#else
+  odeintr_b200::lattice_ensemble_plain_body<odeintr_b200::rk78_stepper>(a);
+#endif
+}
+#endif
 
 // one kernel per stepper the translation unit's method can ask for (the stage count is how the generator names it)
 #define ODEINTR_ENS_ADAPTIVE_KERNEL(NAME, STEPPER)                                                  \
@@ -239,7 +337,7 @@ ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_dopri5_controlled, dopri5_c
 ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_rk54_controlled, rk54_controlled)
 #elif ODEINTR_LATTICE_STAGES == 13  // rk78_a
 ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_rk78_controlled, rk78_controlled)
-#else                              // bs, bsd
+#elif ODEINTR_LATTICE_STAGES == 2  // bs, bsd
 ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_bs_controlled, bs_controlled)
 ODEINTR_ENS_ADAPTIVE_KERNEL(odeintr_lattice_ensemble_bsd_dense, bsd_dense)
 #endif

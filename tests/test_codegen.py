@@ -150,12 +150,13 @@ def test_large_system_translation_units_carry_the_kernels_their_method_can_use()
         assert k == staged | dopri5
     # lattices one block can hold also get the adaptive one-warp / one-block-per-trajectory kernels (K5a)
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk5_i", sys_dim=1024).code)
-    assert k == staged | dopri5 | {"odeintr_lattice_ensemble_dopri5_dense", "odeintr_lattice_ensemble_dopri5_controlled"}
+    assert k == staged | dopri5 | {"odeintr_lattice_ensemble_dopri5_dense", "odeintr_lattice_ensemble_dopri5_controlled",
+                                   "odeintr_lattice_ensemble_plain"}
     for method in ("euler", "rk54", "rk54_a", "rk78", "rk78_a", "bs", "bsd"):
         k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, True, method, sys_dim=1 << 20).code)
         assert k == staged
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "rk78_a", sys_dim=300).code)
-    assert k == staged | {"odeintr_lattice_ensemble_rk78_controlled"}
+    assert k == staged | {"odeintr_lattice_ensemble_rk78_controlled", "odeintr_lattice_ensemble_plain"}
     k = _kernels(codegen.generate_sys_openmp("b", BISTABLE_1D, BISTABLE_PARS, False, "bs", sys_dim=300).code)
     assert k == staged | {"odeintr_lattice_ensemble_bs_controlled", "odeintr_lattice_ensemble_bsd_dense"}
     for src in (BISTABLE_2D, BISTABLE_DOC):

@@ -196,3 +196,29 @@ def test_adaptive_ensemble_of_wider_systems_other_steppers(cells, method):
     fin = env["bis_no_record"](x0, 2.05, 0.1)
     ref = ora.integrate_adaptive(x0[:, 3].copy(), 0, 2.05, 0.1, pars=[D[3], 1.0, b[3]])
     close(fin[:, 3], ref["x"], 1e-6, bound=bound)
+
+
+@pytest.mark.parametrize("method", ["euler", "rk54", "rk5", "rk78"])
+def test_fixed_step_ensemble_of_wider_systems_other_steppers(method):
+    # the fixed-step methods besides rk4 on an ensemble of lattices (K1's plain steppers and host-computed schedule on the
+    # distributed state of lattice_ensemble_adaptive.cuh): every trajectory carries the oracle's bits
+    for cells, m in ((37, 9), (300, 7)):
+        rng = np.random.default_rng(cells + 9)
+        x0 = rng.uniform(0, 1, (cells, m))
+        D = rng.uniform(0.05, 0.3, m)
+        b = rng.uniform(0.3, 0.7, m)
+        env = {}
+        odeintr_b200.compile_sys_openmp("bis", BISTABLE_1D, BISTABLE_PARS, False, method=method, sys_dim=cells, env=env)
+        ora = bo.build(BISTABLE_1D, BISTABLE_PARS, False, method, sys_dim=cells)
+        env["bis_set_params"](D=D, a=1.0, b=b)
+        rec = env["bis"](x0, 2.0, 0.1)
+        assert rec.x.shape == (21, cells, m)
+        for i in range(m):
+            ref = ora.integrate_const(x0[:, i].copy(), 0, 2.0, 0.1, pars=[D[i], 1.0, b[i]])
+            assert np.array_equal(bits(rec.x[:, :, i]), bits(ref["rec"])), (cells, i)
+        at = np.array([0.5, 1.0, 10.0 ** 0.25, 2.2])
+        rec = env["bis_at"](x0, at, 0.2)
+        i = m - 1
+        adv = ora.integrate_const(x0[:, i].copy(), 0.0, at[0], 0.2, record=False, pars=[D[i], 1.0, b[i]])
+        ref = ora.integrate_times(adv["x"], at, 0.2, pars=[D[i], 1.0, b[i]])
+        assert np.array_equal(bits(rec.x[:, :, i]), bits(ref["rec"]))

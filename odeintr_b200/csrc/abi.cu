@@ -243,6 +243,7 @@ struct odeintr_system_s {
   int warp_blocks = 0;          // its resident blocks per SM (0 = not available for the current radius)
   cudaStream_t stream2 = nullptr;        // sharded runs: the halo exchange travels here, beside the interior kernels
   cudaEvent_t ev_edges = nullptr, ev_xchg = nullptr;
+  cudaEvent_t ev_mid = nullptr, ev_side = nullptr;  // fused step pairs: the middle (main stream) and the edges (second stream) of a pair run side by side
   cudaKernel_t k_pilot = nullptr;
   cudaKernel_t k_serial = nullptr;  // general large-system snippet: the right-hand side is one serial kernel (correctness path)
   int order_mode = 0;           // K6: 0 = instances in index order, 1 = sorted by the pilot's cost proxy, 2 = caller's permutation
@@ -2109,6 +2110,8 @@ int odeintr_destroy(odeintr_system_t h) {
     if (h->pipe_done[s]) cudaEventDestroy(h->pipe_done[s]);
     if (h->pipe_stream[s]) cudaStreamDestroy(h->pipe_stream[s]);
   }
+  if (h->ev_mid) cudaEventDestroy(h->ev_mid);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
   if (h->ev_edges) cudaEventDestroy(h->ev_edges);
   if (h->ev_xchg) cudaEventDestroy(h->ev_xchg);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
@@ -2622,6 +2625,8 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
       CU_TRY(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi_prio));
       CU_TRY(cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
       CU_TRY(cudaEventCreateWithFlags(&h->ev_xchg, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     }
     double* cur = h->sh_x;
     double* other = h->lat_buf_a.p;
@@ -2637,6 +2642,7 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
     };
     long long p_ilo = 0, p_ihi = 0;
     bool p_tma = false;
+    bool have_side = false, have_mid = false;  // the second stream carries edges the main stream has not waited for / vice versa
     double* mid = h->lat_buf_acc.p;
     const bool pairs = mid && h->lat_buf_acc.cap >= (size_t)h->sh_fields * (size_t)h->sh_pitch &&
                        slab_pair_possible(h, &p_ilo, &p_ihi, &p_tma, cur, other);
@@ -2654,22 +2660,39 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
           if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
           if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
         } else {
-          if (s == 0 && (rc = exchange_async(cur))) return rc;
-          if (first_of_round) {
-            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
-            CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_xchg, 0));
-            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
-            if (feeds_exchange && (rc = exchange_async(other))) return rc;  // a round of two steps
-          } else {
-            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma))) return rc;
-            if (feeds_exchange && (rc = exchange_async(other))) return rc;
-            if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
+          // The edges of a pair (two launches of a few blocks, then -- at the end of a round -- the ring exchange) travel
+          // on the second stream BESIDE the fused pass over the middle on the main stream: each side waits only for the
+          // other side's previous pair (the middle reads a margin of what the edges produced and vice versa).  At 2^25
+          // cells per GPU the two edge launches were 10 % of a step when they ran in line with the middle.
+          if (s == 0 && (rc = exchange_async(cur))) return rc;  // (the second stream now follows the main one)
+          (void)first_of_round;  // the exchange that feeds this round was queued on the second stream ahead of these edges
+          if (have_side) CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+          if (have_mid) CU_TRY(cudaStreamWaitEvent(h->stream2, h->ev_mid, 0));
+          {
+            cudaStream_t main_stream = h->stream;
+            h->stream = h->stream2;
+            rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_EDGES, p_ilo, p_ihi, p_tma);
+            h->stream = main_stream;
+            if (rc) return rc;
           }
+          CU_TRY(cudaEventRecord(h->ev_side, h->stream2));  // (before the exchange: the next middle does not wait for it)
+          have_side = true;
+          if (feeds_exchange) {
+            if ((rc = lattice_exchange(h, other, h->stream2))) return rc;
+            CU_TRY(cudaEventRecord(h->ev_xchg, h->stream2));
+          }
+          if ((rc = slab_tiled_pair(h, cur, mid, other, t, t2, dt, phase, SLAB_MIDDLE, p_ilo, p_ihi, p_tma))) return rc;
+          CU_TRY(cudaEventRecord(h->ev_mid, h->stream));
+          have_mid = true;
         }
         launches += h->last_launches;
         std::swap(cur, other);
         ++s;
         continue;
+      }
+      if (have_side) {  // a single step after fused pairs: everything the second stream still carries comes first
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+        have_side = false;
       }
       if (!overlap) {
         if (phase == 0 && (rc = lattice_exchange(h, cur, h->stream))) return rc;
@@ -2692,8 +2715,16 @@ int odeintr_lattice_shard_run(odeintr_system_t h, long long first_step, long lon
           if ((rc = slab_tiled_step(h, cur, other, t, dt, phase, SLAB_MIDDLE))) return rc;
         }
       }
+      if (overlap && pairs) {  // pairs that follow let their edges wait for this step
+        CU_TRY(cudaEventRecord(h->ev_mid, h->stream));
+        have_mid = true;
+      }
       launches += h->last_launches;
       std::swap(cur, other);
+    }
+    if (overlap && h->stream2 && h->ev_side) {  // whatever the second stream still carries belongs to this call
+      CU_TRY(cudaEventRecord(h->ev_side, h->stream2));
+      CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
     }
     h->last_launches = launches;
     if (cur != h->sh_x) {

@@ -951,10 +951,23 @@ def lattice2d_secondary(lib, dp_peak):
                 ms.append(s.last_kernel_ms())
         t = statistics.mean(ms) * 1e-3
         rate = n * steps / t
+        launches = s.last_launches()
+        # parity + CPU sample on a 2048 x 2048 lattice: the same steps through the oracle
+        ms_ = 2048
+        ns, steps_s = ms_ * ms_, 10
+        xs = (np.arange(ns) % 7 < 3).astype(np.float64)
+        env = {}
+        ss = odeintr_b200.compile_sys_openmp("b2s", BISTABLE_2D, {"D": 0.1, "a": 1.0, "b": 0.5}, True, method="rk4",
+                                             sys_dim=ns, env=env).system
+        got = env["b2s_no_record"](xs, steps_s * dt, dt)
+        ss.close()
+        ref, cpu = _cpu_lattice_sample(BISTABLE_2D, {"D": 0.1, "a": 1.0, "b": 0.5}, ns, steps_s, dt, xs)
         return {"workload": "periodic 8192 x 8192 bistable lattice through laplace2D (the reference's compile_sys_openmp "
                             "example), rk4 fixed step, %d steps per pass, 512 MiB per array > L2" % steps,
                 "metric": "lattice_rk4_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
-                "ms_per_step": 1e3 * t / steps, "halo": s.get_halo(), "gpu_launches": s.last_launches(),
+                "ms_per_step": 1e3 * t / steps, "halo": s.get_halo(), "gpu_launches": launches,
+                "parity": {"bit_exact_vs_oracle_2048x2048_10_steps": bool(np.array_equal(got.view(np.uint64), ref.view(np.uint64)))},
+                "cpu_baseline": cpu,
                 "roofline": {"bound": "fp64", "achieved": rate * 66.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
                              "frac": rate * 66.0 / dp_peak, "kernel": "odeintr_lattice_rk4_stream2d"}}
     finally:
@@ -1037,7 +1050,9 @@ def lattice_ensemble_secondary(lib, dp_peak):
     try:
         rng = np.random.default_rng(1)
         x0 = rng.integers(0, 2, (cells, m)).astype(np.float64)
-        s.set_params(D=rng.uniform(0.05, 0.3, m), a=1.0, b=rng.uniform(0.3, 0.7, m))
+        Dv = rng.uniform(0.05, 0.3, m)
+        bv = rng.uniform(0.3, 0.7, m)
+        s.set_params(D=Dv, a=1.0, b=bv)
         ms = []
         for rep in range(4):
             s.set_state(x0)
@@ -1047,10 +1062,26 @@ def lattice_ensemble_secondary(lib, dp_peak):
                 ms.append(s.last_kernel_ms())
         t = statistics.mean(ms) * 1e-3
         rate = cells * m * steps / t
+        launches = s.last_launches()
+        # parity + CPU sample: three of the trajectories through the oracle, one at a time (the reference's own loop)
+        from oracle import build_oracle
+
+        fin = s.get_state()
+        ora = build_oracle.build(BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, False, "rk4", sys_dim=cells)
+        ok = True
+        t0 = time.perf_counter()
+        picks = (0, m // 2, m - 1)
+        for i in picks:
+            r = ora.integrate_adaptive(x0[:, i].copy(), 0.0, steps * 0.01, 0.01, pars=[float(Dv[i]), 1.0, float(bv[i])])
+            ok = ok and bool(np.array_equal(np.ascontiguousarray(fin[:, i]).view(np.uint64), r["x"].view(np.uint64)))
+        tc = time.perf_counter() - t0
         return {"workload": "%d trajectories x %d-cell bistable lattice, per-trajectory parameters, rk4, %d steps, "
                             "observer every 100 steps" % (m, cells, steps),
                 "metric": "lattice_ensemble_cell_steps_per_s", "value": rate, "unit": "cell-steps/s",
-                "ms_per_pass": 1e3 * t, "gpu_launches": s.last_launches(),
+                "ms_per_pass": 1e3 * t, "gpu_launches": launches,
+                "parity": {"bit_exact_vs_oracle_3_trajectories": ok},
+                "cpu_baseline": {"value": cells * steps * len(picks) / tc, "unit": "cell-steps/s", "cores": 1, "kind": "port",
+                                 "sample": "%d trajectories one at a time (%.2f s), single thread" % (len(picks), tc)},
                 "roofline": {"bound": "fp64", "achieved": rate * 54.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
                              "frac": rate * 54.0 / dp_peak, "kernel": "odeintr_lattice_ensemble"}}
     finally:

@@ -837,7 +837,10 @@ int lattice_step_halo(odeintr_system_t h, const lattice_window& w, double t, dou
       // strips of 56 columns x segments of stream2d_rows rows, one warp each, strips fastest (neighbouring warps walk
       // down neighbouring strips: whole rows of the lattice are touched together)
       const long long tasks = ((side + 55) / 56) * ((side + h->stream2d_rows - 1) / h->stream2d_rows);
-      const unsigned sgrid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)h->sm_count * h->stream2d_blocks);
+      unsigned sgrid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)h->sm_count * h->stream2d_blocks);
+      // (tests: a grid of a block or two makes every warp walk through several tasks, as on lattices with more tasks
+      //  than resident warps)
+      if (const char* c = std::getenv("ODEINTR_STREAM_MAX_BLOCKS")) sgrid = std::max(1u, std::min(sgrid, (unsigned)std::atoi(c)));
       void* sparams[1] = {&ta};
       CU_TRY(cudaLaunchKernel((const void*)h->k_stream2d, dim3(sgrid), dim3(256), sparams, 0, h->stream));
       h->last_launches += 1;

@@ -161,7 +161,8 @@ struct lattice_dopri5 {
       const long long side = h->lat_side;
       const long long tasks = ((side + 51) / 52) * ((side + h->stream5_rows - 1) / h->stream5_rows);
       const long long wpb = h->stream5_threads / 32;
-      const unsigned grid = (unsigned)std::min<long long>((tasks + wpb - 1) / wpb, (long long)h->sm_count * h->stream5_blocks);
+      unsigned grid = (unsigned)std::min<long long>((tasks + wpb - 1) / wpb, (long long)h->sm_count * h->stream5_blocks);
+      if (const char* c = std::getenv("ODEINTR_STREAM_MAX_BLOCKS")) grid = std::max(1u, std::min(grid, (unsigned)std::atoi(c)));  // (tests)
       void* params[1] = {&a};
       if (cudaLaunchKernel((const void*)h->k_stream5, dim3(grid), dim3((unsigned)h->stream5_threads), params, 0, h->stream) != cudaSuccess) {
         if (!rc) rc = fail(ODEINTR_E_CUDA, "launch of odeintr_lattice_dopri5_stream2d failed");

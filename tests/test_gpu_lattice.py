@@ -800,6 +800,27 @@ def test_large_system_bulirsch_stoer(case, method):
     assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0, 4.05, 0.1)["x"]))
 
 
+@pytest.mark.parametrize("method", ["rk4", "rk5_i"])
+def test_2d_lattice_streaming_kernels_several_tasks_per_warp(method, monkeypatch):
+    # On the benchmark lattices (8192 x 8192: ~3500 tasks over 1184 / 2368 resident warps) every warp of the persistent
+    # streaming kernels walks through several (strip, row segment) tasks, re-priming its register pipeline for each.  At
+    # test sizes there are fewer tasks than warps, so the grid is capped at two blocks here: 6 strips x 14 segments = 84
+    # tasks over 16 warps.  Oracle's bits, for K4s2 and K4ds2.
+    m = 330
+    monkeypatch.setenv("ODEINTR_STREAM_MAX_BLOCKS", "2")
+    monkeypatch.setenv("ODEINTR_STREAM2_ROWS", "24")
+    monkeypatch.setenv("ODEINTR_STREAM5_ROWS", "24")
+    env = {}
+    code = odeintr_b200.compile_sys_openmp("mt", BISTABLE_2D, BISTABLE_PARS, True, method=method, sys_dim=m * m, env=env)
+    ora = bo.build(BISTABLE_2D, BISTABLE_PARS, True, method, sys_dim=m * m)
+    x0 = np.random.default_rng(m + 1).uniform(0, 1, m * m)
+    fin = env["mt_no_record"](x0, 0.7, 0.1)
+    assert np.array_equal(bits(fin), bits(ora.integrate_adaptive(x0, 0.0, 0.7, 0.1)["x"]))
+    if method == "rk5_i":
+        st = code.system.stats()
+        assert code.system.last_launches() <= st["accepted"][0] + st["rejected"][0] + 3  # the streaming kernel took the attempts
+
+
 @pytest.mark.parametrize("method", ["rk5_i", "rk5_a", "rk5"])
 @pytest.mark.parametrize("case", ["laplace2D_128", "documented_192", "laplace2D_66", "staged_128"])
 def test_2d_lattice_streaming_dopri5_bit_exact(case, method, monkeypatch):

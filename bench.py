@@ -397,7 +397,8 @@ def main():
                      ("lattice_rk4", lattice_secondary), ("lattice_chain_rk4", chain_secondary),
                      ("lattice_dopri5", lattice_dopri5_secondary),
                      ("lattice2d_rk4", lattice2d_secondary), ("lattice2d_dopri5", lattice2d_dopri5_secondary),
-                     ("lattice_ensemble_rk4", lattice_ensemble_secondary))
+                     ("lattice_ensemble_rk4", lattice_ensemble_secondary),
+                     ("lattice_ensemble_dopri5", lattice_ensemble_adaptive_secondary))
             for key, fn in table:
                 t_sec = time.perf_counter()
                 try:
@@ -1085,6 +1086,64 @@ def lattice_ensemble_secondary(lib, dp_peak):
                                  "sample": "%d trajectories one at a time (%.2f s), single thread" % (len(picks), tc)},
                 "roofline": {"bound": "fp64", "achieved": rate * 54.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
                              "frac": rate * 54.0 / dp_peak, "kernel": "odeintr_lattice_ensemble"}}
+    finally:
+        s.close()
+
+
+def lattice_ensemble_adaptive_secondary(lib, dp_peak):
+    """Ensemble of wider systems under compile_sys_openmp's DEFAULT method: 2^12 trajectories of a 1024-cell bistable
+    lattice with per-trajectory parameters, rk5_i (adaptive dopri5, dense output at 4 times), one block per trajectory
+    with its own step sizes (K5a, lattice_ensemble_adaptive.cuh).  111 DP instructions per cell and attempt."""
+    import numpy as np
+
+    import odeintr_b200
+    from odeintr_b200 import _abi
+
+    cells, m = 1024, 1 << 12
+    s = odeintr_b200.compile_sys_openmp("bisa", BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, False, sys_dim=cells).system
+    try:
+        rng = np.random.default_rng(2)
+        x0 = rng.uniform(0, 1, (cells, m))
+        Dv = rng.uniform(0.05, 0.3, m)
+        bv = rng.uniform(0.3, 0.7, m)
+        s.set_params(D=Dv, a=1.0, b=bv)
+        at = np.array([0.0, 1.0, 5.0, 10.0])
+        ms = []
+        for rep in range(3):
+            s.set_state(x0)
+            if lib.odeintr_integrate_times(s._h, at.ctypes.data_as(_abi.c_dbl_p), at.size, 0.1) != 0:
+                raise RuntimeError(_abi.last_error())
+            if rep:
+                ms.append(s.last_kernel_ms())
+        st = s.stats()
+        fin = s.get_state()
+        tries = int(st["accepted"].sum() + st["rejected"].sum())
+        t = statistics.mean(ms) * 1e-3
+        rate = cells * tries / t
+        launches = s.last_launches()
+        from oracle import build_oracle
+
+        ora = build_oracle.build(BISTABLE_1D, {"D": 0.1, "a": 1.0, "b": 0.5}, False, "rk5_i", sys_dim=cells)
+        worst, counts_equal, cpu_tries = 0.0, True, 0
+        t0 = time.perf_counter()
+        picks = (0, m // 2, m - 1)
+        for i in picks:
+            r = ora.integrate_times(x0[:, i].copy(), at, 0.1, pars=[float(Dv[i]), 1.0, float(bv[i])])
+            last = r["rec"][-1]
+            worst = max(worst, float(np.max(np.abs(fin[:, i] - last) / (1.0 + np.abs(last)))))
+            counts_equal = counts_equal and int(st["accepted"][i]) == r["accepted"] and int(st["rejected"][i]) == r["rejected"]
+            cpu_tries += r["accepted"] + r["rejected"]
+        tc = time.perf_counter() - t0
+        return {"workload": "%d trajectories x %d-cell bistable lattice, per-trajectory parameters, default method rk5_i, "
+                            "NAME_at(x0, c(0, 1, 5, 10))" % (m, cells),
+                "metric": "lattice_ensemble_cell_attempts_per_s", "value": rate, "unit": "cell-attempts/s",
+                "ms_per_pass": 1e3 * t, "gpu_launches": launches, "attempts": tries,
+                "parity": {"max_err_over_1_plus_abs_3_trajectories": worst, "tolerance_10_rtol": 1e-5, "ok": bool(worst <= 1e-5),
+                           "step_counts_equal": bool(counts_equal)},
+                "roofline": {"bound": "fp64", "achieved": rate * 111.0 / 1e12, "peak": dp_peak / 1e12, "unit": "TFLOP/s",
+                             "frac": rate * 111.0 / dp_peak, "kernel": "odeintr_lattice_ensemble_dopri5_dense"},
+                "cpu_baseline": {"value": cells * cpu_tries / tc, "unit": "cell-attempts/s", "cores": 1, "kind": "port",
+                                 "sample": "%d trajectories one at a time (%.2f s), single thread" % (len(picks), tc)}}
     finally:
         s.close()
 

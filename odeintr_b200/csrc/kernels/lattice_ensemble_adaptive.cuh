@@ -54,9 +54,13 @@ struct block_system {
     if (NT == 32) __syncwarp();
     else __syncthreads();
   }
-  // (not inlined: the steppers call it seven times per attempt and every integrate loop instantiates them -- inlined
-  // the translation unit grows to 20 MB and takes a minute to compile; the call costs nothing next to the barrier)
-  __device__ __noinline__ void sys(const vec<NE>& x, vec<NE>& k, const double t) {
+  // The right-hand side sits behind a call: the steppers ask for it seven times per attempt and every integrate loop
+  // instantiates them -- inlined, the translation unit grows to 20 MB and takes minutes to compile.  The call takes
+  // and returns the thread's entries BY VALUE, so that the steppers' stage vectors stay in registers (with references
+  // every vector that ever meets the right-hand side would live in local memory).
+  ODEINTR_DEV void sys(const vec<NE>& x, vec<NE>& k, const double t) { k = rhs(x, t); }
+  __device__ __noinline__ vec<NE> rhs(const vec<NE> x, const double t) {
+    vec<NE> k;
     double* const R = ring[phase];
     phase ^= 1;
 #pragma unroll
@@ -89,6 +93,7 @@ struct block_system {
 #pragma unroll
       for (int f = 0; f < F; ++f) k[c * F + f] = kk[f];
     }
+    return k;
   }
   // maximum over the trajectory's threads, known to all of them afterwards
   ODEINTR_DEV double block_max(double e) {

@@ -41,8 +41,7 @@ struct block_system {
   static constexpr int NE = C * F;
   typedef lattice_rel_view<true> View;
   UserSys user;
-  View view;
-  rel_index idx;
+  int bad;           // a read beyond the stencil radius was seen
   double* ring[2];   // stage-state rings of this trajectory (fields x (L + 2 halo))
   double* red;       // per-warp partial maxima, two alternating rows
   int phase, rphase;
@@ -78,6 +77,14 @@ struct block_system {
       }
     }
     barrier();
+    // the view and the symbolic index are rebuilt here from compile-time constants: read back from the object (which
+    // lives in local memory on this side of the call) the lattice length would be a run-time number and every state
+    // access of the snippet would pay 64-bit divisions for its field / displacement split (ncu: 12 800 instructions per
+    // warp and attempt, 3 % of them FP64)
+    View view;
+    view.n_total = L; view.width = W; view.halo = h; view.bad = 0;
+    rel_index idx;
+    idx.off = 0; idx.cells = L; idx.rel = true;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = tid + c * NT;
@@ -93,6 +100,7 @@ struct block_system {
 #pragma unroll
       for (int f = 0; f < F; ++f) k[c * F + f] = kk[f];
     }
+    bad |= view.bad;
     return k;
   }
   // maximum over the trajectory's threads, known to all of them afterwards
@@ -167,8 +175,7 @@ ODEINTR_DEV void lattice_ensemble_adaptive_body(const odeintr_lattice_ensemble_a
     for (int f = 0; f < F; ++f) sys.fld[f] = static_cast<int>(off[f] / L);
   }
   const long long start = sys.user.cell_start(), bound = sys.user.cell_bound();
-  sys.view.n_total = L; sys.view.width = W; sys.view.halo = h; sys.view.bad = 0;
-  sys.idx.off = 0; sys.idx.cells = L; sys.idx.rel = true;
+  sys.bad = 0;
 
   vec<NE> x;
 #pragma unroll
@@ -228,7 +235,7 @@ ODEINTR_DEV void lattice_ensemble_adaptive_body(const odeintr_lattice_ensemble_a
     if (a.rows) a.rows[inst] = obs.rows;
     if (a.rows_min) atomicMin(a.rows_min, obs.rows);
   }
-  if (sys.view.bad) *b.flag = 1;
+  if (sys.bad) *b.flag = 1;
 }
 
 // The fixed-step methods other than rk4 (euler, rk54, rk5, rk78; rk4 has the register-blocked kernel of
@@ -261,8 +268,7 @@ ODEINTR_DEV void lattice_ensemble_plain_body(const odeintr_lattice_ensemble_args
     for (int f = 0; f < F; ++f) sys.fld[f] = static_cast<int>(off[f] / L);
   }
   const long long start = sys.user.cell_start(), bound = sys.user.cell_bound();
-  sys.view.n_total = L; sys.view.width = W; sys.view.halo = h; sys.view.bad = 0;
-  sys.idx.off = 0; sys.idx.cells = L; sys.idx.rel = true;
+  sys.bad = 0;
   vec<NE> x;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
@@ -309,7 +315,7 @@ ODEINTR_DEV void lattice_ensemble_plain_body(const odeintr_lattice_ensemble_args
       for (int f = 0; f < F; ++f) a.x[(static_cast<long long>(sys.fld[f]) * L + j) * a.ld + inst] = x[c * F + f];
     }
   }
-  if (sys.view.bad) *b.flag = 1;
+  if (sys.bad) *b.flag = 1;
 }
 
 }  // namespace odeintr_b200

@@ -53,12 +53,13 @@ struct block_system {
     if (NT == 32) __syncwarp();
     else __syncthreads();
   }
-  // The right-hand side sits behind a call: the steppers ask for it seven times per attempt and every integrate loop
-  // instantiates them -- inlined, the translation unit grows to 20 MB and takes minutes to compile.  The call takes
-  // and returns the thread's entries BY VALUE, so that the steppers' stage vectors stay in registers (with references
-  // every vector that ever meets the right-hand side would live in local memory).
+  // The steppers ask for the right-hand side through vec<NE> references; it takes and returns the thread's entries by
+  // value so that the stage vectors stay in registers.  (History, profiles/r02_k5a.md: first behind a call because the
+  // inlined form compiled for minutes -- until ncu showed 12 800 instructions per warp and attempt, 3 % of them FP64: the
+  // view's lattice length was a run-time member, so every state access paid 64-bit divisions.  With the view rebuilt
+  // from constants below the inlined form compiles in seconds and runs 7x faster than that first version.)
   ODEINTR_DEV void sys(const vec<NE>& x, vec<NE>& k, const double t) { k = rhs(x, t); }
-  __device__ __noinline__ vec<NE> rhs(const vec<NE> x, const double t) {
+  ODEINTR_DEV vec<NE> rhs(const vec<NE> x, const double t) {
     vec<NE> k;
     double* const R = ring[phase];
     phase ^= 1;
@@ -77,10 +78,8 @@ struct block_system {
       }
     }
     barrier();
-    // the view and the symbolic index are rebuilt here from compile-time constants: read back from the object (which
-    // lives in local memory on this side of the call) the lattice length would be a run-time number and every state
-    // access of the snippet would pay 64-bit divisions for its field / displacement split (ncu: 12 800 instructions per
-    // warp and attempt, 3 % of them FP64)
+    // the view and the symbolic index are built here from compile-time constants: the snippet's index expressions then
+    // fold to fixed shared-memory offsets (a run-time lattice length costs 64-bit divisions per state access)
     View view;
     view.n_total = L; view.width = W; view.halo = h; view.bad = 0;
     rel_index idx;

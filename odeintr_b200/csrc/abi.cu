@@ -165,6 +165,7 @@ std::vector<std::string> nvrtc_options(unsigned flags) {
   if (const char* c = std::getenv("ODEINTR_STREAM2_L2_AHEAD")) o.push_back(std::string("-DODEINTR_STREAM2_L2_AHEAD=") + c);
   if (std::getenv("ODEINTR_STREAM5_LATE_NORM")) o.push_back("-DODEINTR_STREAM5_LATE_NORM=1");
   if (std::getenv("ODEINTR_DP5_LITERALS")) o.push_back("-DODEINTR_DP5_LITERALS=1");
+  if (const char* c = std::getenv("ODEINTR_ENS_ADAPTIVE_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_ENS_ADAPTIVE_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM5_THREADS")) o.push_back(std::string("-DODEINTR_STREAM5_THREADS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM5_MIN_BLOCKS")) o.push_back(std::string("-DODEINTR_STREAM5_MIN_BLOCKS=") + c);
   if (const char* c = std::getenv("ODEINTR_STREAM2_ROWS")) o.push_back(std::string("-DODEINTR_STREAM2_ROWS=") + c);

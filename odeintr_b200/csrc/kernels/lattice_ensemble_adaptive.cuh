@@ -335,8 +335,11 @@ odeintr_lattice_ensemble_plain(const odeintr_lattice_ensemble_args a) {
 #endif
 
 // one kernel per stepper the translation unit's method can ask for (the stage count is how the generator names it)
+#ifndef ODEINTR_ENS_ADAPTIVE_MIN_BLOCKS  // resident blocks per SM the adaptive kernels are compiled for (register cap)
+#define ODEINTR_ENS_ADAPTIVE_MIN_BLOCKS 2  // measured (profiles/r02_k5a.md): 128 registers / 2 blocks 1.89 ms, 156 / 1 block 2.73 ms
+#endif
 #define ODEINTR_ENS_ADAPTIVE_KERNEL(NAME, STEPPER)                                                  \
-  extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP)             \
+  extern "C" __global__ void __launch_bounds__(ODEINTR_ENS_THREADS * ODEINTR_ENS_GROUP, ODEINTR_ENS_ADAPTIVE_MIN_BLOCKS) \
   NAME(const odeintr_lattice_ensemble_adaptive_args a) {                                            \
     odeintr_b200::lattice_ensemble_adaptive_body<odeintr_b200::STEPPER>(a);                         \
   }

@@ -128,6 +128,93 @@ def test_two_rank_exchange_every_k_steps_matches_oracle(interval):
     assert np.array_equal(got.view(np.uint64), rec["rec"][-1].view(np.uint64))
 
 
+def _window_step(buf, lo, hi, dt):
+    """cells [lo, hi) of the next state from buf (valid on [lo - 4, hi + 4)), as a new array of hi - lo values"""
+    w = buf[lo - 4:hi + 4].copy()
+    return _sharded_rk4_step(w, 4, dt)[4:-4]
+
+
+def _worker_pairs(rank, world, port, n_total, steps, dt, x0, interval, q):
+    """odeintr_lattice_shard_run with FUSED STEP PAIRS (abi.cu: slab_pair_possible / slab_tiled_pair), in the slab's
+    local numbering: two consecutive steps of a round produce the middle [ilo, ihi) in one pass that reads `cur` only
+    (a margin of 2 x 4 cells), the edges [lo1, ilo + 4) u [ihi - 4, hi1) go cur -> mid, then [lo2, ilo) u [ihi, hi2)
+    mid -> other; steps a round cannot pair are single steps.  The region arithmetic is the C-ABI's."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m1, halo = 4, 1
+    g = m1 * interval
+    b, e = shard_range(n_total, rank, world)
+    n = e - b
+    cur = np.zeros(n + 2 * g)
+    cur[g:g + n] = x0[b:e]
+    c0 = g  # local index of the first owned cell
+    e_lo, e_hi = c0 + g, c0 + n - g
+    ilo, ihi = max(e_lo, c0 + 2 * m1 + halo), min(e_hi, c0 + n - 2 * m1 - halo)
+    assert ihi - ilo > 4 * m1
+    s = 0
+    while s < steps:
+        phase = s % interval
+        if phase == 0:
+            t = torch.from_numpy(cur).reshape(1, -1)
+            exchange_halos(t, g, rank, world)
+            cur = t.numpy().reshape(-1).copy()
+        lo1, hi1 = c0 - g + m1 * (phase + 1), c0 + n + g - m1 * (phase + 1)
+        other = np.full_like(cur, np.nan)
+        if phase + 1 < interval and s + 1 < steps:
+            lo2, hi2 = lo1 + m1, hi1 - m1
+            mid = np.full_like(cur, np.nan)
+            # edges, first step: everything the second step of the edges reads
+            mid[lo1:min(ilo + m1, hi1)] = _window_step(cur, lo1, min(ilo + m1, hi1), dt)
+            mid[max(ihi - m1, lo1):hi1] = _window_step(cur, max(ihi - m1, lo1), hi1, dt)
+            other[lo2:ilo] = _window_step(mid, lo2, ilo, dt)
+            other[ihi:hi2] = _window_step(mid, ihi, hi2, dt)
+            # the middle: both steps from `cur` alone (what the fused pass keeps in registers)
+            first = np.full_like(cur, np.nan)
+            first[ilo - m1:ihi + m1] = _window_step(cur, ilo - m1, ihi + m1, dt)
+            other[ilo:ihi] = _window_step(first, ilo, ihi, dt)
+            s += 2
+        else:
+            other[lo1:hi1] = _window_step(cur, lo1, hi1, dt)
+            s += 1
+        cur = other
+    q.put((rank, True, cur[c0:c0 + n].copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("interval,steps", [(8, 19), (3, 7), (2, 5)])
+def test_two_rank_fused_step_pairs_match_oracle(interval, steps):
+    # the pair schedule of odeintr_lattice_shard_run: whatever the round length (odd rounds leave a single step, calls
+    # that end mid-round too), no launch ever reads a cell that is not valid (NaN would spread) and the owned cells carry
+    # the oracle's bits
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import build_oracle as bo
+    from systems import BISTABLE_1D, BISTABLE_PARS
+
+    n_total, dt = 331, 0.1
+    x0 = np.random.default_rng(29).uniform(0, 1, n_total)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pairs, args=(r, 2, port, n_total, steps, dt, x0, interval, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = dict()
+    for _ in range(2):
+        rank, _, part = q.get(timeout=240)
+        parts[rank] = part
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.concatenate([parts[0], parts[1]])
+    ora = bo.build(BISTABLE_1D, BISTABLE_PARS, True, "rk4", sys_dim=n_total)
+    rec = ora.integrate_const(x0, 0.0, steps * dt + dt / 2, dt)
+    assert rec["rows"] == steps + 1
+    assert np.array_equal(got.view(np.uint64), rec["rec"][-1].view(np.uint64))
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_wide_halo_rk4_matches_oracle():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
